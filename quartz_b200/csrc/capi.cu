@@ -1,0 +1,480 @@
+// C ABI (include/quartz_gpu.h).  Host glue only: owns device buffers, lowers graphs, launches kernels.
+// No CPU evaluation path exists here by design — if CUDA is unusable every device entry point fails loudly.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/quartz_gpu.h"
+#include "fused.h"
+#include "graph.h"
+#include "kernels.h"
+#include "lower.h"
+
+using namespace qg;
+
+struct qg_net { Graph g; };
+struct qg_ctx {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  long launches;
+};
+struct qg_bank {
+  qg_ctx* ctx;
+  Tape tape;
+  long V;
+  int Vp;
+  int path;
+  Instr* d_code = nullptr;
+  uint16_t* d_out_x = nullptr;
+  float* d_params = nullptr;
+  float* d_state = nullptr;
+  float* d_state_init = nullptr;
+  float* d_rings = nullptr;
+  Ring* d_ring_tab = nullptr;
+  ResetRange* d_resets = nullptr;
+  float* d_tables = nullptr;
+  float* d_scratch = nullptr;
+  size_t scratch_bytes = 0;
+  float* d_in = nullptr;
+  size_t in_bytes = 0;
+  FusedPlan fused;
+};
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      g_err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;                       \
+      return QG_ERR_CUDA;                                                                                \
+    }                                                                                                    \
+  } while (0)
+
+template <typename F>
+static qg_net* guard_net(F f) {
+  try {
+    return new qg_net{f()};
+  } catch (const std::exception& e) {
+    g_err = std::string("internal error: ") + e.what();
+    return nullptr;
+  }
+}
+static std::vector<const Graph*> gv(const qg_net* const* nets, int n) {
+  std::vector<const Graph*> v;
+  for (int i = 0; i < n; i++) v.push_back(nets && nets[i] ? &nets[i]->g : nullptr);
+  return v;
+}
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
+  *dst = nullptr;
+  if (src.empty()) { CU(cudaMalloc((void**)dst, sizeof(T))); return QG_OK; }
+  CU(cudaMalloc((void**)dst, src.size() * sizeof(T)));
+  CU(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return QG_OK;
+}
+
+extern "C" {
+
+const char* qg_last_error(void) { return g_err.c_str(); }
+const char* qg_version(void) { return "quartz_gpu 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------ graph construction
+qg_net* qg_str_to_net(const char* op) { return guard_net([&] { return str_to_net(op ? op : ""); }); }
+qg_net* qg_net_new(int ni, int no) { return guard_net([&] { return Graph(ni, no); }); }
+qg_net* qg_net_clone(const qg_net* n) { return n ? guard_net([&] { return n->g; }) : nullptr; }
+void qg_net_free(qg_net* n) { delete n; }
+int qg_net_inputs(const qg_net* n) { return n ? n->g.inputs() : 0; }
+int qg_net_outputs(const qg_net* n) { return n ? n->g.outputs() : 0; }
+int qg_net_size(const qg_net* n) { return n ? n->g.size() : 0; }
+int qg_net_set_sample_rate(qg_net* n, double sr) {
+  if (!n) return fail(QG_ERR_ARG, "null net");
+  n->g.set_sample_rate(sr);
+  return QG_OK;
+}
+const char* qg_net_unsupported(const qg_net* n) { return (n && !n->g.unsupported.empty()) ? n->g.unsupported.c_str() : nullptr; }
+qg_net* qg_connect(const char* op, const qg_net* const* nets, int n, double number, int node_limit) {
+  return guard_net([&] { return connect(op ? op : "", gv(nets, n), number, node_limit); });
+}
+qg_net* qg_array_op(const char* kind, const char* op_str, const float* arr, int n) {
+  return guard_net([&] { return array_op(kind ? kind : "", op_str ? op_str : "", std::vector<float>(arr, arr + n)); });
+}
+qg_net* qg_get(const float* arr, int n) { return guard_net([&] { return make_get(std::vector<float>(arr, arr + n)); }); }
+qg_net* qg_quantize(const float* arr, int n) { return guard_net([&] { return make_quantize(std::vector<float>(arr, arr + n)); }); }
+qg_net* qg_wave(const float* arr, int n) { return guard_net([&] { return make_wave(std::vector<float>(arr, arr + n)); }); }
+qg_net* qg_feedback(const qg_net* net, int has_delay, double delay) {
+  return guard_net([&] { return net ? make_feedback(net->g, has_delay != 0, delay) : Graph(0, 0); });
+}
+qg_net* qg_kr(const qg_net* net, double n, int preserve_time) {
+  return guard_net([&] { return net ? make_kr(net->g, n, preserve_time != 0) : Graph(0, 0); });
+}
+qg_net* qg_reset_every(const qg_net* net, double s) { return guard_net([&] { return net ? make_reset(net->g, s) : Graph(0, 0); }); }
+qg_net* qg_trig_reset(const qg_net* net, int variable) {
+  return guard_net([&] { return net ? make_trig_reset(net->g, variable != 0) : Graph(0, 0); });
+}
+qg_net* qg_seq_select(int is_seq, const qg_net* const* nets, int n) {
+  return guard_net([&] { return make_seq_select(is_seq != 0, gv(nets, n)); });
+}
+qg_net* qg_live_io(const char* name) { return guard_net([&] { return make_live_io(name ? name : ""); }); }
+
+int qg_net_raw_count(const qg_net* n) {
+  if (!n) return 0;
+  std::vector<float> r;
+  collect_raw(n->g, &r);
+  return (int)r.size();
+}
+int qg_net_raw_params(const qg_net* n, float* out, int cap) {
+  if (!n) return 0;
+  std::vector<float> r;
+  collect_raw(n->g, &r);
+  for (int i = 0; i < (int)r.size() && i < cap; i++) out[i] = r[i];
+  return (int)r.size();
+}
+uint64_t qg_net_signature(const qg_net* n) { return n ? structure_signature(n->g) : 0; }
+int qg_net_tape_info(const qg_net* n, int* n_instr, int* n_params, int* n_state, int* n_temps, int* divergent) {
+  if (!n) return fail(QG_ERR_ARG, "null net");
+  Tape t;
+  std::string err;
+  if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
+  if (n_instr) *n_instr = (int)t.h.n_instr;
+  if (n_params) *n_params = (int)t.h.n_params;
+  if (n_state) *n_state = (int)t.h.n_state;
+  if (n_temps) *n_temps = (int)t.h.n_temps;
+  if (divergent) *divergent = (t.h.flags & TAPE_DIVERGENT) ? 1 : 0;
+  return QG_OK;
+}
+
+// ------------------------------------------------------------------------------------ device
+qg_ctx* qg_ctx_create(int device, void* stream) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_err = std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); quartz_gpu has no CPU fallback";
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { g_err = "device index out of range"; return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return nullptr; }
+  qg_ctx* c = new (std::nothrow) qg_ctx();
+  if (!c) return nullptr;
+  c->device = device;
+  c->launches = 0;
+  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; g_err = "cudaStreamCreate failed"; return nullptr; }
+    c->own_stream = true;
+  }
+  return c;
+}
+void qg_ctx_destroy(qg_ctx* c) {
+  if (!c) return;
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+int qg_ctx_synchronize(qg_ctx* c) {
+  if (!c) return fail(QG_ERR_ARG, "null ctx");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return QG_OK;
+}
+long qg_ctx_launch_count(const qg_ctx* c) { return c ? c->launches : 0; }
+void* qg_device_alloc(qg_ctx* c, size_t bytes) {
+  if (!c) return nullptr;
+  void* p = nullptr;
+  cudaSetDevice(c->device);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) { g_err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); return nullptr; }
+  return p;
+}
+void qg_device_free(qg_ctx* c, void* p) { if (c) cudaSetDevice(c->device); if (p) cudaFree(p); }
+void* qg_host_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; }
+  return p;
+}
+void qg_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+static void bank_release(qg_bank* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaFree(b->d_code); cudaFree(b->d_out_x); cudaFree(b->d_params); cudaFree(b->d_state); cudaFree(b->d_state_init);
+  cudaFree(b->d_rings); cudaFree(b->d_ring_tab); cudaFree(b->d_resets); cudaFree(b->d_tables); cudaFree(b->d_scratch);
+  cudaFree(b->d_in);
+  delete b;
+}
+
+static int bank_init_state(qg_bank* b, const uint64_t* salts) {
+  qg_ctx* c = b->ctx;
+  const Tape& t = b->tape;
+  int NS = (int)t.h.n_state;
+  uint32_t* d_def = nullptr;
+  HashInit* d_hi = nullptr;
+  uint64_t* d_salts = nullptr;
+  int rc = upload(&d_def, t.state_init, c->stream);
+  if (rc) return rc;
+  rc = upload(&d_hi, t.hash_init, c->stream);
+  if (rc) return rc;
+  if (salts) {
+    std::vector<uint64_t> s((size_t)b->Vp, 0);
+    for (long v = 0; v < b->V; v++) s[v] = salts[v];
+    rc = upload(&d_salts, s, c->stream);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));   // `s` is about to go out of scope
+  }
+  if (NS > 0) {
+    CU(launch_init_state(b->d_state_init, d_def, NS, b->Vp, d_hi, (int)t.hash_init.size(), d_salts, c->stream));
+    c->launches++;
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  cudaFree(d_def); cudaFree(d_hi); cudaFree(d_salts);
+  return QG_OK;
+}
+
+static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, const uint64_t* salts) {
+  qg_ctx* c = b->ctx;
+  Tape& t = b->tape;
+  CU(cudaSetDevice(c->device));
+  const int P = (int)t.h.n_params, NS = (int)t.h.n_state, R = (int)t.h.n_raw;
+  b->Vp = (int)((b->V + 127) / 128 * 128);
+  size_t need = ((size_t)P + 2 * (size_t)NS + (size_t)t.h.ring_floats) * b->Vp * sizeof(float);
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  if (need > free_b) return fail(QG_ERR_CUDA, "bank needs " + std::to_string(need >> 20) + " MiB of HBM, only " +
+                                                  std::to_string(free_b >> 20) + " MiB free");
+  int rc;
+  if ((rc = upload(&b->d_code, t.code, c->stream))) return rc;
+  if ((rc = upload(&b->d_out_x, t.out_x, c->stream))) return rc;
+  if ((rc = upload(&b->d_ring_tab, t.rings, c->stream))) return rc;
+  if ((rc = upload(&b->d_resets, t.resets, c->stream))) return rc;
+  if ((rc = upload(&b->d_tables, t.tables, c->stream))) return rc;
+  CU(cudaMalloc((void**)&b->d_params, std::max<size_t>(1, (size_t)P * b->Vp) * sizeof(float)));
+  CU(cudaMalloc((void**)&b->d_state, std::max<size_t>(1, (size_t)NS * b->Vp) * sizeof(float)));
+  CU(cudaMalloc((void**)&b->d_state_init, std::max<size_t>(1, (size_t)NS * b->Vp) * sizeof(float)));
+  CU(cudaMalloc((void**)&b->d_rings, std::max<size_t>(1, (size_t)t.h.ring_floats * b->Vp) * sizeof(float)));
+  // ---- parameters: derive per voice on the host (same libm as the reference would use), or broadcast the template
+  if (raw_matrix && R > 0 && P > 0) {
+    for (int r = 0; r < R; r++) {
+      if (!t.raw_structural[r]) continue;
+      for (long v = 0; v < b->V; v++)
+        if (memcmp(&raw_matrix[(size_t)v * R + r], &t.raw[r], 4) != 0)
+          return fail(QG_ERR_MISMATCH, "raw parameter " + std::to_string(r) + " shapes the tape (delay length / reset period) and must be equal for every voice");
+    }
+    std::vector<float> host((size_t)P * b->Vp);
+    std::vector<float> pv(P);
+    for (long v = 0; v < b->Vp; v++) {
+      long src = v < b->V ? v : b->V - 1;
+      for (int p = 0; p < P; p++) pv[p] = t.params[p];
+      t.derive(raw_matrix + (size_t)src * R, pv.data());
+      for (int p = 0; p < P; p++) host[(size_t)p * b->Vp + v] = pv[p];
+    }
+    CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } else if (P > 0) {
+    float* d_tmpl = nullptr;
+    if ((rc = upload(&d_tmpl, t.params, c->stream))) return rc;
+    CU(launch_broadcast_params(b->d_params, d_tmpl, P, b->Vp, c->stream));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tmpl);
+  }
+  if ((rc = bank_init_state(b, salts))) return rc;
+  b->fused = plan_fused(t);
+  return qg_bank_reset(b);
+}
+
+qg_bank* qg_bank_create(qg_ctx* ctx, const qg_net* tmpl, long n_voices, const float* raw, const uint64_t* salts) {
+  if (!ctx || !tmpl || n_voices <= 0) { g_err = "qg_bank_create: bad arguments"; return nullptr; }
+  qg_bank* b = new (std::nothrow) qg_bank();
+  if (!b) return nullptr;
+  b->ctx = ctx; b->V = n_voices; b->path = QG_PATH_AUTO;
+  std::string err;
+  try {
+    if (!lower(tmpl->g, &b->tape, &err)) { g_err = err; delete b; return nullptr; }
+    if (bank_build(b, raw, salts) != QG_OK) { bank_release(b); return nullptr; }
+  } catch (const std::exception& e) {
+    g_err = std::string("internal error: ") + e.what();
+    bank_release(b);
+    return nullptr;
+  }
+  return b;
+}
+
+qg_bank* qg_bank_from_nets(qg_ctx* ctx, const qg_net* const* nets, long n, const uint64_t* salts) {
+  if (!ctx || !nets || n <= 0 || !nets[0]) { g_err = "qg_bank_from_nets: bad arguments"; return nullptr; }
+  try {
+    uint64_t sig = structure_signature(nets[0]->g);
+    std::vector<float> r0;
+    collect_raw(nets[0]->g, &r0);
+    size_t R = r0.size();
+    std::vector<float> raw((size_t)n * std::max<size_t>(R, 1));
+    for (long v = 0; v < n; v++) {
+      if (!nets[v] || structure_signature(nets[v]->g) != sig) {
+        g_err = "qg_bank_from_nets: net " + std::to_string(v) + " does not have the structure of net 0";
+        return nullptr;
+      }
+      std::vector<float> r;
+      collect_raw(nets[v]->g, &r);
+      if (r.size() != R) { g_err = "qg_bank_from_nets: parameter count mismatch"; return nullptr; }
+      for (size_t k = 0; k < R; k++) raw[(size_t)v * R + k] = r[k];
+    }
+    return qg_bank_create(ctx, nets[0], n, R ? raw.data() : nullptr, salts);
+  } catch (const std::exception& e) {
+    g_err = std::string("internal error: ") + e.what();
+    return nullptr;
+  }
+}
+
+void qg_bank_free(qg_bank* b) { bank_release(b); }
+
+int qg_bank_reset(qg_bank* b) {
+  if (!b) return fail(QG_ERR_ARG, "null bank");
+  qg_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  size_t ns = (size_t)b->tape.h.n_state * b->Vp * sizeof(float);
+  if (ns) CU(cudaMemcpyAsync(b->d_state, b->d_state_init, ns, cudaMemcpyDeviceToDevice, c->stream));
+  size_t rb = (size_t)b->tape.h.ring_floats * b->Vp * sizeof(float);
+  if (rb) CU(cudaMemsetAsync(b->d_rings, 0, rb, c->stream));
+  return QG_OK;
+}
+int qg_bank_set_path(qg_bank* b, int path) {
+  if (!b) return fail(QG_ERR_ARG, "null bank");
+  b->path = path;
+  return QG_OK;
+}
+const char* qg_bank_kernel(const qg_bank* b) {
+  if (!b) return "";
+  if (b->path == QG_PATH_AUTO && b->fused.id != FUSED_NONE) return fused_name(b->fused.id);
+  return (b->tape.h.flags & TAPE_DIVERGENT) ? "k_interp<divergent>" : "k_interp<uniform>";
+}
+long qg_bank_out_rows(const qg_bank* b, int group) {
+  if (!b) return 0;
+  if (group < 1) group = 1;
+  return (b->V / group) * (long)b->tape.h.n_outputs;
+}
+
+static int check_group(const qg_bank* b, int layout, int group) {
+  if (group < 1) return fail(QG_ERR_ARG, "group must be >= 1");
+  if (group > 1) {
+    if (layout != QG_LAYOUT_VOICE_MAJOR) return fail(QG_ERR_ARG, "group mixes need the voice-major layout");
+    if (group > 32 || (32 % group) != 0) return fail(QG_ERR_ARG, "group must be one of 1,2,4,8,16,32");
+    if (b->V % group) return fail(QG_ERR_ARG, "voice count must be a multiple of group");
+  }
+  return QG_OK;
+}
+
+static int render_impl(qg_bank* b, long T, int layout, int group, const float* d_in, float* d_out) {
+  qg_ctx* c = b->ctx;
+  const Tape& t = b->tape;
+  CU(cudaSetDevice(c->device));
+  if (T <= 0) return QG_OK;
+  int rc = check_group(b, layout, group);
+  if (rc) return rc;
+  if (b->path == QG_PATH_AUTO && b->fused.id != FUSED_NONE && !d_in && layout == QG_LAYOUT_VOICE_MAJOR) {
+    FusedArgs fa;
+    fa.params = b->d_params; fa.state = b->d_state; fa.V = (int)b->V; fa.Vp = b->Vp; fa.T = T; fa.group = group; fa.out = d_out;
+    int l = 0;
+    CU(launch_fused(b->fused, fa, c->stream, &l));
+    c->launches += l;
+    return QG_OK;
+  }
+  InterpArgs a;
+  memset(&a, 0, sizeof a);
+  a.code = b->d_code; a.n_instr = (int)t.h.n_instr;
+  a.P = (int)t.h.n_params; a.NS = (int)t.h.n_state; a.NT = (int)t.h.n_temps;
+  a.n_in = (int)t.h.n_inputs; a.n_out = (int)t.h.n_outputs; a.out_x = b->d_out_x;
+  a.params = b->d_params; a.state = b->d_state; a.state_init = b->d_state_init; a.rings = b->d_rings;
+  a.ring_tab = b->d_ring_tab; a.resets = b->d_resets; a.tables = b->d_tables;
+  a.in = d_in; a.out = d_out; a.V = (int)b->V; a.Vp = b->Vp; a.T = T;
+  a.in_frame_major = layout == QG_LAYOUT_FRAME_MAJOR; a.out_frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
+  a.group = group;
+  int l = 0;
+  cudaError_t e = launch_interp(a, (t.h.flags & TAPE_DIVERGENT) != 0, c->stream, &l);
+  c->launches += l;
+  if (e == cudaErrorInvalidConfiguration) return fail(QG_ERR_UNSUPPORTED, "tape needs more shared memory per voice than one SM offers");
+  CU(e);
+  return QG_OK;
+}
+
+int qg_bank_render_device(qg_bank* b, long T, int layout, int group, float* d_out) {
+  if (!b || !d_out) return fail(QG_ERR_ARG, "qg_bank_render_device: bad arguments");
+  if (b->tape.h.n_inputs != 0) return fail(QG_ERR_ARITY, "render needs a net with 0 inputs (process.rs:1345)");
+  return render_impl(b, T, layout, group, nullptr, d_out);
+}
+
+static int ensure(float** p, size_t* have, size_t need) {
+  if (*have >= need) return QG_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  CU(cudaMalloc((void**)p, need));
+  *have = need;
+  return QG_OK;
+}
+
+int qg_bank_render(qg_bank* b, long T, int layout, int group, float* h_out) {
+  if (!b || !h_out) return fail(QG_ERR_ARG, "qg_bank_render: bad arguments");
+  if (b->tape.h.n_inputs != 0) return fail(QG_ERR_ARITY, "render needs a net with 0 inputs (process.rs:1345)");
+  if (group < 1) group = 1;
+  size_t bytes = (size_t)(b->V / group) * b->tape.h.n_outputs * (size_t)T * sizeof(float);
+  if (bytes == 0) return QG_OK;
+  CU(cudaSetDevice(b->ctx->device));
+  int rc = ensure(&b->d_scratch, &b->scratch_bytes, bytes);
+  if (rc) return rc;
+  rc = render_impl(b, T, layout, group, nullptr, b->d_scratch);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_out, b->d_scratch, bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
+  CU(cudaStreamSynchronize(b->ctx->stream));
+  return QG_OK;
+}
+
+int qg_bank_process(qg_bank* b, long T, int layout, const float* h_in, float* h_out) {
+  if (!b) return fail(QG_ERR_ARG, "null bank");
+  const Tape& t = b->tape;
+  size_t ib = (size_t)b->V * t.h.n_inputs * (size_t)T * sizeof(float);
+  size_t ob = (size_t)b->V * t.h.n_outputs * (size_t)T * sizeof(float);
+  if ((ib && !h_in) || (ob && !h_out)) return fail(QG_ERR_ARG, "qg_bank_process: null buffer");
+  CU(cudaSetDevice(b->ctx->device));
+  int rc;
+  if ((rc = ensure(&b->d_in, &b->in_bytes, std::max<size_t>(ib, 4)))) return rc;
+  if ((rc = ensure(&b->d_scratch, &b->scratch_bytes, std::max<size_t>(ob, 4)))) return rc;
+  if (ib) CU(cudaMemcpyAsync(b->d_in, h_in, ib, cudaMemcpyHostToDevice, b->ctx->stream));
+  rc = render_impl(b, T, layout, 1, b->d_in, b->d_scratch);
+  if (rc) return rc;
+  if (ob) CU(cudaMemcpyAsync(h_out, b->d_scratch, ob, cudaMemcpyDeviceToHost, b->ctx->stream));
+  CU(cudaStreamSynchronize(b->ctx->stream));
+  return QG_OK;
+}
+
+int qg_mix_rows_device(qg_ctx* c, const float* d_rows, long rows, long n, float scale, float* d_out) {
+  if (!c || !d_rows || !d_out) return fail(QG_ERR_ARG, "qg_mix_rows_device: bad arguments");
+  CU(cudaSetDevice(c->device));
+  CU(launch_mix_rows(d_rows, (int)rows, n, scale, d_out, c->stream));
+  c->launches++;
+  return QG_OK;
+}
+
+// ------------------------------------------------------------------------------------ reference-shaped helpers
+int qg_net_render(qg_ctx* ctx, const qg_net* net, long n, float* h_out) {
+  if (!ctx || !net || !h_out) return fail(QG_ERR_ARG, "qg_net_render: bad arguments");
+  if (net->g.inputs() != 0) return fail(QG_ERR_ARITY, "render needs a net with 0 inputs (process.rs:1345)");
+  qg_bank* b = qg_bank_create(ctx, net, 1, nullptr, nullptr);
+  if (!b) return QG_ERR_UNSUPPORTED;
+  int rc = qg_bank_render(b, n, QG_LAYOUT_FRAME_MAJOR, 1, h_out);
+  qg_bank_free(b);
+  return rc;
+}
+int qg_net_tick(qg_ctx* ctx, const qg_net* net, const float* in, int n_in, float* out, int n_out) {
+  if (!ctx || !net) return fail(QG_ERR_ARG, "qg_net_tick: bad arguments");
+  if (net->g.inputs() != n_in || net->g.outputs() != n_out) return fail(QG_ERR_ARITY, "tick: arity mismatch (process.rs:1322)");
+  qg_bank* b = qg_bank_create(ctx, net, 1, nullptr, nullptr);
+  if (!b) return QG_ERR_UNSUPPORTED;
+  int rc = qg_bank_process(b, 1, QG_LAYOUT_FRAME_MAJOR, in, out);
+  qg_bank_free(b);
+  return rc;
+}
+
+}  // extern "C"

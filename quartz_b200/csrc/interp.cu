@@ -1,0 +1,661 @@
+// K1 — fused op-tape interpreter: one lane = one voice, the whole render loop runs inside the kernel.
+//
+// Replaces the reference's per-sample virtual dispatch (`for _ in 0..len { net.tick(&[], &mut s) }`,
+// /root/reference/src/process.rs:1347-1351 -> FunDSP Net::tick -> Box<dyn AudioUnit>::tick per vertex).
+// Data layout (DESIGN.md "HBM layout"): every per-voice table is [index][voice] so the 32 lanes of a warp read
+// one 128-byte line; per-lane working values X live in shared memory as X[index][thread] (bank = thread, so
+// every access is conflict-free); outputs are staged through a per-warp 32x33 shared tile and written as
+// 128-byte rows (voice-major) or, for group mixes, summed left-to-right over the voices of a group (K6).
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "dev_math.cuh"
+#include "kernels.h"
+#include "tape.h"
+
+namespace qg {
+
+struct Lane {
+  float* x;        // shared: X[i] at x[i * nt]
+  int nt;
+  int v;           // voice index (padded space)
+  int Vp;
+  float* rings;
+  const Ring* ring_tab;
+  const float* tables;
+  const float* state_init;
+  const ResetRange* resets;
+  int P;
+};
+
+#define X(i) L.x[(int)(i) * L.nt]
+#define XU(i) __float_as_uint(X(i))
+#define SETU(i, u) X(i) = __uint_as_float(u)
+
+__device__ __forceinline__ float& ring_at(const Lane& L, uint32_t ring, uint32_t pos) {
+  return L.rings[(size_t)(L.ring_tab[ring].offset + pos) * (size_t)L.Vp + (size_t)L.v];
+}
+
+__device__ __noinline__ void reset_range(const Lane& L, uint32_t id) {
+  ResetRange r = L.resets[id];
+  for (int s = r.s_lo; s < r.s_hi; s++) X(s) = L.state_init[(size_t)(s - L.P) * L.Vp + L.v];
+  for (int g = r.ring_lo; g < r.ring_hi; g++) {
+    uint32_t len = L.ring_tab[g].length;
+    for (uint32_t k = 0; k < len; k++) ring_at(L, g, k) = 0.0f;
+  }
+}
+
+// in-place radix-2 FFT over two of the lane's HBM rings (re, im); inverse scales by 1/N
+__device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim, int lg, const float* tw, bool inverse) {
+  uint32_t N = 1u << lg;
+  for (uint32_t i = 1, j = 0; i < N; i++) {
+    uint32_t bit = N >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) {
+      float a = ring_at(L, rre, i), b = ring_at(L, rim, i);
+      ring_at(L, rre, i) = ring_at(L, rre, j); ring_at(L, rim, i) = ring_at(L, rim, j);
+      ring_at(L, rre, j) = a; ring_at(L, rim, j) = b;
+    }
+  }
+  for (uint32_t len = 2; len <= N; len <<= 1) {
+    uint32_t half = len >> 1, step = N / len;
+    for (uint32_t k = 0; k < half; k++) {
+      float wr = tw[2 * k * step], wi = tw[2 * k * step + 1];
+      if (inverse) wi = -wi;
+      for (uint32_t i = k; i < N; i += len) {
+        float ur = ring_at(L, rre, i), ui = ring_at(L, rim, i);
+        float vr = ring_at(L, rre, i + half), vi = ring_at(L, rim, i + half);
+        float tr = vr * wr - vi * wi, ti = vr * wi + vi * wr;
+        ring_at(L, rre, i) = ur + tr; ring_at(L, rim, i) = ui + ti;
+        ring_at(L, rre, i + half) = ur - tr; ring_at(L, rim, i + half) = ui - ti;
+      }
+    }
+  }
+  if (inverse) {
+    float s = 1.0f / (float)N;
+    for (uint32_t i = 0; i < N; i++) { ring_at(L, rre, i) *= s; ring_at(L, rim, i) *= s; }
+  }
+}
+
+// Execute one instruction for this lane.  `pc` is only touched by control-flow ops.
+__device__ __forceinline__ void exec(const Instr& I, const Lane& L, int& pc) {
+  switch (I.op) {
+    case OP_NOP: break;
+    case OP_MOV: X(I.out) = X(I.in[0]); break;
+    case OP_ZERO: X(I.out) = 0.0f; break;
+    case OP_LD_STATE: X(I.out) = X(I.s); break;
+    case OP_ST_STATE: X(I.s) = X(I.in[0]); break;
+    case OP_ADD: X(I.out) = X(I.in[0]) + X(I.in[1]); break;
+    case OP_SUB: X(I.out) = X(I.in[0]) - X(I.in[1]); break;
+    case OP_MUL: X(I.out) = X(I.in[0]) * X(I.in[1]); break;
+    case OP_GT: X(I.out) = X(I.in[0]) > X(I.in[1]) ? 1.0f : 0.0f; break;
+    case OP_LT: X(I.out) = X(I.in[0]) < X(I.in[1]) ? 1.0f : 0.0f; break;
+    case OP_EQ: X(I.out) = X(I.in[0]) == X(I.in[1]) ? 1.0f : 0.0f; break;
+    case OP_NE: X(I.out) = X(I.in[0]) != X(I.in[1]) ? 1.0f : 0.0f; break;
+    case OP_GE: X(I.out) = X(I.in[0]) >= X(I.in[1]) ? 1.0f : 0.0f; break;
+    case OP_LE: X(I.out) = X(I.in[0]) <= X(I.in[1]) ? 1.0f : 0.0f; break;
+    case OP_MIN: X(I.out) = fminf(X(I.in[0]), X(I.in[1])); break;
+    case OP_MAX: X(I.out) = fmaxf(X(I.in[0]), X(I.in[1])); break;
+    case OP_POW: X(I.out) = powf(X(I.in[0]), X(I.in[1])); break;
+    case OP_REM: X(I.out) = d_rem_euclid(X(I.in[0]), X(I.in[1])); break;
+    case OP_LOG: X(I.out) = logf(X(I.in[0])) / logf(X(I.in[1])); break;
+    case OP_BITAND: X(I.out) = (float)(d_as_i32(X(I.in[0])) & d_as_i32(X(I.in[1]))); break;
+    case OP_BITOR: X(I.out) = (float)(d_as_i32(X(I.in[0])) | d_as_i32(X(I.in[1]))); break;
+    case OP_BITXOR: X(I.out) = (float)(d_as_i32(X(I.in[0])) ^ d_as_i32(X(I.in[1]))); break;
+    case OP_SHL: X(I.out) = (float)(int32_t)((uint32_t)d_as_i32(X(I.in[0])) << (uint32_t)(d_as_usize(X(I.in[1])) & 31)); break;
+    case OP_SHR: X(I.out) = (float)(d_as_i32(X(I.in[0])) >> (uint32_t)(d_as_usize(X(I.in[1])) & 31)); break;
+    case OP_HYPOT: X(I.out) = hypotf(X(I.in[0]), X(I.in[1])); break;
+    case OP_ATAN2: X(I.out) = atan2f(X(I.in[0]), X(I.in[1])); break;
+    case OP_DISSONANCE: {
+      float f0 = X(I.in[0]), f1 = X(I.in[1]);
+      float q = fabsf(f0 - f1) / (0.021f * fminf(f0, f1) + 19.0f);
+      X(I.out) = 5.531753f * (expf(-0.84f * q) - expf(-1.38f * q));
+      break;
+    }
+    case OP_SIN_HZ: X(I.out) = sinf(X(I.in[1]) * X(I.in[0]) * QG_TAU); break;
+    case OP_COS_HZ: X(I.out) = cosf(X(I.in[1]) * X(I.in[0]) * QG_TAU); break;
+    case OP_SQR_HZ: { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = x < 0.5f ? 1.0f : -1.0f; break; }
+    case OP_TRI_HZ: { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = fabsf(x - 0.5f) * 4.0f - 1.0f; break; }
+    case OP_PDHALF_BI: {   // functions.rs:677-688
+      float x = X(I.in[0]), mid = d_clamp(X(I.in[1]), -1.0f, 1.0f);
+      if (x < mid) { float ls = mid != -1.0f ? 1.0f / (mid + 1.0f) : 0.0f; X(I.out) = ls * x; }
+      else { float rs = mid != 1.0f ? 1.0f / (1.0f - mid) : 0.0f; X(I.out) = rs * (x - mid) + 0.5f; }
+      break;
+    }
+    case OP_PDHALF_UNI: {   // functions.rs:689-706
+      float x = X(I.in[0]), m = X(I.in[1]);
+      float mid = m >= 1.0f ? 1.0f : (m <= -1.0f ? 0.0f : (m + 1.0f) / 2.0f);
+      if (x < mid) { float ls = mid != 0.0f ? 0.5f / mid : 0.0f; X(I.out) = ls * x; }
+      else { float rs = mid != 1.0f ? 0.5f / (1.0f - mid) : 0.0f; X(I.out) = rs * (x - mid) + 0.5f; }
+      break;
+    }
+    case OP_LERP: X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
+    case OP_LERP11: X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); break;
+    case OP_DELERP: X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
+    case OP_DELERP11: X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; break;
+    case OP_XERP: X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
+    case OP_XERP11: X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); break;
+    case OP_DEXERP: X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
+    case OP_DEXERP11: X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; break;
+    case OP_SPLINE: X(I.out) = d_spline(X(I.in[0]), X(I.in[1]), X(I.in[2]), X(I.in[3]), X(I.in[4])); break;
+    case OP_ABS: X(I.out) = fabsf(X(I.in[0])); break;
+    case OP_SIGNUM: X(I.out) = d_signum(X(I.in[0])); break;
+    case OP_FLOOR: X(I.out) = floorf(X(I.in[0])); break;
+    case OP_FRACT: X(I.out) = d_fract(X(I.in[0])); break;
+    case OP_CEIL: X(I.out) = ceilf(X(I.in[0])); break;
+    case OP_ROUND: X(I.out) = roundf(X(I.in[0])); break;
+    case OP_SQRT: X(I.out) = sqrtf(X(I.in[0])); break;
+    case OP_EXP: X(I.out) = expf(X(I.in[0])); break;
+    case OP_EXP2: X(I.out) = exp2f(X(I.in[0])); break;
+    case OP_EXP10: X(I.out) = d_exp10(X(I.in[0])); break;
+    case OP_LN_1P_FN: X(I.out) = log1pf(X(I.in[0])); break;
+    case OP_EXP_M1_FN: X(I.out) = expm1f(X(I.in[0])); break;
+    case OP_LN: X(I.out) = logf(X(I.in[0])); break;
+    case OP_LOG2: X(I.out) = log2f(X(I.in[0])); break;
+    case OP_LOG10: X(I.out) = log10f(X(I.in[0])); break;
+    case OP_SIN: X(I.out) = sinf(X(I.in[0])); break;
+    case OP_COS: X(I.out) = cosf(X(I.in[0])); break;
+    case OP_TAN: X(I.out) = tanf(X(I.in[0])); break;
+    case OP_ASIN: X(I.out) = asinf(X(I.in[0])); break;
+    case OP_ACOS: X(I.out) = acosf(X(I.in[0])); break;
+    case OP_ATAN: X(I.out) = atanf(X(I.in[0])); break;
+    case OP_SINH: X(I.out) = sinhf(X(I.in[0])); break;
+    case OP_COSH: X(I.out) = coshf(X(I.in[0])); break;
+    case OP_TANH: X(I.out) = tanhf(X(I.in[0])); break;
+    case OP_ASINH: X(I.out) = asinhf(X(I.in[0])); break;
+    case OP_ACOSH: X(I.out) = acoshf(X(I.in[0])); break;
+    case OP_ATANH: X(I.out) = atanhf(X(I.in[0])); break;
+    case OP_SQUARED: { float x = X(I.in[0]); X(I.out) = x * x; break; }
+    case OP_CUBED: { float x = X(I.in[0]); X(I.out) = x * x * x; break; }
+    case OP_DB_AMP: X(I.out) = d_exp10(X(I.in[0]) / 20.0f); break;
+    case OP_AMP_DB: X(I.out) = log10f(X(I.in[0])) * 20.0f; break;
+    case OP_A_WEIGHT: X(I.out) = d_a_weight(X(I.in[0])); break;
+    case OP_SOFTSIGN: { float x = X(I.in[0]); X(I.out) = x / (1.0f + fabsf(x)); break; }
+    case OP_SMOOTH3: { float x = X(I.in[0]); X(I.out) = (3.0f - 2.0f * x) * x * x; break; }
+    case OP_SMOOTH5: X(I.out) = d_smooth5(X(I.in[0])); break;
+    case OP_SMOOTH7: { float x = X(I.in[0]), x2 = x * x; X(I.out) = x2 * x2 * (35.0f - 84.0f * x + (70.0f - 20.0f * x) * x2); break; }
+    case OP_SMOOTH9: {
+      float x = X(I.in[0]), x2 = x * x;
+      X(I.out) = ((((70.0f * x - 315.0f) * x + 540.0f) * x - 420.0f) * x + 126.0f) * x2 * x2 * x;
+      break;
+    }
+    case OP_UPARC: { float x = X(I.in[0]); X(I.out) = 1.0f - sqrtf(fmaxf(0.0f, 1.0f - x * x)); break; }
+    case OP_DOWNARC: { float x = X(I.in[0]); X(I.out) = sqrtf(fmaxf(0.0f, (2.0f - x) * x)); break; }
+    case OP_SINE_EASE: X(I.out) = (1.0f - cosf(X(I.in[0]) * QG_PI)) * 0.5f; break;
+    case OP_SEMITONE_RATIO: X(I.out) = exp2f(X(I.in[0]) / 12.0f); break;
+    case OP_RND1: X(I.out) = d_rnd1(d_as_usize(X(I.in[0]))); break;
+    case OP_RND2: X(I.out) = d_rnd2(d_as_usize(X(I.in[0]))); break;
+    case OP_DEG: X(I.out) = X(I.in[0]) * 57.2957795130823208767981548141051703f; break;
+    case OP_RAD: X(I.out) = X(I.in[0]) * (QG_PI / 180.0f); break;
+    case OP_RECIP: X(I.out) = 1.0f / X(I.in[0]); break;
+    case OP_NORMAL: { float x = X(I.in[0]); X(I.out) = d_is_normal(x) ? x : 0.0f; break; }
+    case OP_CLIP: X(I.out) = d_clamp(X(I.in[0]), X(I.p), X(I.p + 1)); break;
+    case OP_WRAP2: { float p0 = X(I.p), r = X(I.p + 1); X(I.out) = fmodf(fmodf(X(I.in[0]) - p0, r) + r, r) + p0; break; }
+    case OP_WRAP1: { float x0 = X(I.p), x = X(I.in[0]); X(I.out) = x - x0 * floorf(x / x0); break; }
+    case OP_MIRROR: {   // functions.rs:1167-1180
+      float p0 = X(I.p), p1 = X(I.p + 1), r = X(I.p + 2), x = X(I.in[0]);
+      float n = d_is_normal(x) ? x : 0.0f, res;
+      if (n >= p0 && n <= p1) res = n;
+      else {
+        float distance = fminf(n - p1, p0 - n);
+        float folds = floorf(distance / r);
+        if ((n > p1 && fmodf(folds, 2.0f) == 0.0f) || (n < p0 && fmodf(folds, 2.0f) != 0.0f)) res = p0 + (distance - folds * r);
+        else res = p1 - (distance - folds * r);
+      }
+      X(I.out) = res;
+      break;
+    }
+    case OP_POL: { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = hypotf(a, b); X(I.out + 1) = atan2f(b, a); break; }
+    case OP_CAR: { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = a * cosf(b); X(I.out + 1) = a * sinf(b); break; }
+    case OP_DIVN: X(I.out) = X(I.in[0]) / (float)I.n; break;
+    case OP_PAN: { float x = X(I.in[0]); X(I.out) = X(I.p) * x; X(I.out + 1) = X(I.p + 1) * x; break; }
+    case OP_PAN_VAR: {
+      float x = X(I.in[0]), pan = X(I.in[1]);
+      if (pan != X(I.s)) { float l, r; pan_weights(pan, &l, &r); X(I.s) = pan; X(I.s + 1) = l; X(I.s + 2) = r; }
+      X(I.out) = X(I.s + 1) * x; X(I.out + 1) = X(I.s + 2) * x;
+      break;
+    }
+    case OP_ROTATE: {
+      float a = X(I.in[0]), b = X(I.in[1]), c = X(I.p), s = X(I.p + 1);
+      X(I.out) = c * a - s * b; X(I.out + 1) = s * a + c * b;
+      break;
+    }
+    // ---------------------------------------------------------------- sources
+    case OP_SINE: {
+      float ph = X(I.s);
+      float np = ph + X(I.in[0]) * X(I.p);
+      np -= floorf(np);
+      X(I.s) = np;
+      X(I.out) = sinf(ph * QG_TAU);
+      break;
+    }
+    case OP_NOISE: { uint32_t c = XU(I.s) + 1u; SETU(I.s, c); X(I.out) = d_noise(c); break; }
+    case OP_IMPULSE: { uint32_t f = XU(I.s); X(I.out) = f ? 0.0f : 1.0f; SETU(I.s, 1u); break; }
+    case OP_RAMP: {   // nodes.rs:476-483
+      float val = X(I.s);
+      X(I.out) = val;
+      val += X(I.in[0]) / X(I.p);
+      if (val >= 1.0f) val -= 1.0f;
+      X(I.s) = val;
+      break;
+    }
+    case OP_WAVE: {
+      uint32_t i = XU(I.s);
+      X(I.out) = L.tables[I.aux + i];
+      i += 1;
+      if (i >= I.aux2) i = 0;
+      SETU(I.s, i);
+      break;
+    }
+    // ---------------------------------------------------------------- filters
+    case OP_SVF: {
+      float ic1 = X(I.s), ic2 = X(I.s + 1);
+      X(I.out) = d_svf_tick(X(I.in[0]), ic1, ic2, X(I.p), X(I.p + 1), X(I.p + 2), X(I.p + 3), X(I.p + 4), X(I.p + 5));
+      X(I.s) = ic1; X(I.s + 1) = ic2;
+      break;
+    }
+    case OP_SVF_VAR: {
+      int mode = I.n & 0xff, nvar = I.n >> 8;
+      float hz = nvar >= 1 ? X(I.in[1]) : X(I.p), q = nvar >= 2 ? X(I.in[2]) : X(I.p + 1), g = nvar >= 3 ? X(I.in[3]) : X(I.p + 2);
+      if (hz != X(I.s + 8) || q != X(I.s + 9) || g != X(I.s + 10)) {
+        float c[6];
+        svf_coefs(mode, hz, q, g, X(I.p + 3), c);
+        for (int k = 0; k < 6; k++) X(I.s + 2 + k) = c[k];
+        X(I.s + 8) = hz; X(I.s + 9) = q; X(I.s + 10) = g;
+      }
+      float ic1 = X(I.s), ic2 = X(I.s + 1);
+      X(I.out) = d_svf_tick(X(I.in[0]), ic1, ic2, X(I.s + 2), X(I.s + 3), X(I.s + 4), X(I.s + 5), X(I.s + 6), X(I.s + 7));
+      X(I.s) = ic1; X(I.s + 1) = ic2;
+      break;
+    }
+    case OP_BIQUAD: {
+      float x0 = X(I.in[0]), x1 = X(I.s), x2 = X(I.s + 1), y1 = X(I.s + 2), y2 = X(I.s + 3);
+      float y0 = X(I.p + 2) * x0 + X(I.p + 3) * x1 + X(I.p + 4) * x2 - X(I.p) * y1 - X(I.p + 1) * y2;
+      X(I.s) = x0; X(I.s + 1) = x1; X(I.s + 2) = y0; X(I.s + 3) = y1;
+      X(I.out) = y0;
+      break;
+    }
+    case OP_BIQUAD_VAR: {
+      int kind = I.n & 0xff, nvar = I.n >> 8;
+      float c0 = X(I.in[1]), c1 = nvar >= 2 ? X(I.in[2]) : X(I.s + 10);
+      if (c0 != X(I.s + 9) || c1 != X(I.s + 10)) {
+        float c[5];
+        biquad_coefs(kind, c0, c1, X(I.p), c);
+        for (int k = 0; k < 5; k++) X(I.s + 4 + k) = c[k];
+        X(I.s + 9) = c0; X(I.s + 10) = c1;
+      }
+      float x0 = X(I.in[0]), x1 = X(I.s), x2 = X(I.s + 1), y1 = X(I.s + 2), y2 = X(I.s + 3);
+      float y0 = X(I.s + 6) * x0 + X(I.s + 7) * x1 + X(I.s + 8) * x2 - X(I.s + 4) * y1 - X(I.s + 5) * y2;
+      X(I.s) = x0; X(I.s + 1) = x1; X(I.s + 2) = y0; X(I.s + 3) = y1;
+      X(I.out) = y0;
+      break;
+    }
+    case OP_ONEPOLE: case OP_ONEPOLE_VAR: {
+      float coeff;
+      if (I.op == OP_ONEPOLE) coeff = X(I.p);
+      else {
+        float p = X(I.in[1]);
+        if (p != X(I.s + 3)) { X(I.s + 3) = p; X(I.s + 2) = onepole_coef(I.n, p, X(I.p)); }
+        coeff = X(I.s + 2);
+      }
+      float x = X(I.in[0]), x1 = X(I.s), y1 = X(I.s + 1), y;
+      switch (I.n) {
+        case 0: y = (1.0f - coeff) * x + coeff * y1; break;
+        case 1: y = coeff * (y1 + x - x1); break;
+        case 2: y = x - x1 + coeff * y1; break;
+        default: y = coeff * (x - y1) + x1; break;
+      }
+      X(I.s) = x; X(I.s + 1) = y;
+      X(I.out) = y;
+      break;
+    }
+    case OP_PINKPASS: {
+      float w = X(I.in[0]);
+      float b0 = 0.99886f * X(I.s) + w * 0.0555179f;
+      float b1 = 0.99332f * X(I.s + 1) + w * 0.0750759f;
+      float b2 = 0.96900f * X(I.s + 2) + w * 0.1538520f;
+      float b3 = 0.86650f * X(I.s + 3) + w * 0.3104856f;
+      float b4 = 0.55000f * X(I.s + 4) + w * 0.5329522f;
+      float b5 = -0.7616f * X(I.s + 5) - w * 0.0168980f;
+      float pink = b0 + b1 + b2 + b3 + b4 + b5 + X(I.s + 6) + w * 0.5362f;
+      X(I.s) = b0; X(I.s + 1) = b1; X(I.s + 2) = b2; X(I.s + 3) = b3; X(I.s + 4) = b4; X(I.s + 5) = b5;
+      X(I.s + 6) = w * 0.115926f;
+      X(I.out) = pink * 0.11f;
+      break;
+    }
+    case OP_FIR: {
+      int n = I.n;
+      for (int k = n - 1; k > 0; k--) X(I.s + k) = X(I.s + k - 1);
+      X(I.s) = X(I.in[0]);
+      float acc = 0.0f;
+      for (int k = 0; k < n; k++) acc += X(I.p + k) * X(I.s + k);
+      X(I.out) = acc;
+      break;
+    }
+    // ---------------------------------------------------------------- delays
+    case OP_TICK: { float v = X(I.s); X(I.s) = X(I.in[0]); X(I.out) = v; break; }
+    case OP_DELAY: {
+      uint32_t i = XU(I.s), len = L.ring_tab[I.aux].length;
+      float& slot = ring_at(L, I.aux, i);
+      float o = slot;
+      slot = X(I.in[0]);
+      i = i + 1 == len ? 0 : i + 1;
+      SETU(I.s, i);
+      X(I.out) = o;
+      break;
+    }
+    case OP_TAP: {
+      uint32_t idx = XU(I.s), len = L.ring_tab[I.aux].length, mask = len - 1;
+      ring_at(L, I.aux, idx) = X(I.in[0]);
+      float tap = d_clamp(X(I.in[1]), X(I.p), X(I.p + 1)) * X(I.p + 2);
+      if (tap != tap) tap = 0.0f;
+      uint32_t fl = (uint32_t)d_as_usize(tap);
+      float d = tap - (float)fl;
+      uint32_t i1 = (idx + len - fl) & mask;
+      if (I.n) {
+        uint32_t i0 = (i1 + 1) & mask, i2 = (i1 + len - 1) & mask, i3 = (i1 + len - 2) & mask;
+        X(I.out) = d_spline(ring_at(L, I.aux, i0), ring_at(L, I.aux, i1), ring_at(L, I.aux, i2), ring_at(L, I.aux, i3), d);
+      } else {
+        uint32_t i2 = (i1 + len - 1) & mask;
+        X(I.out) = d_lerp(ring_at(L, I.aux, i1), ring_at(L, I.aux, i2), d);
+      }
+      SETU(I.s, (idx + 1) & mask);
+      break;
+    }
+    case OP_SAMP_DELAY: {   // nodes.rs:726-731: push_front, pop_back, then index from the front
+      uint32_t head = XU(I.s), len = L.ring_tab[I.aux].length;
+      head = head == 0 ? len - 1 : head - 1;
+      ring_at(L, I.aux, head) = X(I.in[0]);
+      SETU(I.s, head);
+      uint64_t k = d_as_usize(X(I.in[1]));
+      float o = 0.0f;
+      if (k < (uint64_t)len) { uint32_t pos = head + (uint32_t)k; if (pos >= len) pos -= len; o = ring_at(L, I.aux, pos); }
+      X(I.out) = o;
+      break;
+    }
+    case OP_ENVELOPE: {
+      int shape = I.n & 0xff, nin = I.n >> 8;
+      float t = X(I.s), t0 = X(I.s + 1), t1 = X(I.s + 2), v0 = X(I.s + 3), v1 = X(I.s + 4);
+      if (t >= t1) {
+        float c[4] = {X(I.p), X(I.p + 1), X(I.p + 2), X(I.p + 3)};
+        float in[4] = {0, 0, 0, 0};
+        for (int k = 0; k < nin && k < 4; k++) in[k] = X(I.in[k]);
+        if (XU(I.s + 7)) { v1 = d_env_eval(shape, nin, 0.0f, c, in); SETU(I.s + 7, 0u); }
+        uint64_t th = (uint64_t)XU(I.s + 5) | ((uint64_t)XU(I.s + 6) << 32);
+        t0 = t1;
+        v0 = v1;
+        float next = d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
+        t1 = t0 + next;
+        v1 = d_env_eval(shape, nin, t1, c, in);
+        th += 1;
+        SETU(I.s + 5, (uint32_t)th); SETU(I.s + 6, (uint32_t)(th >> 32));
+        X(I.s + 1) = t0; X(I.s + 2) = t1; X(I.s + 3) = v0; X(I.s + 4) = v1;
+      }
+      float u = d_delerp(t0, t1, t);
+      X(I.s) = t + X(I.p + 4);
+      X(I.out) = d_lerp(v0, v1, u);
+      break;
+    }
+    case OP_DECLICK: {
+      float t = X(I.s), dur = X(I.p), x = X(I.in[0]);
+      if (t < dur) { X(I.out) = x * d_smooth5(t / dur); X(I.s) = t + X(I.p + 1); }
+      else X(I.out) = x;
+      break;
+    }
+    // ---------------------------------------------------------------- in-tree stateful nodes
+    case OP_SHIFT_REG: {   // nodes.rs:173-185
+      if (X(I.in[1]) != 0.0f) {
+        for (int k = 7; k > 0; k--) X(I.s + k) = X(I.s + k - 1);
+        X(I.s) = X(I.in[0]);
+      }
+      for (int k = 0; k < 8; k++) X(I.out + k) = X(I.s + k);
+      break;
+    }
+    case OP_SNH: {   // nodes.rs:811-816
+      if (X(I.in[1]) != 0.0f) X(I.s) = X(I.in[0]);
+      X(I.out) = X(I.s);
+      break;
+    }
+    case OP_QUANTIZE: {   // nodes.rs:213-228
+      float n = X(I.in[0]), range = X(I.p);
+      float wrapped = n - range * floorf(n / range);
+      float nearest = 0.0f, dist = FLT_MAX;
+      for (uint32_t k = 0; k < I.aux2; k++) {
+        float v = L.tables[I.aux + k];
+        float d = fabsf(wrapped - v);
+        if (d < dist) { nearest = v; dist = d; }
+      }
+      X(I.out) = n + nearest - wrapped;
+      break;
+    }
+    case OP_ARR_GET: {   // nodes.rs:143-149
+      uint64_t k = d_as_usize(X(I.in[0]));
+      X(I.out) = k < (uint64_t)I.aux2 ? L.tables[I.aux + (uint32_t)k] : 0.0f;
+      break;
+    }
+    // ---------------------------------------------------------------- control flow
+    case OP_KR_BEGIN: {   // nodes.rs:272-275
+      uint32_t c = XU(I.s);
+      if (c == 0) SETU(I.s, I.aux2);
+      else pc = (int)I.aux;
+      break;
+    }
+    case OP_KR_END: SETU(I.s, XU(I.s) - 1u); break;
+    case OP_RESET_EVERY: {   // nodes.rs:353-358
+      uint32_t c = XU(I.s);
+      if (c >= I.aux) { reset_range(L, I.aux2); c = 0; }
+      SETU(I.s, c + 1u);
+      break;
+    }
+    case OP_RESET_IF: if (X(I.in[0]) != 0.0f) reset_range(L, I.aux2); break;
+    case OP_RESET_V: {   // nodes.rs:435-440
+      uint32_t c = XU(I.s);
+      uint64_t lim = d_as_usize(roundf(X(I.in[0]) * X(I.p)));
+      if ((uint64_t)c >= lim) { reset_range(L, I.aux2); c = 0; }
+      SETU(I.s, c + 1u);
+      break;
+    }
+    case OP_JNE_IDX: if (d_as_usize(X(I.in[0])) != (uint64_t)I.aux2) pc = (int)I.aux; break;
+    // ---------------------------------------------------------------- feedback
+    case OP_FB_READ: X(I.out) = X(I.in[0]) + ring_at(L, I.aux, XU(I.s)); break;
+    case OP_FB_WRITE: {
+      uint32_t i = XU(I.s);
+      ring_at(L, I.aux, i) = X(I.in[0]);
+      if (I.n) { uint32_t len = L.ring_tab[I.aux].length; SETU(I.s, i + 1 == len ? 0 : i + 1); }
+      break;
+    }
+    // ---------------------------------------------------------------- spectral nodes (per-lane path)
+    case OP_RFFT: {   // nodes.rs:625-642
+      uint32_t N = 1u << I.n, i = XU(I.s), nx = i + 1 == N ? 0 : i + 1;
+      SETU(I.s, nx);
+      if (i == 0) {
+        for (uint32_t k = 0; k < N; k++) { ring_at(L, I.aux + 1, k) = ring_at(L, I.aux, k); ring_at(L, I.aux + 2, k) = 0.0f; }
+        lane_fft(L, I.aux + 1, I.aux + 2, I.n, L.tables + I.aux2, false);
+      }
+      ring_at(L, I.aux, i) = X(I.in[0]);
+      if (i <= N / 2) { X(I.out) = ring_at(L, I.aux + 1, i); X(I.out + 1) = ring_at(L, I.aux + 2, i); }
+      else { X(I.out) = ring_at(L, I.aux + 1, N - i); X(I.out + 1) = -ring_at(L, I.aux + 2, N - i); }
+      break;
+    }
+    case OP_IFFT: {   // nodes.rs:681-693
+      uint32_t N = 1u << I.n, i = XU(I.s), nx = i + 1 == N ? 0 : i + 1;
+      SETU(I.s, nx);
+      if (i == 0) {
+        for (uint32_t k = 0; k < N; k++) { ring_at(L, I.aux + 2, k) = ring_at(L, I.aux, k); ring_at(L, I.aux + 3, k) = ring_at(L, I.aux + 1, k); }
+        lane_fft(L, I.aux + 2, I.aux + 3, I.n, L.tables + I.aux2, true);
+      }
+      ring_at(L, I.aux, i) = X(I.in[0]); ring_at(L, I.aux + 1, i) = X(I.in[1]);
+      X(I.out) = ring_at(L, I.aux + 2, i); X(I.out + 1) = ring_at(L, I.aux + 3, i);
+      break;
+    }
+    default: break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+template <bool DIVERGENT>
+__global__ void __launch_bounds__(128) k_interp(InterpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  Instr* code = reinterpret_cast<Instr*>(smem_raw);
+  float* xs = reinterpret_cast<float*>(smem_raw + (size_t)a.n_instr * sizeof(Instr));
+  const int nx = a.P + a.NS + a.NT;
+  float* tiles = xs + (size_t)nx * nt;                       // [n_out][nwarps][32][33] when a.tile
+  {   // stage the tape
+    const uint4* src = reinterpret_cast<const uint4*>(a.code);
+    uint4* dst = reinterpret_cast<uint4*>(code);
+    for (int i = tid; i < a.n_instr * 2; i += nt) dst[i] = src[i];
+  }
+  const int v = blockIdx.x * nt + tid;                       // padded voice index, always < Vp
+  Lane L;
+  L.x = xs + tid; L.nt = nt; L.v = v; L.Vp = a.Vp; L.rings = a.rings; L.ring_tab = a.ring_tab; L.tables = a.tables;
+  L.state_init = a.state_init; L.resets = a.resets; L.P = a.P;
+  for (int p = 0; p < a.P; p++) X(p) = a.params[(size_t)p * a.Vp + v];
+  for (int s = 0; s < a.NS; s++) X(a.P + s) = a.state[(size_t)s * a.Vp + v];
+  for (int k = 0; k < a.NT; k++) X(a.P + a.NS + k) = 0.0f;
+  __syncthreads();
+
+  const int warp_v0 = blockIdx.x * nt + warp * 32;
+  const int in_base = a.P + a.NS;
+  for (long t = 0; t < a.T; t++) {
+    for (int c = 0; c < a.n_in; c++) {
+      size_t idx = a.in_frame_major ? ((size_t)t * a.V + v) * a.n_in + c : ((size_t)v * a.n_in + c) * a.T + t;
+      X(in_base + c) = v < a.V ? a.in[idx] : 0.0f;
+    }
+    if (!DIVERGENT) {
+      int pc = 0;
+      for (int i = 0; i < a.n_instr; i++) exec(code[i], L, pc);
+    } else {
+      // SIMT-stack emulation: always run the lowest pending instruction; lanes that jumped ahead wait there
+      int pc = 0;
+      for (;;) {
+        int m = __reduce_min_sync(0xffffffffu, pc);
+        if (m >= a.n_instr) break;
+        if (pc == m) { pc = m + 1; exec(code[m], L, pc); }
+      }
+    }
+    // ---- outputs
+    if (a.out_frame_major) {
+      if (v < a.V)
+        for (int c = 0; c < a.n_out; c++) a.out[((size_t)t * a.V + v) * a.n_out + c] = X(a.out_x[c]);
+    } else {
+      const int tt = (int)(t & 31);
+      for (int c = 0; c < a.n_out; c++) tiles[(((size_t)c * nwarps + warp) * 32 + lane) * 33 + tt] = X(a.out_x[c]);
+      if (tt == 31 || t == a.T - 1) {
+        __syncwarp();
+        const long t_base = t - tt;
+        const int ncols = tt + 1;
+        for (int c = 0; c < a.n_out; c++) {
+          const float* tile = tiles + ((size_t)c * nwarps + warp) * 32 * 33;
+          if (a.group <= 1) {
+            for (int r = 0; r < 32; r++) {
+              int vv = warp_v0 + r;
+              if (vv < a.V && lane < ncols) a.out[((size_t)vv * a.n_out + c) * a.T + t_base + lane] = tile[r * 33 + lane];
+            }
+          } else {
+            // K6 group mix: voices of a group are summed left to right, then scaled by 1/G (`(v0+v1+..) >> mul(1/G)`)
+            const int G = a.group;
+            const float inv = 1.0f / (float)G;
+            for (int g0 = 0; g0 < 32; g0 += G) {
+              int gi = (warp_v0 + g0) / G;
+              if (warp_v0 + g0 + G <= a.V && lane < ncols) {
+                float acc = tile[g0 * 33 + lane];
+                for (int r = 1; r < G; r++) acc += tile[(g0 + r) * 33 + lane];
+                a.out[((size_t)gi * a.n_out + c) * a.T + t_base + lane] = acc * inv;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  for (int s = 0; s < a.NS; s++) a.state[(size_t)s * a.Vp + v] = X(a.P + s);
+}
+
+// state_init[s][v] = default word, then hash-seeded words (phase / noise seed / envelope hash), salted per voice
+__global__ void k_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
+                             const uint64_t* salts) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= Vp) return;
+  for (int s = 0; s < NS; s++) state_init[(size_t)s * Vp + v] = __uint_as_float(defaults[s]);
+  uint64_t salt = salts ? salts[v] : 0ull;
+  for (int k = 0; k < n_hi; k++) {
+    uint64_t h = hi[k].hash;
+    if (salt) h = d_atto(h, salt);
+    uint32_t w;
+    switch (hi[k].kind) {
+      case INIT_SINE_PHASE: w = __float_as_uint(d_rnd1(h)); break;
+      case INIT_NOISE_SEED: w = (uint32_t)h; break;
+      case INIT_HASH_LO: w = (uint32_t)h; break;
+      default: w = (uint32_t)(h >> 32); break;
+    }
+    state_init[(size_t)hi[k].state * Vp + v] = __uint_as_float(w);
+  }
+}
+
+__global__ void k_broadcast_params(float* params, const float* tmpl, int P, int Vp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)P * Vp) params[i] = tmpl[i / Vp];
+}
+
+// full mix of the rows of a [R][T] buffer into one [T] row: rows are added in index order (per output sample)
+__global__ void k_mix_rows(const float* rows, int R, long T, float scale, float* out) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float acc = 0.0f;
+  for (int r = 0; r < R; r++) acc += rows[(size_t)r * T + t];
+  out[t] = acc * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static size_t interp_smem(const InterpArgs& a, int nt, bool tile) {
+  size_t b = (size_t)a.n_instr * sizeof(Instr) + (size_t)(a.P + a.NS + a.NT) * nt * sizeof(float);
+  if (tile) b += (size_t)a.n_out * (nt / 32) * 32 * 33 * sizeof(float);
+  return b;
+}
+
+cudaError_t launch_interp(const InterpArgs& a_in, bool divergent, cudaStream_t stream, int* launches) {
+  InterpArgs a = a_in;
+  bool tile = !a.out_frame_major && a.n_out > 0;
+  int nt = 128;
+  const size_t limit = 200 * 1024;
+  while (nt > 32 && interp_smem(a, nt, tile) > limit) nt >>= 1;
+  if (interp_smem(a, nt, tile) > limit) return cudaErrorInvalidConfiguration;
+  // few voices: smaller blocks spread the voices over more SMs
+  while (nt > 32 && (a.Vp / nt) < 148) nt >>= 1;
+  size_t smem = interp_smem(a, nt, tile);
+  int blocks = a.Vp / nt;
+  cudaError_t e;
+  if (divergent) {
+    e = cudaFuncSetAttribute(k_interp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_interp<true><<<blocks, nt, smem, stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(k_interp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_interp<false><<<blocks, nt, smem, stream>>>(a);
+  }
+  if (launches) *launches += 1;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
+                              const uint64_t* salts, cudaStream_t stream) {
+  k_init_state<<<(Vp + 127) / 128, 128, 0, stream>>>(state_init, defaults, NS, Vp, hi, n_hi, salts);
+  return cudaGetLastError();
+}
+cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream) {
+  size_t n = (size_t)P * Vp;
+  if (n == 0) return cudaSuccess;
+  k_broadcast_params<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(params, tmpl, P, Vp);
+  return cudaGetLastError();
+}
+cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream) {
+  k_mix_rows<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(rows, R, T, scale, out);
+  return cudaGetLastError();
+}
+
+}  // namespace qg

@@ -1,0 +1,37 @@
+// Kernel argument blocks and launchers (device code lives in interp.cu / fused.cu / fft.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tape.h"
+
+namespace qg {
+
+struct InterpArgs {
+  const Instr* code;
+  int n_instr;
+  int P, NS, NT;              // parameter / state / temporary counts (X = [P | NS | NT])
+  int n_in, n_out;
+  const uint16_t* out_x;      // X index of each output
+  const float* params;        // [P][Vp]
+  float* state;               // [NS][Vp]
+  const float* state_init;    // [NS][Vp]
+  float* rings;               // [ring_floats][Vp]
+  const Ring* ring_tab;
+  const ResetRange* resets;
+  const float* tables;
+  const float* in;            // net inputs (process/apply): voice-major [V][n_in][T] or frame-major [T][V][n_in]
+  float* out;                 // voice-major [V/group][n_out][T] or frame-major [T][V][n_out]
+  int V, Vp;                  // voices, voices padded to a multiple of 128
+  long T;
+  int in_frame_major, out_frame_major;
+  int group;                  // K6: sum consecutive voices in groups of `group` (1, 2, 4, 8, 16 or 32), scaled by 1/group
+};
+
+cudaError_t launch_interp(const InterpArgs& a, bool divergent, cudaStream_t stream, int* launches);
+cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
+                              const uint64_t* salts, cudaStream_t stream);
+cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream);
+cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream);
+
+}  // namespace qg

@@ -1,0 +1,678 @@
+// Graph -> op tape.  This is the "op-string to GPU op-tape lowering" that sits beside the reference's
+// str_to_net (/root/reference/src/functions.rs:111): every primitive node becomes one or a few fixed-size
+// instructions in evaluation order; nested nets (nodes.rs Kr/Select/Reset*/FeedbackUnit) are inlined as
+// predicated / jumped-over instruction ranges.
+#include "lower.h"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "coefs.h"
+
+namespace qg {
+
+namespace {
+
+const uint16_t NONE = 0xFFFF;
+const uint16_t R_STATE = 0x4000, R_TEMP = 0x8000;   // region tags, rewritten to absolute X indices at the end
+
+uint64_t as_usize(float x) {
+  if (!(x > 0.0f)) return 0;
+  if (x >= 18446744073709551616.0f) return UINT64_MAX;
+  return (uint64_t)x;
+}
+uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+struct Lower {
+  Tape& t;
+  std::string err;
+  int n_temps = 0;
+  int zero_p = -1;
+  explicit Lower(Tape& t_) : t(t_) {}
+
+  uint16_t temp(int n = 1) { int i = n_temps; n_temps += n; return (uint16_t)(R_TEMP | i); }
+  uint16_t param(float v) { t.params.push_back(v); return (uint16_t)(t.params.size() - 1); }
+  uint16_t params(int n, float v = 0.0f) { uint16_t b = (uint16_t)t.params.size(); t.params.resize(t.params.size() + n, v); return b; }
+  uint16_t state(int n = 1, uint32_t init = 0) {
+    uint16_t b = (uint16_t)t.state_init.size();
+    t.state_init.resize(t.state_init.size() + n, init);
+    return (uint16_t)(R_STATE | b);
+  }
+  uint16_t zero() { if (zero_p < 0) zero_p = param(0.0f); return (uint16_t)zero_p; }
+  uint32_t ring(uint32_t len) {
+    Ring r;
+    r.offset = t.h.ring_floats;
+    r.length = len;
+    t.h.ring_floats += len;
+    t.rings.push_back(r);
+    return (uint32_t)t.rings.size() - 1;
+  }
+  uint32_t table(const std::vector<float>& v) {
+    uint32_t off = (uint32_t)t.tables.size();
+    t.tables.insert(t.tables.end(), v.begin(), v.end());
+    return off;
+  }
+  // raw parameters of a node enter the tape-wide raw vector; returns their base index
+  uint32_t raw(const Node& n, bool structural = false) {
+    uint32_t b = (uint32_t)t.raw.size();
+    for (float v : n.raw) { t.raw.push_back(v); t.raw_structural.push_back(structural ? 1 : 0); }
+    return b;
+  }
+  void deriver(uint32_t kind, uint32_t raw_base, uint32_t n_raw, uint32_t p_base, uint32_t n_p, int mode, int aux, double sr) {
+    Deriver d{kind, raw_base, n_raw, p_base, n_p, mode, aux, (float)sr};
+    t.derivers.push_back(d);
+  }
+  Instr& emit(uint16_t op) {
+    Instr i;
+    memset(&i, 0, sizeof i);
+    i.op = op;
+    i.out = NONE; i.p = NONE; i.s = NONE;
+    for (uint16_t& x : i.in) x = NONE;
+    t.code.push_back(i);
+    return t.code.back();
+  }
+  void hash_init(uint16_t s, uint32_t kind, uint64_t hash) {
+    HashInit h;
+    h.state = (uint32_t)(s & 0x3fff);
+    h.kind = kind;
+    h.hash = hash;
+    t.hash_init.push_back(h);
+  }
+
+  std::vector<uint16_t> graph(const Graph& g, const std::vector<uint16_t>& inputs);
+  std::vector<uint16_t> node(const Node& n, const std::vector<uint16_t>& in);
+};
+
+std::vector<uint16_t> Lower::graph(const Graph& g, const std::vector<uint16_t>& inputs) {
+  if (!g.unsupported.empty() && err.empty())
+    err = "op '" + g.unsupported + "' exists in the reference but has no GPU lowering yet (FunDSP source unavailable)";
+  std::vector<std::vector<uint16_t>> vals(g.nodes.size());
+  auto resolve = [&](const Src& s) -> uint16_t {
+    if (s.node >= 0) return vals[s.node][s.port];
+    if (s.node == -1 && s.port < (int)inputs.size()) return inputs[s.port];
+    return zero();
+  };
+  for (size_t i = 0; i < g.nodes.size(); i++) {
+    const Node& n = g.nodes[i];
+    std::vector<uint16_t> in;
+    for (const Src& s : n.in) in.push_back(resolve(s));
+    vals[i] = node(n, in);
+    if (!err.empty()) return {};
+  }
+  std::vector<uint16_t> outs;
+  for (const Src& s : g.outs) outs.push_back(resolve(s));
+  return outs;
+}
+
+std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in) {
+  std::vector<uint16_t> out;
+  switch (n.kind) {
+    case NK_CONST: {
+      uint32_t rb = raw(n);
+      uint16_t p = params((int)n.raw.size());
+      deriver(D_COPY, rb, (uint32_t)n.raw.size(), p, (uint32_t)n.raw.size(), 0, 0, n.sr);
+      for (size_t i = 0; i < n.raw.size(); i++) out.push_back((uint16_t)(p + i));
+      break;
+    }
+    case NK_PASS: out.push_back(in[0]); break;
+    case NK_SINK: break;
+    case NK_SPLIT: for (int i = 0; i < n.n_out; i++) out.push_back(in[0]); break;
+    case NK_REVERSE: for (int i = 0; i < n.n_out; i++) out.push_back(in[n.n_in - 1 - i]); break;
+    case NK_ZERO_SRC: for (int i = 0; i < n.n_out; i++) out.push_back(zero()); break;
+    case NK_JOIN: {
+      uint16_t acc = in[0];
+      for (int i = 1; i < n.n_in; i++) {
+        Instr& a = emit(OP_ADD);
+        a.in[0] = acc; a.in[1] = in[i]; a.out = temp();
+        acc = a.out;
+      }
+      Instr& d = emit(OP_DIVN);
+      d.in[0] = acc; d.n = (uint16_t)n.n_in; d.out = temp();
+      out.push_back(d.out);
+      break;
+    }
+    case NK_PAN: {
+      if (n.n_in == 1) {
+        uint32_t rb = raw(n);
+        uint16_t p = params(2);
+        deriver(D_PAN, rb, 1, p, 2, 0, 0, n.sr);
+        Instr& i = emit(OP_PAN);
+        i.in[0] = in[0]; i.p = p; i.out = temp(2);
+        out = {i.out, (uint16_t)(i.out + 1)};
+      } else {
+        uint16_t s = state(3);
+        t.state_init[s & 0x3fff] = fbits(std::numeric_limits<float>::quiet_NaN());   // cached pan: force first update
+        Instr& i = emit(OP_PAN_VAR);
+        i.in[0] = in[0]; i.in[1] = in[1]; i.s = s; i.out = temp(2);
+        out = {i.out, (uint16_t)(i.out + 1)};
+      }
+      break;
+    }
+    case NK_UNARY: {
+      Instr& i = emit(n.devop);
+      i.in[0] = in[0]; i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_BIN: {
+      uint16_t b;
+      if (n.n_in == 1) {
+        uint32_t rb = raw(n);
+        b = params(1);
+        deriver(D_COPY, rb, 1, b, 1, 0, 0, n.sr);
+      } else b = in[1];
+      Instr& i = emit(n.devop);
+      i.in[0] = in[0]; i.in[1] = b; i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_TERN: {
+      Instr* ip;
+      if (n.n_in == 1) {
+        uint32_t rb = raw(n);
+        uint16_t p = params(2);
+        deriver(D_COPY, rb, 2, p, 2, 0, 0, n.sr);
+        ip = &emit(n.devop);
+        ip->in[0] = p; ip->in[1] = (uint16_t)(p + 1); ip->in[2] = in[0];
+      } else {
+        ip = &emit(n.devop);
+        ip->in[0] = in[0]; ip->in[1] = in[1]; ip->in[2] = in[2];
+      }
+      ip->out = temp();
+      out.push_back(ip->out);
+      break;
+    }
+    case NK_SPLINE: {
+      Instr& i = emit(OP_SPLINE);
+      for (int k = 0; k < 5; k++) i.in[k] = in[k];
+      i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_NARY_CONST: {
+      uint32_t rb = raw(n);
+      int c = (int)n.raw.size();
+      uint16_t p = params(c);
+      deriver(D_COPY, rb, c, p, c, 0, 0, n.sr);
+      for (int k = 0; k < c; k++) {
+        Instr& i = emit(n.devop);
+        i.in[0] = in[k]; i.in[1] = (uint16_t)(p + k); i.out = temp();
+        out.push_back(i.out);
+      }
+      break;
+    }
+    case NK_MAP22: {
+      Instr& i = emit(n.devop);
+      i.in[0] = in[0]; i.in[1] = in[1]; i.out = temp(2);
+      out = {i.out, (uint16_t)(i.out + 1)};
+      break;
+    }
+    case NK_CLIP: case NK_WRAP1: {
+      uint32_t rb = raw(n);
+      int c = (int)n.raw.size();
+      uint16_t p = params(c);
+      deriver(D_COPY, rb, c, p, c, 0, 0, n.sr);
+      Instr& i = emit(n.kind == NK_CLIP ? OP_CLIP : OP_WRAP1);
+      i.in[0] = in[0]; i.p = p; i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_WRAP2: case NK_MIRROR: {
+      uint32_t rb = raw(n);
+      int np = n.kind == NK_WRAP2 ? 2 : 3;
+      uint16_t p = params(np);
+      deriver(n.kind == NK_WRAP2 ? D_WRAP2 : D_MIRROR, rb, 2, p, np, 0, 0, n.sr);
+      Instr& i = emit(n.kind == NK_WRAP2 ? OP_WRAP2 : OP_MIRROR);
+      i.in[0] = in[0]; i.p = p; i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_ROTATE: {
+      uint32_t rb = raw(n);
+      uint16_t p = params(2);
+      deriver(D_ROTATE, rb, 2, p, 2, 0, 0, n.sr);
+      Instr& i = emit(OP_ROTATE);
+      i.in[0] = in[0]; i.in[1] = in[1]; i.p = p; i.out = temp(2);
+      out = {i.out, (uint16_t)(i.out + 1)};
+      break;
+    }
+    case NK_SINE: {
+      uint16_t p = params(1), s = state(1);
+      deriver(D_INV_SR, 0, 0, p, 1, 0, 0, n.sr);
+      hash_init(s, INIT_SINE_PHASE, n.hash);
+      Instr& i = emit(OP_SINE);
+      i.in[0] = in[0]; i.p = p; i.s = s; i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_NOISE: {
+      uint16_t s = state(1);
+      hash_init(s, INIT_NOISE_SEED, n.hash);
+      Instr& i = emit(OP_NOISE);
+      i.s = s; i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_IMPULSE: {
+      Instr& i = emit(OP_IMPULSE);
+      i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_RAMP: {
+      uint16_t p = params(1);
+      deriver(D_RAMP_SR, 0, 0, p, 1, 0, 0, n.sr);
+      Instr& i = emit(OP_RAMP);
+      i.in[0] = in[0]; i.p = p; i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_WAVE: {
+      if (n.table.empty()) { out.push_back(zero()); break; }
+      Instr& i = emit(OP_WAVE);
+      i.s = state(1); i.aux = table(n.table); i.aux2 = (uint32_t)n.table.size(); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_SVF: {
+      int npar = n.mode >= 6 ? 3 : 2, nfixed = n.aux;
+      uint32_t rb = raw(n);
+      if (nfixed == npar) {
+        uint16_t p = params(6);
+        deriver(D_SVF, rb, npar, p, 6, n.mode, 0, n.sr);
+        Instr& i = emit(OP_SVF);
+        i.in[0] = in[0]; i.p = p; i.s = state(2); i.out = temp();
+        out.push_back(i.out);
+      } else {
+        uint16_t p = params(4);
+        deriver(D_SVF_DEFAULTS, rb, nfixed, p, 4, n.mode, npar, n.sr);
+        uint16_t s = state(11);
+        t.state_init[(s & 0x3fff) + 8] = fbits(std::numeric_limits<float>::quiet_NaN());   // cached hz: force first update
+        Instr& i = emit(OP_SVF_VAR);
+        int nvar = npar - nfixed;
+        for (int k = 0; k <= nvar; k++) i.in[k] = in[k];
+        i.n = (uint16_t)(n.mode | (nvar << 8));
+        i.p = p; i.s = s; i.out = temp();
+        out.push_back(i.out);
+      }
+      break;
+    }
+    case NK_BIQUAD: {
+      int kind = n.mode, nvar = n.aux;
+      uint32_t rb = raw(n);
+      if (nvar == 0) {
+        uint16_t p = params(5);
+        if (kind == 0) deriver(D_COPY, rb, 5, p, 5, 0, 0, n.sr);
+        else deriver(D_BIQUAD, rb, kind == 1 ? 1 : 2, p, 5, kind, 0, n.sr);
+        Instr& i = emit(OP_BIQUAD);
+        i.in[0] = in[0]; i.p = p; i.s = state(4); i.out = temp();
+        out.push_back(i.out);
+      } else {
+        uint16_t p = params(1);
+        deriver(D_RAMP_SR, 0, 0, p, 1, 0, 0, n.sr);
+        uint16_t s = state(11);
+        t.state_init[(s & 0x3fff) + 9] = fbits(std::numeric_limits<float>::quiet_NaN());
+        t.state_init[(s & 0x3fff) + 10] = fbits(110.0f);   // resonator() default bandwidth until the input arrives
+        Instr& i = emit(OP_BIQUAD_VAR);
+        for (int k = 0; k <= nvar; k++) i.in[k] = in[k];
+        i.n = (uint16_t)(kind | (nvar << 8));
+        i.p = p; i.s = s; i.out = temp();
+        out.push_back(i.out);
+      }
+      break;
+    }
+    case NK_ONEPOLE: {
+      int kind = n.mode;
+      if (n.n_in == 1) {
+        uint32_t rb = raw(n);
+        uint16_t p = params(1);
+        deriver(D_ONEPOLE, rb, 1, p, 1, kind, 0, n.sr);
+        Instr& i = emit(OP_ONEPOLE);
+        i.in[0] = in[0]; i.n = (uint16_t)kind; i.p = p; i.s = state(2); i.out = temp();
+        out.push_back(i.out);
+      } else {
+        uint16_t p = params(1);
+        deriver(D_RAMP_SR, 0, 0, p, 1, 0, 0, n.sr);
+        uint16_t s = state(4);
+        t.state_init[(s & 0x3fff) + 3] = fbits(std::numeric_limits<float>::quiet_NaN());
+        Instr& i = emit(OP_ONEPOLE_VAR);
+        i.in[0] = in[0]; i.in[1] = in[1]; i.n = (uint16_t)kind; i.p = p; i.s = s; i.out = temp();
+        out.push_back(i.out);
+      }
+      break;
+    }
+    case NK_PINKPASS: {
+      Instr& i = emit(OP_PINKPASS);
+      i.in[0] = in[0]; i.s = state(7); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_FIR: {
+      uint32_t rb = raw(n);
+      int c = (int)n.raw.size();
+      uint16_t p = params(c);
+      deriver(D_COPY, rb, c, p, c, 0, 0, n.sr);
+      Instr& i = emit(OP_FIR);
+      i.in[0] = in[0]; i.n = (uint16_t)c; i.p = p; i.s = state(c); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_TICK: {
+      Instr& i = emit(OP_TICK);
+      i.in[0] = in[0]; i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_DELAY: {
+      raw(n, true);
+      double len = std::round((double)n.raw[0] * n.sr);
+      uint32_t L = len < 1.0 ? 1u : (len > 4.0e8 ? 400000000u : (uint32_t)len);
+      Instr& i = emit(OP_DELAY);
+      i.in[0] = in[0]; i.aux = ring(L); i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_TAP: {
+      uint32_t rb = raw(n, true);
+      uint16_t p = params(3);
+      deriver(D_TAP, rb, 2, p, 3, 0, 0, n.sr);
+      double need = std::ceil((double)n.raw[1] * n.sr) + 4.0;
+      uint32_t L = 4;
+      while ((double)L < need && L < (1u << 30)) L <<= 1;
+      Instr& i = emit(OP_TAP);
+      i.in[0] = in[0]; i.in[1] = in[1]; i.n = (uint16_t)n.mode; i.aux = ring(L); i.p = p; i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_SAMP_DELAY: {
+      if (n.aux <= 0) { out.push_back(zero()); break; }
+      Instr& i = emit(OP_SAMP_DELAY);
+      i.in[0] = in[0]; i.in[1] = in[1]; i.aux = ring((uint32_t)n.aux); i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_ENVELOPE: {
+      uint32_t rb = raw(n);
+      int c = (int)n.raw.size();
+      uint16_t p = params(5);
+      deriver(D_COPY, rb, c, p, c, 0, 0, n.sr);
+      deriver(D_INV_SR, 0, 0, p + 4, 1, 0, 0, n.sr);
+      uint16_t s = state(8);
+      t.state_init[(s & 0x3fff) + 7] = 1u;   // first
+      hash_init((uint16_t)(s + 5), INIT_HASH_LO, n.hash);
+      hash_init((uint16_t)(s + 6), INIT_HASH_HI, n.hash);
+      Instr& i = emit(OP_ENVELOPE);
+      for (int k = 0; k < n.n_in && k < 4; k++) i.in[k] = in[k];
+      i.n = (uint16_t)(n.mode | (n.n_in << 8));
+      i.p = p; i.s = s; i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_DECLICK: {
+      uint32_t rb = raw(n);
+      uint16_t p = params(2);
+      deriver(D_COPY, rb, 1, p, 1, 0, 0, n.sr);
+      deriver(D_INV_SR, 0, 0, p + 1, 1, 0, 0, n.sr);
+      Instr& i = emit(OP_DECLICK);
+      i.in[0] = in[0]; i.p = p; i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_SHIFT_REG: {
+      Instr& i = emit(OP_SHIFT_REG);
+      i.in[0] = in[0]; i.in[1] = in[1]; i.s = state(8); i.out = temp(8);
+      for (int k = 0; k < 8; k++) out.push_back((uint16_t)(i.out + k));
+      break;
+    }
+    case NK_SNH: {
+      Instr& i = emit(OP_SNH);
+      i.in[0] = in[0]; i.in[1] = in[1]; i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_QUANTIZE: {
+      uint32_t rb = raw(n);
+      uint16_t p = params(1);
+      deriver(D_COPY, rb, 1, p, 1, 0, 0, n.sr);
+      Instr& i = emit(OP_QUANTIZE);
+      i.in[0] = in[0]; i.p = p; i.aux = table(n.table); i.aux2 = (uint32_t)n.table.size(); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_ARR_GET: {
+      Instr& i = emit(OP_ARR_GET);
+      i.in[0] = in[0]; i.aux = table(n.table); i.aux2 = (uint32_t)n.table.size(); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_KR: {   // nodes.rs:271-278
+      t.h.flags |= TAPE_DIVERGENT;
+      uint16_t cnt = state(1);
+      uint16_t vals = n.n_out ? state(n.n_out) : NONE;
+      size_t begin = t.code.size();
+      {
+        Instr& b = emit(OP_KR_BEGIN);
+        b.s = cnt; b.aux2 = (uint32_t)n.aux;
+      }
+      std::vector<uint16_t> o = graph(n.kids[0], in);
+      if (!err.empty()) return {};
+      for (int k = 0; k < n.n_out; k++) {
+        Instr& st = emit(OP_ST_STATE);
+        st.in[0] = o[k]; st.s = (uint16_t)(vals + k);
+      }
+      t.code[begin].aux = (uint32_t)t.code.size();
+      Instr& e = emit(OP_KR_END);
+      e.s = cnt;
+      for (int k = 0; k < n.n_out; k++) out.push_back((uint16_t)(vals + k));   // the held values ARE the outputs
+      break;
+    }
+    case NK_FEEDBACK: {   // FeedbackUnit: out = x(in + out delayed by max(1, round(delay*sr)) samples)
+      raw(n, true);
+      double len = std::round((double)n.raw[0] * n.sr);
+      uint32_t L = len < 1.0 ? 1u : (len > 4.0e8 ? 400000000u : (uint32_t)len);
+      int ch = n.n_in;
+      uint16_t idx = state(1);
+      std::vector<uint32_t> rg;
+      std::vector<uint16_t> mixed;
+      for (int c = 0; c < ch; c++) {
+        rg.push_back(ring(L));
+        Instr& r = emit(OP_FB_READ);
+        r.in[0] = in[c]; r.aux = rg[c]; r.s = idx; r.out = temp();
+        mixed.push_back(r.out);
+      }
+      std::vector<uint16_t> o = graph(n.kids[0], mixed);
+      if (!err.empty()) return {};
+      for (int c = 0; c < ch; c++) {
+        Instr& w = emit(OP_FB_WRITE);
+        w.in[0] = o[c]; w.aux = rg[c]; w.s = idx; w.n = (uint16_t)(c == ch - 1 ? 1 : 0);
+      }
+      out = o;
+      break;
+    }
+    case NK_SELECT: {   // nodes.rs:27-33
+      t.h.flags |= TAPE_DIVERGENT;
+      uint16_t o = temp();
+      { Instr& z = emit(OP_ZERO); z.out = o; }
+      for (size_t k = 0; k < n.kids.size(); k++) {
+        size_t j = t.code.size();
+        { Instr& b = emit(OP_JNE_IDX); b.in[0] = in[0]; b.aux2 = (uint32_t)k; }
+        std::vector<uint16_t> ko = graph(n.kids[k], {});
+        if (!err.empty()) return {};
+        { Instr& m = emit(OP_MOV); m.in[0] = ko[0]; m.out = o; }
+        t.code[j].aux = (uint32_t)t.code.size();
+      }
+      out.push_back(o);
+      break;
+    }
+    case NK_RESET: {   // Reset / TrigReset / ResetV, nodes.rs:332-453
+      uint16_t cnt = n.mode == 1 ? NONE : state(1);
+      size_t j = t.code.size();
+      if (n.mode == 0) {
+        Instr& r = emit(OP_RESET_EVERY);
+        r.s = cnt;
+        r.aux = (uint32_t)std::min<uint64_t>(as_usize(std::round(n.raw[0] * (float)n.sr)), 0xffffffffULL);
+      } else if (n.mode == 1) {
+        Instr& r = emit(OP_RESET_IF);
+        r.in[0] = in[0];
+      } else {
+        uint16_t p = params(1);
+        deriver(D_RAMP_SR, 0, 0, p, 1, 0, 0, n.sr);
+        Instr& r = emit(OP_RESET_V);
+        r.in[0] = in[0]; r.s = cnt; r.p = p;
+      }
+      if (n.mode == 0) raw(n, true);
+      ResetRange rr;
+      rr.s_lo = (uint16_t)t.state_init.size();
+      rr.ring_lo = (uint16_t)t.rings.size();
+      std::vector<uint16_t> o = graph(n.kids[0], {});
+      if (!err.empty()) return {};
+      rr.s_hi = (uint16_t)t.state_init.size();
+      rr.ring_hi = (uint16_t)t.rings.size();
+      t.code[j].aux2 = (uint32_t)t.resets.size();
+      t.resets.push_back(rr);
+      out.push_back(o[0]);
+      break;
+    }
+    case NK_RFFT: case NK_IFFT: {   // nodes.rs:601-700, per-lane path
+      uint32_t N = (uint32_t)n.aux;
+      int lg = 0;
+      while ((1u << lg) < N) lg++;
+      bool r = n.kind == NK_RFFT;
+      uint32_t first = ring(N);
+      ring(N); ring(N);
+      if (!r) ring(N);
+      // twiddle table: w_k = exp(-2*pi*i*k/N), k < N/2, rounded from f64 like a precomputed f32 table
+      std::vector<float> tw(N);
+      for (uint32_t k = 0; k < N / 2; k++) {
+        double a = -2.0 * 3.14159265358979323846 * (double)k / (double)N;
+        tw[2 * k] = (float)std::cos(a);
+        tw[2 * k + 1] = (float)std::sin(a);
+      }
+      uint16_t s = state(1, (uint32_t)n.mode);   // count starts at `start`
+      Instr& i = emit(r ? OP_RFFT : OP_IFFT);
+      i.in[0] = in[0];
+      if (!r) i.in[1] = in[1];
+      i.n = (uint16_t)lg; i.aux = first; i.aux2 = table(tw); i.s = s; i.out = temp(2);
+      out = {i.out, (uint16_t)(i.out + 1)};
+      break;
+    }
+    case NK_SEQ:
+      err = "seq() has no GPU lowering yet";
+      break;
+    default:
+      err = "internal: unknown node kind";
+  }
+  return out;
+}
+
+uint64_t mix(uint64_t h, uint64_t v) { return atto(h, v ^ 0x9e3779b97f4a7c15ULL); }
+
+uint64_t sig_graph(const Graph& g, uint64_t h) {
+  h = mix(h, 0xabc0 + g.nodes.size());
+  h = mix(h, (uint64_t)g.n_in);
+  for (const Node& n : g.nodes) {
+    h = mix(h, n.kind); h = mix(h, n.devop); h = mix(h, (uint64_t)n.n_in); h = mix(h, (uint64_t)n.n_out);
+    h = mix(h, (uint64_t)(uint32_t)n.mode); h = mix(h, (uint64_t)(uint32_t)n.aux); h = mix(h, n.raw.size());
+    uint64_t srb; double sr = n.sr; memcpy(&srb, &sr, 8); h = mix(h, srb);
+    bool structural = n.kind == NK_DELAY || n.kind == NK_TAP || n.kind == NK_FEEDBACK || (n.kind == NK_RESET && n.mode == 0);
+    if (structural) for (float v : n.raw) h = mix(h, fbits(v));
+    for (float v : n.table) h = mix(h, fbits(v));
+    for (const Src& s : n.in) { h = mix(h, (uint64_t)(uint32_t)s.node); h = mix(h, (uint64_t)(uint32_t)s.port); }
+    for (const Graph& k : n.kids) h = sig_graph(k, h);
+  }
+  for (const Src& s : g.outs) { h = mix(h, (uint64_t)(uint32_t)s.node); h = mix(h, (uint64_t)(uint32_t)s.port); }
+  return h;
+}
+
+void raw_graph(const Graph& g, std::vector<float>* raw) {
+  for (const Node& n : g.nodes) {
+    // must visit in exactly the order Lower::node() calls raw(): own parameters first, then nested nets —
+    // except reset(), whose duration is registered before its kid like everything else.
+    switch (n.kind) {
+      case NK_SAMP_DELAY: case NK_KR: case NK_SELECT: case NK_SEQ: case NK_ARR_GET: case NK_WAVE: break;
+      case NK_RESET: if (n.mode == 0) raw->insert(raw->end(), n.raw.begin(), n.raw.end()); break;
+      default: raw->insert(raw->end(), n.raw.begin(), n.raw.end());
+    }
+    for (const Graph& k : n.kids) raw_graph(k, raw);
+  }
+}
+
+}  // namespace
+
+void collect_raw(const Graph& g, std::vector<float>* raw) { raw_graph(g, raw); }
+uint64_t structure_signature(const Graph& g) { return sig_graph(g, 0x51475450ULL); }
+
+void Tape::derive(const float* r, float* P) const {
+  for (const Deriver& d : derivers) {
+    const float* in = r + d.raw_base;
+    float* o = P + d.p_base;
+    switch (d.kind) {
+      case D_COPY: for (uint32_t i = 0; i < d.n_raw; i++) o[i] = in[i]; break;
+      case D_SVF: svf_coefs(d.mode, in[0], in[1], d.n_raw >= 3 ? in[2] : 1.0f, d.sr, o); break;
+      case D_SVF_DEFAULTS: {
+        // P = hz q gain sr; the fixed parameters are the trailing ones of (hz, q[, gain])
+        int npar = d.aux, nfixed = (int)d.n_raw;
+        o[0] = 440.0f; o[1] = 1.0f; o[2] = 1.0f; o[3] = d.sr;
+        for (int k = 0; k < nfixed; k++) o[npar - nfixed + k] = in[k];
+        break;
+      }
+      case D_BIQUAD: biquad_coefs(d.mode, in[0], d.n_raw >= 2 ? in[1] : 0.0f, d.sr, o); break;
+      case D_ONEPOLE: o[0] = onepole_coef(d.mode, in[0], d.sr); break;
+      case D_WRAP2: { float lo = fminf(in[0], in[1]), hi = fmaxf(in[0], in[1]); o[0] = lo; o[1] = hi - lo; break; }
+      case D_MIRROR: { float lo = fminf(in[0], in[1]), hi = fmaxf(in[0], in[1]); o[0] = lo; o[1] = hi; o[2] = hi - lo; break; }
+      case D_ROTATE: o[0] = cosf(in[0]) * in[1]; o[1] = sinf(in[0]) * in[1]; break;
+      case D_PAN: pan_weights(in[0], &o[0], &o[1]); break;
+      case D_RAMP_SR: o[0] = d.sr; break;
+      case D_INV_SR: o[0] = (float)(1.0 / (double)d.sr); break;
+      case D_TAP: o[0] = in[0]; o[1] = in[1]; o[2] = d.sr; break;
+    }
+  }
+}
+
+bool lower(const Graph& g, Tape* out, std::string* err) {
+  Tape& t = *out;
+  t = Tape();
+  memset(&t.h, 0, sizeof t.h);
+  Lower L(t);
+  std::vector<uint16_t> ins;
+  for (int i = 0; i < g.n_in; i++) ins.push_back(L.temp());
+  std::vector<uint16_t> outs = L.graph(g, ins);
+  if (!L.err.empty()) { if (err) *err = L.err; return false; }
+  size_t P = t.params.size(), NS = t.state_init.size();
+  if (P >= 0x4000 || NS >= 0x4000 || (size_t)L.n_temps >= 0x7fff || P + NS + L.n_temps >= 0xfff0) {
+    if (err) *err = "graph too large for one tape (parameter/state/temporary index overflow)";
+    return false;
+  }
+  auto fix = [&](uint16_t x) -> uint16_t {
+    if (x == NONE) return 0;
+    if (x & R_TEMP) return (uint16_t)(P + NS + (x & 0x7fff));
+    if (x & R_STATE) return (uint16_t)(P + (x & 0x3fff));
+    return x;
+  };
+  for (Instr& i : t.code) {
+    i.out = fix(i.out); i.p = fix(i.p); i.s = fix(i.s);
+    for (uint16_t& x : i.in) x = fix(x);
+  }
+  for (ResetRange& r : t.resets) { r.s_lo = (uint16_t)(P + r.s_lo); r.s_hi = (uint16_t)(P + r.s_hi); }
+  for (uint16_t o : outs) t.out_x.push_back(fix(o));
+  t.h.magic = TAPE_MAGIC; t.h.version = TAPE_VERSION;
+  t.h.n_instr = (uint32_t)t.code.size();
+  t.h.n_params = (uint32_t)P; t.h.n_state = (uint32_t)NS; t.h.n_temps = (uint32_t)L.n_temps;
+  t.h.n_inputs = (uint32_t)g.n_in; t.h.n_outputs = (uint32_t)outs.size();
+  t.h.n_rings = (uint32_t)t.rings.size();
+  t.h.n_resets = (uint32_t)t.resets.size();
+  t.h.n_hash_init = (uint32_t)t.hash_init.size();
+  t.h.table_floats = (uint32_t)t.tables.size();
+  t.h.n_raw = (uint32_t)t.raw.size();
+  t.h.sample_rate = (float)g.sr;
+  t.signature = structure_signature(g);
+  // the derivers define the template parameter values
+  std::vector<float> p(P, 0.0f);
+  for (size_t i = 0; i < P; i++) p[i] = t.params[i];
+  t.derive(t.raw.data(), p.data());
+  t.params = p;
+  return true;
+}
+
+}  // namespace qg

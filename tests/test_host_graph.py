@@ -1,0 +1,114 @@
+"""Host-side logic of the product (no GPU): op-string parsing, arity rules, composition guards and structural
+bookkeeping must agree with the reference's documented behaviour and with the oracle's independent restatement."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import quartz_b200 as qb
+from quartz_b200 import Net, _ffi
+from tests import cases
+from tests.graphs import L, build, pipe, stack
+from tests.oracle_ffi import ONet, OracleUnsupported
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "quartz_gpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(qg_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(qb.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/quartz_gpu.h but not exported"
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+
+
+@pytest.mark.parametrize("op,ni,no", cases.ARITY, ids=[c[0] for c in cases.ARITY])
+def test_str_to_net_arity(op, ni, no):
+    n = Net.str_to_net(op)
+    assert (n.inputs(), n.outputs()) == (ni, no)
+    try:
+        o = ONet.str_to_net(op)
+    except OracleUnsupported:
+        return
+    assert (o.inputs(), o.outputs()) == (ni, no)
+
+
+@pytest.mark.parametrize("name,expr,n,tol", cases.RENDER, ids=[c[0] for c in cases.RENDER])
+def test_graph_shape_matches_oracle(name, expr, n, tol):
+    a, b = build(expr, Net), build(expr, ONet)
+    assert (a.inputs(), a.outputs(), a.size()) == (b.inputs(), b.outputs(), b.size())
+    assert a.unsupported() is None
+    info = a.tape_info()
+    assert info["n_instr"] >= 0 and info["n_temps"] >= a.inputs()
+
+
+def test_connective_guards_follow_process_rs():
+    s, lp2 = Net.str_to_net("sine(440)"), Net.str_to_net("lowpass()")
+    # >> requires outputs == inputs, otherwise the rhs is skipped (process.rs:1839)
+    g = Net.connect(">>", [s, lp2])
+    assert (g.inputs(), g.outputs(), g.size()) == (0, 1, 1)
+    # + requires equal outputs (process.rs:1751)
+    g = Net.connect("+", [s, Net.str_to_net("dc(1,2)")])
+    assert g.outputs() == 1 and g.size() == 1
+    # repeat count (process.rs:1744-1745)
+    g = Net.connect("|", [s], number=4)
+    assert (g.outputs(), g.size()) == (4, 4)
+    # node limit (process.rs:1752-1754): growth stops once size() reaches the limit
+    g = Net.connect("|", [s], number=50, node_limit=10)
+    assert g.size() == 10
+    # `-` needs both sides and equal outputs (process.rs:1788-1797)
+    assert Net.connect("-", [s]).outputs() == 0
+    d = Net.connect("-", [s, s])
+    assert (d.outputs(), d.size()) == (1, 3)
+    # ! passes missing outputs through (process.rs:1873)
+    t = Net.connect("!", [Net.str_to_net("sink()")])
+    assert (t.inputs(), t.outputs()) == (1, 1)
+    # feedback needs outs == ins (process.rs:1500); reset needs 0-in/1-out (process.rs:1568)
+    assert Net.feedback(s).outputs() == 0
+    assert Net.reset_every(lp2, 1.0).outputs() == 0
+    assert Net.reset_every(s, 1.0).outputs() == 1
+    # seq/select keep only 0-in/1-out nets (process.rs:1638)
+    sel = Net.select([s, lp2, s])
+    assert (sel.inputs(), sel.outputs()) == (1, 1)
+
+
+def test_unsupported_ops_fail_loudly_not_silently():
+    for op in ("saw(220)", "reverb_stereo(10,2)", "moog(1000,0.5)", "pluck(220,0.5,0.5)"):
+        n = Net.str_to_net(op)
+        assert n.unsupported() is not None
+        with pytest.raises(qb.QuartzGpuError):
+            n.tape_info()
+        # the flag survives composition
+        g = Net.connect(">>", [n, Net.str_to_net("mul(0.5)")])
+        assert g.unsupported() is not None
+
+
+def test_raw_parameters_and_signature():
+    a = build(pipe("sine(220)", "lowpass(800,2)"), Net)
+    b = build(pipe("sine(330)", "lowpass(1200,0.7)"), Net)
+    c = build(pipe("sine(330)", "highpass(1200,0.7)"), Net)
+    assert a.raw_params().tolist() == [220.0, 800.0, 2.0]
+    assert a.signature() == b.signature() != c.signature()
+    # delay time shapes the tape (ring length) -> part of the signature
+    d1, d2 = Net.str_to_net("delay(0.01)"), Net.str_to_net("delay(0.02)")
+    assert d1.signature() != d2.signature()
+
+
+def test_clone_is_a_deep_copy():
+    a = build(pipe("white()", "lowpass(800,2)"), Net)
+    b = a.clone()
+    b.set_sample_rate(48000)
+    assert a.signature() != b.signature()
+
+
+def test_device_entry_points_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(qb.QuartzGpuError):
+        Net.str_to_net("sine(440)").render(16)

@@ -1,0 +1,30 @@
+import numpy as np
+
+
+def assert_parity(got, ref, tol, what=""):
+    """Parity bar from BASELINE.md section 5: bit-exact for integer/trigger state; for f32 audio max abs error
+    <= 1e-4 and residual <= -90 dBFS, both relative to max(1, peak of the reference)."""
+    got = np.asarray(got, dtype=np.float32)
+    ref = np.asarray(ref, dtype=np.float32)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    if got.size == 0:
+        return
+    if tol == "exact":
+        same = (got.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(got) & np.isnan(ref))
+        assert same.all(), f"{what}: {int((~same).sum())}/{got.size} words differ; first at {np.argwhere(~same)[0]}: " \
+                           f"{got[tuple(np.argwhere(~same)[0])]!r} vs {ref[tuple(np.argwhere(~same)[0])]!r}"
+        return
+    nan_ok = np.isnan(got) == np.isnan(ref)
+    assert nan_ok.all(), f"{what}: NaN pattern differs"
+    inf = np.isinf(ref)
+    assert (got[inf] == ref[inf]).all(), f"{what}: inf pattern differs"
+    fin = np.isfinite(ref)
+    if not fin.any():
+        return
+    g, r = got[fin].astype(np.float64), ref[fin].astype(np.float64)
+    scale = max(1.0, float(np.abs(r).max()))
+    err = np.abs(g - r)
+    assert err.max() <= 1e-4 * scale, f"{what}: max abs err {err.max():.3e} (scale {scale:.3g})"
+    rms = float(np.sqrt(np.mean((g - r) ** 2))) / scale
+    db = 20 * np.log10(max(rms, 1e-30))
+    assert db <= -90.0, f"{what}: residual {db:.1f} dBFS"
