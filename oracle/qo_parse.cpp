@@ -421,7 +421,7 @@ NetP str_to_net(const std::string& op_in, int* status) {
       {"semitone_ratio", [](float x) { return semitone_ratio(x); }},
       {"rnd1", [](float x) { return (float)rnd1(as_usize(x)); }},
       {"rnd2", [](float x) { return (float)rnd2(as_usize(x)); }},
-      {"deg", [](float x) { return x * (180.0f / PI_F); }},
+      {"deg", [](float x) { return x * 57.2957795130823208767981548141051703f; }},   // f32::to_degrees constant
       {"rad", [](float x) { return x * (PI_F / 180.0f); }},
       {"recip", [](float x) { return 1.0f / x; }},
       {"normal", [](float x) { return is_normal(x) ? x : 0.0f; }},

@@ -10,7 +10,8 @@
 
 namespace qg {
 
-__device__ __forceinline__ uint64_t d_as_usize(float x) { return __float2ull_rz(x); }   // saturating, NaN -> 0
+// saturating, NaN -> 0 (cvt.rzi.u64.f32 alone maps NaN to 0x8000000000000000)
+__device__ __forceinline__ uint64_t d_as_usize(float x) { return x != x ? 0ull : __float2ull_rz(x); }
 __device__ __forceinline__ int32_t d_as_i32(float x) { return __float2int_rz(x); }       // saturating, NaN -> 0
 __device__ __forceinline__ bool d_is_normal(float x) {
   float a = fabsf(x);

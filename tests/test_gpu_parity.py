@@ -22,9 +22,8 @@ def test_asset_golden_vectors_on_gpu(case):
     net = build(case["net"], Net)
     exp = np.array(case["output_bits"], dtype=np.uint32).view(np.float32)
     if case["kind"] == "apply":
+        # libdevice exp2f/sinf/hypotf may differ from the CPU libm in the last ulp: f32 tolerance, not bits
         assert_parity(net.tick(case["input"]), exp, "float", case["name"])
-        if "sin" not in json.dumps(case["net"]):   # pure arithmetic + exp2: expect the exact reference bits
-            assert_parity(net.tick(case["input"]), exp, "exact", case["name"])
     else:
         net.set_sample_rate(case["sample_rate"])
         assert_parity(net.render(case["len"])[:, 0], exp, "float", case["name"])
@@ -70,12 +69,12 @@ def test_bank_per_voice_parameters_and_salts():
     tmpl = build(pipe("white()", "lowpass(1000,1)"), Net).set_sample_rate(48000)
     bank = Bank(tmpl, V, raw=np.stack([hz, q], axis=1), salts=salts).set_path(qb.PATH_INTERP)
     got = bank.render(T)[:, 0, :]
-    onets = [build(pipe("white()", f"lowpass({hz[v]!r},{q[v]!r})"), ONet).set_sample_rate(48000).set_salt(int(salts[v]))
+    onets = [build(pipe("white()", f"lowpass({float(hz[v])!r},{float(q[v])!r})"), ONet).set_sample_rate(48000).set_salt(int(salts[v]))
              for v in range(V)]
     ref = render_bank(onets, T)
     assert_parity(got, ref, "float", "bank")
     # same thing built from V separate nets (one `render` circle per voice in the reference)
-    nets = [build(pipe("white()", f"lowpass({hz[v]!r},{q[v]!r})"), Net).set_sample_rate(48000) for v in range(V)]
+    nets = [build(pipe("white()", f"lowpass({float(hz[v])!r},{float(q[v])!r})"), Net).set_sample_rate(48000) for v in range(V)]
     bank2 = Bank(None, nets=nets, salts=salts).set_path(qb.PATH_INTERP)
     assert_parity(bank2.render(T)[:, 0, :], ref, "float", "bank_from_nets")
     # frame-major layout is the transpose
