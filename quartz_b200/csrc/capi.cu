@@ -42,6 +42,8 @@ struct qg_bank {
   size_t scratch_bytes = 0;
   float* d_in = nullptr;
   size_t in_bytes = 0;
+  float* d_fused_scratch = nullptr;
+  size_t fused_scratch_bytes = 0;
   FusedPlan fused;
 };
 
@@ -204,7 +206,7 @@ static void bank_release(qg_bank* b) {
   cudaSetDevice(b->ctx->device);
   cudaFree(b->d_code); cudaFree(b->d_out_x); cudaFree(b->d_params); cudaFree(b->d_state); cudaFree(b->d_state_init);
   cudaFree(b->d_rings); cudaFree(b->d_ring_tab); cudaFree(b->d_resets); cudaFree(b->d_tables); cudaFree(b->d_scratch);
-  cudaFree(b->d_in);
+  cudaFree(b->d_in); cudaFree(b->d_fused_scratch);
   delete b;
 }
 
@@ -377,6 +379,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   if (b->path == QG_PATH_AUTO && b->fused.id != FUSED_NONE && !d_in && layout == QG_LAYOUT_VOICE_MAJOR) {
     FusedArgs fa;
     fa.params = b->d_params; fa.state = b->d_state; fa.V = (int)b->V; fa.Vp = b->Vp; fa.T = T; fa.group = group; fa.out = d_out;
+    fa.scratch = &b->d_fused_scratch; fa.scratch_bytes = &b->fused_scratch_bytes; fa.sample_rate = t.h.sample_rate;
     int l = 0;
     CU(launch_fused(b->fused, fa, c->stream, &l));
     c->launches += l;

@@ -1,10 +1,412 @@
-// Hand-fused kernels (see fused.h).
+// Hand-fused kernels for hot tape shapes (see fused.h).
+//
+// K2  k_noise_svf_scan — `white() >> <fixed SVF>` banks (BASELINE configs[1]): ONE WARP PER VOICE, time-parallel.
+//     The SVF with fixed coefficients is LTI:  s' = A s + B x,  y = C s + D x  with s = (ic1, ic2).  A block of
+//     32*K consecutive samples is split over the 32 lanes (K contiguous samples each):
+//       1. every lane runs its K samples from zero state (noise is counter-based, so lane j just starts its
+//          counter at base + j*K) and keeps the K zero-state outputs in registers;
+//       2. the per-lane end states are combined with a 5-step warp-shuffle scan of the affine maps
+//          s -> A^K s + c_j  (Kogge-Stone, matrices A^K, A^2K, ... A^16K precomputed per voice in f64);
+//       3. every lane adds the homogeneous response C A^i s_start to its K outputs;
+//       4. the 32*K outputs (one contiguous 1 KB run of the voice's row) are staged in shared memory and written
+//          with ONE bulk async copy (cp.async.bulk.global.shared::cta -> UBLKCP), double-buffered.
+//     Small banks use S time segments per voice: a state-only pre-pass computes each segment's zero-state end
+//     state, the segment start states are chained on the fly (block-level scan), then every segment renders.
+//     Arithmetic uses explicit FMAs and a re-associated recurrence: parity is the f32 audio tolerance
+//     (<= 1e-4 abs, <= -90 dBFS), demonstrated at full length in tests/test_gpu_fused.py; noise samples and the
+//     persisted counter are bit-exact.
 #include "fused.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev_math.cuh"
+#include "tape.h"
 
 namespace qg {
 
-FusedPlan plan_fused(const Tape&) { return FusedPlan(); }
-const char* fused_name(int id) { return id == FUSED_NOISE_SVF ? "k_noise_svf_scan" : id == FUSED_SINE_SVF_ENV ? "k_polysynth" : "none"; }
-cudaError_t launch_fused(const FusedPlan&, const FusedArgs&, cudaStream_t, int*) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int K = 8;            // samples per lane per block
+constexpr int B = 32 * K;       // samples per warp block (1 KB of output)
+
+struct Mat2 { float a, b, c, d; };   // [[a b],[c d]]
+
+__device__ __forceinline__ void bulk_store_1k(float* gdst, const float* ssrc) {
+  // one elected lane: shared -> global bulk async copy of B floats
+  unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "n"(B * 4) : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+struct SvfC { float a1, a2, a3, m0, m1, m2; };
+
+// zero-state / any-state SVF tick with explicit FMAs; returns the mode output
+__device__ __forceinline__ float svf_fma(float x, float& ic1, float& ic2, const SvfC& c) {
+  float v3 = x - ic2;
+  float v1 = __fmaf_rn(c.a2, v3, c.a1 * ic1);
+  float v2 = __fmaf_rn(c.a3, v3, __fmaf_rn(c.a2, ic1, ic2));
+  ic1 = __fmaf_rn(2.0f, v1, -ic1);
+  ic2 = __fmaf_rn(2.0f, v2, -ic2);
+  return __fmaf_rn(c.m2, v2, __fmaf_rn(c.m1, v1, c.m0 * x));
+}
+
+// MODE 0: write samples; MODE 1: state-only pre-pass (zero start state, no output) for segment chaining
+template <int MODE>
+__global__ void __launch_bounds__(128) k_noise_svf_scan(const float* __restrict__ params, float* __restrict__ state, int Vp,
+                                                        int V, long T, int S, long seg_len, int p_svf, int s_noise,
+                                                        int s_svf, float* __restrict__ out, float* __restrict__ seg_state) {
+  __shared__ __align__(128) float stage[4][2][B];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long w = (long)blockIdx.x * 4 + warp;        // warp id = voice * S + segment
+  const int v = (int)(w / S), seg = (int)(w % S);
+  if (v >= V) return;
+  SvfC c;
+  c.a1 = params[(size_t)(p_svf + 0) * Vp + v]; c.a2 = params[(size_t)(p_svf + 1) * Vp + v];
+  c.a3 = params[(size_t)(p_svf + 2) * Vp + v]; c.m0 = params[(size_t)(p_svf + 3) * Vp + v];
+  c.m1 = params[(size_t)(p_svf + 4) * Vp + v]; c.m2 = params[(size_t)(p_svf + 5) * Vp + v];
+  // state-space form of the tick:  s' = A s + B x ; y = C s + D x
+  const double a1 = c.a1, a2 = c.a2, a3 = c.a3;
+  const double A11 = 2 * a1 - 1, A12 = -2 * a2, A21 = 2 * a2, A22 = 1 - 2 * a3;
+  const float fA11 = (float)A11, fA12 = (float)A12, fA21 = (float)A21, fA22 = (float)A22;
+  // y_h = m1*v1_h + m2*v2_h with v1_h = a1 s1 - a2 s2, v2_h = a2 s1 + (1 - a3) s2
+  const float C1 = (float)((double)c.m1 * a1 + (double)c.m2 * a2), C2 = (float)(-(double)c.m1 * a2 + (double)c.m2 * (1 - a3));
+  // powers A^(K*2^i), i = 0..4, in f64 then rounded
+  Mat2 Mp[5];
+  {
+    double m11 = 1, m12 = 0, m21 = 0, m22 = 1;
+    for (int i = 0; i < K; i++) {
+      double n11 = A11 * m11 + A12 * m21, n12 = A11 * m12 + A12 * m22, n21 = A21 * m11 + A22 * m21, n22 = A21 * m12 + A22 * m22;
+      m11 = n11; m12 = n12; m21 = n21; m22 = n22;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      Mp[i] = Mat2{(float)m11, (float)m12, (float)m21, (float)m22};
+      double n11 = m11 * m11 + m12 * m21, n12 = m11 * m12 + m12 * m22, n21 = m21 * m11 + m22 * m21, n22 = m21 * m12 + m22 * m22;
+      m11 = n11; m12 = n12; m21 = n21; m22 = n22;
+    }
+  }
+  const long t_begin = (long)seg * seg_len;
+  const long t_end = (t_begin + seg_len < T) ? t_begin + seg_len : T;
+  const uint32_t counter0 = __float_as_uint(state[(size_t)s_noise * Vp + v]);
+  float S1, S2;   // start state of the current block (warp-uniform)
+  if (MODE == 1 || seg > 0) {
+    if (MODE == 1) { S1 = 0.0f; S2 = 0.0f; }
+    else { S1 = seg_state[((size_t)v * (S + 1) + seg) * 2]; S2 = seg_state[((size_t)v * (S + 1) + seg) * 2 + 1]; }
+  } else { S1 = state[(size_t)s_svf * Vp + v]; S2 = state[(size_t)(s_svf + 1) * Vp + v]; }
+  float* orow = MODE == 0 ? out + (size_t)v * T : nullptr;
+  const bool can_bulk = MODE == 0 && ((((size_t)(uintptr_t)orow) & 15) == 0) && ((T & 3) == 0);
+
+  long t = t_begin;
+  int buf = 0;
+  for (; t + B <= t_end; t += B) {
+    // ---- 1. zero-state run of this lane's K samples
+    float y[K];
+    float z1 = 0.0f, z2 = 0.0f;
+    const uint32_t cb = counter0 + (uint32_t)t + (uint32_t)(lane * K);
+#pragma unroll
+    for (int i = 0; i < K; i++) y[i] = svf_fma(d_noise(cb + (uint32_t)i + 1u), z1, z2, c);
+    // ---- 2. warp scan of the affine maps: E_j = true end state of lane j
+    float e1 = z1, e2 = z2;
+    if (lane == 0) {
+      e1 = __fmaf_rn(Mp[0].a, S1, __fmaf_rn(Mp[0].b, S2, e1));
+      e2 = __fmaf_rn(Mp[0].c, S1, __fmaf_rn(Mp[0].d, S2, e2));
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const int d = 1 << i;
+      float r1 = __shfl_up_sync(0xffffffffu, e1, d), r2 = __shfl_up_sync(0xffffffffu, e2, d);
+      if (lane >= d) {
+        e1 = __fmaf_rn(Mp[i].a, r1, __fmaf_rn(Mp[i].b, r2, e1));
+        e2 = __fmaf_rn(Mp[i].c, r1, __fmaf_rn(Mp[i].d, r2, e2));
+      }
+    }
+    float h1 = __shfl_up_sync(0xffffffffu, e1, 1), h2 = __shfl_up_sync(0xffffffffu, e2, 1);
+    if (lane == 0) { h1 = S1; h2 = S2; }
+    S1 = __shfl_sync(0xffffffffu, e1, 31);
+    S2 = __shfl_sync(0xffffffffu, e2, 31);
+    if (MODE == 0) {
+      // ---- 3. homogeneous correction
+#pragma unroll
+      for (int i = 0; i < K; i++) {
+        y[i] = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y[i]));
+        float n1 = __fmaf_rn(fA11, h1, fA12 * h2), n2 = __fmaf_rn(fA21, h1, fA22 * h2);
+        h1 = n1; h2 = n2;
+      }
+      // ---- 4. stage + bulk store
+      if (can_bulk) {
+        if (lane == 0) bulk_wait_read_1();          // the copy that last read this buffer has drained
+        __syncwarp();
+        float4* sp = reinterpret_cast<float4*>(&stage[warp][buf][lane * K]);
+#pragma unroll
+        for (int i = 0; i < K / 4; i++) sp[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store_1k(orow + t, &stage[warp][buf][0]);
+        buf ^= 1;
+      } else {
+#pragma unroll
+        for (int i = 0; i < K; i++) orow[t + lane * K + i] = y[i];
+      }
+    }
+  }
+  // ---- tail (< B samples): sequential on every lane (redundant), lane 0 stores
+  {
+    float s1 = S1, s2 = S2;
+    for (long tt = t; tt < t_end; tt++) {
+      float yv = svf_fma(d_noise(counter0 + (uint32_t)tt + 1u), s1, s2, c);
+      if (MODE == 0 && lane == 0) orow[tt] = yv;
+    }
+    S1 = s1; S2 = s2;
+  }
+  if (MODE == 1) {
+    if (lane == 0) { seg_state[((size_t)v * (S + 1) + seg) * 2] = S1; seg_state[((size_t)v * (S + 1) + seg) * 2 + 1] = S2; }
+  } else {
+    if (can_bulk && lane == 0) bulk_wait_all();
+    if (seg == S - 1 && lane == 0) {
+      if (S == 1) {
+        state[(size_t)s_svf * Vp + v] = S1;
+        state[(size_t)(s_svf + 1) * Vp + v] = S2;
+        state[(size_t)s_noise * Vp + v] = __uint_as_float(counter0 + (uint32_t)T);
+      } else {
+        // other segments of this voice may not have read the persisted state yet: publish through slot S,
+        // k_finalize_segments copies it into the bank state after the render kernel
+        seg_state[((size_t)v * (S + 1) + S) * 2] = S1;
+        seg_state[((size_t)v * (S + 1) + S) * 2 + 1] = S2;
+      }
+    }
+  }
+}
+
+__global__ void k_finalize_segments(float* __restrict__ state, int Vp, int V, long T, int S, int s_noise, int s_svf,
+                                    const float* __restrict__ seg_state) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  state[(size_t)s_svf * Vp + v] = seg_state[((size_t)v * (S + 1) + S) * 2];
+  state[(size_t)(s_svf + 1) * Vp + v] = seg_state[((size_t)v * (S + 1) + S) * 2 + 1];
+  state[(size_t)s_noise * Vp + v] = __uint_as_float(__float_as_uint(state[(size_t)s_noise * Vp + v]) + (uint32_t)T);
+}
+
+// Chain the segment start states: start_0 = persisted state, start_{g+1} = A^len_g start_g + zs_end_g.
+// One thread per voice; A^len by square-and-multiply in f64.
+__global__ void k_chain_segments(const float* __restrict__ params, const float* __restrict__ state, int Vp, int V, long T, int S,
+                                 long seg_len, int p_svf, int s_svf, float* __restrict__ seg_state) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const double a1 = params[(size_t)(p_svf + 0) * Vp + v], a2 = params[(size_t)(p_svf + 1) * Vp + v], a3 = params[(size_t)(p_svf + 2) * Vp + v];
+  const double A11 = 2 * a1 - 1, A12 = -2 * a2, A21 = 2 * a2, A22 = 1 - 2 * a3;
+  double s1 = state[(size_t)s_svf * Vp + v], s2 = state[(size_t)(s_svf + 1) * Vp + v];
+  for (int g = 0; g < S; g++) {
+    float z1 = seg_state[((size_t)v * (S + 1) + g) * 2], z2 = seg_state[((size_t)v * (S + 1) + g) * 2 + 1];
+    seg_state[((size_t)v * (S + 1) + g) * 2] = (float)s1;
+    seg_state[((size_t)v * (S + 1) + g) * 2 + 1] = (float)s2;
+    long len = (long)(g + 1) * seg_len <= T ? seg_len : T - (long)g * seg_len;
+    if (len < 0) len = 0;
+    double p11 = 1, p12 = 0, p21 = 0, p22 = 1, b11 = A11, b12 = A12, b21 = A21, b22 = A22;
+    for (long e = len; e > 0; e >>= 1) {
+      if (e & 1) {
+        double n11 = b11 * p11 + b12 * p21, n12 = b11 * p12 + b12 * p22, n21 = b21 * p11 + b22 * p21, n22 = b21 * p12 + b22 * p22;
+        p11 = n11; p12 = n12; p21 = n21; p22 = n22;
+      }
+      double n11 = b11 * b11 + b12 * b21, n12 = b11 * b12 + b12 * b22, n21 = b21 * b11 + b22 * b21, n22 = b21 * b12 + b22 * b22;
+      b11 = n11; b12 = n12; b21 = n21; b22 = n22;
+    }
+    double n1 = p11 * s1 + p12 * s2 + (double)z1, n2 = p21 * s1 + p22 * s2 + (double)z2;
+    s1 = n1; s2 = n2;
+  }
+}
+
+// K1f  k_polysynth — `sine(f) >> <fixed SVF>` * ar(a, ak, r, rk), optional group mix (BASELINE configs[2]).
+//      One lane per voice, time sequential, every per-voice quantity in registers.
+//      * phase and envelope time accumulate with the reference's exact operation order (no FMA): a 1-ulp slip
+//        would drift over 480,000 samples;
+//      * lfo() control points are jittered per voice (hash-seeded), so a naive `if (t >= t1)` makes ~28 % of all
+//        warp-steps execute the expensive segment update for a single lane.  Instead the NEXT control point is
+//        computed ahead of time at warp-uniform window boundaries (window < shortest possible segment), and the
+//        per-sample crossing only rotates registers;
+//      * SVF / envelope interpolation use FMA and a per-segment reciprocal: f32 audio tolerance, not bits;
+//      * group mix (K6): a 32x33 shared tile per warp, lane j adds column j over the group's voices left to right.
+struct EnvC { float c0, c1, c2, c3; };
+__device__ __forceinline__ float env_ar(float tt, const EnvC& e) {   // functions.rs:547-555
+  if (tt < e.c0) return powf(tt / e.c0, e.c1);
+  if (tt < e.c0 + e.c2) return powf((e.c2 - (tt - e.c0)) / e.c2, e.c3);
+  return 0.0f;
+}
+
+__global__ void __launch_bounds__(128) k_polysynth(const float* __restrict__ params, float* __restrict__ state, int Vp, int V,
+                                                   long T, int G, int window, int p_f, int p_sd, int p_svf, int p_env,
+                                                   int s_ph, int s_svf, int s_env, float* __restrict__ out) {
+  __shared__ float tile[4][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = blockIdx.x * 128 + threadIdx.x;          // < Vp (padded voices run on copies of the last voice)
+  const int warp_v0 = blockIdx.x * 128 + warp * 32;
+#define PRM(i) params[(size_t)(i) * Vp + v]
+#define ST(i) state[(size_t)(i) * Vp + v]
+  const float inc = PRM(p_f) * PRM(p_sd);                // input[0] * sample_duration
+  SvfC c = {PRM(p_svf), PRM(p_svf + 1), PRM(p_svf + 2), PRM(p_svf + 3), PRM(p_svf + 4), PRM(p_svf + 5)};
+  EnvC e = {PRM(p_env), PRM(p_env + 1), PRM(p_env + 2), PRM(p_env + 3)};
+  const float esd = PRM(p_env + 4);
+  float phase = ST(s_ph), ic1 = ST(s_svf), ic2 = ST(s_svf + 1);
+  float et = ST(s_env), t0 = ST(s_env + 1), t1 = ST(s_env + 2), v0 = ST(s_env + 3), v1 = ST(s_env + 4);
+  uint64_t th = (uint64_t)__float_as_uint(ST(s_env + 5)) | ((uint64_t)__float_as_uint(ST(s_env + 6)) << 32);
+  uint32_t first = __float_as_uint(ST(s_env + 7));
+  // prologue: bring the envelope to "inside a segment" exactly like the per-sample code would on its first tick
+  if (et >= t1) {
+    if (first) { v1 = env_ar(0.0f, e); first = 0u; }
+    t0 = t1; v0 = v1;
+    t1 = t0 + d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
+    v1 = env_ar(t1, e);
+    th += 1;
+  }
+  float inv = 1.0f / (t1 - t0);
+  float nt1 = 0.0f, nv1 = 0.0f;
+  bool have_next = false;
+  for (long tb = 0; tb < T; tb += window) {
+    if (!have_next) {                                    // warp-uniform point: look one control point ahead
+      nt1 = t1 + d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
+      nv1 = env_ar(nt1, e);
+      have_next = true;
+    }
+    const int n = (int)((T - tb) < window ? (T - tb) : window);
+    for (int i = 0; i < n; i++) {
+      const long t = tb + i;
+      // ---- sine (FunDSP Sine::tick): output from the phase before the increment
+      const float p = phase;
+      phase = p + inc;
+      phase -= floorf(phase);
+      const float x = sinf(p * QG_TAU);
+      // ---- SVF
+      const float y = svf_fma(x, ic1, ic2, c);
+      // ---- envelope (lfo): at most one crossing per window by construction
+      if (et >= t1) {
+        t0 = t1; v0 = v1; t1 = nt1; v1 = nv1;
+        th += 1;
+        have_next = false;
+        inv = 1.0f / (t1 - t0);
+      }
+      const float u = (et - t0) * inv;
+      et += esd;
+      const float env = __fmaf_rn(v1, u, v0 * (1.0f - u));
+      const float o = y * env;
+      // ---- output tile
+      const int tt = (int)(t & 31);
+      tile[warp][lane][tt] = o;
+      if (tt == 31 || t == T - 1) {
+        __syncwarp();
+        const long t_base = t - tt;
+        if (lane <= tt) {
+          if (G <= 1) {
+            for (int r = 0; r < 32; r++)
+              if (warp_v0 + r < V) out[(size_t)(warp_v0 + r) * T + t_base + lane] = tile[warp][r][lane];
+          } else {
+            const float sc = 1.0f / (float)G;
+            for (int g0 = 0; g0 < 32; g0 += G) {
+              if (warp_v0 + g0 + G <= V) {
+                float acc = tile[warp][g0][lane];
+                for (int r = 1; r < G; r++) acc += tile[warp][g0 + r][lane];
+                out[(size_t)((warp_v0 + g0) / G) * T + t_base + lane] = acc * sc;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (v < V) {
+    ST(s_ph) = phase; ST(s_svf) = ic1; ST(s_svf + 1) = ic2;
+    ST(s_env) = et; ST(s_env + 1) = t0; ST(s_env + 2) = t1; ST(s_env + 3) = v0; ST(s_env + 4) = v1;
+    ST(s_env + 5) = __uint_as_float((uint32_t)th); ST(s_env + 6) = __uint_as_float((uint32_t)(th >> 32));
+    ST(s_env + 7) = __uint_as_float(first);
+  }
+#undef PRM
+#undef ST
+}
+
+}  // namespace
+
+FusedPlan plan_fused(const Tape& t) {
+  FusedPlan pl;
+  const auto& c = t.code;
+  if (t.h.n_inputs == 0 && t.h.n_outputs == 1 && c.size() == 2 && c[0].op == OP_NOISE && c[1].op == OP_SVF &&
+      c[1].in[0] == c[0].out && t.out_x.size() == 1 && t.out_x[0] == c[1].out) {
+    pl.id = FUSED_NOISE_SVF;
+    pl.p[0] = c[1].p;                                   // a1 a2 a3 m0 m1 m2 (X index == parameter index)
+    pl.s[0] = c[0].s - (int)t.h.n_params;               // noise counter
+    pl.s[1] = c[1].s - (int)t.h.n_params;               // ic1, ic2
+    return pl;
+  }
+  // sine(f) >> svf(fixed)  *  ar(a,ak,r,rk)
+  const int P = (int)t.h.n_params;
+  if (t.h.n_inputs == 0 && t.h.n_outputs == 1 && c.size() == 4 && c[0].op == OP_SINE && c[0].in[0] < P && c[1].op == OP_SVF &&
+      c[1].in[0] == c[0].out && c[2].op == OP_ENVELOPE && c[2].n == 2 && c[3].op == OP_MUL && c[3].in[0] == c[1].out &&
+      c[3].in[1] == c[2].out && t.out_x.size() == 1 && t.out_x[0] == c[3].out) {
+    pl.id = FUSED_SINE_SVF_ENV;
+    pl.p[0] = c[0].in[0]; pl.p[1] = c[0].p; pl.p[2] = c[1].p; pl.p[3] = c[2].p;
+    pl.s[0] = c[0].s - P; pl.s[1] = c[1].s - P; pl.s[2] = c[2].s - P;
+  }
+  return pl;
+}
+
+const char* fused_name(int id) {
+  return id == FUSED_NOISE_SVF ? "k_noise_svf_scan" : id == FUSED_SINE_SVF_ENV ? "k_polysynth" : "none";
+}
+
+cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t stream, int* launches) {
+  if (pl.id == FUSED_NOISE_SVF) {
+    if (a.group != 1) return cudaErrorNotSupported;
+    // segments per voice: enough warps to fill 148 SMs x ~24 warps when the bank is small
+    int S = 1;
+    const long target_warps = 148L * 24;
+    if (a.V < target_warps) {
+      S = (int)((target_warps + a.V - 1) / a.V);
+      long max_s = a.T / (8L * B);
+      if (S > max_s) S = (int)(max_s < 1 ? 1 : max_s);
+    }
+    long seg_len = ((a.T + S - 1) / S + B - 1) / B * B;
+    S = (int)((a.T + seg_len - 1) / seg_len);
+    if (S < 1) S = 1;
+    long warps = (long)a.V * S;
+    unsigned blocks = (unsigned)((warps + 3) / 4);
+    float* seg = nullptr;
+    if (S > 1) {
+      size_t need = (size_t)a.V * (S + 1) * 2 * sizeof(float);
+      if (need > *a.scratch_bytes) {
+        if (*a.scratch) cudaFree(*a.scratch);
+        *a.scratch = nullptr; *a.scratch_bytes = 0;
+        cudaError_t e = cudaMalloc((void**)a.scratch, need);
+        if (e != cudaSuccess) return e;
+        *a.scratch_bytes = need;
+      }
+      seg = *a.scratch;
+      k_noise_svf_scan<1><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1],
+                                                      nullptr, seg);
+      k_chain_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], seg);
+      if (launches) *launches += 2;
+    }
+    k_noise_svf_scan<0><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg);
+    if (launches) *launches += 1;
+    if (S > 1) {
+      k_finalize_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.state, a.Vp, a.V, a.T, S, pl.s[0], pl.s[1], seg);
+      if (launches) *launches += 1;
+    }
+    return cudaGetLastError();
+  }
+  if (pl.id == FUSED_SINE_SVF_ENV) {
+    if (a.group < 1 || a.group > 32 || (32 % a.group) != 0) return cudaErrorNotSupported;
+    // window < shortest lfo segment (0.75 * 2 ms), in samples
+    int window = (int)(0.0015 * (double)a.sample_rate) - 2;
+    if (window > 64) window = 64;
+    if (window < 8) return cudaErrorNotSupported;
+    k_polysynth<<<a.Vp / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, window, pl.p[0], pl.p[1], pl.p[2],
+                                                pl.p[3], pl.s[0], pl.s[1], pl.s[2], a.out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+  }
+  return cudaErrorNotSupported;
+}
 
 }  // namespace qg

@@ -22,6 +22,9 @@ struct FusedArgs {
   long T;
   int group;
   float* out;
+  float** scratch;        // bank-owned scratch buffer (segment states), grown on demand
+  size_t* scratch_bytes;
+  float sample_rate;
 };
 
 FusedPlan plan_fused(const Tape& t);

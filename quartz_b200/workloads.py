@@ -1,0 +1,99 @@
+"""Synthetic workloads = BASELINE.json `configs`, with the seeded per-voice tables of SURVEY.md section 8(d).
+
+Every workload is described backend-neutrally (graph expression + per-voice op-string parameters + salts) so the
+same description drives the GPU bank (bench.py, tests) and the CPU oracle (parity tests, cpu_baseline)."""
+import numpy as np
+
+FS = 48000.0
+SEED = 0x51574152545A   # "QWARTZ"-ish constant from SURVEY.md section 8(d)
+
+
+def splitmix64(x):
+    x = (np.asarray(x, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def uniform01(voice, stream):
+    """counter-based U[0,1) per (voice, stream)"""
+    with np.errstate(over="ignore"):
+        h = splitmix64(np.uint64(SEED) ^ (np.asarray(voice, dtype=np.uint64) * np.uint64(0x100000001B3) + np.uint64(stream)))
+    return (h >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def _loguniform(u, lo, hi):
+    return np.exp(np.log(lo) + u * (np.log(hi) - np.log(lo)))
+
+
+def _L(op):
+    return {"op": op}
+
+
+def _pipe(*xs):
+    return {"op": ">>", "n": 0.0, "inputs": [_L(x) if isinstance(x, str) else x for x in xs]}
+
+
+def _sr(g):
+    return {"op": "sr()", "net": g, "n": FS}
+
+
+class Workload:
+    """name, template graph expression, per-voice raw matrix [V, R], salts [V], samples T, group size G"""
+
+    def __init__(self, name, expr, raw, salts, T, group, voice_expr, bytes_per_unit, bound, note):
+        self.name, self.expr, self.raw, self.salts, self.T, self.group = name, expr, raw, salts, T, group
+        self.voice_expr = voice_expr          # f(v) -> graph expression of voice v with its own constants
+        self.bytes_per_unit = bytes_per_unit  # ALGORITHMIC HBM bytes per voice-sample
+        self.bound = bound
+        self.note = note
+        self.V = len(salts)
+
+
+def salts_for(voices):
+    with np.errstate(over="ignore"):
+        s = splitmix64(np.asarray(voices, dtype=np.uint64) ^ np.uint64(SEED))
+    return np.where(s == 0, np.uint64(1), s)
+
+
+def c1_hello(T=480000):
+    """hello_440: sine(440) mono, 10 s at 48 kHz (configs[0])"""
+    expr = _sr(_L("sine(440)"))
+    return Workload("c1_hello_440", expr, np.zeros((1, 1), np.float32) + 440.0, np.zeros(1, np.uint64), T, 1,
+                    lambda v: expr, 4.0, "latency", "1 voice; parity + wall time only")
+
+
+def c2_lowpass_bank(V=4096, T=2880000, v0=0):
+    """noise -> lowpass(hz_v, q_v), per-voice outputs kept (configs[1])"""
+    voices = np.arange(v0, v0 + V)
+    hz = _loguniform(uniform01(voices, 1), 50.0, 12000.0).astype(np.float32)
+    q = (0.5 + uniform01(voices, 2) * 7.5).astype(np.float32)
+    raw = np.stack([hz, q], axis=1)
+    expr = _sr(_pipe("white()", "lowpass(1000,1)"))
+    return Workload("c2_noise_lowpass_bank", expr, raw, salts_for(voices), T, 1,
+                    lambda v: _sr(_pipe("white()", f"lowpass({float(hz[v])!r},{float(q[v])!r})")),
+                    4.0, "hbm", "4 B written per voice-sample")
+
+
+def c3_polysynth(V=65536, T=480000, G=32, v0=0):
+    """sine(f_v) -> lowpass(hz_v, q_v) -> * ar(a_v, 1, r_v, 4) -> groups of G voices, scaled 1/G (configs[2])"""
+    voices = np.arange(v0, v0 + V)
+    f = _loguniform(uniform01(voices, 3), 55.0, 3520.0).astype(np.float32)
+    hz = _loguniform(uniform01(voices, 4), 200.0, 8000.0).astype(np.float32)
+    q = (0.5 + uniform01(voices, 5) * 3.5).astype(np.float32)
+    a = (0.005 + uniform01(voices, 6) * 0.495).astype(np.float32)
+    r = (0.1 + uniform01(voices, 7) * 3.9).astype(np.float32)
+    one, four = np.ones(V, np.float32), np.full(V, 4.0, np.float32)
+    raw = np.stack([f, hz, q, a, one, r, four], axis=1)
+
+    def voice(v):
+        osc = _pipe(f"sine({float(f[v])!r})", f"lowpass({float(hz[v])!r},{float(q[v])!r})")
+        return _sr({"op": "*", "n": 0.0, "inputs": [osc, _L(f"ar({float(a[v])!r},1,{float(r[v])!r},4)")]})
+
+    expr = _sr({"op": "*", "n": 0.0, "inputs": [_pipe("sine(440)", "lowpass(1000,1)"), _L("ar(0.01,1,0.5,4)")]})
+    return Workload("c3_polysynth_65536", expr, raw, salts_for(voices), T, G, voice, 4.0 / G, "fp32",
+                    "osc->lowpass->envelope, mixed in groups of 32")
+
+
+WORKLOADS = {"c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth}
