@@ -82,7 +82,7 @@ def cpu_baseline(wl, seconds_target=12.0, threads=None):
     rate = nv0 * Tc / (time.perf_counter() - t0)
     T = wl.T
     nv = int(rate * seconds_target / T) // quantum * quantum
-    nv = max(nv0, min(nv, wl.V, int(3e9 / (4 * T)) * wl.group // quantum * quantum))   # <= 3 GB of oracle output
+    nv = max(nv0, min(nv, wl.V, int(12e9 / (4 * T)) * wl.group // quantum * quantum))   # <= 12 GB of oracle output
     if nv <= nv0:
         nv = nv0
         T = int(min(wl.T, max(Tc, rate * seconds_target / nv)))
@@ -162,7 +162,10 @@ def main():
         torch.cuda.synchronize()
 
     wl = make_workload(args.workload, rank)
-    stream = torch.cuda.current_stream()
+    # the library launches on the stream it is given; use a real (non-legacy) torch stream so that torch CUDA
+    # events bracket exactly those launches
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = qb.Context(local_rank, stream=stream.cuda_stream)
     tmpl = __import__("tests.graphs", fromlist=["build"]).build(wl.expr, qb.Net)
     bank = qb.Bank(tmpl, wl.V, raw=wl.raw, salts=wl.salts, ctx=ctx)

@@ -2,13 +2,13 @@
 //
 // K2  k_noise_svf_scan — `white() >> <fixed SVF>` banks (BASELINE configs[1]): ONE WARP PER VOICE, time-parallel.
 //     The SVF with fixed coefficients is LTI:  s' = A s + B x,  y = C s + D x  with s = (ic1, ic2).  A block of
-//     32*K consecutive samples is split over the 32 lanes (K contiguous samples each):
+//     32*K consecutive samples (K = 16) is split over the 32 lanes (K contiguous samples each):
 //       1. every lane runs its K samples from zero state (noise is counter-based, so lane j just starts its
-//          counter at base + j*K) and keeps the K zero-state outputs in registers;
+//          counter at base + j*K) and parks the K zero-state outputs in shared memory (conflict-free float4 rows);
 //       2. the per-lane end states are combined with a 5-step warp-shuffle scan of the affine maps
 //          s -> A^K s + c_j  (Kogge-Stone, matrices A^K, A^2K, ... A^16K precomputed per voice in f64);
 //       3. every lane adds the homogeneous response C A^i s_start to its K outputs;
-//       4. the 32*K outputs (one contiguous 1 KB run of the voice's row) are staged in shared memory and written
+//       4. the 32*K outputs (one contiguous 2 KB run of the voice's row) are staged in shared memory and written
 //          with ONE bulk async copy (cp.async.bulk.global.shared::cta -> UBLKCP), double-buffered.
 //     Small banks use S time segments per voice: a state-only pre-pass computes each segment's zero-state end
 //     state, the segment start states are chained on the fly (block-level scan), then every segment renders.
@@ -27,12 +27,10 @@ namespace qg {
 
 namespace {
 
-constexpr int K = 8;            // samples per lane per block
-constexpr int B = 32 * K;       // samples per warp block (1 KB of output)
+constexpr int K = 16;           // samples per lane per block
+constexpr int B = 32 * K;       // samples per warp block (2 KB of output)
 
-struct Mat2 { float a, b, c, d; };   // [[a b],[c d]]
-
-__device__ __forceinline__ void bulk_store_1k(float* gdst, const float* ssrc) {
+__device__ __forceinline__ void bulk_store_block(float* gdst, const float* ssrc) {
   // one elected lane: shared -> global bulk async copy of B floats
   unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "n"(B * 4) : "memory");
@@ -44,23 +42,35 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 struct SvfC { float a1, a2, a3, m0, m1, m2; };
 
-// zero-state / any-state SVF tick with explicit FMAs; returns the mode output
+// zero-state / any-state SVF tick with explicit FMAs; returns the mode output.
+// LP: the lowpass mix (m0, m1, m2) = (0, 0, 1) is known at plan time, the output is v2 itself.
+template <bool LP = false>
 __device__ __forceinline__ float svf_fma(float x, float& ic1, float& ic2, const SvfC& c) {
   float v3 = x - ic2;
   float v1 = __fmaf_rn(c.a2, v3, c.a1 * ic1);
   float v2 = __fmaf_rn(c.a3, v3, __fmaf_rn(c.a2, ic1, ic2));
   ic1 = __fmaf_rn(2.0f, v1, -ic1);
   ic2 = __fmaf_rn(2.0f, v2, -ic2);
+  if (LP) return v2;
   return __fmaf_rn(c.m2, v2, __fmaf_rn(c.m1, v1, c.m0 * x));
 }
 
+// per-warp shared memory: zero-state outputs [K/4][32 lanes] float4 (conflict-free), two contiguous output blocks for
+// the bulk copies, and the scan matrices A^(K*2^i)
+struct __align__(128) WarpSmem {
+  float out[2][B];
+  float4 zs[K / 4][32];
+  float mp[5][4];
+};
+
 // MODE 0: write samples; MODE 1: state-only pre-pass (zero start state, no output) for segment chaining
-template <int MODE>
-__global__ void __launch_bounds__(128) k_noise_svf_scan(const float* __restrict__ params, float* __restrict__ state, int Vp,
-                                                        int V, long T, int S, long seg_len, int p_svf, int s_noise,
-                                                        int s_svf, float* __restrict__ out, float* __restrict__ seg_state) {
-  __shared__ __align__(128) float stage[4][2][B];
+template <int MODE, bool LP>
+__global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restrict__ params, float* __restrict__ state, int Vp,
+                                                           int V, long T, int S, long seg_len, int p_svf, int s_noise,
+                                                           int s_svf, float* __restrict__ out, float* __restrict__ seg_state) {
+  __shared__ WarpSmem sm[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpSmem& W = sm[warp];
   const long w = (long)blockIdx.x * 4 + warp;        // warp id = voice * S + segment
   const int v = (int)(w / S), seg = (int)(w % S);
   if (v >= V) return;
@@ -74,21 +84,20 @@ __global__ void __launch_bounds__(128) k_noise_svf_scan(const float* __restrict_
   const float fA11 = (float)A11, fA12 = (float)A12, fA21 = (float)A21, fA22 = (float)A22;
   // y_h = m1*v1_h + m2*v2_h with v1_h = a1 s1 - a2 s2, v2_h = a2 s1 + (1 - a3) s2
   const float C1 = (float)((double)c.m1 * a1 + (double)c.m2 * a2), C2 = (float)(-(double)c.m1 * a2 + (double)c.m2 * (1 - a3));
-  // powers A^(K*2^i), i = 0..4, in f64 then rounded
-  Mat2 Mp[5];
-  {
+  // powers A^(K*2^i), i = 0..4, in f64 then rounded; kept in shared memory (read as broadcasts once per block)
+  if (lane == 0) {
     double m11 = 1, m12 = 0, m21 = 0, m22 = 1;
     for (int i = 0; i < K; i++) {
       double n11 = A11 * m11 + A12 * m21, n12 = A11 * m12 + A12 * m22, n21 = A21 * m11 + A22 * m21, n22 = A21 * m12 + A22 * m22;
       m11 = n11; m12 = n12; m21 = n21; m22 = n22;
     }
-#pragma unroll
     for (int i = 0; i < 5; i++) {
-      Mp[i] = Mat2{(float)m11, (float)m12, (float)m21, (float)m22};
+      W.mp[i][0] = (float)m11; W.mp[i][1] = (float)m12; W.mp[i][2] = (float)m21; W.mp[i][3] = (float)m22;
       double n11 = m11 * m11 + m12 * m21, n12 = m11 * m12 + m12 * m22, n21 = m21 * m11 + m22 * m21, n22 = m21 * m12 + m22 * m22;
       m11 = n11; m12 = n12; m21 = n21; m22 = n22;
     }
   }
+  __syncwarp();
   const long t_begin = (long)seg * seg_len;
   const long t_end = (t_begin + seg_len < T) ? t_begin + seg_len : T;
   const uint32_t counter0 = __float_as_uint(state[(size_t)s_noise * Vp + v]);
@@ -103,25 +112,31 @@ __global__ void __launch_bounds__(128) k_noise_svf_scan(const float* __restrict_
   long t = t_begin;
   int buf = 0;
   for (; t + B <= t_end; t += B) {
-    // ---- 1. zero-state run of this lane's K samples
-    float y[K];
+    // ---- 1. zero-state run of this lane's K samples; outputs parked in shared memory
     float z1 = 0.0f, z2 = 0.0f;
     const uint32_t cb = counter0 + (uint32_t)t + (uint32_t)(lane * K);
 #pragma unroll
-    for (int i = 0; i < K; i++) y[i] = svf_fma(d_noise(cb + (uint32_t)i + 1u), z1, z2, c);
-    // ---- 2. warp scan of the affine maps: E_j = true end state of lane j
+    for (int i4 = 0; i4 < K / 4; i4++) {
+      float4 y;
+      y.x = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 1u), z1, z2, c);
+      y.y = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 2u), z1, z2, c);
+      y.z = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 3u), z1, z2, c);
+      y.w = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 4u), z1, z2, c);
+      if (MODE == 0) W.zs[i4][lane] = y;
+    }
+    // ---- 2. warp scan of the affine maps s -> A^K s + c_j: e = true end state of lane j
     float e1 = z1, e2 = z2;
     if (lane == 0) {
-      e1 = __fmaf_rn(Mp[0].a, S1, __fmaf_rn(Mp[0].b, S2, e1));
-      e2 = __fmaf_rn(Mp[0].c, S1, __fmaf_rn(Mp[0].d, S2, e2));
+      e1 = __fmaf_rn(W.mp[0][0], S1, __fmaf_rn(W.mp[0][1], S2, e1));
+      e2 = __fmaf_rn(W.mp[0][2], S1, __fmaf_rn(W.mp[0][3], S2, e2));
     }
 #pragma unroll
     for (int i = 0; i < 5; i++) {
       const int d = 1 << i;
       float r1 = __shfl_up_sync(0xffffffffu, e1, d), r2 = __shfl_up_sync(0xffffffffu, e2, d);
       if (lane >= d) {
-        e1 = __fmaf_rn(Mp[i].a, r1, __fmaf_rn(Mp[i].b, r2, e1));
-        e2 = __fmaf_rn(Mp[i].c, r1, __fmaf_rn(Mp[i].d, r2, e2));
+        e1 = __fmaf_rn(W.mp[i][0], r1, __fmaf_rn(W.mp[i][1], r2, e1));
+        e2 = __fmaf_rn(W.mp[i][2], r1, __fmaf_rn(W.mp[i][3], r2, e2));
       }
     }
     float h1 = __shfl_up_sync(0xffffffffu, e1, 1), h2 = __shfl_up_sync(0xffffffffu, e2, 1);
@@ -129,27 +144,33 @@ __global__ void __launch_bounds__(128) k_noise_svf_scan(const float* __restrict_
     S1 = __shfl_sync(0xffffffffu, e1, 31);
     S2 = __shfl_sync(0xffffffffu, e2, 31);
     if (MODE == 0) {
-      // ---- 3. homogeneous correction
-#pragma unroll
-      for (int i = 0; i < K; i++) {
-        y[i] = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y[i]));
-        float n1 = __fmaf_rn(fA11, h1, fA12 * h2), n2 = __fmaf_rn(fA21, h1, fA22 * h2);
-        h1 = n1; h2 = n2;
-      }
-      // ---- 4. stage + bulk store
+      // ---- 3. homogeneous correction, written to the contiguous output block
       if (can_bulk) {
         if (lane == 0) bulk_wait_read_1();          // the copy that last read this buffer has drained
         __syncwarp();
-        float4* sp = reinterpret_cast<float4*>(&stage[warp][buf][lane * K]);
+      }
+      float4* ob = reinterpret_cast<float4*>(&W.out[buf][lane * K]);
 #pragma unroll
-        for (int i = 0; i < K / 4; i++) sp[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+      for (int i4 = 0; i4 < K / 4; i4++) {
+        float4 y = W.zs[i4][lane];
+        float n1, n2;
+        y.x = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.x));
+        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
+        y.y = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.y));
+        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
+        y.z = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.z));
+        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
+        y.w = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.w));
+        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
+        if (can_bulk) ob[i4] = y;
+        else { float* g = orow + t + lane * K + 4 * i4; g[0] = y.x; g[1] = y.y; g[2] = y.z; g[3] = y.w; }
+      }
+      // ---- 4. one bulk async copy per block (UBLKCP), double-buffered
+      if (can_bulk) {
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) bulk_store_1k(orow + t, &stage[warp][buf][0]);
+        if (lane == 0) bulk_store_block(orow + t, &W.out[buf][0]);
         buf ^= 1;
-      } else {
-#pragma unroll
-        for (int i = 0; i < K; i++) orow[t + lane * K + i] = y[i];
       }
     }
   }
@@ -157,7 +178,7 @@ __global__ void __launch_bounds__(128) k_noise_svf_scan(const float* __restrict_
   {
     float s1 = S1, s2 = S2;
     for (long tt = t; tt < t_end; tt++) {
-      float yv = svf_fma(d_noise(counter0 + (uint32_t)tt + 1u), s1, s2, c);
+      float yv = svf_fma<LP>(d_noise(counter0 + (uint32_t)tt + 1u), s1, s2, c);
       if (MODE == 0 && lane == 0) orow[tt] = yv;
     }
     S1 = s1; S2 = s2;
@@ -337,6 +358,8 @@ FusedPlan plan_fused(const Tape& t) {
     pl.p[0] = c[1].p;                                   // a1 a2 a3 m0 m1 m2 (X index == parameter index)
     pl.s[0] = c[0].s - (int)t.h.n_params;               // noise counter
     pl.s[1] = c[1].s - (int)t.h.n_params;               // ic1, ic2
+    // the mix (m0, m1, m2) is a function of the filter mode alone for lowpass: identical for every voice
+    pl.p[1] = (t.params[c[1].p + 3] == 0.0f && t.params[c[1].p + 4] == 0.0f && t.params[c[1].p + 5] == 1.0f) ? 1 : 0;
     return pl;
   }
   // sine(f) >> svf(fixed)  *  ar(a,ak,r,rk)
@@ -382,12 +405,13 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
         *a.scratch_bytes = need;
       }
       seg = *a.scratch;
-      k_noise_svf_scan<1><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1],
-                                                      nullptr, seg);
+      if (pl.p[1]) k_noise_svf_scan<1, true><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
+      else k_noise_svf_scan<1, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
       k_chain_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], seg);
       if (launches) *launches += 2;
     }
-    k_noise_svf_scan<0><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg);
+    if (pl.p[1]) k_noise_svf_scan<0, true><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg);
+    else k_noise_svf_scan<0, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg);
     if (launches) *launches += 1;
     if (S > 1) {
       k_finalize_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.state, a.Vp, a.V, a.T, S, pl.s[0], pl.s[1], seg);
