@@ -1,0 +1,144 @@
+//! quartz-gpu: Rust binding of libquartz_gpu.so (include/quartz_gpu.h).
+//!
+//! `GpuNet` mirrors the subset of `fundsp::net::Net` that quartz's patch interpreter uses when it builds audio
+//! graphs (src/functions.rs:111 `str_to_net`, src/process.rs:1669-1876 connective ops) and `GpuRender` implements
+//! `AudioUnit` (the trait quartz itself implements for `Kr`/`SwapUnit`, src/nodes.rs:256-327) by serving samples
+//! from a GPU-rendered look-ahead buffer, so `render` (src/process.rs:1349) and the cpal callback
+//! (src/audio.rs:85-118) can consume it unchanged.
+use std::ffi::{c_char, c_double, c_float, c_int, c_long, c_void, CStr, CString};
+
+#[repr(C)] pub struct qg_net { _p: [u8; 0] }
+#[repr(C)] pub struct qg_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct qg_bank { _p: [u8; 0] }
+
+extern "C" {
+    fn qg_last_error() -> *const c_char;
+    fn qg_str_to_net(op: *const c_char) -> *mut qg_net;
+    fn qg_net_clone(n: *const qg_net) -> *mut qg_net;
+    fn qg_net_free(n: *mut qg_net);
+    fn qg_net_inputs(n: *const qg_net) -> c_int;
+    fn qg_net_outputs(n: *const qg_net) -> c_int;
+    fn qg_net_size(n: *const qg_net) -> c_int;
+    fn qg_net_set_sample_rate(n: *mut qg_net, sr: c_double) -> c_int;
+    fn qg_connect(op: *const c_char, nets: *const *const qg_net, n: c_int, number: c_double, node_limit: c_int) -> *mut qg_net;
+    fn qg_ctx_create(device: c_int, stream: *mut c_void) -> *mut qg_ctx;
+    fn qg_ctx_destroy(c: *mut qg_ctx);
+    fn qg_bank_create(c: *mut qg_ctx, t: *const qg_net, v: c_long, raw: *const c_float, salts: *const u64) -> *mut qg_bank;
+    fn qg_bank_free(b: *mut qg_bank);
+    fn qg_bank_reset(b: *mut qg_bank) -> c_int;
+    fn qg_bank_render(b: *mut qg_bank, n: c_long, layout: c_int, group: c_int, out: *mut c_float) -> c_int;
+}
+
+pub fn last_error() -> String {
+    unsafe { CStr::from_ptr(qg_last_error()).to_string_lossy().into_owned() }
+}
+
+/// Host-side graph with value semantics (quartz deep-clones a Net on every hop).
+pub struct GpuNet(*mut qg_net);
+unsafe impl Send for GpuNet {}
+unsafe impl Sync for GpuNet {}
+
+impl GpuNet {
+    /// src/functions.rs:111
+    pub fn from_op(op: &str) -> GpuNet {
+        let c = CString::new(op).unwrap_or_default();
+        GpuNet(unsafe { qg_str_to_net(c.as_ptr()) })
+    }
+    pub fn inputs(&self) -> usize { unsafe { qg_net_inputs(self.0) as usize } }
+    pub fn outputs(&self) -> usize { unsafe { qg_net_outputs(self.0) as usize } }
+    pub fn size(&self) -> usize { unsafe { qg_net_size(self.0) as usize } }
+    pub fn set_sample_rate(&mut self, sr: f64) { unsafe { qg_net_set_sample_rate(self.0, sr); } }
+    /// connective circle (src/process.rs:1719-1876): op in {"+","*","-",">>","|","&","^","!"}
+    pub fn connect(op: &str, nets: &[&GpuNet], number: f32, node_limit: usize) -> GpuNet {
+        let c = CString::new(op).unwrap_or_default();
+        let ptrs: Vec<*const qg_net> = nets.iter().map(|n| n.0 as *const qg_net).collect();
+        GpuNet(unsafe { qg_connect(c.as_ptr(), ptrs.as_ptr(), ptrs.len() as c_int, number as c_double, node_limit as c_int) })
+    }
+}
+impl Clone for GpuNet {
+    fn clone(&self) -> Self { GpuNet(unsafe { qg_net_clone(self.0) }) }
+}
+impl Drop for GpuNet {
+    fn drop(&mut self) { unsafe { qg_net_free(self.0) } }
+}
+
+/// One GPU + stream.
+pub struct GpuContext(*mut qg_ctx);
+unsafe impl Send for GpuContext {}
+impl GpuContext {
+    pub fn new(device: i32) -> Result<GpuContext, String> {
+        let p = unsafe { qg_ctx_create(device, std::ptr::null_mut()) };
+        if p.is_null() { Err(last_error()) } else { Ok(GpuContext(p)) }
+    }
+}
+impl Drop for GpuContext {
+    fn drop(&mut self) { unsafe { qg_ctx_destroy(self.0) } }
+}
+
+/// `render` op replacement (src/process.rs:1345-1351): `len` ticks of a 0-input, 1-output net.
+pub fn render(ctx: &GpuContext, net: &GpuNet, len: usize) -> Result<Vec<f32>, String> {
+    if net.inputs() != 0 || net.outputs() != 1 { return Ok(Vec::new()); }   // the reference's arity guard
+    let bank = unsafe { qg_bank_create(ctx.0, net.0, 1, std::ptr::null(), std::ptr::null()) };
+    if bank.is_null() { return Err(last_error()); }
+    let mut out = vec![0f32; len];
+    let rc = unsafe { qg_bank_render(bank, len as c_long, 0, 1, out.as_mut_ptr()) };
+    unsafe { qg_bank_free(bank) };
+    if rc != 0 { Err(last_error()) } else { Ok(out) }
+}
+
+/// AudioUnit served from GPU-rendered blocks (0 inputs, C outputs); what `slot.set(.., Box::new(..))`
+/// (src/process.rs:1897) receives instead of the CPU Net.
+pub struct GpuRender {
+    bank: *mut qg_bank,
+    outputs: usize,
+    block: Vec<f32>,     // voice-major [outputs][BLOCK]
+    pos: usize,
+}
+unsafe impl Send for GpuRender {}
+unsafe impl Sync for GpuRender {}
+const BLOCK: usize = 4096;
+
+impl GpuRender {
+    pub fn new(ctx: &GpuContext, net: &GpuNet) -> Result<GpuRender, String> {
+        let bank = unsafe { qg_bank_create(ctx.0, net.0, 1, std::ptr::null(), std::ptr::null()) };
+        if bank.is_null() { return Err(last_error()); }
+        let outputs = net.outputs();
+        Ok(GpuRender { bank, outputs, block: vec![0.0; outputs * BLOCK], pos: BLOCK })
+    }
+    fn refill(&mut self) {
+        unsafe { qg_bank_render(self.bank, BLOCK as c_long, 0, 1, self.block.as_mut_ptr()); }
+        self.pos = 0;
+    }
+}
+impl Drop for GpuRender {
+    fn drop(&mut self) { unsafe { qg_bank_free(self.bank) } }
+}
+impl Clone for GpuRender {
+    fn clone(&self) -> Self { unimplemented!("clone the GpuNet and build a new GpuRender: device state is not shared") }
+}
+
+impl fundsp::audiounit::AudioUnit for GpuRender {
+    fn reset(&mut self) { unsafe { qg_bank_reset(self.bank); } self.pos = BLOCK; }
+    fn set_sample_rate(&mut self, _sample_rate: f64) { /* baked into the tape: rebuild from a GpuNet after sr() */ }
+    fn tick(&mut self, _input: &[f32], output: &mut [f32]) {
+        if self.pos == BLOCK { self.refill(); }
+        for c in 0..self.outputs { output[c] = self.block[c * BLOCK + self.pos]; }
+        self.pos += 1;
+    }
+    fn process(&mut self, size: usize, _input: &fundsp::buffer::BufferRef, output: &mut fundsp::buffer::BufferMut) {
+        for i in 0..size {
+            if self.pos == BLOCK { self.refill(); }
+            for c in 0..self.outputs { output.set_f32(c, i, self.block[c * BLOCK + self.pos]); }
+            self.pos += 1;
+        }
+    }
+    fn inputs(&self) -> usize { 0 }
+    fn outputs(&self) -> usize { self.outputs }
+    fn route(&mut self, input: &fundsp::signal::SignalFrame, _frequency: f64) -> fundsp::signal::SignalFrame {
+        fundsp::signal::Routing::Arbitrary(0.0).route(input, self.outputs)
+    }
+    fn get_id(&self) -> u64 { 1130 }
+    fn ping(&mut self, _probe: bool, hash: fundsp::math::AttoHash) -> fundsp::math::AttoHash { hash.hash(self.get_id()) }
+    fn footprint(&self) -> usize { core::mem::size_of::<Self>() }
+    fn allocate(&mut self) {}
+}
