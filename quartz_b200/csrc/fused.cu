@@ -257,24 +257,26 @@ __device__ __forceinline__ float env_ar(float tt, const EnvC& e) {   // function
   return 0.0f;
 }
 
-__global__ void __launch_bounds__(128) k_polysynth(const float* __restrict__ params, float* __restrict__ state, int Vp, int V,
-                                                   long T, int G, int window, int p_f, int p_sd, int p_svf, int p_env,
+constexpr int PS_THREADS = 64;   // 2 warps per block: 1024 blocks for 65,536 voices spread evenly (6.9 per SM)
+template <bool LP>
+__global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restrict__ params, float* __restrict__ state, int Vp, int V,
+                                                   long T, int G, int look_tiles, int p_f, int p_sd, int p_svf, int p_env,
                                                    int s_ph, int s_svf, int s_env, float* __restrict__ out) {
-  __shared__ float tile[4][32][33];
+  __shared__ float tile[PS_THREADS / 32][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int v = blockIdx.x * 128 + threadIdx.x;          // < Vp (padded voices run on copies of the last voice)
-  const int warp_v0 = blockIdx.x * 128 + warp * 32;
+  const int v = blockIdx.x * PS_THREADS + threadIdx.x;   // < Vp (padded voices run on copies of the last voice)
+  const int warp_v0 = blockIdx.x * PS_THREADS + warp * 32;
 #define PRM(i) params[(size_t)(i) * Vp + v]
 #define ST(i) state[(size_t)(i) * Vp + v]
   const float inc = PRM(p_f) * PRM(p_sd);                // input[0] * sample_duration
-  SvfC c = {PRM(p_svf), PRM(p_svf + 1), PRM(p_svf + 2), PRM(p_svf + 3), PRM(p_svf + 4), PRM(p_svf + 5)};
-  EnvC e = {PRM(p_env), PRM(p_env + 1), PRM(p_env + 2), PRM(p_env + 3)};
+  const SvfC c = {PRM(p_svf), PRM(p_svf + 1), PRM(p_svf + 2), PRM(p_svf + 3), PRM(p_svf + 4), PRM(p_svf + 5)};
+  const EnvC e = {PRM(p_env), PRM(p_env + 1), PRM(p_env + 2), PRM(p_env + 3)};
   const float esd = PRM(p_env + 4);
   float phase = ST(s_ph), ic1 = ST(s_svf), ic2 = ST(s_svf + 1);
   float et = ST(s_env), t0 = ST(s_env + 1), t1 = ST(s_env + 2), v0 = ST(s_env + 3), v1 = ST(s_env + 4);
   uint64_t th = (uint64_t)__float_as_uint(ST(s_env + 5)) | ((uint64_t)__float_as_uint(ST(s_env + 6)) << 32);
   uint32_t first = __float_as_uint(ST(s_env + 7));
-  // prologue: bring the envelope to "inside a segment" exactly like the per-sample code would on its first tick
+  // prologue: bring the envelope "inside a segment" exactly like the per-sample code would on its first tick
   if (et >= t1) {
     if (first) { v1 = env_ar(0.0f, e); first = 0u; }
     t0 = t1; v0 = v1;
@@ -283,59 +285,61 @@ __global__ void __launch_bounds__(128) k_polysynth(const float* __restrict__ par
     th += 1;
   }
   float inv = 1.0f / (t1 - t0);
-  float nt1 = 0.0f, nv1 = 0.0f;
+  float nt1 = 0.0f, nv1 = 0.0f, ninv = 0.0f;
   bool have_next = false;
-  for (long tb = 0; tb < T; tb += window) {
-    if (!have_next) {                                    // warp-uniform point: look one control point ahead
+  float* my_tile = &tile[warp][lane][0];
+
+  auto sample = [&](int i) {
+    // ---- sine (FunDSP Sine::tick): output from the phase before the increment
+    const float p = phase;
+    phase = p + inc;
+    phase -= floorf(phase);
+    const float x = sinf(p * QG_TAU);
+    // ---- SVF
+    const float y = svf_fma<LP>(x, ic1, ic2, c);
+    // ---- envelope (lfo): at most one crossing between two look-ahead points, the body only rotates registers
+    if (et >= t1) {
+      t0 = t1; v0 = v1; t1 = nt1; v1 = nv1; inv = ninv;
+      th += 1;
+      have_next = false;
+    }
+    const float u = (et - t0) * inv;
+    et += esd;
+    my_tile[i] = y * __fmaf_rn(v1, u, v0 * (1.0f - u));
+  };
+
+  long tile_idx = 0;
+  for (long tb = 0; tb < T; tb += 32, tile_idx++) {
+    if ((tile_idx % look_tiles) == 0 && !have_next) {      // warp-uniform point: look one control point ahead
       nt1 = t1 + d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
       nv1 = env_ar(nt1, e);
+      ninv = 1.0f / (nt1 - t1);
       have_next = true;
     }
-    const int n = (int)((T - tb) < window ? (T - tb) : window);
-    for (int i = 0; i < n; i++) {
-      const long t = tb + i;
-      // ---- sine (FunDSP Sine::tick): output from the phase before the increment
-      const float p = phase;
-      phase = p + inc;
-      phase -= floorf(phase);
-      const float x = sinf(p * QG_TAU);
-      // ---- SVF
-      const float y = svf_fma(x, ic1, ic2, c);
-      // ---- envelope (lfo): at most one crossing per window by construction
-      if (et >= t1) {
-        t0 = t1; v0 = v1; t1 = nt1; v1 = nv1;
-        th += 1;
-        have_next = false;
-        inv = 1.0f / (t1 - t0);
-      }
-      const float u = (et - t0) * inv;
-      et += esd;
-      const float env = __fmaf_rn(v1, u, v0 * (1.0f - u));
-      const float o = y * env;
-      // ---- output tile
-      const int tt = (int)(t & 31);
-      tile[warp][lane][tt] = o;
-      if (tt == 31 || t == T - 1) {
-        __syncwarp();
-        const long t_base = t - tt;
-        if (lane <= tt) {
-          if (G <= 1) {
-            for (int r = 0; r < 32; r++)
-              if (warp_v0 + r < V) out[(size_t)(warp_v0 + r) * T + t_base + lane] = tile[warp][r][lane];
-          } else {
-            const float sc = 1.0f / (float)G;
-            for (int g0 = 0; g0 < 32; g0 += G) {
-              if (warp_v0 + g0 + G <= V) {
-                float acc = tile[warp][g0][lane];
-                for (int r = 1; r < G; r++) acc += tile[warp][g0 + r][lane];
-                out[(size_t)((warp_v0 + g0) / G) * T + t_base + lane] = acc * sc;
-              }
-            }
+    const int n = (T - tb) < 32 ? (int)(T - tb) : 32;
+    if (n == 32) {
+#pragma unroll 8
+      for (int i = 0; i < 32; i++) sample(i);
+    } else {
+      for (int i = 0; i < n; i++) sample(i);
+    }
+    __syncwarp();
+    if (lane < n) {
+      if (G <= 1) {
+        for (int r = 0; r < 32; r++)
+          if (warp_v0 + r < V) out[(size_t)(warp_v0 + r) * T + tb + lane] = tile[warp][r][lane];
+      } else {
+        const float sc = 1.0f / (float)G;
+        for (int g0 = 0; g0 < 32; g0 += G) {
+          if (warp_v0 + g0 + G <= V) {
+            float acc = tile[warp][g0][lane];
+            for (int r = 1; r < G; r++) acc += tile[warp][g0 + r][lane];
+            out[(size_t)((warp_v0 + g0) / G) * T + tb + lane] = acc * sc;
           }
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   }
   if (v < V) {
     ST(s_ph) = phase; ST(s_svf) = ic1; ST(s_svf + 1) = ic2;
@@ -370,6 +374,7 @@ FusedPlan plan_fused(const Tape& t) {
     pl.id = FUSED_SINE_SVF_ENV;
     pl.p[0] = c[0].in[0]; pl.p[1] = c[0].p; pl.p[2] = c[1].p; pl.p[3] = c[2].p;
     pl.s[0] = c[0].s - P; pl.s[1] = c[1].s - P; pl.s[2] = c[2].s - P;
+    pl.p[4] = (t.params[c[1].p + 3] == 0.0f && t.params[c[1].p + 4] == 0.0f && t.params[c[1].p + 5] == 1.0f) ? 1 : 0;
   }
   return pl;
 }
@@ -421,12 +426,13 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
   }
   if (pl.id == FUSED_SINE_SVF_ENV) {
     if (a.group < 1 || a.group > 32 || (32 % a.group) != 0) return cudaErrorNotSupported;
-    // window < shortest lfo segment (0.75 * 2 ms), in samples
-    int window = (int)(0.0015 * (double)a.sample_rate) - 2;
-    if (window > 64) window = 64;
-    if (window < 8) return cudaErrorNotSupported;
-    k_polysynth<<<a.Vp / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, window, pl.p[0], pl.p[1], pl.p[2],
-                                                pl.p[3], pl.s[0], pl.s[1], pl.s[2], a.out);
+    // the envelope look-ahead runs every `look_tiles` tiles of 32 samples and must be shorter than the shortest
+    // lfo segment (0.75 * 2 ms)
+    const double min_seg = 0.0015 * (double)a.sample_rate - 2.0;
+    int look_tiles = min_seg >= 64.0 ? 2 : (min_seg >= 32.0 ? 1 : 0);
+    if (look_tiles == 0) return cudaErrorNotSupported;
+    if (pl.p[4]) k_polysynth<true><<<a.Vp / PS_THREADS, PS_THREADS, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, look_tiles, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], a.out);
+    else k_polysynth<false><<<a.Vp / PS_THREADS, PS_THREADS, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, look_tiles, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], a.out);
     if (launches) *launches += 1;
     return cudaGetLastError();
   }
