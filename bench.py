@@ -94,13 +94,10 @@ def cpu_baseline(wl, seconds_target=12.0, threads=None):
             "sample": f"{nv} voices x {T} samples of {wl.name} (oracle/, {threads} threads, {dt:.1f} s)"}
 
 
-def make_workload(name, rank):
-    from quartz_b200 import workloads
-    f = workloads.WORKLOADS[name]
-    wl0 = f()
-    if name == "c1":
-        return wl0
-    return f(v0=rank * wl0.V)   # weak scaling: every rank renders a full-size, differently seeded bank
+def make_workload(name, rank, world=1):
+    from quartz_b200 import shard, workloads
+    # weak scaling: every rank renders a full-size, differently seeded bank
+    return shard.shard_workload(workloads.WORKLOADS[name], world, rank)
 
 
 def run_reference(args, rank, world):
@@ -161,7 +158,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    wl = make_workload(args.workload, rank)
+    wl = make_workload(args.workload, rank, world)
     # the library launches on the stream it is given; use a real (non-legacy) torch stream so that torch CUDA
     # events bracket exactly those launches
     stream = torch.cuda.Stream()

@@ -64,7 +64,8 @@ struct __align__(128) WarpSmem {
 };
 
 // MODE 0: write samples; MODE 1: state-only pre-pass (zero start state, no output) for segment chaining
-template <int MODE, bool LP>
+// BULK: rows are 16-byte aligned (decided on the host) -> bulk async stores; otherwise plain scalar stores
+template <int MODE, bool LP, bool BULK>
 __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restrict__ params, float* __restrict__ state, int Vp,
                                                            int V, long T, int S, long seg_len, int p_svf, int s_noise,
                                                            int s_svf, float* __restrict__ out, float* __restrict__ seg_state) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
     else { S1 = seg_state[((size_t)v * (S + 1) + seg) * 2]; S2 = seg_state[((size_t)v * (S + 1) + seg) * 2 + 1]; }
   } else { S1 = state[(size_t)s_svf * Vp + v]; S2 = state[(size_t)(s_svf + 1) * Vp + v]; }
   float* orow = MODE == 0 ? out + (size_t)v * T : nullptr;
-  const bool can_bulk = MODE == 0 && ((((size_t)(uintptr_t)orow) & 15) == 0) && ((T & 3) == 0);
+  constexpr bool can_bulk = MODE == 0 && BULK;
 
   long t = t_begin;
   int buf = 0;
@@ -410,13 +411,16 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
         *a.scratch_bytes = need;
       }
       seg = *a.scratch;
-      if (pl.p[1]) k_noise_svf_scan<1, true><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
-      else k_noise_svf_scan<1, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
+      if (pl.p[1]) k_noise_svf_scan<1, true, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
+      else k_noise_svf_scan<1, false, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
       k_chain_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], seg);
       if (launches) *launches += 2;
     }
-    if (pl.p[1]) k_noise_svf_scan<0, true><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg);
-    else k_noise_svf_scan<0, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg);
+    const bool bulk = ((((size_t)(uintptr_t)a.out) & 15) == 0) && ((a.T & 3) == 0);
+#define QG_LAUNCH_K2(LPV, BV) k_noise_svf_scan<0, LPV, BV><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg)
+    if (pl.p[1]) { if (bulk) QG_LAUNCH_K2(true, true); else QG_LAUNCH_K2(true, false); }
+    else { if (bulk) QG_LAUNCH_K2(false, true); else QG_LAUNCH_K2(false, false); }
+#undef QG_LAUNCH_K2
     if (launches) *launches += 1;
     if (S > 1) {
       k_finalize_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.state, a.Vp, a.V, a.T, S, pl.s[0], pl.s[1], seg);
