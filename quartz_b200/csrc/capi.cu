@@ -45,6 +45,8 @@ struct qg_bank {
   float* d_fused_scratch = nullptr;
   size_t fused_scratch_bytes = 0;
   FusedPlan fused;
+  TvPlan tv;
+  int ring_mode = 0;   // 0: rings laid out [pos][voice] (lane kernels); 1: [voice][pos] (time-vector kernel)
 };
 
 static thread_local std::string g_err;
@@ -286,6 +288,7 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   }
   if ((rc = bank_init_state(b, salts))) return rc;
   b->fused = plan_fused(t);
+  b->tv = plan_tv(t, (size_t)180 * 1024);
   return qg_bank_reset(b);
 }
 
@@ -343,14 +346,26 @@ int qg_bank_reset(qg_bank* b) {
   if (rb) CU(cudaMemsetAsync(b->d_rings, 0, rb, c->stream));
   return QG_OK;
 }
+// which kernel family serves voice-major, group-1 renders: 0 lane interpreter, 1 fused, 2 time-vector interpreter
+static int bank_family(const qg_bank* b) {
+  if (b->path == QG_PATH_INTERP) return 0;
+  if (b->path == QG_PATH_TV) return b->tv.ok ? 2 : 0;
+  if (b->fused.id != FUSED_NONE) return 1;
+  if (b->tv.ok && (b->tv.has_fft || b->V <= 2048)) return 2;
+  return 0;
+}
 int qg_bank_set_path(qg_bank* b, int path) {
   if (!b) return fail(QG_ERR_ARG, "null bank");
+  int before = bank_family(b) == 2;
   b->path = path;
+  if ((bank_family(b) == 2) != before) return qg_bank_reset(b);   // the two interpreters lay delay lines out differently
   return QG_OK;
 }
 const char* qg_bank_kernel(const qg_bank* b) {
   if (!b) return "";
-  if (b->path == QG_PATH_AUTO && b->fused.id != FUSED_NONE) return fused_name(b->fused.id);
+  int f = bank_family(b);
+  if (f == 1) return fused_name(b->fused.id);
+  if (f == 2) return "k_interp_tv";
   return (b->tape.h.flags & TAPE_DIVERGENT) ? "k_interp<divergent>" : "k_interp<uniform>";
 }
 long qg_bank_out_rows(const qg_bank* b, int group) {
@@ -376,7 +391,24 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   if (T <= 0) return QG_OK;
   int rc = check_group(b, layout, group);
   if (rc) return rc;
-  if (b->path == QG_PATH_AUTO && b->fused.id != FUSED_NONE && !d_in && layout == QG_LAYOUT_VOICE_MAJOR) {
+  const int family = bank_family(b);
+  if (family == 2 && layout == QG_LAYOUT_VOICE_MAJOR && group == 1) {
+    TvArgs ta;
+    memset(&ta, 0, sizeof ta);
+    ta.code = b->d_code; ta.n_instr = (int)t.h.n_instr;
+    ta.P = (int)t.h.n_params; ta.NS = (int)t.h.n_state; ta.NT = (int)t.h.n_temps;
+    ta.n_in = (int)t.h.n_inputs; ta.n_out = (int)t.h.n_outputs; ta.out_x = b->d_out_x;
+    ta.params = b->d_params; ta.state = b->d_state; ta.rings = b->d_rings; ta.ring_floats = t.h.ring_floats;
+    ta.ring_tab = b->d_ring_tab; ta.tables = b->d_tables; ta.in = d_in; ta.out = d_out;
+    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n;
+    int l = 0;
+    CU(launch_interp_tv(ta, c->stream, &l));
+    c->launches += l;
+    return QG_OK;
+  }
+  if (family == 2) return fail(QG_ERR_ARG, "this bank runs on the time-vector interpreter: voice-major layout and group 1 only "
+                                           "(qg_bank_set_path(QG_PATH_INTERP) selects the lane interpreter)");
+  if (family == 1 && !d_in && layout == QG_LAYOUT_VOICE_MAJOR) {
     FusedArgs fa;
     fa.params = b->d_params; fa.state = b->d_state; fa.V = (int)b->V; fa.Vp = b->Vp; fa.T = T; fa.group = group; fa.out = d_out;
     fa.scratch = &b->d_fused_scratch; fa.scratch_bytes = &b->fused_scratch_bytes; fa.sample_rate = t.h.sample_rate;
@@ -422,15 +454,53 @@ int qg_bank_render(qg_bank* b, long T, int layout, int group, float* h_out) {
   if (!b || !h_out) return fail(QG_ERR_ARG, "qg_bank_render: bad arguments");
   if (b->tape.h.n_inputs != 0) return fail(QG_ERR_ARITY, "render needs a net with 0 inputs (process.rs:1345)");
   if (group < 1) group = 1;
-  size_t bytes = (size_t)(b->V / group) * b->tape.h.n_outputs * (size_t)T * sizeof(float);
+  const size_t rows = (size_t)(b->V / group) * b->tape.h.n_outputs;
+  const size_t bytes = rows * (size_t)T * sizeof(float);
   if (bytes == 0) return QG_OK;
-  CU(cudaSetDevice(b->ctx->device));
+  qg_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  // Large voice-major renders are produced in time chunks through two device staging buffers so that the
+  // device->host copy of chunk k overlaps the render of chunk k+1 (state persists across chunks by construction).
+  const size_t chunk_target = (size_t)512 << 20;
+  if (layout == QG_LAYOUT_VOICE_MAJOR && bytes > 2 * chunk_target && rows > 0) {
+    long Tc = (long)(chunk_target / (rows * sizeof(float)));
+    Tc = Tc / 512 * 512;
+    if (Tc >= 512 && Tc < T) {
+      const size_t cb = rows * (size_t)Tc * sizeof(float);
+      int rc = ensure(&b->d_scratch, &b->scratch_bytes, 2 * cb);
+      if (rc) return rc;
+      cudaStream_t copy_stream;
+      CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+      cudaEvent_t rendered[2], copied[2];
+      for (int i = 0; i < 2; i++) { CU(cudaEventCreateWithFlags(&rendered[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)); }
+      int k = 0;
+      rc = QG_OK;
+      for (long t0 = 0; t0 < T && rc == QG_OK; t0 += Tc, k ^= 1) {
+        long n = T - t0 < Tc ? T - t0 : Tc;
+        float* d = b->d_scratch + (size_t)k * rows * Tc;
+        if (t0 >= 2 * Tc) CU(cudaStreamWaitEvent(c->stream, copied[k], 0));      // staging buffer k is free again
+        rc = render_impl(b, n, layout, group, nullptr, d);                        // rows of n samples, pitch n
+        if (rc) break;
+        CU(cudaEventRecord(rendered[k], c->stream));
+        CU(cudaStreamWaitEvent(copy_stream, rendered[k], 0));
+        CU(cudaMemcpy2DAsync(h_out + t0, (size_t)T * sizeof(float), d, (size_t)n * sizeof(float), (size_t)n * sizeof(float), rows,
+                             cudaMemcpyDeviceToHost, copy_stream));
+        CU(cudaEventRecord(copied[k], copy_stream));
+      }
+      cudaError_t e1 = cudaStreamSynchronize(copy_stream), e2 = cudaStreamSynchronize(c->stream);
+      for (int i = 0; i < 2; i++) { cudaEventDestroy(rendered[i]); cudaEventDestroy(copied[i]); }
+      cudaStreamDestroy(copy_stream);
+      if (rc) return rc;
+      CU(e1); CU(e2);
+      return QG_OK;
+    }
+  }
   int rc = ensure(&b->d_scratch, &b->scratch_bytes, bytes);
   if (rc) return rc;
   rc = render_impl(b, T, layout, group, nullptr, b->d_scratch);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(h_out, b->d_scratch, bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
-  CU(cudaStreamSynchronize(b->ctx->stream));
+  CU(cudaMemcpyAsync(h_out, b->d_scratch, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return QG_OK;
 }
 

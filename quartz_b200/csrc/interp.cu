@@ -16,6 +16,7 @@
 
 namespace qg {
 
+// Execution context of one voice in lane mode (one thread = one voice).
 struct Lane {
   float* x;        // shared: X[i] at x[i * nt]
   int nt;
@@ -27,16 +28,32 @@ struct Lane {
   const float* state_init;
   const ResetRange* resets;
   int P;
+  __device__ __forceinline__ float& at(int i) const { return x[i * nt]; }
+  __device__ __forceinline__ float& ring(uint32_t r, uint32_t pos) const {
+    return rings[(size_t)(ring_tab[r].offset + pos) * (size_t)Vp + (size_t)v];
+  }
+};
+// Execution context of one SAMPLE of one voice in time-vector mode (one CTA = one voice, threads = samples of a hop):
+// parameters/state are per-voice scalars, temporaries are arrays of H samples.  Only stateless ops go through exec().
+struct TvSample {
+  float* ps;       // shared: [P + NS] scalars
+  float* tmp;      // shared: temporaries, already offset by the sample index; stride H
+  int PS, H;
+  const float* tables;
+  __device__ __forceinline__ float& at(int i) const { return i < PS ? ps[i] : tmp[(i - PS) * H]; }
+  __device__ __forceinline__ float& ring(uint32_t, uint32_t) const { return ps[0]; }   // never used by stateless ops
 };
 
-#define X(i) L.x[(int)(i) * L.nt]
+#define X(i) L.at((int)(i))
 #define XU(i) __float_as_uint(X(i))
 #define SETU(i, u) X(i) = __uint_as_float(u)
 
-__device__ __forceinline__ float& ring_at(const Lane& L, uint32_t ring, uint32_t pos) {
-  return L.rings[(size_t)(L.ring_tab[ring].offset + pos) * (size_t)L.Vp + (size_t)L.v];
-}
+template <class LaneT>
+__device__ __forceinline__ float& ring_at(const LaneT& L, uint32_t ring, uint32_t pos) { return L.ring(ring, pos); }
+__device__ __forceinline__ uint32_t ring_len(const Lane& L, uint32_t r) { return L.ring_tab[r].length; }
+__device__ __forceinline__ uint32_t ring_len(const TvSample&, uint32_t) { return 1u; }
 
+__device__ __noinline__ void reset_range(const TvSample&, uint32_t) {}
 __device__ __noinline__ void reset_range(const Lane& L, uint32_t id) {
   ResetRange r = L.resets[id];
   for (int s = r.s_lo; s < r.s_hi; s++) X(s) = L.state_init[(size_t)(s - L.P) * L.Vp + L.v];
@@ -47,6 +64,7 @@ __device__ __noinline__ void reset_range(const Lane& L, uint32_t id) {
 }
 
 // in-place radix-2 FFT over two of the lane's HBM rings (re, im); inverse scales by 1/N
+__device__ __noinline__ void lane_fft(const TvSample&, uint32_t, uint32_t, int, const float*, bool) {}
 __device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim, int lg, const float* tw, bool inverse) {
   uint32_t N = 1u << lg;
   for (uint32_t i = 1, j = 0; i < N; i++) {
@@ -80,7 +98,8 @@ __device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim,
 }
 
 // Execute one instruction for this lane.  `pc` is only touched by control-flow ops.
-__device__ __forceinline__ void exec(const Instr& I, const Lane& L, int& pc) {
+template <class LaneT>
+__device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
   switch (I.op) {
     case OP_NOP: break;
     case OP_MOV: X(I.out) = X(I.in[0]); break;
@@ -337,7 +356,7 @@ __device__ __forceinline__ void exec(const Instr& I, const Lane& L, int& pc) {
     // ---------------------------------------------------------------- delays
     case OP_TICK: { float v = X(I.s); X(I.s) = X(I.in[0]); X(I.out) = v; break; }
     case OP_DELAY: {
-      uint32_t i = XU(I.s), len = L.ring_tab[I.aux].length;
+      uint32_t i = XU(I.s), len = ring_len(L, I.aux);
       float& slot = ring_at(L, I.aux, i);
       float o = slot;
       slot = X(I.in[0]);
@@ -347,7 +366,7 @@ __device__ __forceinline__ void exec(const Instr& I, const Lane& L, int& pc) {
       break;
     }
     case OP_TAP: {
-      uint32_t idx = XU(I.s), len = L.ring_tab[I.aux].length, mask = len - 1;
+      uint32_t idx = XU(I.s), len = ring_len(L, I.aux), mask = len - 1;
       ring_at(L, I.aux, idx) = X(I.in[0]);
       float tap = d_clamp(X(I.in[1]), X(I.p), X(I.p + 1)) * X(I.p + 2);
       if (tap != tap) tap = 0.0f;
@@ -365,7 +384,7 @@ __device__ __forceinline__ void exec(const Instr& I, const Lane& L, int& pc) {
       break;
     }
     case OP_SAMP_DELAY: {   // nodes.rs:726-731: push_front, pop_back, then index from the front
-      uint32_t head = XU(I.s), len = L.ring_tab[I.aux].length;
+      uint32_t head = XU(I.s), len = ring_len(L, I.aux);
       head = head == 0 ? len - 1 : head - 1;
       ring_at(L, I.aux, head) = X(I.in[0]);
       SETU(I.s, head);
@@ -463,7 +482,7 @@ __device__ __forceinline__ void exec(const Instr& I, const Lane& L, int& pc) {
     case OP_FB_WRITE: {
       uint32_t i = XU(I.s);
       ring_at(L, I.aux, i) = X(I.in[0]);
-      if (I.n) { uint32_t len = L.ring_tab[I.aux].length; SETU(I.s, i + 1 == len ? 0 : i + 1); }
+      if (I.n) { uint32_t len = ring_len(L, I.aux); SETU(I.s, i + 1 == len ? 0 : i + 1); }
       break;
     }
     // ---------------------------------------------------------------- spectral nodes (per-lane path)
@@ -608,6 +627,216 @@ __global__ void k_mix_rows(const float* rows, int R, long T, float scale, float*
   float acc = 0.0f;
   for (int r = 0; r < R; r++) acc += rows[(size_t)r * T + t];
   out[t] = acc * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ K3/K4 + time-vector mode
+// k_interp_tv: ONE CTA PER VOICE, threads = the samples of a hop (H <= 512).  For banks with few voices and long
+// feed-forward graphs (the spectral patches: BASELINE configs[3]) lane-per-voice leaves the GPU empty; here every op
+// of the tape is applied to a whole hop at once.  Stateless ops reuse exec(); counter-like sources jump; delay lines
+// are block-copied; rfft/ifft (nodes.rs:601-700) become cooperative shared-memory radix-2 transforms (K3/K4) that run
+// exactly when the node's counter wraps — hops are aligned to the frame grid by construction (H | N, H | start).
+
+// cooperative radix-2 FFT of N = 1 << lg points held in shared memory (re, im); same butterfly arithmetic and
+// twiddle table as the per-lane path, inverse scales by 1/N
+__device__ void tv_fft(float* fr, float* fi, int lg, const float* tw, bool inverse, int tid, int nth) {
+  const uint32_t N = 1u << lg;
+  for (uint32_t len = 2; len <= N; len <<= 1) {
+    const uint32_t half = len >> 1, step = N / len;
+    for (uint32_t b = tid; b < N / 2; b += nth) {
+      const uint32_t k = b & (half - 1), i = (b / half) * len + k;
+      float wr = tw[2 * k * step], wi = tw[2 * k * step + 1];
+      if (inverse) wi = -wi;
+      const float ur = fr[i], ui = fi[i], vr = fr[i + half], vi = fi[i + half];
+      const float tr = vr * wr - vi * wi, ti = vr * wi + vi * wr;
+      fr[i] = ur + tr; fi[i] = ui + ti;
+      fr[i + half] = ur - tr; fi[i + half] = ui - ti;
+    }
+    __syncthreads();
+  }
+  if (inverse) {
+    const float sc = 1.0f / (float)N;
+    for (uint32_t k = tid; k < N; k += nth) { fr[k] *= sc; fi[k] *= sc; }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nth = blockDim.x, v = blockIdx.x, H = a.H, PS = a.P + a.NS;
+  Instr* code = reinterpret_cast<Instr*>(smem_raw);
+  float* ps = reinterpret_cast<float*>(smem_raw + (size_t)a.n_instr * sizeof(Instr));
+  float* tmp = ps + ((PS + 3) & ~3);
+  float* oldv = tmp + (size_t)a.NT * H;
+  float* fr = oldv + H;
+  float* fi = fr + a.fft_n;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.code);
+    uint4* dst = reinterpret_cast<uint4*>(code);
+    for (int i = tid; i < a.n_instr * 2; i += nth) dst[i] = src[i];
+  }
+  for (int p = tid; p < a.P; p += nth) ps[p] = a.params[(size_t)p * a.Vp + v];
+  for (int s = tid; s < a.NS; s += nth) ps[a.P + s] = a.state[(size_t)s * a.Vp + v];
+  for (size_t k = tid; k < (size_t)a.NT * H; k += nth) tmp[k] = 0.0f;
+  float* rg = a.rings + (size_t)v * a.ring_floats;        // voice-major rings in this mode
+#define RING(r) (rg + a.ring_tab[r].offset)
+#define TMP(i) (tmp + (size_t)((int)(i) - PS) * H)         // temporaries only
+#define SRC(i, j) ((int)(i) < PS ? ps[(int)(i)] : tmp[(size_t)((int)(i) - PS) * H + (j)])
+  __syncthreads();
+  for (long t0 = 0; t0 < a.T; t0 += H) {
+    const int n = (int)(a.T - t0 < H ? a.T - t0 : H);
+    for (int c = 0; c < a.n_in; c++)
+      for (int j = tid; j < n; j += nth) tmp[(size_t)c * H + j] = a.in[((size_t)v * a.n_in + c) * a.T + t0 + j];
+    __syncthreads();
+    for (int pc = 0; pc < a.n_instr; pc++) {
+      const Instr I = code[pc];
+      if (op_is_stateless(I.op)) {
+        for (int j = tid; j < n; j += nth) {
+          TvSample L{ps, tmp + j, PS, H, a.tables};
+          int dummy = 0;
+          exec(I, L, dummy);
+        }
+      } else {
+        switch (I.op) {
+          case OP_NOISE: {
+            const uint32_t c = __float_as_uint(ps[I.s]);
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = d_noise(c + (uint32_t)j + 1u);
+            if (tid == 0) ps[I.s] = __uint_as_float(c + (uint32_t)n);
+            break;
+          }
+          case OP_WAVE: {
+            const uint32_t idx = __float_as_uint(ps[I.s]);
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = a.tables[I.aux + (idx + (uint32_t)j) % I.aux2];
+            if (tid == 0) ps[I.s] = __uint_as_float((idx + (uint32_t)n) % I.aux2);
+            break;
+          }
+          case OP_IMPULSE: {
+            const uint32_t f = __float_as_uint(ps[I.s]);
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = (f == 0u && j == 0) ? 1.0f : 0.0f;
+            if (tid == 0) ps[I.s] = __uint_as_float(1u);
+            break;
+          }
+          case OP_TICK: {
+            const float prev = ps[I.s];
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = j == 0 ? prev : SRC(I.in[0], j - 1);
+            if (tid == 0) ps[I.s] = SRC(I.in[0], n - 1);
+            break;
+          }
+          case OP_DELAY: {
+            const uint32_t Lr = a.ring_tab[I.aux].length, idx = __float_as_uint(ps[I.s]);
+            float* r = RING(I.aux);
+            __syncthreads();
+            for (int j = tid; j < n; j += nth)
+              TMP(I.out)[j] = (uint32_t)j < Lr ? r[(idx + (uint32_t)j) % Lr] : SRC(I.in[0], j - (int)Lr);
+            __syncthreads();
+            const int jlo = n > (int)Lr ? n - (int)Lr : 0;
+            for (int j = jlo + tid; j < n; j += nth) r[(idx + (uint32_t)j) % Lr] = SRC(I.in[0], j);
+            if (tid == 0) ps[I.s] = __uint_as_float((idx + (uint32_t)n) % Lr);
+            break;
+          }
+          case OP_TAP: {   // write-then-read per sample; `oldv` keeps what the hop overwrites (ring length >= H)
+            const uint32_t Lr = a.ring_tab[I.aux].length, mask = Lr - 1, idx = __float_as_uint(ps[I.s]);
+            float* r = RING(I.aux);
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) oldv[j] = r[(idx + (uint32_t)j) & mask];
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) r[(idx + (uint32_t)j) & mask] = SRC(I.in[0], j);
+            __syncthreads();
+            const float mn = ps[I.p], mx = ps[I.p + 1], sr = ps[I.p + 2];
+            for (int j = tid; j < n; j += nth) {
+              float tap = d_clamp(SRC(I.in[1], j), mn, mx) * sr;
+              if (tap != tap) tap = 0.0f;
+              const uint32_t fl = (uint32_t)d_as_usize(tap);
+              const float d = tap - (float)fl;
+              const uint32_t i1 = (idx + (uint32_t)j + Lr - (fl & mask)) & mask;
+              auto rd = [&](uint32_t p) -> float {
+                const uint32_t jj = (p - idx) & mask;
+                return (jj < (uint32_t)n && jj > (uint32_t)j) ? oldv[jj] : r[p];
+              };
+              if (I.n) {
+                const uint32_t i0 = (i1 + 1) & mask, i2 = (i1 + Lr - 1) & mask, i3 = (i1 + Lr - 2) & mask;
+                TMP(I.out)[j] = d_spline(rd(i0), rd(i1), rd(i2), rd(i3), d);
+              } else {
+                const uint32_t i2 = (i1 + Lr - 1) & mask;
+                TMP(I.out)[j] = d_lerp(rd(i1), rd(i2), d);
+              }
+            }
+            if (tid == 0) ps[I.s] = __uint_as_float((idx + (uint32_t)n) & mask);
+            break;
+          }
+          case OP_RFFT: {   // nodes.rs:625-642
+            const int lg = I.n;
+            const uint32_t N = 1u << lg, i0 = __float_as_uint(ps[I.s]);
+            float *rin = RING(I.aux), *rre = RING(I.aux + 1), *rim = RING(I.aux + 2);
+            __syncthreads();
+            if (i0 == 0) {   // K3: the frame is complete -> transform it before this hop's samples are stored
+              for (uint32_t k = tid; k < N; k += nth) { const uint32_t rv = __brev(k) >> (32 - lg); fr[rv] = rin[k]; fi[rv] = 0.0f; }
+              __syncthreads();
+              tv_fft(fr, fi, lg, a.tables + I.aux2, false, tid, nth);
+              for (uint32_t k = tid; k < N; k += nth) { rre[k] = fr[k]; rim[k] = fi[k]; }
+              __syncthreads();
+            }
+            for (int j = tid; j < n; j += nth) {
+              const uint32_t i = i0 + (uint32_t)j;
+              rin[i] = SRC(I.in[0], j);
+              if (i <= N / 2) { TMP(I.out)[j] = rre[i]; TMP(I.out + 1)[j] = rim[i]; }
+              else { TMP(I.out)[j] = rre[N - i]; TMP(I.out + 1)[j] = -rim[N - i]; }
+            }
+            if (tid == 0) ps[I.s] = __uint_as_float((i0 + (uint32_t)n) & (N - 1));
+            break;
+          }
+          case OP_IFFT: {   // nodes.rs:681-693
+            const int lg = I.n;
+            const uint32_t N = 1u << lg, i0 = __float_as_uint(ps[I.s]);
+            float *ire = RING(I.aux), *iim = RING(I.aux + 1), *ore = RING(I.aux + 2), *oim = RING(I.aux + 3);
+            __syncthreads();
+            if (i0 == 0) {   // K4: full complex inverse transform of the collected bins
+              for (uint32_t k = tid; k < N; k += nth) { const uint32_t rv = __brev(k) >> (32 - lg); fr[rv] = ire[k]; fi[rv] = iim[k]; }
+              __syncthreads();
+              tv_fft(fr, fi, lg, a.tables + I.aux2, true, tid, nth);
+              for (uint32_t k = tid; k < N; k += nth) { ore[k] = fr[k]; oim[k] = fi[k]; }
+              __syncthreads();
+            }
+            for (int j = tid; j < n; j += nth) {
+              const uint32_t i = i0 + (uint32_t)j;
+              ire[i] = SRC(I.in[0], j); iim[i] = SRC(I.in[1], j);
+              TMP(I.out)[j] = ore[i]; TMP(I.out + 1)[j] = oim[i];
+            }
+            if (tid == 0) ps[I.s] = __uint_as_float((i0 + (uint32_t)n) & (N - 1));
+            break;
+          }
+          default: break;
+        }
+      }
+      __syncthreads();
+    }
+    for (int c = 0; c < a.n_out; c++) {
+      const int ox = a.out_x[c];
+      for (int j = tid; j < n; j += nth) a.out[((size_t)v * a.n_out + c) * a.T + t0 + j] = SRC(ox, j);
+    }
+    __syncthreads();
+  }
+  for (int s = tid; s < a.NS; s += nth) a.state[(size_t)s * a.Vp + v] = ps[a.P + s];
+#undef RING
+#undef TMP
+#undef SRC
+}
+
+size_t tv_smem_bytes(const TvArgs& a) {
+  return (size_t)a.n_instr * sizeof(Instr) + (size_t)(((a.P + a.NS) + 3) & ~3) * 4 + (size_t)a.NT * a.H * 4 + (size_t)a.H * 4 +
+         (size_t)a.fft_n * 8;
+}
+
+cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches) {
+  size_t smem = tv_smem_bytes(a);
+  cudaError_t e = cudaFuncSetAttribute(k_interp_tv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_interp_tv<<<a.V, 256, smem, stream>>>(a);
+  if (launches) *launches += 1;
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ launchers

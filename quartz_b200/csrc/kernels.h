@@ -28,6 +28,29 @@ struct InterpArgs {
   int group;                  // K6: sum consecutive voices in groups of `group` (1, 2, 4, 8, 16 or 32), scaled by 1/group
 };
 
+// time-vector mode (one CTA per voice, threads = samples of a hop); rings are voice-major [V][ring_floats]
+struct TvArgs {
+  const Instr* code;
+  int n_instr;
+  int P, NS, NT;
+  int n_in, n_out;
+  const uint16_t* out_x;
+  const float* params;        // [P][Vp]
+  float* state;               // [NS][Vp]
+  float* rings;               // [V][ring_floats]
+  uint32_t ring_floats;
+  const Ring* ring_tab;
+  const float* tables;
+  const float* in;            // voice-major [V][n_in][T]
+  float* out;                 // voice-major [V][n_out][T]
+  int V, Vp;
+  long T;
+  int H;                      // hop (samples per pass), divides every FFT size and start offset
+  int fft_n;                  // largest FFT size in the tape (shared-memory transform buffer), 0 if none
+};
+size_t tv_smem_bytes(const TvArgs& a);
+cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches);
+
 cudaError_t launch_interp(const InterpArgs& a, bool divergent, cudaStream_t stream, int* launches);
 cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
                               const uint64_t* salts, cudaStream_t stream);

@@ -4,6 +4,7 @@
 // predicated / jumped-over instruction ranges.
 #include "lower.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -628,6 +629,40 @@ void Tape::derive(const float* r, float* P) const {
       case D_TAP: o[0] = in[0]; o[1] = in[1]; o[2] = d.sr; break;
     }
   }
+}
+
+TvPlan plan_tv(const Tape& t, size_t smem_limit) {
+  TvPlan pl;
+  if (t.h.flags & TAPE_DIVERGENT) return pl;
+  int H = 512, fft_n = 0;
+  uint32_t min_tap_ring = 0xffffffffu;
+  auto gcd = [](int a, int b) { while (b) { int r = a % b; a = b; b = r; } return a; };
+  for (const Instr& i : t.code) {
+    if (op_is_stateless(i.op)) continue;
+    switch (i.op) {
+      case OP_NOISE: case OP_WAVE: case OP_IMPULSE: case OP_TICK: case OP_DELAY: break;
+      case OP_TAP: min_tap_ring = std::min(min_tap_ring, t.rings[i.aux].length); break;
+      case OP_RFFT: case OP_IFFT: {
+        int N = 1 << i.n;
+        if (N > 8192) return pl;                       // transform buffer must fit in shared memory
+        int start = (int)t.state_init[i.s - t.h.n_params];
+        H = gcd(H, N);
+        if (start) H = gcd(H, start);
+        fft_n = std::max(fft_n, N);
+        pl.has_fft = true;
+        break;
+      }
+      default: return pl;
+    }
+  }
+  auto bytes = [&](int h) {
+    return (size_t)t.h.n_instr * sizeof(Instr) + (size_t)(t.h.n_params + t.h.n_state + 4) * 4 + (size_t)t.h.n_temps * h * 4 +
+           (size_t)h * 4 + (size_t)fft_n * 8;
+  };
+  while (H >= 32 && (bytes(H) > smem_limit || (uint32_t)H > min_tap_ring)) H >>= 1;
+  if (H < 32) return pl;
+  pl.ok = true; pl.H = H; pl.fft_n = fft_n;
+  return pl;
 }
 
 bool lower(const Graph& g, Tape* out, std::string* err) {

@@ -50,6 +50,16 @@ struct Tape {
   void derive(const float* raw_in, float* p_out) const;
 };
 
+// Time-vector execution plan (k_interp_tv): possible when every op is stateless or one of the block-capable stateful
+// ops (noise, wave, impulse, tick, delay, tap, rfft, ifft).  H = hop in samples.
+struct TvPlan {
+  bool ok = false;
+  bool has_fft = false;
+  int H = 0;
+  int fft_n = 0;
+};
+TvPlan plan_tv(const Tape& t, size_t smem_limit);
+
 // Lower a graph.  Returns false (and fills `err`) when the graph contains something that has no GPU lowering —
 // the product never falls back to a CPU path.
 bool lower(const Graph& g, Tape* out, std::string* err);

@@ -99,6 +99,17 @@ enum Op : uint16_t {
   OP_COUNT_
 };
 
+#if defined(__CUDACC__)
+#define QG_TAPE_HD __host__ __device__
+#else
+#define QG_TAPE_HD
+#endif
+// ops that read only the current sample's operands (no per-voice memory): they can be applied to any sample of a hop
+QG_TAPE_HD inline bool op_is_stateless(uint16_t op) {
+  return op == OP_NOP || op == OP_MOV || op == OP_ZERO || (op >= OP_ADD && op <= OP_PAN) || op == OP_ROTATE ||
+         op == OP_QUANTIZE || op == OP_ARR_GET;
+}
+
 struct Instr {
   uint16_t op;
   uint16_t out;      // first output temporary (multi-output ops write out, out+1, ...)

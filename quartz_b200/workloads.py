@@ -96,4 +96,42 @@ def c3_polysynth(V=65536, T=480000, G=32, v0=0):
                     "osc->lowpass->envelope, mixed in groups of 32")
 
 
-WORKLOADS = {"c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth}
+def hann(n):
+    i = np.arange(n, dtype=np.float64)
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * i / n)).astype(np.float32)
+
+
+def spectral_graph(N, J, thr, window):
+    """One channel of the spectral-gate patch (structure of assets/spectral-gate) with N-point
+    transforms and J overlapping instances (hop N/J): noise input x window -> J x [rfft -> gate -> ifft] -> real part x
+    window -> join(J)."""
+    hop = N // J
+    delays = [j * hop for j in range(J)]
+    starts = [(N - d) % N for d in delays]
+
+    def stack(xs):
+        return {"op": "|", "n": 0.0, "inputs": xs}
+
+    def win():
+        taps = [_L("pass()")] + [_L(f"delay({float(np.float32(d / FS))!r})") for d in delays[1:]]
+        return _pipe({"op": "wave()", "arr": [float(x) for x in window]}, f"split({J})", stack(taps))
+
+    gate = _pipe("pol()", stack([_pipe({"op": "^", "n": 0.0, "inputs": [_L(f">({thr!r})"), _L("pass()")]},
+                                       {"op": "*", "n": 0.0, "inputs": [_L("pass()"), _L("pass()")]}), _L("pass()")]), "car()")
+    chains = [_pipe(f"rfft({N},{s})", gate, f"ifft({N},{s})") for s in starts]
+    xw = {"op": "*", "n": 0.0, "inputs": [_pipe("white()", f"split({J})"), win()]}
+    keep_real = "chan(" + ",".join(["1", "0"] * J) + ")"
+    syn = _pipe(xw, stack(chains), keep_real)
+    return _sr(_pipe({"op": "*", "n": 0.0, "inputs": [syn, win()]}, f"join({J})"))
+
+
+def c4_spectral(V=1024, T=1440000, N=2048, J=4, thr=16.0, v0=0):
+    """spectral gate: N-pt STFT, hop N/J, V channels (configs[3])"""
+    voices = np.arange(v0, v0 + V)
+    expr = spectral_graph(N, J, float(thr), hann(N))
+    # bytes: 4 B written per channel-sample (input is generated on chip); flops ~ 346 per channel-sample (SURVEY 8d)
+    return Workload(f"c4_spectral_gate_{N}", expr, None, salts_for(voices), T, 1, lambda v: expr, 4.0, "fp32",
+                    f"{J} x [rfft({N}) -> gate -> ifft({N})], hop {N // J}")
+
+
+WORKLOADS = {"c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth, "c4": c4_spectral}
