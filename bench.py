@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — voice-samples/s @ 48 kHz for quartz's audio-graph hot path on N B200s (one process per GPU).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
 
 A "step" is one offline render of the workload (all voices x all samples).  Default workload = BASELINE.json
 configs[1] (4,096 noise->lowpass voices, 60 s, per-voice outputs kept: the HBM-write-bound configuration).
@@ -128,7 +128,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "interp"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -400,7 +400,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     ta.n_in = (int)t.h.n_inputs; ta.n_out = (int)t.h.n_outputs; ta.out_x = b->d_out_x;
     ta.params = b->d_params; ta.state = b->d_state; ta.rings = b->d_rings; ta.ring_floats = t.h.ring_floats;
     ta.ring_tab = b->d_ring_tab; ta.tables = b->d_tables; ta.in = d_in; ta.out = d_out;
-    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n;
+    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n; ta.align_s = b->tv.align_s;
     int l = 0;
     CU(launch_interp_tv(ta, c->stream, &l));
     c->launches += l;

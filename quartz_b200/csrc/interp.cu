@@ -682,8 +682,16 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
 #define TMP(i) (tmp + (size_t)((int)(i) - PS) * H)         // temporaries only
 #define SRC(i, j) ((int)(i) < PS ? ps[(int)(i)] : tmp[(size_t)((int)(i) - PS) * H + (j)])
   __syncthreads();
-  for (long t0 = 0; t0 < a.T; t0 += H) {
-    const int n = (int)(a.T - t0 < H ? a.T - t0 : H);
+  // a previous call may have stopped in the middle of a hop: the first pass only completes that hop, so that
+  // transform frames stay aligned with hop boundaries (all rfft/ifft counters are congruent modulo H)
+  int first = 0;
+  if (a.align_s >= 0) {
+    const uint32_t ph = __float_as_uint(ps[a.align_s]) % (uint32_t)H;
+    first = ph ? H - (int)ph : 0;
+  }
+  for (long t0 = 0; t0 < a.T;) {
+    int n = (int)(a.T - t0 < H ? a.T - t0 : H);
+    if (t0 == 0 && first > 0 && first < n) n = first;
     for (int c = 0; c < a.n_in; c++)
       for (int j = tid; j < n; j += nth) tmp[(size_t)c * H + j] = a.in[((size_t)v * a.n_in + c) * a.T + t0 + j];
     __syncthreads();
@@ -818,6 +826,7 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
       for (int j = tid; j < n; j += nth) a.out[((size_t)v * a.n_out + c) * a.T + t0 + j] = SRC(ox, j);
     }
     __syncthreads();
+    t0 += n;
   }
   for (int s = tid; s < a.NS; s += nth) a.state[(size_t)s * a.Vp + v] = ps[a.P + s];
 #undef RING

@@ -650,6 +650,7 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
         if (start) H = gcd(H, start);
         fft_n = std::max(fft_n, N);
         pl.has_fft = true;
+        pl.align_s = i.s;
         break;
       }
       default: return pl;
@@ -659,8 +660,8 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
     return (size_t)t.h.n_instr * sizeof(Instr) + (size_t)(t.h.n_params + t.h.n_state + 4) * 4 + (size_t)t.h.n_temps * h * 4 +
            (size_t)h * 4 + (size_t)fft_n * 8;
   };
-  while (H >= 32 && (bytes(H) > smem_limit || (uint32_t)H > min_tap_ring)) H >>= 1;
-  if (H < 32) return pl;
+  while (H >= 8 && (bytes(H) > smem_limit || (uint32_t)H > min_tap_ring)) H >>= 1;
+  if (H < 8) return pl;
   pl.ok = true; pl.H = H; pl.fft_n = fft_n;
   return pl;
 }

@@ -57,6 +57,7 @@ struct TvPlan {
   bool has_fft = false;
   int H = 0;
   int fft_n = 0;
+  int align_s = -1;   // X index of one rfft/ifft counter
 };
 TvPlan plan_tv(const Tape& t, size_t smem_limit);
 

@@ -101,7 +101,7 @@ def hann(n):
     return (0.5 - 0.5 * np.cos(2.0 * np.pi * i / n)).astype(np.float32)
 
 
-def spectral_graph(N, J, thr, window):
+def spectral_graph(N, J, thr, window, source="white()"):
     """One channel of the spectral-gate patch (structure of assets/spectral-gate) with N-point
     transforms and J overlapping instances (hop N/J): noise input x window -> J x [rfft -> gate -> ifft] -> real part x
     window -> join(J)."""
@@ -119,7 +119,7 @@ def spectral_graph(N, J, thr, window):
     gate = _pipe("pol()", stack([_pipe({"op": "^", "n": 0.0, "inputs": [_L(f">({thr!r})"), _L("pass()")]},
                                        {"op": "*", "n": 0.0, "inputs": [_L("pass()"), _L("pass()")]}), _L("pass()")]), "car()")
     chains = [_pipe(f"rfft({N},{s})", gate, f"ifft({N},{s})") for s in starts]
-    xw = {"op": "*", "n": 0.0, "inputs": [_pipe("white()", f"split({J})"), win()]}
+    xw = {"op": "*", "n": 0.0, "inputs": [_pipe(source, f"split({J})"), win()]}
     keep_real = "chan(" + ",".join(["1", "0"] * J) + ")"
     syn = _pipe(xw, stack(chains), keep_real)
     return _sr(_pipe({"op": "*", "n": 0.0, "inputs": [syn, win()]}, f"join({J})"))
