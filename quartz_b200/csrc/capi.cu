@@ -392,7 +392,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   int rc = check_group(b, layout, group);
   if (rc) return rc;
   const int family = bank_family(b);
-  if (family == 2 && layout == QG_LAYOUT_VOICE_MAJOR && group == 1) {
+  if (family == 2 && group == 1) {
     TvArgs ta;
     memset(&ta, 0, sizeof ta);
     ta.code = b->d_code; ta.n_instr = (int)t.h.n_instr;
@@ -400,13 +400,13 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     ta.n_in = (int)t.h.n_inputs; ta.n_out = (int)t.h.n_outputs; ta.out_x = b->d_out_x;
     ta.params = b->d_params; ta.state = b->d_state; ta.rings = b->d_rings; ta.ring_floats = t.h.ring_floats;
     ta.ring_tab = b->d_ring_tab; ta.tables = b->d_tables; ta.in = d_in; ta.out = d_out;
-    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n; ta.align_s = b->tv.align_s;
+    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n; ta.align_s = b->tv.align_s; ta.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
     int l = 0;
     CU(launch_interp_tv(ta, c->stream, &l));
     c->launches += l;
     return QG_OK;
   }
-  if (family == 2) return fail(QG_ERR_ARG, "this bank runs on the time-vector interpreter: voice-major layout and group 1 only "
+  if (family == 2) return fail(QG_ERR_ARG, "this bank runs on the time-vector interpreter, which has no group mix "
                                            "(qg_bank_set_path(QG_PATH_INTERP) selects the lane interpreter)");
   if (family == 1 && !d_in && layout == QG_LAYOUT_VOICE_MAJOR) {
     FusedArgs fa;

@@ -693,16 +693,21 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
     int n = (int)(a.T - t0 < H ? a.T - t0 : H);
     if (t0 == 0 && first > 0 && first < n) n = first;
     for (int c = 0; c < a.n_in; c++)
-      for (int j = tid; j < n; j += nth) tmp[(size_t)c * H + j] = a.in[((size_t)v * a.n_in + c) * a.T + t0 + j];
+      for (int j = tid; j < n; j += nth)
+        tmp[(size_t)c * H + j] = a.frame_major ? a.in[((size_t)(t0 + j) * a.V + v) * a.n_in + c] : a.in[((size_t)v * a.n_in + c) * a.T + t0 + j];
     __syncthreads();
     for (int pc = 0; pc < a.n_instr; pc++) {
       const Instr I = code[pc];
       if (op_is_stateless(I.op)) {
+        // a run of stateless ops is applied sample by sample without intermediate barriers
+        int pe = pc + 1;
+        while (pe < a.n_instr && op_is_stateless(code[pe].op)) pe++;
         for (int j = tid; j < n; j += nth) {
           TvSample L{ps, tmp + j, PS, H, a.tables};
           int dummy = 0;
-          exec(I, L, dummy);
+          for (int q = pc; q < pe; q++) exec(code[q], L, dummy);
         }
+        pc = pe - 1;
       } else {
         switch (I.op) {
           case OP_NOISE: {
@@ -823,7 +828,10 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
     }
     for (int c = 0; c < a.n_out; c++) {
       const int ox = a.out_x[c];
-      for (int j = tid; j < n; j += nth) a.out[((size_t)v * a.n_out + c) * a.T + t0 + j] = SRC(ox, j);
+      for (int j = tid; j < n; j += nth) {
+        const size_t o = a.frame_major ? ((size_t)(t0 + j) * a.V + v) * a.n_out + c : ((size_t)v * a.n_out + c) * a.T + t0 + j;
+        a.out[o] = SRC(ox, j);
+      }
     }
     __syncthreads();
     t0 += n;

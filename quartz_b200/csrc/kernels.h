@@ -47,6 +47,7 @@ struct TvArgs {
   long T;
   int H;                      // hop (samples per pass), divides every FFT size and start offset
   int fft_n;                  // largest FFT size in the tape (shared-memory transform buffer), 0 if none
+  int frame_major;            // 1: in/out are frame-major [T][V][ch] instead of voice-major [V][ch][T]
   int align_s;                // X index of one rfft/ifft counter (hop alignment across calls), -1 if none
 };
 size_t tv_smem_bytes(const TvArgs& a);

@@ -675,6 +675,52 @@ bool lower(const Graph& g, Tape* out, std::string* err) {
   for (int i = 0; i < g.n_in; i++) ins.push_back(L.temp());
   std::vector<uint16_t> outs = L.graph(g, ins);
   if (!L.err.empty()) { if (err) *err = L.err; return false; }
+  // ---- temporary reuse (uniform tapes only): a temporary dies after its last reader; outputs of multi-output ops
+  // stay contiguous.  Shrinks the per-voice working set (shared memory) of long feed-forward graphs.
+  if (!(t.h.flags & TAPE_DIVERGENT) && L.n_temps > 0) {
+    const int NTv = L.n_temps;
+    auto n_out_of = [](const Instr& i) -> int {
+      switch (i.op) {
+        case OP_POL: case OP_CAR: case OP_PAN: case OP_PAN_VAR: case OP_ROTATE: case OP_RFFT: case OP_IFFT: return 2;
+        case OP_SHIFT_REG: return 8;
+        default: return i.out == NONE ? 0 : 1;
+      }
+    };
+    std::vector<int> last(NTv, -1);
+    const int END = (int)t.code.size();
+    for (int k = 0; k < (int)t.code.size(); k++)
+      for (uint16_t x : t.code[k].in)
+        if (x != NONE && (x & R_TEMP)) last[x & 0x7fff] = k;
+    for (uint16_t o : outs)
+      if (o & R_TEMP) last[o & 0x7fff] = END;
+    std::vector<int> phys(NTv, -1), free_at;      // free_at[slot] = instruction index after which the slot is free
+    for (int i = 0; i < g.n_in; i++) { phys[i] = i; free_at.push_back(END); }   // net inputs are refilled every sample
+    for (int k = 0; k < (int)t.code.size(); k++) {
+      Instr& ins = t.code[k];
+      int no = n_out_of(ins);
+      if (no == 0 || !(ins.out & R_TEMP)) continue;
+      int v0 = ins.out & 0x7fff;
+      int die = k;
+      for (int q = 0; q < no; q++) die = std::max(die, last[v0 + q]);
+      // first fit: `no` contiguous slots all free strictly before k (a slot read by instruction k may not be reused by k)
+      int base = -1;
+      for (int s0 = 0; s0 + no <= (int)free_at.size() && base < 0; s0++) {
+        bool ok = true;
+        for (int q = 0; q < no; q++) ok = ok && free_at[s0 + q] < k;
+        if (ok) base = s0;
+      }
+      if (base < 0) { base = (int)free_at.size(); free_at.resize(base + no, -1); }
+      for (int q = 0; q < no; q++) { phys[v0 + q] = base + q; free_at[base + q] = die; }
+    }
+    auto rn = [&](uint16_t x) -> uint16_t {
+      if (x == NONE || !(x & R_TEMP)) return x;
+      int p = phys[x & 0x7fff];
+      return (uint16_t)(R_TEMP | (p < 0 ? 0 : p));
+    };
+    for (Instr& ins : t.code) { ins.out = rn(ins.out); for (uint16_t& x : ins.in) x = rn(x); }
+    for (uint16_t& o : outs) o = rn(o);
+    L.n_temps = std::max<int>((int)free_at.size(), 1);
+  }
   size_t P = t.params.size(), NS = t.state_init.size();
   if (P >= 0x4000 || NS >= 0x4000 || (size_t)L.n_temps >= 0x7fff || P + NS + L.n_temps >= 0xfff0) {
     if (err) *err = "graph too large for one tape (parameter/state/temporary index overflow)";
