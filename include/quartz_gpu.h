@@ -63,7 +63,8 @@ qg_net* qg_kr(const qg_net* net, double n, int preserve_time);
 qg_net* qg_reset_every(const qg_net* net, double seconds);
 qg_net* qg_trig_reset(const qg_net* net, int variable);
 qg_net* qg_seq_select(int is_seq, const qg_net* const* nets, int n_nets);
-qg_net* qg_live_io(const char* name);
+qg_net* qg_live_io(const char* name);   /* in() adc() buffin() buffout() monitor(): offline equivalents */
+qg_net* qg_var(float value);             /* var(): src/process.rs:1373-1385 */
 /* lowering introspection */
 int qg_net_raw_count(const qg_net* net);                       /* number of op-string parameters, lowering order */
 int qg_net_raw_params(const qg_net* net, float* out, int cap);

@@ -165,9 +165,13 @@ void* qo_live_io(const char* name) {
   std::string s(name);
   if (s == "in()" || s == "adc()") return Net::wrap(UnitP(new ZeroSource(2, ID_INPUT))).release();
   if (s == "buffout()") return Net::wrap(UnitP(new ZeroSource(1, ID_BUFFOUT))).release();
+  if (s == "monitor()") return Net::wrap(UnitP(new Pass())).release();
   if (s == "buffin()") return Net::wrap(UnitP(new Map(1, 1, [](const float* i, float* o) { o[0] = i[0]; }))).release();
   return new Net(0, 0);
 }
+
+// var() (process.rs:1373-1385): Shared-backed constant holding the circle's Number
+void* qo_var(float value) { return Net::wrap(UnitP(new Constant({value}))).release(); }
 
 // apply (process.rs:1322-1325): one frame
 int qo_tick(void* h, const float* in, int n_in, float* out, int n_out) {

@@ -34,6 +34,7 @@ SIGNATURES = {
     "qg_trig_reset": (vp, [vp, ci]),
     "qg_seq_select": (vp, [ci, C.POINTER(vp), ci]),
     "qg_live_io": (vp, [C.c_char_p]),
+    "qg_var": (vp, [cf]),
     "qg_net_raw_count": (ci, [vp]),
     "qg_net_raw_params": (ci, [vp, fp, ci]),
     "qg_net_signature": (u64, [vp]),

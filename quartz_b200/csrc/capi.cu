@@ -126,6 +126,7 @@ qg_net* qg_seq_select(int is_seq, const qg_net* const* nets, int n) {
   return guard_net([&] { return make_seq_select(is_seq != 0, gv(nets, n)); });
 }
 qg_net* qg_live_io(const char* name) { return guard_net([&] { return make_live_io(name ? name : ""); }); }
+qg_net* qg_var(float value) { return guard_net([&] { return make_var(value); }); }
 
 int qg_net_raw_count(const qg_net* n) {
   if (!n) return 0;

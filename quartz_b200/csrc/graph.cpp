@@ -232,12 +232,20 @@ Graph make_seq_select(bool is_seq, const std::vector<const Graph*>& nets) {   //
     if (g && g->inputs() == 0 && g->outputs() == 1) n.kids.push_back(*g);
   return wrap_node(n, is_seq ? ID_SEQ : ID_SELECT);
 }
+Graph make_var(float value) {   // var(): a Shared-backed constant (process.rs:1373-1385), value = the circle's Number
+  Node n;
+  n.kind = NK_CONST; n.n_in = 0; n.n_out = 1; n.raw = {value};
+  return wrap_node(n, ID_CONSTANT);
+}
 Graph make_live_io(const std::string& name) {
   // InputNode / BuffOut: every try_recv() misses offline -> 0.0 (nodes.rs:516-517, 786); BuffIn passes (nodes.rs:761-762)
   Node n;
   if (name == "in()" || name == "adc()") { n.kind = NK_ZERO_SRC; n.n_out = 2; return wrap_node(n, ID_INPUT); }
   if (name == "buffout()") { n.kind = NK_ZERO_SRC; n.n_out = 1; return wrap_node(n, ID_BUFFOUT); }
   if (name == "buffin()") { n.kind = NK_PASS; n.n_in = 1; n.n_out = 1; return wrap_node(n, ID_MAP); }
+  // monitor(&s, Meter::Sample) passes its input through while publishing it (process.rs:1404); timer(&s) has no
+  // inputs or outputs (process.rs:1406): offline they reduce to a pass-through / an empty net
+  if (name == "monitor()") { n.kind = NK_PASS; n.n_in = 1; n.n_out = 1; return wrap_node(n, ID_PASS); }
   return Graph(0, 0);
 }
 

@@ -36,6 +36,7 @@ enum : uint64_t {
   ID_PIPE = 2, ID_STACK = 3, ID_BRANCH = 4, ID_BUS = 10, ID_BINOP = 11, ID_NET = 63, ID_FEEDBACK = 79, ID_WAVE = 65,
   ID_SELECT = 1213, ID_SEQ = 1729, ID_ARRGET = 1312, ID_SHIFTREG = 1110, ID_QUANTIZER = 1111, ID_KR = 1112,
   ID_RESET = 1113, ID_TRIGRESET = 1114, ID_RESETV = 1115, ID_RAMP = 1116, ID_INPUT = 1117,
+  ID_VAR = 70, ID_MONITOR = 56,
   ID_RFFT = 1120, ID_IFFT = 1121, ID_SAMPDELAY = 1122, ID_BUFFIN = 1123, ID_BUFFOUT = 1124, ID_SNH = 1125,
 };
 
@@ -111,6 +112,7 @@ Graph make_reset(const Graph& net, double s);
 Graph make_trig_reset(const Graph& net, bool variable);
 Graph make_seq_select(bool is_seq, const std::vector<const Graph*>& nets);
 Graph make_live_io(const std::string& name);
+Graph make_var(float value);
 // connective circles (process.rs:1719-1876) and array ops (process.rs:1669-1717)
 Graph connect(const std::string& op, const std::vector<const Graph*>& nets, double number, int node_limit);
 Graph array_op(const std::string& kind, const std::string& op_str, const std::vector<float>& arr);

@@ -477,6 +477,58 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       break;
     }
     case OP_JNE_IDX: if (d_as_usize(X(I.in[0])) != (uint64_t)I.aux2) pc = (int)I.aux; break;
+    case OP_SEQ_TRIG: {   // nodes.rs:76-91
+      const int nk = I.n;
+      if (X(I.in[0]) != 0.0f) {
+        const uint64_t k = d_as_usize(X(I.in[1]));
+        if (k < (uint64_t)nk) {
+          const int b = I.s + 1 + 5 * (int)k;
+          reset_range(L, I.aux2 + (uint32_t)k);
+          const uint64_t dl = d_as_usize(roundf(X(I.in[2]) * X(I.p))), du = d_as_usize(roundf(X(I.in[3]) * X(I.p)));
+          const uint32_t stamp = XU(I.s) + 1u;
+          SETU(I.s, stamp);
+          SETU(b, 1u);
+          SETU(b + 1, dl > 0xffffffffull ? 0xffffffffu : (uint32_t)dl);
+          SETU(b + 2, du > 0xffffffffull ? 0xffffffffu : (uint32_t)du);
+          SETU(b + 3, stamp);
+        }
+      }
+      for (int k = 0; k < nk; k++) {   // events.retain(|x| x.2 != 0)
+        const int b = I.s + 1 + 5 * k;
+        if (XU(b) && XU(b + 2) == 0u) SETU(b, 0u);
+        SETU(b + 4, 0u);
+      }
+      break;
+    }
+    case OP_SEQ_GATE: {   // nodes.rs:95-105
+      const int b = I.s + 1 + 5 * (int)I.n;
+      bool tick = false;
+      if (XU(b)) {
+        if (XU(b + 1) == 0u) { SETU(b + 2, XU(b + 2) - 1u); SETU(b + 4, 1u); tick = true; }
+        else SETU(b + 1, XU(b + 1) - 1u);
+      }
+      if (!tick) pc = (int)I.aux;
+      break;
+    }
+    case OP_SEQ_END: {   // out += buffer, in event-list (= push) order
+      const int nk = I.n;
+      float acc = 0.0f;
+      uint32_t done = 0u;
+      for (int r = 0; r < nk; r++) {
+        int best = -1;
+        uint32_t bs = 0xffffffffu;
+        for (int k = 0; k < nk; k++) {
+          const int b = I.s + 1 + 5 * k;
+          const uint32_t stamp = XU(b + 3);
+          if (XU(b + 4) && stamp > done && stamp <= bs) { bs = stamp; best = k; }
+        }
+        if (best < 0) break;
+        acc += X(I.in[0] + best);
+        done = bs;
+      }
+      X(I.out) = acc;
+      break;
+    }
     // ---------------------------------------------------------------- feedback
     case OP_FB_READ: X(I.out) = X(I.in[0]) + ring_at(L, I.aux, XU(I.s)); break;
     case OP_FB_WRITE: {

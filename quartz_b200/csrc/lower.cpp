@@ -558,9 +558,42 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
       out = {i.out, (uint16_t)(i.out + 1)};
       break;
     }
-    case NK_SEQ:
-      err = "seq() has no GPU lowering yet";
+    case NK_SEQ: {   // nodes.rs:74-106.  State: event counter, then per net: active, delay, dur, order stamp, ticking flag
+      t.h.flags |= TAPE_DIVERGENT;
+      int nk = (int)n.kids.size();
+      if (nk == 0) { out.push_back(zero()); break; }
+      if (nk > 64) { err = "seq(): more than 64 nets"; break; }
+      uint16_t p = params(1);
+      deriver(D_RAMP_SR, 0, 0, p, 1, 0, 0, n.sr);
+      uint16_t st = state(1 + 5 * nk);
+      uint16_t vals = temp(nk);
+      uint32_t first_range = (uint32_t)t.resets.size();
+      t.resets.resize(t.resets.size() + nk);           // one reset range per net, filled in below
+      {
+        Instr& tr = emit(OP_SEQ_TRIG);
+        for (int k = 0; k < 4; k++) tr.in[k] = in[k];
+        tr.s = st; tr.p = p; tr.n = (uint16_t)nk; tr.aux2 = first_range;
+      }
+      for (int k = 0; k < nk; k++) {
+        { Instr& z = emit(OP_ZERO); z.out = (uint16_t)(vals + k); }
+        size_t j = t.code.size();
+        { Instr& gt = emit(OP_SEQ_GATE); gt.s = st; gt.n = (uint16_t)k; }
+        ResetRange rr;
+        rr.s_lo = (uint16_t)t.state_init.size();
+        rr.ring_lo = (uint16_t)t.rings.size();
+        std::vector<uint16_t> ko = graph(n.kids[k], {});
+        if (!err.empty()) return {};
+        rr.s_hi = (uint16_t)t.state_init.size();
+        rr.ring_hi = (uint16_t)t.rings.size();
+        t.resets[first_range + k] = rr;
+        { Instr& m = emit(OP_MOV); m.in[0] = ko[0]; m.out = (uint16_t)(vals + k); }
+        t.code[j].aux = (uint32_t)t.code.size();
+      }
+      Instr& e = emit(OP_SEQ_END);
+      e.in[0] = vals; e.s = st; e.n = (uint16_t)nk; e.out = temp();
+      out.push_back(e.out);
       break;
+    }
     default:
       err = "internal: unknown node kind";
   }

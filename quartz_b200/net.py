@@ -135,6 +135,10 @@ class Net:
     def live_io(name):
         return Net(lib().qg_live_io(name.encode()))
 
+    @staticmethod
+    def var(value):
+        return Net(lib().qg_var(float(value)))
+
     # operators, as on a FunDSP Net (no arity guard here: the guards belong to connect(), like in process.rs)
     def __rshift__(self, o):
         return Net.connect(">>", [self, o])

@@ -45,8 +45,10 @@ def build(e, B, node_limit=500):
         return B.select([build(k, B, node_limit) for k in e["inputs"]])
     if op in ARRAY_OPS:
         return B.array_op(op, e["str"], e["arr"])
-    if op in ("in()", "adc()", "buffin()", "buffout()"):
+    if op in ("in()", "adc()", "buffin()", "buffout()", "monitor()"):
         return B.live_io(op)
+    if op == "var()":
+        return B.var(e.get("n", 0.0))
     return B.str_to_net(op)
 
 

@@ -38,6 +38,7 @@ def lib():
             "qo_feedback": (vp, [vp, ci, cd]), "qo_kr": (vp, [vp, cd, ci]),
             "qo_reset_every": (vp, [vp, cd]), "qo_trig_reset": (vp, [vp, ci]),
             "qo_seq_select": (vp, [ci, C.POINTER(vp), ci]), "qo_live_io": (vp, [C.c_char_p]),
+            "qo_var": (vp, [C.c_float]),
             "qo_tick": (ci, [vp, fp, ci, fp, ci]), "qo_render": (ci, [vp, cl, fp]),
             "qo_process": (ci, [vp, cl, fp, fp]),
             "qo_render_bank": (ci, [C.POINTER(vp), ci, cl, ci, ci, fp]),
@@ -145,6 +146,10 @@ class ONet:
     @staticmethod
     def live_io(name):
         return ONet(lib().qo_live_io(name.encode()))
+
+    @staticmethod
+    def var(value):
+        return ONet(lib().qo_var(float(value)))
 
     # ---- AudioUnit surface
     def clone(self):
