@@ -104,6 +104,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     wl = make_workload(args.workload, 0)
+    wl = wl[-1] if isinstance(wl, list) else wl
     vals = []
     cb = None
     for i in range(args.warmup + args.steps):
@@ -128,7 +129,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "interp"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -158,23 +159,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    wl = make_workload(args.workload, rank, world)
+    wls = make_workload(args.workload, rank, world)
+    wls = wls if isinstance(wls, list) else [wls]
+    wl = wls[0]
     # the library launches on the stream it is given; use a real (non-legacy) torch stream so that torch CUDA
     # events bracket exactly those launches
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = qb.Context(local_rank, stream=stream.cuda_stream)
-    tmpl = __import__("tests.graphs", fromlist=["build"]).build(wl.expr, qb.Net)
-    bank = qb.Bank(tmpl, wl.V, raw=wl.raw, salts=wl.salts, ctx=ctx)
+    build_graph = __import__("tests.graphs", fromlist=["build"]).build
+    tmpls = [build_graph(w.expr, qb.Net) for w in wls]
+    tmpl = tmpls[0]
+    banks = [qb.Bank(t, w.V, raw=w.raw, salts=w.salts, ctx=ctx) for t, w in zip(tmpls, wls)]
+    bank = banks[0]
     if args.path == "interp":
-        bank.set_path(qb.PATH_INTERP)
-    rows = (wl.V // wl.group) * tmpl.outputs()
-    out_bytes = rows * wl.T * 4
-    d_out = torch.empty(rows * wl.T, dtype=torch.float32, device="cuda")
+        [b.set_path(qb.PATH_INTERP) for b in banks]
+    rows_l = [(w.V // w.group) * t.outputs() for t, w in zip(tmpls, wls)]
+    rows = sum(rows_l)
+    T = wl.T
+    out_bytes = rows * T * 4
+    d_out = torch.empty(rows * T, dtype=torch.float32, device="cuda")
+    offs = np.concatenate([[0], np.cumsum(rows_l)])[:-1] * T * 4
 
     def step():
-        bank.reset()
-        bank.render_device(wl.T, d_out.data_ptr(), group=wl.group)
+        for b, w, o in zip(banks, wls, offs):
+            b.reset()
+            b.render_device(w.T, d_out.data_ptr() + int(o), group=w.group)
 
     for _ in range(args.warmup):
         step()
@@ -203,24 +213,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    units = wl.V * wl.T
+    units = sum(w.V * w.T for w in wls)
     value = world * units / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API with host buffers (bank build from host tables + render + D2H)
     e2e = None
     if not args.no_e2e:
         n_e2e = max(1, min(args.steps, 3))
-        h_out = torch.empty(rows * wl.T, dtype=torch.float32).pin_memory()
-        h_np = h_out.numpy().reshape(wl.V // wl.group, tmpl.outputs(), wl.T)
+        h_out = torch.empty(rows * T, dtype=torch.float32).pin_memory()
+        h_all = h_out.numpy()
+        h_views = [h_all[int(o) // 4: int(o) // 4 + r * T].reshape(w.V // w.group, t.outputs(), T)
+                   for o, r, w, t in zip(offs, rows_l, wls, tmpls)]
+        h_np = h_views[0]
         del d_out
         torch.cuda.empty_cache()
-        h2d = wl.raw.nbytes + wl.salts.nbytes
+        h2d = sum((0 if w.raw is None else w.raw.nbytes) + w.salts.nbytes for w in wls)
 
         def e2e_step():
-            b2 = qb.Bank(tmpl, wl.V, raw=wl.raw, salts=wl.salts, ctx=ctx)
-            if args.path == "interp":
-                b2.set_path(qb.PATH_INTERP)
-            b2.render(wl.T, group=wl.group, out=h_np)
+            for t, w, hv in zip(tmpls, wls, h_views):
+                b2 = qb.Bank(t, w.V, raw=w.raw, salts=w.salts, ctx=ctx)
+                if args.path == "interp":
+                    b2.set_path(qb.PATH_INTERP)
+                b2.render(w.T, group=w.group, out=hv)
+                del b2
 
         e2e_step()
         barrier()
@@ -239,7 +254,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = _peaks()
-        alg_bytes = units * wl.bytes_per_unit
+        alg_bytes = sum(w.V * w.T * w.bytes_per_unit for w in wls)
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -249,8 +264,9 @@ def main():
             "metric": "voice-samples/s @48 kHz", "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "voices": wl.V, "samples": wl.T, "sample_rate": 48000, "group": wl.group,
-                       "layout": "voice-major [V/G][T] f32", "kernel": bank.kernel(), "note": wl.note,
+            "config": {"workload": wl.name if len(wls) == 1 else args.workload + ":" + "+".join(w.name for w in wls),
+                       "voices": sum(w.V for w in wls), "samples": wl.T, "sample_rate": 48000, "group": wl.group,
+                       "layout": "voice-major [V/G][T] f32", "kernel": "+".join(sorted({b.kernel() for b in banks})), "note": wl.note,
                        "l2": f"each step writes {out_bytes / 1e9:.1f} GB of output (>> 126 MB L2), state re-initialised per step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": bank.kernel(), "kernel_ms": kern_ms,
@@ -262,7 +278,7 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            line["cpu_baseline"] = cpu_baseline(wls[0] if len(wls) == 1 else wls[-1])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -19,6 +19,9 @@ def shard_workload(make, world, rank, strong=False, **kw):
     """weak scaling: every rank renders a full-size bank over its own voice ids [rank*V, (rank+1)*V);
     strong scaling: the global bank of V voices is split across ranks."""
     full = make(**kw)
+    if isinstance(full, list):          # multi-bank workload (one bank per voice archetype)
+        total = sum(w.V for w in full)
+        return make(v0=rank * total, **kw) if not strong else make(V=total // world, v0=rank * (total // world), **kw)
     if full.V == 1:
         return full
     if not strong:

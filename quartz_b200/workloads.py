@@ -134,4 +134,52 @@ def c4_spectral(V=1024, T=1440000, N=2048, J=4, thr=16.0, v0=0):
                     f"{J} x [rfft({N}) -> gate -> ifft({N})], hop {N // J}")
 
 
-WORKLOADS = {"c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth, "c4": c4_spectral}
+MINOR = [0.0, 2.0, 3.0, 5.0, 7.0, 8.0, 10.0, 12.0]
+
+
+def c5_mixed(V=1048576, T=96000, G=32, v0=0):
+    """1M-voice mixed graph (configs[4]): four voice archetypes, V/4 voices each, group-mixed G=32, T = 2 s.
+    Returns a LIST of workloads (one bank per archetype — a bank shares one tape)."""
+    n = V // 4
+    out = []
+    # A: pitch-quantised ramp oscillator (in-tree nodes only: ramp, quantize, semitone_ratio)
+    va = np.arange(v0, v0 + n)
+    rate = (0.5 + uniform01(va, 11) * 7.5).astype(np.float32)
+    base = _loguniform(uniform01(va, 12), 55.0, 440.0).astype(np.float32)
+
+    def a_expr(r, b):
+        pitch = _pipe(f"dc({r!r})", "ramp()", "mul(24)", {"op": "quantize()", "arr": MINOR}, "semitone_ratio()", f"mul({b!r})")
+        return _sr(_pipe(pitch, "ramp()", "mul(TAU)", "sin()"))
+    out.append(Workload("c5a_quantised_osc", a_expr(2.0, 110.0), np.stack([rate, np.full(n, 24, np.float32), np.full(n, 12, np.float32),
+                        base, np.full(n, 6.2831855, np.float32)], axis=1), salts_for(va), T, G,
+                        lambda v: a_expr(float(rate[v]), float(base[v])), 4.0 / G, "fp32", "ramp osc + quantize + semitone_ratio"))
+    # B: noise into a shift register clocked by ramp() >> <(0.5) >> rise(), 8 taps averaged
+    vb = np.arange(v0 + n, v0 + 2 * n)
+    clk = _loguniform(uniform01(vb, 13), 20.0, 2000.0).astype(np.float32)
+
+    def b_expr(c):
+        return _sr(_pipe({"op": "|", "n": 0.0, "inputs": [_L("white()"), _pipe(f"dc({c!r})", "ramp()", "<(0.5)", "rise()")]},
+                         "shift_reg()", "join(8)"))
+    out.append(Workload("c5b_shift_reg", b_expr(100.0), np.stack([clk, np.full(n, 0.5, np.float32)], axis=1), salts_for(vb), T, G,
+                        lambda v: b_expr(float(clk[v])), 4.0 / G, "fp32", "white -> shift_reg clocked by a ramp edge detector"))
+    # C: one-pole feedback  y = g (x + y[n-1])
+    vc = np.arange(v0 + 2 * n, v0 + 3 * n)
+    g = (0.5 + uniform01(vc, 14) * 0.49).astype(np.float32)
+
+    def c_expr(gg):
+        return _sr(_pipe("white()", {"op": "feedback()", "net": _L(f"mul({gg!r})"), "delay": None}))
+    out.append(Workload("c5c_feedback", c_expr(0.9), np.stack([np.zeros(n, np.float32), g], axis=1), salts_for(vc), T, G,
+                        lambda v: c_expr(float(g[v])), 8.0 + 4.0 / G, "hbm", "1-sample feedback line in HBM: 8 B state traffic per voice-sample"))
+    # D: delay(1024 samples) + lowpole
+    vd = np.arange(v0 + 3 * n, v0 + 4 * n)
+    hz = _loguniform(uniform01(vd, 15), 100.0, 8000.0).astype(np.float32)
+    dt = float(np.float32(1024.0 / FS))
+
+    def d_expr(h):
+        return _sr(_pipe("white()", f"delay({dt!r})", f"lowpole({h!r})"))
+    out.append(Workload("c5d_delay_lowpole", d_expr(1000.0), np.stack([np.full(n, dt, np.float32), hz], axis=1), salts_for(vd), T, G,
+                        lambda v: d_expr(float(hz[v])), 8.0 + 4.0 / G, "hbm", "1024-sample delay ring in HBM: 8 B state traffic per voice-sample"))
+    return out
+
+
+WORKLOADS = {"c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth, "c4": c4_spectral, "c5": c5_mixed}
