@@ -241,7 +241,10 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
+            ts = time.perf_counter()
             e2e_step()
+            if os.environ.get("QG_BENCH_DEBUG"):
+                print(f"e2e step {time.perf_counter() - ts:.4f} s", file=sys.stderr)
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
         if world > 1:

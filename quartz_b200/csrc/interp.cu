@@ -167,7 +167,7 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
     case OP_ROUND: X(I.out) = roundf(X(I.in[0])); break;
     case OP_SQRT: X(I.out) = sqrtf(X(I.in[0])); break;
     case OP_EXP: X(I.out) = expf(X(I.in[0])); break;
-    case OP_EXP2: X(I.out) = exp2f(X(I.in[0])); break;
+    case OP_EXP2: X(I.out) = d_exp2_cr(X(I.in[0])); break;
     case OP_EXP10: X(I.out) = d_exp10(X(I.in[0])); break;
     case OP_LN_1P_FN: X(I.out) = log1pf(X(I.in[0])); break;
     case OP_EXP_M1_FN: X(I.out) = expm1f(X(I.in[0])); break;
@@ -203,7 +203,7 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
     case OP_UPARC: { float x = X(I.in[0]); X(I.out) = 1.0f - sqrtf(fmaxf(0.0f, 1.0f - x * x)); break; }
     case OP_DOWNARC: { float x = X(I.in[0]); X(I.out) = sqrtf(fmaxf(0.0f, (2.0f - x) * x)); break; }
     case OP_SINE_EASE: X(I.out) = (1.0f - cosf(X(I.in[0]) * QG_PI)) * 0.5f; break;
-    case OP_SEMITONE_RATIO: X(I.out) = exp2f(X(I.in[0]) / 12.0f); break;
+    case OP_SEMITONE_RATIO: X(I.out) = d_exp2_cr(X(I.in[0]) / 12.0f); break;
     case OP_RND1: X(I.out) = d_rnd1(d_as_usize(X(I.in[0]))); break;
     case OP_RND2: X(I.out) = d_rnd2(d_as_usize(X(I.in[0]))); break;
     case OP_DEG: X(I.out) = X(I.in[0]) * 57.2957795130823208767981548141051703f; break;
