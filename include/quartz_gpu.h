@@ -99,6 +99,11 @@ int qg_bank_render_device(qg_bank* bank, long n_samples, int layout, int group, 
 int qg_bank_render(qg_bank* bank, long n_samples, int layout, int group, float* h_out);
 /* Block path with inputs: h_in voice-major [V][inputs][n] or frame-major [n][V][inputs] (same layout as the output). */
 int qg_bank_process(qg_bank* bank, long n_samples, int layout, const float* h_in, float* h_out);
+/* var() (src/process.rs:1382-1385): overwrite one op-string parameter for every voice; takes effect on the next render. */
+int qg_bank_set_raw(qg_bank* bank, int raw_index, float value);
+/* Stream path (src/audio.rs:85-118) for a one-voice bank: n frames, non-normal -> 0, clamp to [-1,1], interleaved L R;
+ * mono graphs get a silent right channel, other arities play silence (src/process.rs:1896-1905). */
+int qg_bank_render_stereo(qg_bank* bank, long n_frames, float* h_frames);
 /* Sum the rows of a device buffer [rows][n] into d_out[n] (rows added in index order), scaled. */
 int qg_mix_rows_device(qg_ctx* ctx, const float* d_rows, long rows, long n, float scale, float* d_out);
 

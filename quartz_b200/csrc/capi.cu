@@ -44,6 +44,7 @@ struct qg_bank {
   size_t in_bytes = 0;
   float* d_fused_scratch = nullptr;
   size_t fused_scratch_bytes = 0;
+  std::vector<float> raw;      // host copy of the per-voice raw parameters [V][R] (empty: every voice = template)
   FusedPlan fused;
   TvPlan tv;
   int ring_mode = 0;   // 0: rings laid out [pos][voice] (lane kernels); 1: [voice][pos] (time-vector kernel)
@@ -262,6 +263,7 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   CU(cudaMalloc((void**)&b->d_state_init, std::max<size_t>(1, (size_t)NS * b->Vp) * sizeof(float)));
   CU(cudaMalloc((void**)&b->d_rings, std::max<size_t>(1, (size_t)t.h.ring_floats * b->Vp) * sizeof(float)));
   // ---- parameters: derive per voice on the host (same libm as the reference would use), or broadcast the template
+  if (raw_matrix && R > 0) b->raw.assign(raw_matrix, raw_matrix + (size_t)b->V * R);
   if (raw_matrix && R > 0 && P > 0) {
     for (int r = 0; r < R; r++) {
       if (!t.raw_structural[r]) continue;
@@ -373,6 +375,44 @@ long qg_bank_out_rows(const qg_bank* b, int group) {
   if (!b) return 0;
   if (group < 1) group = 1;
   return (b->V / group) * (long)b->tape.h.n_outputs;
+}
+
+// var() semantics (process.rs:1382-1385): the control plane rewrites one op-string parameter while the graph runs.
+// The new value applies to every voice from the next render call on; state is untouched.
+int qg_bank_set_raw(qg_bank* b, int raw_index, float value) {
+  if (!b) return fail(QG_ERR_ARG, "null bank");
+  Tape& t = b->tape;
+  const int R = (int)t.h.n_raw, P = (int)t.h.n_params;
+  if (raw_index < 0 || raw_index >= R) return fail(QG_ERR_ARG, "raw parameter index out of range");
+  if (t.raw_structural[raw_index]) return fail(QG_ERR_MISMATCH, "this parameter shapes the tape (delay length / reset period): rebuild the bank");
+  qg_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  t.raw[raw_index] = value;
+  if (P == 0) return QG_OK;
+  if (b->raw.empty()) {
+    std::vector<float> pv(t.params);
+    t.derive(t.raw.data(), pv.data());
+    t.params = pv;
+    float* d_tmpl = nullptr;
+    int rc = upload(&d_tmpl, t.params, c->stream);
+    if (rc) return rc;
+    CU(launch_broadcast_params(b->d_params, d_tmpl, P, b->Vp, c->stream));
+    c->launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tmpl);
+  } else {
+    std::vector<float> host((size_t)P * b->Vp), pv(P);
+    for (long v = 0; v < b->V; v++) b->raw[(size_t)v * R + raw_index] = value;
+    for (long v = 0; v < b->Vp; v++) {
+      long src = v < b->V ? v : b->V - 1;
+      for (int p = 0; p < P; p++) pv[p] = t.params[p];
+      t.derive(b->raw.data() + (size_t)src * R, pv.data());
+      for (int p = 0; p < P; p++) host[(size_t)p * b->Vp + v] = pv[p];
+    }
+    CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return QG_OK;
 }
 
 static int check_group(const qg_bank* b, int layout, int group) {
@@ -520,6 +560,29 @@ int qg_bank_process(qg_bank* b, long T, int layout, const float* h_in, float* h_
   if (rc) return rc;
   if (ob) CU(cudaMemcpyAsync(h_out, b->d_scratch, ob, cudaMemcpyDeviceToHost, b->ctx->stream));
   CU(cudaStreamSynchronize(b->ctx->stream));
+  return QG_OK;
+}
+
+// Stream path: n sanitised, clamped, interleaved stereo frames of a one-voice bank (src/audio.rs:85-118)
+int qg_bank_render_stereo(qg_bank* b, long n, float* h_frames) {
+  if (!b || !h_frames) return fail(QG_ERR_ARG, "qg_bank_render_stereo: bad arguments");
+  if (b->V != 1 || b->tape.h.n_inputs != 0) return fail(QG_ERR_ARITY, "stream path needs one 0-input graph (process.rs:1896)");
+  if (n <= 0) return QG_OK;
+  qg_ctx* c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  const int no = (int)b->tape.h.n_outputs;
+  const size_t sb = (size_t)std::max(no, 1) * n * sizeof(float), fb = (size_t)2 * n * sizeof(float);
+  int rc = ensure(&b->d_scratch, &b->scratch_bytes, sb + fb);
+  if (rc) return rc;
+  float* d_frames = b->d_scratch + (size_t)std::max(no, 1) * n;
+  if (no == 1 || no == 2) {
+    rc = render_impl(b, n, QG_LAYOUT_VOICE_MAJOR, 1, nullptr, b->d_scratch);
+    if (rc) return rc;
+  }
+  CU(launch_stereo_frames(b->d_scratch, (no == 1 || no == 2) ? no : 0, n, d_frames, c->stream));
+  c->launches++;
+  CU(cudaMemcpyAsync(h_frames, d_frames, fb, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return QG_OK;
 }
 

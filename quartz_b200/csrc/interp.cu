@@ -672,6 +672,20 @@ __global__ void k_broadcast_params(float* params, const float* tmpl, int P, int 
   if (i < (size_t)P * Vp) params[i] = tmpl[i / Vp];
 }
 
+// Stream path (src/audio.rs:85-118): frames pulled by the device callback are sanitised (non-normal -> 0), clamped
+// to [-1, 1] and interleaved L R.  src = voice-major rows [n_ch][n] of ONE graph; mono graphs get a silent right channel
+// (process.rs:1897 `net | dc(0.)`), any other arity plays silence (process.rs:1901).
+__global__ void k_stereo_frames(const float* __restrict__ src, int n_ch, long n, float* __restrict__ frames) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  float l = 0.0f, r = 0.0f;
+  if (n_ch == 1) l = src[t];
+  else if (n_ch == 2) { l = src[t]; r = src[n + t]; }
+  l = d_is_normal(l) ? d_clamp(l, -1.0f, 1.0f) : 0.0f;
+  r = d_is_normal(r) ? d_clamp(r, -1.0f, 1.0f) : 0.0f;
+  reinterpret_cast<float2*>(frames)[t] = make_float2(l, r);
+}
+
 // full mix of the rows of a [R][T] buffer into one [T] row: rows are added in index order (per output sample)
 __global__ void k_mix_rows(const float* rows, int R, long T, float scale, float* out) {
   long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -949,6 +963,10 @@ cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int
   size_t n = (size_t)P * Vp;
   if (n == 0) return cudaSuccess;
   k_broadcast_params<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(params, tmpl, P, Vp);
+  return cudaGetLastError();
+}
+cudaError_t launch_stereo_frames(const float* src, int n_ch, long n, float* frames, cudaStream_t stream) {
+  k_stereo_frames<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, n_ch, n, frames);
   return cudaGetLastError();
 }
 cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream) {

@@ -57,6 +57,7 @@ cudaError_t launch_interp(const InterpArgs& a, bool divergent, cudaStream_t stre
 cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
                               const uint64_t* salts, cudaStream_t stream);
 cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream);
+cudaError_t launch_stereo_frames(const float* src, int n_ch, long n, float* frames, cudaStream_t stream);
 cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream);
 
 }  // namespace qg

@@ -292,6 +292,16 @@ class Bank:
         check(lib().qg_bank_render(self.h, int(n), layout, group, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def set_raw(self, raw_index, value):
+        """var(): rewrite one op-string parameter for every voice (process.rs:1382-1385)"""
+        check(lib().qg_bank_set_raw(self.h, int(raw_index), float(value)))
+
+    def render_stereo(self, n):
+        """stream path (audio.rs:85-118): [n, 2] sanitised, clamped, interleaved frames of a one-voice bank"""
+        out = np.zeros((n, 2), dtype=np.float32)
+        check(lib().qg_bank_render_stereo(self.h, int(n), out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def render_device(self, n, d_out, layout=LAYOUT_VOICE_MAJOR, group=1):
         check(lib().qg_bank_render_device(self.h, int(n), layout, group, C.c_void_p(d_out)))
 

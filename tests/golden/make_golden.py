@@ -135,3 +135,20 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def scene_graphs():
+    """out() graphs of the example scenes that only use ops with a GPU lowering -> tests/golden/scenes/out_graphs.json
+    (produced by quartz_b200/scene.py, the importer the product ships)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from quartz_b200.scene import Scene
+    res = {}
+    for name in ["ar", "circular-scope", "pd", "scope", "shift_reg", "spectral-delay", "spectral-gate"]:
+        sc = Scene.load(os.path.join(REF, name))
+        res[name] = sc.expr((sc.find("out()") + sc.find("dac()"))[0])
+    os.makedirs(os.path.join(os.path.dirname(OUT), "scenes"), exist_ok=True)
+    json.dump(res, open(os.path.join(os.path.dirname(OUT), "scenes", "out_graphs.json"), "w"))
+
+
+if __name__ == "__main__":
+    scene_graphs()
