@@ -7,9 +7,10 @@
 //          counter at base + j*K) and parks the K zero-state outputs in shared memory (conflict-free float4 rows);
 //       2. the per-lane end states are combined with a 5-step warp-shuffle scan of the affine maps
 //          s -> A^K s + c_j  (Kogge-Stone, matrices A^K, A^2K, ... A^16K precomputed per voice in f64);
-//       3. every lane adds the homogeneous response C A^i s_start to its K outputs;
+//       3. every lane adds the homogeneous response (C A^i) s_start to its K outputs (rows C A^i precomputed per voice);
 //       4. the 32*K outputs (one contiguous 2 KB run of the voice's row) are staged in shared memory and written
-//          with ONE bulk async copy (cp.async.bulk.global.shared::cta -> UBLKCP), double-buffered.
+//          with ONE bulk async copy (cp.async.bulk.global.shared::cta -> UBLKCP);
+//       the zero-state run of block b+1 is software-pipelined into the shuffle chain of block b.
 //     Small banks use S time segments per voice: a state-only pre-pass computes each segment's zero-state end
 //     state, the segment start states are chained on the fly (block-level scan), then every segment renders.
 //     Arithmetic uses explicit FMAs and a re-associated recurrence: parity is the f32 audio tolerance
@@ -17,6 +18,8 @@
 //     persisted counter are bit-exact.
 #include "fused.h"
 
+#include <cuda.h>
+#include <cstring>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,7 +39,14 @@ __device__ __forceinline__ void bulk_store_block(float* gdst, const float* ssrc)
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "n"(B * 4) : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
+// TMA tensor store of one 16-row x 128-byte box (SWIZZLE_128B layout in shared memory) -> SASS UTMASTG
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, const float* ssrc, int row0) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap), "r"(0), "r"(row0), "r"(s)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
@@ -55,20 +65,40 @@ __device__ __forceinline__ float svf_fma(float x, float& ic1, float& ic2, const 
   return __fmaf_rn(c.m2, v2, __fmaf_rn(c.m1, v1, c.m0 * x));
 }
 
+// same tick fed with the un-scaled noise integer hf (x = hf * 2^-31, an exact power-of-two scaling): the scaling rides on
+// the FMAs that consume x, results are bit-identical to svf_fma(hf * 2^-31)
+template <bool LP>
+__device__ __forceinline__ float svf_fma_noise(float hf, float& ic1, float& ic2, const SvfC& c, float m0s) {
+  const float k = 1.0f / 2147483648.0f;
+  float v3 = __fmaf_rn(hf, k, -ic2);
+  float v1 = __fmaf_rn(c.a2, v3, c.a1 * ic1);
+  float v2 = __fmaf_rn(c.a3, v3, __fmaf_rn(c.a2, ic1, ic2));
+  ic1 = __fmaf_rn(2.0f, v1, -ic1);
+  ic2 = __fmaf_rn(2.0f, v2, -ic2);
+  if (LP) return v2;
+  return __fmaf_rn(c.m2, v2, __fmaf_rn(c.m1, v1, m0s * hf));
+}
+__device__ __forceinline__ float noise_int(uint32_t counter) { return (float)(int32_t)d_hash32x(counter); }
+
 // per-warp shared memory: zero-state outputs [K/4][32 lanes] float4 (conflict-free), two contiguous output blocks for
 // the bulk copies, and the scan matrices A^(K*2^i)
-struct __align__(128) WarpSmem {
-  float out[2][B];
-  float4 zs[K / 4][32];
-  float mp[5][4];
+struct __align__(1024) WarpSmem {
+  float out[B];          // block handed to the bulk copy: linear, or 16 rows x 128 B in the TMA 128-byte swizzle
+  float4 zs[2][K / 4][32];   // zero-state outputs of the current / next block (software pipeline)
+  float4 mp[5];          // A^(K*2^i) as (a, b, c, d)
+  float4 rc[K / 2];      // homogeneous response rows C*A^i: (r1_i, r2_i, r1_{i+1}, r2_{i+1})
 };
 
 // MODE 0: write samples; MODE 1: state-only pre-pass (zero start state, no output) for segment chaining
-// BULK: rows are 16-byte aligned (decided on the host) -> bulk async stores; otherwise plain scalar stores
-template <int MODE, bool LP, bool BULK>
+// STORE (decided on the host from the output alignment): 0 plain scalar stores; 1 linear bulk async copy of the 2 KB block
+// (rows 16-byte aligned); 2 TMA tensor store from a 128-byte-swizzled tile (T % 32 == 0): with 64-byte lane strides the
+// linear layout makes every STS.128 a 4-way bank conflict and the shared-memory pipe becomes the limiter — the swizzled
+// tile is conflict-free.
+template <int MODE, bool LP, int STORE>
 __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restrict__ params, float* __restrict__ state, int Vp,
                                                            int V, long T, int S, long seg_len, int p_svf, int s_noise,
-                                                           int s_svf, float* __restrict__ out, float* __restrict__ seg_state) {
+                                                           int s_svf, float* __restrict__ out, float* __restrict__ seg_state,
+                                                           const __grid_constant__ CUtensorMap tmap) {
   __shared__ WarpSmem sm[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpSmem& W = sm[warp];
@@ -82,18 +112,23 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
   // state-space form of the tick:  s' = A s + B x ; y = C s + D x
   const double a1 = c.a1, a2 = c.a2, a3 = c.a3;
   const double A11 = 2 * a1 - 1, A12 = -2 * a2, A21 = 2 * a2, A22 = 1 - 2 * a3;
-  const float fA11 = (float)A11, fA12 = (float)A12, fA21 = (float)A21, fA22 = (float)A22;
-  // y_h = m1*v1_h + m2*v2_h with v1_h = a1 s1 - a2 s2, v2_h = a2 s1 + (1 - a3) s2
-  const float C1 = (float)((double)c.m1 * a1 + (double)c.m2 * a2), C2 = (float)(-(double)c.m1 * a2 + (double)c.m2 * (1 - a3));
-  // powers A^(K*2^i), i = 0..4, in f64 then rounded; kept in shared memory (read as broadcasts once per block)
+  // y_h = m1*v1_h + m2*v2_h with v1_h = a1 s1 - a2 s2, v2_h = a2 s1 + (1 - a3) s2   (row vector C below)
+  const float m0s = c.m0 * (1.0f / 2147483648.0f);
+  // per-voice constants in f64, rounded once, kept in shared memory (read as broadcasts):
+  //   rc[i] = C * A^i  (the homogeneous output response i samples after a block start state), i < K
+  //   mp[i] = A^(K*2^i), i = 0..4  (scan matrices)
   if (lane == 0) {
+    const double c1 = (double)c.m1 * a1 + (double)c.m2 * a2, c2 = -(double)c.m1 * a2 + (double)c.m2 * (1 - a3);
     double m11 = 1, m12 = 0, m21 = 0, m22 = 1;
+    float* rcf = reinterpret_cast<float*>(W.rc);
     for (int i = 0; i < K; i++) {
+      rcf[2 * i] = (float)(c1 * m11 + c2 * m21);
+      rcf[2 * i + 1] = (float)(c1 * m12 + c2 * m22);
       double n11 = A11 * m11 + A12 * m21, n12 = A11 * m12 + A12 * m22, n21 = A21 * m11 + A22 * m21, n22 = A21 * m12 + A22 * m22;
       m11 = n11; m12 = n12; m21 = n21; m22 = n22;
     }
     for (int i = 0; i < 5; i++) {
-      W.mp[i][0] = (float)m11; W.mp[i][1] = (float)m12; W.mp[i][2] = (float)m21; W.mp[i][3] = (float)m22;
+      W.mp[i] = make_float4((float)m11, (float)m12, (float)m21, (float)m22);
       double n11 = m11 * m11 + m12 * m21, n12 = m11 * m12 + m12 * m22, n21 = m21 * m11 + m22 * m21, n22 = m21 * m12 + m22 * m22;
       m11 = n11; m12 = n12; m21 = n21; m22 = n22;
     }
@@ -108,70 +143,91 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
     else { S1 = seg_state[((size_t)v * (S + 1) + seg) * 2]; S2 = seg_state[((size_t)v * (S + 1) + seg) * 2 + 1]; }
   } else { S1 = state[(size_t)s_svf * Vp + v]; S2 = state[(size_t)(s_svf + 1) * Vp + v]; }
   float* orow = MODE == 0 ? out + (size_t)v * T : nullptr;
-  constexpr bool can_bulk = MODE == 0 && BULK;
+  constexpr bool can_bulk = MODE == 0 && STORE >= 1;
+  constexpr bool swz = MODE == 0 && STORE == 2;
 
   long t = t_begin;
-  int buf = 0;
-  for (; t + B <= t_end; t += B) {
-    // ---- 1. zero-state run of this lane's K samples; outputs parked in shared memory
+  // zero-state run of 4 of this lane's samples of the block starting at tb (outputs parked in shared memory)
+  auto zero_state4 = [&](long tb, int i4, int zb, float& z1, float& z2) {
+    const uint32_t cb = counter0 + (uint32_t)tb + (uint32_t)(lane * K) + (uint32_t)(4 * i4);
+    float4 y;
+    y.x = svf_fma_noise<LP>(noise_int(cb + 1u), z1, z2, c, m0s);
+    y.y = svf_fma_noise<LP>(noise_int(cb + 2u), z1, z2, c, m0s);
+    y.z = svf_fma_noise<LP>(noise_int(cb + 3u), z1, z2, c, m0s);
+    y.w = svf_fma_noise<LP>(noise_int(cb + 4u), z1, z2, c, m0s);
+    if (MODE == 0) W.zs[zb][i4][lane] = y;
+  };
+  // one Kogge-Stone step of the affine-map scan (branch-free): e <- A^(K d) e(lane - d) + e
+  auto scan_step = [&](int i, float& e1, float& e2) {
+    const int d = 1 << i;
+    const float4 m = W.mp[i];
+    float r1 = __shfl_up_sync(0xffffffffu, e1, d), r2 = __shfl_up_sync(0xffffffffu, e2, d);
+    r1 = lane >= d ? r1 : 0.0f;
+    r2 = lane >= d ? r2 : 0.0f;
+    e1 = __fmaf_rn(m.x, r1, __fmaf_rn(m.y, r2, e1));
+    e2 = __fmaf_rn(m.z, r1, __fmaf_rn(m.w, r2, e2));
+  };
+  if (t + B <= t_end) {
+    // software pipeline: while block b is being scanned (a chain of 5 dependent shuffles) and corrected, the
+    // zero-state run of block b+1 — independent work — is interleaved between the scan steps
+    int zb = 0;
     float z1 = 0.0f, z2 = 0.0f;
-    const uint32_t cb = counter0 + (uint32_t)t + (uint32_t)(lane * K);
 #pragma unroll
-    for (int i4 = 0; i4 < K / 4; i4++) {
-      float4 y;
-      y.x = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 1u), z1, z2, c);
-      y.y = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 2u), z1, z2, c);
-      y.z = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 3u), z1, z2, c);
-      y.w = svf_fma<LP>(d_noise(cb + (uint32_t)(4 * i4) + 4u), z1, z2, c);
-      if (MODE == 0) W.zs[i4][lane] = y;
-    }
-    // ---- 2. warp scan of the affine maps s -> A^K s + c_j: e = true end state of lane j
-    float e1 = z1, e2 = z2;
-    if (lane == 0) {
-      e1 = __fmaf_rn(W.mp[0][0], S1, __fmaf_rn(W.mp[0][1], S2, e1));
-      e2 = __fmaf_rn(W.mp[0][2], S1, __fmaf_rn(W.mp[0][3], S2, e2));
-    }
+    for (int i4 = 0; i4 < K / 4; i4++) zero_state4(t, i4, zb, z1, z2);
+    for (; t + B <= t_end; t += B, zb ^= 1) {
+      const bool has_next = t + 2 * B <= t_end;
+      float e1 = z1, e2 = z2;          // zero-state end state of this lane's chunk
+      float n1 = 0.0f, n2 = 0.0f;      // running zero-state of the next block
+      {
+        const float4 m = W.mp[0];
+        const float s1 = lane == 0 ? S1 : 0.0f, s2 = lane == 0 ? S2 : 0.0f;   // only lane 0 inherits the block start state
+        e1 = __fmaf_rn(m.x, s1, __fmaf_rn(m.y, s2, e1));
+        e2 = __fmaf_rn(m.z, s1, __fmaf_rn(m.w, s2, e2));
+      }
+      static_assert(K / 4 == 4, "the pipeline interleaves 4 scan steps with 4 groups of 4 samples");
+      if (has_next) {
 #pragma unroll
-    for (int i = 0; i < 5; i++) {
-      const int d = 1 << i;
-      float r1 = __shfl_up_sync(0xffffffffu, e1, d), r2 = __shfl_up_sync(0xffffffffu, e2, d);
-      if (lane >= d) {
-        e1 = __fmaf_rn(W.mp[i][0], r1, __fmaf_rn(W.mp[i][1], r2, e1));
-        e2 = __fmaf_rn(W.mp[i][2], r1, __fmaf_rn(W.mp[i][3], r2, e2));
-      }
-    }
-    float h1 = __shfl_up_sync(0xffffffffu, e1, 1), h2 = __shfl_up_sync(0xffffffffu, e2, 1);
-    if (lane == 0) { h1 = S1; h2 = S2; }
-    S1 = __shfl_sync(0xffffffffu, e1, 31);
-    S2 = __shfl_sync(0xffffffffu, e2, 31);
-    if (MODE == 0) {
-      // ---- 3. homogeneous correction, written to the contiguous output block
-      if (can_bulk) {
-        if (lane == 0) bulk_wait_read_1();          // the copy that last read this buffer has drained
-        __syncwarp();
-      }
-      float4* ob = reinterpret_cast<float4*>(&W.out[buf][lane * K]);
+        for (int i = 0; i < 4; i++) { scan_step(i, e1, e2); zero_state4(t + B, i, zb ^ 1, n1, n2); }
+      } else {
 #pragma unroll
-      for (int i4 = 0; i4 < K / 4; i4++) {
-        float4 y = W.zs[i4][lane];
-        float n1, n2;
-        y.x = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.x));
-        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
-        y.y = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.y));
-        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
-        y.z = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.z));
-        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
-        y.w = __fmaf_rn(C1, h1, __fmaf_rn(C2, h2, y.w));
-        n1 = __fmaf_rn(fA11, h1, fA12 * h2); n2 = __fmaf_rn(fA21, h1, fA22 * h2); h1 = n1; h2 = n2;
-        if (can_bulk) ob[i4] = y;
-        else { float* g = orow + t + lane * K + 4 * i4; g[0] = y.x; g[1] = y.y; g[2] = y.z; g[3] = y.w; }
+        for (int i = 0; i < 4; i++) scan_step(i, e1, e2);
       }
-      // ---- 4. one bulk async copy per block (UBLKCP), double-buffered
-      if (can_bulk) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) bulk_store_block(orow + t, &W.out[buf][0]);
-        buf ^= 1;
+      scan_step(4, e1, e2);
+      float h1 = __shfl_up_sync(0xffffffffu, e1, 1), h2 = __shfl_up_sync(0xffffffffu, e2, 1);
+      if (lane == 0) { h1 = S1; h2 = S2; }
+      S1 = __shfl_sync(0xffffffffu, e1, 31);
+      S2 = __shfl_sync(0xffffffffu, e2, 31);
+      z1 = n1; z2 = n2;
+      if (MODE == 0) {
+        // ---- homogeneous correction, written to the contiguous output block
+        if (can_bulk) {
+          if (lane == 0) bulk_wait_read_0();          // the previous block's copy has finished reading W.out
+          __syncwarp();
+        }
+        float4* ob = reinterpret_cast<float4*>(&W.out[lane * K]);
+        // swizzled tile: lane j owns half of row j/2; 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+        const int srow = lane >> 1, sch = (lane & 1) * 4;
+#pragma unroll
+        for (int i4 = 0; i4 < K / 4; i4++) {
+          float4 y = W.zs[zb][i4][lane];
+          const float4 ra = W.rc[2 * i4], rb = W.rc[2 * i4 + 1];
+          y.x = __fmaf_rn(ra.x, h1, __fmaf_rn(ra.y, h2, y.x));
+          y.y = __fmaf_rn(ra.z, h1, __fmaf_rn(ra.w, h2, y.y));
+          y.z = __fmaf_rn(rb.x, h1, __fmaf_rn(rb.y, h2, y.z));
+          y.w = __fmaf_rn(rb.z, h1, __fmaf_rn(rb.w, h2, y.w));
+          if (swz) reinterpret_cast<float4*>(W.out)[srow * 8 + ((sch + i4) ^ (srow & 7))] = y;
+          else if (can_bulk) ob[i4] = y;
+          else { float* g = orow + t + lane * K + 4 * i4; g[0] = y.x; g[1] = y.y; g[2] = y.z; g[3] = y.w; }
+        }
+        // ---- one bulk async copy per block (UBLKCP)
+        if (can_bulk) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (swz) tma_store_box(&tmap, &W.out[0], (int)(((long)v * T + t) >> 5));
+            else bulk_store_block(orow + t, &W.out[0]);
+          }
+        }
       }
     }
   }
@@ -384,6 +440,30 @@ const char* fused_name(int id) {
   return id == FUSED_NOISE_SVF ? "k_noise_svf_scan" : id == FUSED_SINE_SVF_ENV ? "k_polysynth" : "none";
 }
 
+// 2-D view of a voice-major f32 buffer as rows of 32 samples (128 B); box = 16 rows, shared-memory layout SWIZZLE_128B.
+// cuTensorMapEncodeTiled is fetched through the runtime's driver entry point (no link-time dependency on libcuda).
+static bool encode_rows32(CUtensorMap* tm, float* base, size_t n_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+  }
+  if (!fn) return false;
+  cuuint64_t dims[2] = {32, (cuuint64_t)n_rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {32, 16};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t stream, int* launches) {
   if (pl.id == FUSED_NOISE_SVF) {
     if (a.group != 1) return cudaErrorNotSupported;
@@ -411,15 +491,23 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
         *a.scratch_bytes = need;
       }
       seg = *a.scratch;
-      if (pl.p[1]) k_noise_svf_scan<1, true, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
-      else k_noise_svf_scan<1, false, false><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg);
+      CUtensorMap dummy;
+      memset(&dummy, 0, sizeof dummy);
+      if (pl.p[1]) k_noise_svf_scan<1, true, 0><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
+      else k_noise_svf_scan<1, false, 0><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
       k_chain_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], seg);
       if (launches) *launches += 2;
     }
-    const bool bulk = ((((size_t)(uintptr_t)a.out) & 15) == 0) && ((a.T & 3) == 0);
-#define QG_LAUNCH_K2(LPV, BV) k_noise_svf_scan<0, LPV, BV><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg)
-    if (pl.p[1]) { if (bulk) QG_LAUNCH_K2(true, true); else QG_LAUNCH_K2(true, false); }
-    else { if (bulk) QG_LAUNCH_K2(false, true); else QG_LAUNCH_K2(false, false); }
+    // output path: TMA tensor store needs 32-sample rows on 128-byte boundaries; linear bulk copies need 16-byte rows
+    int store = ((((size_t)(uintptr_t)a.out) & 15) == 0) && ((a.T & 3) == 0) ? 1 : 0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    if (store == 1 && ((((size_t)(uintptr_t)a.out) & 127) == 0) && (a.T % 32) == 0 && ((size_t)a.V * (size_t)a.T / 32) < 0xffffffffull &&
+        encode_rows32(&tmap, a.out, (size_t)a.V * (size_t)a.T / 32))
+      store = 2;
+#define QG_LAUNCH_K2(LPV, SV) k_noise_svf_scan<0, LPV, SV><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg, tmap)
+    if (pl.p[1]) { if (store == 2) QG_LAUNCH_K2(true, 2); else if (store == 1) QG_LAUNCH_K2(true, 1); else QG_LAUNCH_K2(true, 0); }
+    else { if (store == 2) QG_LAUNCH_K2(false, 2); else if (store == 1) QG_LAUNCH_K2(false, 1); else QG_LAUNCH_K2(false, 0); }
 #undef QG_LAUNCH_K2
     if (launches) *launches += 1;
     if (S > 1) {
