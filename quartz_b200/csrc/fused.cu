@@ -342,17 +342,23 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
     v1 = env_ar(t1, e);
     th += 1;
   }
+  // The interpolated envelope lerp(v0, v1, (t - t0) / (t1 - t0)) is advanced incrementally inside a segment
+  // (env += slope per sample, re-anchored at every control point): <= ~120 f32 additions per segment.
   float inv = 1.0f / (t1 - t0);
+  float env = __fmaf_rn(v1 - v0, (et - t0) * inv, v0);
+  float denv = (v1 - v0) * inv * esd;
   float nt1 = 0.0f, nv1 = 0.0f, ninv = 0.0f;
   bool have_next = false;
   float* my_tile = &tile[warp][lane][0];
 
   auto sample = [&](int i) {
-    // ---- sine (FunDSP Sine::tick): output from the phase before the increment
+    // ---- sine (FunDSP Sine::tick): output from the phase before the increment.  The phase recurrence is exact;
+    // sin(2 pi p) uses the SFU (sin.approx, |err| < 2^-20.9 on [-pi, pi]) on the phase folded to [-0.5, 0.5) turns
     const float p = phase;
     phase = p + inc;
     phase -= floorf(phase);
-    const float x = sinf(p * QG_TAU);
+    const float pf = p >= 0.5f ? p - 1.0f : p;
+    const float x = __sinf(pf * QG_TAU);
     // ---- SVF
     const float y = svf_fma<LP>(x, ic1, ic2, c);
     // ---- envelope (lfo): at most one crossing between two look-ahead points, the body only rotates registers
@@ -360,10 +366,12 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
       t0 = t1; v0 = v1; t1 = nt1; v1 = nv1; inv = ninv;
       th += 1;
       have_next = false;
+      env = __fmaf_rn(v1 - v0, (et - t0) * inv, v0);
+      denv = (v1 - v0) * inv * esd;
     }
-    const float u = (et - t0) * inv;
     et += esd;
-    my_tile[i] = y * __fmaf_rn(v1, u, v0 * (1.0f - u));
+    my_tile[i] = y * env;
+    env += denv;
   };
 
   long tile_idx = 0;
