@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
   float env = __fmaf_rn(v1 - v0, (et - t0) * inv, v0);
   float denv = (v1 - v0) * inv * esd;
   float nt1 = 0.0f, nv1 = 0.0f, ninv = 0.0f;
-  bool have_next = false;
+  int have_next = 0;
+  uint32_t ncross = 0;               // control points consumed in this launch (added to the 64-bit hash counter at the end)
   float* my_tile = &tile[warp][lane][0];
 
   auto sample = [&](int i) {
@@ -364,8 +365,8 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
     // ---- envelope (lfo): at most one crossing between two look-ahead points, the body only rotates registers
     if (et >= t1) {
       t0 = t1; v0 = v1; t1 = nt1; v1 = nv1; inv = ninv;
-      th += 1;
-      have_next = false;
+      ncross += 1u;
+      have_next = 0;
       env = __fmaf_rn(v1 - v0, (et - t0) * inv, v0);
       denv = (v1 - v0) * inv * esd;
     }
@@ -377,10 +378,10 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
   long tile_idx = 0;
   for (long tb = 0; tb < T; tb += 32, tile_idx++) {
     if ((tile_idx % look_tiles) == 0 && !have_next) {      // warp-uniform point: look one control point ahead
-      nt1 = t1 + d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
+      nt1 = t1 + d_lerp(0.75f, 1.25f, d_rnd1(th + (uint64_t)ncross)) * 0.002f;
       nv1 = env_ar(nt1, e);
       ninv = 1.0f / (nt1 - t1);
-      have_next = true;
+      have_next = 1;
     }
     const int n = (T - tb) < 32 ? (int)(T - tb) : 32;
     if (n == 32) {
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
     }
     __syncwarp();
   }
+  th += (uint64_t)ncross;
   if (v < V) {
     ST(s_ph) = phase; ST(s_svf) = ic1; ST(s_svf + 1) = ic2;
     ST(s_env) = et; ST(s_env + 1) = t0; ST(s_env + 2) = t1; ST(s_env + 3) = v0; ST(s_env + 4) = v1;
