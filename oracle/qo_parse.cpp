@@ -49,6 +49,51 @@ void inverse_fft(const std::vector<Cpx>& in, std::vector<Cpx>& out) {
   out = a;
 }
 
+// ------------------------------------------------------------------ wavetables (FunDSP wavetable.rs) [U]
+static std::vector<float> make_wave(double pitch, int shape) {
+  size_t harmonics = (size_t)std::floor(22050.0 / pitch);
+  size_t target = 4 * harmonics, length = 32;
+  while (length < target && length < 8192) length <<= 1;
+  std::vector<Cpx> a(length, Cpx{0, 0});
+  for (size_t i = 1; i <= harmonics && i < length / 2; i++) {
+    double f = pitch * (double)i, w;
+    bool odd = (i & 1) != 0;
+    switch (shape) {
+      case 0: w = 1.0 / (double)i; break;
+      case 1: w = odd ? 1.0 / (double)i : 0.0; break;
+      case 2: w = odd ? 1.0 / ((double)i * (double)i) : 0.0; break;
+      default: w = 1.0 / ((double)i * (double)i); break;
+    }
+    double fade = (22050.0 - f) / (22050.0 - 20000.0);
+    fade = fade < 0 ? 0 : (fade > 1 ? 1 : fade);
+    w *= ((6.0 * fade - 15.0) * fade + 10.0) * fade * fade * fade;   // smooth5
+    double ph = (shape == 2 && (i & 3) == 3) ? 0.5 : 0.0;
+    // a sine partial of amplitude w: X[i] = -i w/2 e^{i 2 pi ph}, X[N-i] = conj
+    double re = 0.5 * w * std::sin(2.0 * 3.14159265358979323846 * ph), im = -0.5 * w * std::cos(2.0 * 3.14159265358979323846 * ph);
+    a[i] = Cpx{(float)re, (float)im};
+    a[length - i] = Cpx{(float)re, (float)-im};
+  }
+  fft_inplace(a, true);
+  std::vector<float> wave(length);
+  float mx = 0.0f;
+  for (size_t k = 0; k < length; k++) { wave[k] = a[k].re * (float)length; mx = std::fmax(mx, std::fabs(wave[k])); }
+  if (mx > 0.0f) for (float& x : wave) x /= mx;
+  return wave;
+}
+const WaveTableSet& wavetable_set(int shape) {
+  static WaveTableSet sets[4];
+  WaveTableSet& ts = sets[shape & 3];
+  if (ts.table.empty()) {
+    for (int i = 0;; i++) {
+      double pn = 20.0 * std::pow(2.0, (double)(i + 1) / 4.0);
+      ts.limit.push_back((float)pn);
+      ts.table.push_back(make_wave(pn, shape));
+      if (pn >= 20000.0) break;
+    }
+  }
+  return ts;
+}
+
 // ------------------------------------------------------------------ parse_with_constants (functions.rs:47-109)
 static bool parse_f32(const std::string& s, float* out) {
   if (s.empty()) return false;
@@ -213,8 +258,12 @@ NetP str_to_net(const std::string& op_in, int* status) {
     return W(constant(v));
   }
   if (name == "ramp") return W(new Ramp());
-  if (name == "saw" || name == "square" || name == "triangle" || name == "organ" || name == "hammond" ||
-      name == "soft_saw" || name == "pulse" || name == "lorenz" || name == "rossler" || name == "dsf_saw" ||
+  if (name == "saw" || name == "square" || name == "triangle" || name == "soft_saw") {
+    int shape = name == "saw" ? 0 : name == "square" ? 1 : name == "triangle" ? 2 : 3;
+    if (has(1)) return W(pipe(constant({p[0]}), U(new WaveSynth(shape))));
+    return W(new WaveSynth(shape));
+  }
+  if (name == "organ" || name == "hammond" || name == "pulse" || name == "lorenz" || name == "rossler" || name == "dsf_saw" ||
       name == "dsf_square" || name == "mls") { *status = UNSUPPORTED; return nullptr; }
   if (name == "pluck") { if (has(3)) { *status = UNSUPPORTED; return nullptr; } return NetP(new Net(0, 0)); }
 

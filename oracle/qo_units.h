@@ -26,7 +26,7 @@ enum : uint64_t {
   ID_FIR = 5, ID_TICK = 9, ID_DELAY = 13, ID_TAP = 50, ID_TAPLIN = 51, ID_ENVELOPE = 14001, ID_ENVELOPE_IN = 53,
   ID_JOIN = 41, ID_SPLIT = 40, ID_REVERSE = 45, ID_PAN = 49, ID_CLIP = 88, ID_DECLICK = 23, ID_IMPULSE = 81,
   ID_MIXER = 17, ID_PIPE = 2, ID_STACK = 3, ID_BRANCH = 4, ID_BUS = 10, ID_BINOP = 11, ID_THRU = 31, ID_NET = 63,
-  ID_FEEDBACK = 79, ID_WAVE = 65,
+  ID_FEEDBACK = 79, ID_WAVE = 65, ID_WAVESYNTH = 34,
   // in-tree (nodes.rs)
   ID_SELECT = 1213, ID_SEQ = 1729, ID_ARRGET = 1312, ID_SHIFTREG = 1110, ID_QUANTIZER = 1111, ID_KR = 1112,
   ID_RESET = 1113, ID_TRIGRESET = 1114, ID_RESETV = 1115, ID_RAMP = 1116, ID_INPUT = 1117, ID_SWAP = 1118,
@@ -206,6 +206,58 @@ struct Ramp : Unit {
   }
   uint64_t id() const override { return ID_RAMP; }
   QO_CLONE(Ramp)
+};
+
+// Band-limited wavetable oscillators saw / square / triangle / soft_saw (FunDSP wavetable.rs + WaveSynth) [U]:
+// one table per quarter octave from 20 Hz to 20 kHz, each the inverse FFT of the partials below Nyquist (upper
+// partials faded out between 20 kHz and 22.05 kHz), 4x oversampled power-of-two length, peak-normalised, read with
+// Niemitalo's optimal 4x 4-point 4th-order interpolator.  shape: 0 saw (1/i), 1 square (odd 1/i), 2 triangle (odd 1/i^2,
+// alternating sign), 3 soft_saw (1/i^2).
+struct WaveTableSet {
+  std::vector<float> limit;                 // table i serves frequencies below limit[i]
+  std::vector<std::vector<float>> table;
+};
+const WaveTableSet& wavetable_set(int shape);
+static inline float optimal4x44(float a0, float a1, float a2, float a3, float x) {
+  float z = x - 0.5f;
+  float even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
+  float c0 = even1 * 0.46567255120778489f + even2 * 0.03432729708429672f;
+  float c1 = odd1 * 0.53743830753560162f + odd2 * 0.15429462557307461f;
+  float c2 = even1 * -0.25194210134021744f + even2 * 0.25194744935939062f;
+  float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
+  float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
+  return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
+}
+struct WaveSynth : Unit {
+  int shape;
+  float phase = 0, sd = (float)(1.0 / DEFAULT_SR);
+  size_t hint = 0;
+  uint64_t hash = 0, base = 0;
+  explicit WaveSynth(int shape_) : shape(shape_) {}
+  int ins() const override { return 1; }
+  int outs() const override { return 1; }
+  void reset() override { phase = (float)rnd1(hash); hint = 0; }
+  void set_sr(double sr) override { sd = (float)(1.0 / sr); }
+  void set_hash(uint64_t h) override { base = hash = h; reset(); }
+  void salt(uint64_t s) override { hash = s ? atto(base, s) : base; reset(); }
+  void tick(const float* in, float* out) override {
+    const WaveTableSet& ts = wavetable_set(shape);
+    float f = in[0];
+    phase += f * sd;
+    phase -= std::floor(phase);
+    float af = std::fabs(f);
+    while (hint + 1 < ts.table.size() && af >= ts.limit[hint]) hint++;
+    while (hint > 0 && af < ts.limit[hint - 1]) hint--;
+    const std::vector<float>& t = ts.table[hint];
+    float p = (float)t.size() * phase;
+    size_t i1 = (size_t)p, mask = t.size() - 1;
+    float w = p - (float)i1;
+    size_t i0 = (i1 + t.size() - 1) & mask;
+    i1 &= mask;
+    out[0] = optimal4x44(t[i0], t[i1], t[(i1 + 1) & mask], t[(i1 + 2) & mask], w);
+  }
+  uint64_t id() const override { return ID_WAVESYNTH; }
+  QO_CLONE(WaveSynth)
 };
 
 // ------------------------------------------------------------------ filters

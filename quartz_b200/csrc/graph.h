@@ -19,7 +19,7 @@ static const double DEFAULT_SR = 44100.0;
 enum NodeKind : uint16_t {
   NK_CONST, NK_PASS, NK_SINK, NK_SPLIT, NK_REVERSE, NK_JOIN, NK_PAN, NK_ZERO_SRC,
   NK_UNARY, NK_BIN, NK_TERN, NK_SPLINE, NK_NARY_CONST, NK_MAP22, NK_CLIP, NK_WRAP2, NK_WRAP1, NK_MIRROR, NK_ROTATE,
-  NK_SINE, NK_NOISE, NK_IMPULSE, NK_RAMP, NK_WAVE,
+  NK_SINE, NK_NOISE, NK_IMPULSE, NK_RAMP, NK_WAVE, NK_WAVETABLE,
   NK_SVF, NK_BIQUAD, NK_ONEPOLE, NK_PINKPASS, NK_FIR,
   NK_TICK, NK_DELAY, NK_TAP, NK_SAMP_DELAY, NK_ENVELOPE, NK_DECLICK,
   NK_SHIFT_REG, NK_SNH, NK_QUANTIZE, NK_ARR_GET,
@@ -33,7 +33,7 @@ enum : uint64_t {
   ID_BIQUAD = 15, ID_LOWPOLE = 12, ID_HIGHPOLE = 14, ID_DCBLOCK = 22, ID_ALLPOLE = 46, ID_PINKPASS = 42,
   ID_FIR = 5, ID_TICK = 9, ID_DELAY = 13, ID_TAP = 50, ID_TAPLIN = 51, ID_ENVELOPE = 14001, ID_ENVELOPE_IN = 53,
   ID_JOIN = 41, ID_SPLIT = 40, ID_REVERSE = 45, ID_PAN = 49, ID_DECLICK = 23, ID_IMPULSE = 81,
-  ID_PIPE = 2, ID_STACK = 3, ID_BRANCH = 4, ID_BUS = 10, ID_BINOP = 11, ID_NET = 63, ID_FEEDBACK = 79, ID_WAVE = 65,
+  ID_PIPE = 2, ID_STACK = 3, ID_BRANCH = 4, ID_BUS = 10, ID_BINOP = 11, ID_NET = 63, ID_FEEDBACK = 79, ID_WAVE = 65, ID_WAVESYNTH = 34,
   ID_SELECT = 1213, ID_SEQ = 1729, ID_ARRGET = 1312, ID_SHIFTREG = 1110, ID_QUANTIZER = 1111, ID_KR = 1112,
   ID_RESET = 1113, ID_TRIGRESET = 1114, ID_RESETV = 1115, ID_RAMP = 1116, ID_INPUT = 1117,
   ID_VAR = 70, ID_MONITOR = 56,

@@ -25,11 +25,90 @@ uint64_t as_usize(float x) {
 }
 uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
+// ---- band-limited wavetables (FunDSP wavetable.rs, restated): one table per quarter octave, 20 Hz .. 20 kHz
+void host_ifft(std::vector<float>& re, std::vector<float>& im) {   // in-place radix-2 inverse DFT, unscaled
+  size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; i++) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    for (size_t k = 0; k < len / 2; k++) {
+      double ang = 2.0 * 3.14159265358979323846 * (double)k / (double)len;
+      float wr = (float)std::cos(ang), wi = (float)std::sin(ang);
+      for (size_t i = k; i < n; i += len) {
+        float ur = re[i], ui = im[i], vr = re[i + len / 2], vi = im[i + len / 2];
+        float tr = vr * wr - vi * wi, ti = vr * wi + vi * wr;
+        re[i] = ur + tr; im[i] = ui + ti;
+        re[i + len / 2] = ur - tr; im[i + len / 2] = ui - ti;
+      }
+    }
+  }
+}
+std::vector<float> make_wave(double pitch, int shape) {
+  size_t harmonics = (size_t)std::floor(22050.0 / pitch);
+  size_t target = 4 * harmonics, length = 32;
+  while (length < target && length < 8192) length <<= 1;
+  std::vector<float> re(length, 0.0f), im(length, 0.0f);
+  for (size_t i = 1; i <= harmonics && i < length / 2; i++) {
+    double f = pitch * (double)i, w;
+    bool odd = (i & 1) != 0;
+    switch (shape) {
+      case 0: w = 1.0 / (double)i; break;                               // saw
+      case 1: w = odd ? 1.0 / (double)i : 0.0; break;                   // square
+      case 2: w = odd ? 1.0 / ((double)i * (double)i) : 0.0; break;     // triangle
+      default: w = 1.0 / ((double)i * (double)i); break;                // soft saw
+    }
+    double fade = (22050.0 - f) / (22050.0 - 20000.0);
+    fade = fade < 0 ? 0 : (fade > 1 ? 1 : fade);
+    w *= ((6.0 * fade - 15.0) * fade + 10.0) * fade * fade * fade;
+    double ph = (shape == 2 && (i & 3) == 3) ? 0.5 : 0.0;
+    double r = 0.5 * w * std::sin(2.0 * 3.14159265358979323846 * ph), m = -0.5 * w * std::cos(2.0 * 3.14159265358979323846 * ph);
+    re[i] = (float)r; im[i] = (float)m;
+    re[length - i] = (float)r; im[length - i] = (float)-m;
+  }
+  host_ifft(re, im);
+  float mx = 0.0f;
+  for (float x : re) mx = std::fmax(mx, std::fabs(x));
+  if (mx > 0.0f) for (float& x : re) x /= mx;
+  return re;
+}
+// table-set blob: [n][n x (limit, offset(bits), length(bits))][samples...]; offsets are relative to the blob start
+const std::vector<float>& wavetable_blob(int shape) {
+  static std::vector<float> blobs[4];
+  std::vector<float>& b = blobs[shape & 3];
+  if (b.empty()) {
+    std::vector<float> limits;
+    std::vector<std::vector<float>> tabs;
+    for (int i = 0;; i++) {
+      double pn = 20.0 * std::pow(2.0, (double)(i + 1) / 4.0);
+      limits.push_back((float)pn);
+      tabs.push_back(make_wave(pn, shape));
+      if (pn >= 20000.0) break;
+    }
+    size_t n = tabs.size(), off = 1 + 3 * n;
+    b.push_back((float)n);
+    for (size_t i = 0; i < n; i++) {
+      b.push_back(limits[i]);
+      uint32_t o = (uint32_t)off, l = (uint32_t)tabs[i].size();
+      float fo, fl;
+      memcpy(&fo, &o, 4); memcpy(&fl, &l, 4);
+      b.push_back(fo); b.push_back(fl);
+      off += tabs[i].size();
+    }
+    for (auto& tb : tabs) b.insert(b.end(), tb.begin(), tb.end());
+  }
+  return b;
+}
+
 struct Lower {
   Tape& t;
   std::string err;
   int n_temps = 0;
   int zero_p = -1;
+  int wt_offset[4] = {-1, -1, -1, -1};   // wavetable sets already placed in the tables region
   explicit Lower(Tape& t_) : t(t_) {}
 
   uint16_t temp(int n = 1) { int i = n_temps; n_temps += n; return (uint16_t)(R_TEMP | i); }
@@ -266,6 +345,16 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
       deriver(D_RAMP_SR, 0, 0, p, 1, 0, 0, n.sr);
       Instr& i = emit(OP_RAMP);
       i.in[0] = in[0]; i.p = p; i.s = state(1); i.out = temp();
+      out.push_back(i.out);
+      break;
+    }
+    case NK_WAVETABLE: {
+      uint16_t p = params(1), s = state(2);
+      deriver(D_INV_SR, 0, 0, p, 1, 0, 0, n.sr);
+      hash_init(s, INIT_SINE_PHASE, n.hash);
+      if (wt_offset[n.mode & 3] < 0) wt_offset[n.mode & 3] = (int)table(wavetable_blob(n.mode));
+      Instr& i = emit(OP_WAVETABLE);
+      i.in[0] = in[0]; i.p = p; i.s = s; i.aux = (uint32_t)wt_offset[n.mode & 3]; i.out = temp();
       out.push_back(i.out);
       break;
     }

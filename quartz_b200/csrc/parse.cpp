@@ -220,8 +220,19 @@ Graph str_to_net(const std::string& op_in) {
     return single(ID_CONSTANT, NK_CONST, 0, n, v);
   }
   if (name == "ramp") return single(ID_RAMP, NK_RAMP, 1, 1);
-  if (name == "saw" || name == "square" || name == "triangle" || name == "organ" || name == "hammond" ||
-      name == "soft_saw" || name == "pulse" || name == "lorenz" || name == "rossler" || name == "dsf_saw" ||
+  if (name == "saw" || name == "square" || name == "triangle" || name == "soft_saw") {   // band-limited wavetable oscillators
+    int shape = name == "saw" ? 0 : name == "square" ? 1 : name == "triangle" ? 2 : 3;
+    if (has(1)) {   // saw_hz(f) = constant(f) >> saw()
+      UnitBuilder b;
+      b.mix(ID_PIPE);
+      int c = b.leaf(ID_CONSTANT, NK_CONST, 0, 1, {}, {p[0]});
+      int w = b.leaf(ID_WAVESYNTH, NK_WAVETABLE, 1, 1, {Src{c, 0}});
+      b.N(w).mode = shape;
+      return b.finish(0, {Src{w, 0}});
+    }
+    return single(ID_WAVESYNTH, NK_WAVETABLE, 1, 1, {}, 0, shape);
+  }
+  if (name == "organ" || name == "hammond" || name == "pulse" || name == "lorenz" || name == "rossler" || name == "dsf_saw" ||
       name == "dsf_square" || name == "mls")
     return unsupported(name);
   if (name == "pluck") return has(3) ? unsupported(name) : EMPTY;

@@ -53,7 +53,9 @@ enum Op : uint16_t {
   OP_NOISE,      // S[s]=u32 counter
   OP_IMPULSE,    // S[s]=fired flag
   OP_RAMP,       // S[s]=val; P[p]=sr ; in a = frequency      (nodes.rs:459-492)
-  OP_WAVE,       // S[s]=u32 index; table aux, length n
+  OP_WAVE,       // S[s]=u32 index; table aux, length aux2
+  OP_WAVETABLE,  // band-limited saw/square/triangle/soft_saw: in a = frequency; P[p]=1/sr; S[s]=phase, S[s+1]=u32 table hint;
+                 // aux = table-set header in the tables region: n, then n x (limit, offset, length), see lower.cpp
   // ---- filters
   OP_SVF,        // fixed coefficients P[p..p+5] = a1 a2 a3 m0 m1 m2 ; S[s]=ic1, S[s+1]=ic2
   OP_SVF_VAR,    // n = (mode) | (nvar << 8); inputs a=x, b.. = hz,q,gain ; P[p..p+3]=hz q gain sr defaults ;

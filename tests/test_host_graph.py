@@ -78,7 +78,7 @@ def test_connective_guards_follow_process_rs():
 
 
 def test_unsupported_ops_fail_loudly_not_silently():
-    for op in ("saw(220)", "reverb_stereo(10,2)", "moog(1000,0.5)", "pluck(220,0.5,0.5)"):
+    for op in ("organ(220)", "reverb_stereo(10,2)", "moog(1000,0.5)", "pluck(220,0.5,0.5)"):
         n = Net.str_to_net(op)
         assert n.unsupported() is not None
         with pytest.raises(qb.QuartzGpuError):
