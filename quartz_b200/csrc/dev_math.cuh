@@ -56,14 +56,20 @@ __device__ __forceinline__ float d_noise(uint32_t counter) {
   return (float)(int32_t)d_hash32x(counter) * (1.0f / 2147483648.0f);
 }
 
-__device__ __forceinline__ float d_lerp(float a, float b, float t) { return a * (1.0f - t) + b * t; }
-__device__ __forceinline__ float d_delerp(float a, float b, float x) { return (x - a) / (b - a); }
-__device__ __forceinline__ float d_xerp(float a, float b, float t) { return expf(d_lerp(logf(a), logf(b), t)); }
-__device__ __forceinline__ float d_dexerp(float a, float b, float x) { return logf(x / a) / logf(b / a); }
 // exp2 through f64: pitch maps (semitone_ratio) feed phase accumulators, where a 1-ulp frequency difference against the
 // CPU libm (which rounds correctly) would integrate into an audible phase drift; the f64 result rounds to the same f32
 __device__ __forceinline__ float d_exp2_cr(float x) { return (float)exp2((double)x); }
-__device__ __forceinline__ float d_exp10(float x) { return expf(x * 2.30258509299404568402f); }
+// same reasoning for the rest of the exp/log family (xerp, db_amp, pow ... routinely compute oscillator frequencies)
+__device__ __forceinline__ float d_exp_cr(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float d_log_cr(float x) { return (float)log((double)x); }
+__device__ __forceinline__ float d_log2_cr(float x) { return (float)log2((double)x); }
+__device__ __forceinline__ float d_log10_cr(float x) { return (float)log10((double)x); }
+__device__ __forceinline__ float d_pow_cr(float x, float y) { return (float)pow((double)x, (double)y); }
+__device__ __forceinline__ float d_lerp(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float d_delerp(float a, float b, float x) { return (x - a) / (b - a); }
+__device__ __forceinline__ float d_xerp(float a, float b, float t) { return d_exp_cr(d_lerp(d_log_cr(a), d_log_cr(b), t)); }
+__device__ __forceinline__ float d_dexerp(float a, float b, float x) { return d_log_cr(x / a) / d_log_cr(b / a); }
+__device__ __forceinline__ float d_exp10(float x) { return d_exp_cr(x * 2.30258509299404568402f); }
 __device__ __forceinline__ float d_spline(float y0, float y1, float y2, float y3, float t) {
   return y1 + t / 2.0f * (y2 - y0 + t * (2.0f * y0 - 5.0f * y1 + 4.0f * y2 - y3 + t * (3.0f * (y1 - y2) + y3 - y0)));
 }

@@ -117,9 +117,9 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
     case OP_LE: X(I.out) = X(I.in[0]) <= X(I.in[1]) ? 1.0f : 0.0f; break;
     case OP_MIN: X(I.out) = fminf(X(I.in[0]), X(I.in[1])); break;
     case OP_MAX: X(I.out) = fmaxf(X(I.in[0]), X(I.in[1])); break;
-    case OP_POW: X(I.out) = powf(X(I.in[0]), X(I.in[1])); break;
+    case OP_POW: X(I.out) = d_pow_cr(X(I.in[0]), X(I.in[1])); break;
     case OP_REM: X(I.out) = d_rem_euclid(X(I.in[0]), X(I.in[1])); break;
-    case OP_LOG: X(I.out) = logf(X(I.in[0])) / logf(X(I.in[1])); break;
+    case OP_LOG: X(I.out) = d_log_cr(X(I.in[0])) / d_log_cr(X(I.in[1])); break;
     case OP_BITAND: X(I.out) = (float)(d_as_i32(X(I.in[0])) & d_as_i32(X(I.in[1]))); break;
     case OP_BITOR: X(I.out) = (float)(d_as_i32(X(I.in[0])) | d_as_i32(X(I.in[1]))); break;
     case OP_BITXOR: X(I.out) = (float)(d_as_i32(X(I.in[0])) ^ d_as_i32(X(I.in[1]))); break;
@@ -166,14 +166,14 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
     case OP_CEIL: X(I.out) = ceilf(X(I.in[0])); break;
     case OP_ROUND: X(I.out) = roundf(X(I.in[0])); break;
     case OP_SQRT: X(I.out) = sqrtf(X(I.in[0])); break;
-    case OP_EXP: X(I.out) = expf(X(I.in[0])); break;
+    case OP_EXP: X(I.out) = d_exp_cr(X(I.in[0])); break;
     case OP_EXP2: X(I.out) = d_exp2_cr(X(I.in[0])); break;
     case OP_EXP10: X(I.out) = d_exp10(X(I.in[0])); break;
     case OP_LN_1P_FN: X(I.out) = log1pf(X(I.in[0])); break;
     case OP_EXP_M1_FN: X(I.out) = expm1f(X(I.in[0])); break;
-    case OP_LN: X(I.out) = logf(X(I.in[0])); break;
-    case OP_LOG2: X(I.out) = log2f(X(I.in[0])); break;
-    case OP_LOG10: X(I.out) = log10f(X(I.in[0])); break;
+    case OP_LN: X(I.out) = d_log_cr(X(I.in[0])); break;
+    case OP_LOG2: X(I.out) = d_log2_cr(X(I.in[0])); break;
+    case OP_LOG10: X(I.out) = d_log10_cr(X(I.in[0])); break;
     case OP_SIN: X(I.out) = sinf(X(I.in[0])); break;
     case OP_COS: X(I.out) = cosf(X(I.in[0])); break;
     case OP_TAN: X(I.out) = tanf(X(I.in[0])); break;
@@ -189,7 +189,7 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
     case OP_SQUARED: { float x = X(I.in[0]); X(I.out) = x * x; break; }
     case OP_CUBED: { float x = X(I.in[0]); X(I.out) = x * x * x; break; }
     case OP_DB_AMP: X(I.out) = d_exp10(X(I.in[0]) / 20.0f); break;
-    case OP_AMP_DB: X(I.out) = log10f(X(I.in[0])) * 20.0f; break;
+    case OP_AMP_DB: X(I.out) = d_log10_cr(X(I.in[0])) * 20.0f; break;
     case OP_A_WEIGHT: X(I.out) = d_a_weight(X(I.in[0])); break;
     case OP_SOFTSIGN: { float x = X(I.in[0]); X(I.out) = x / (1.0f + fabsf(x)); break; }
     case OP_SMOOTH3: { float x = X(I.in[0]); X(I.out) = (3.0f - 2.0f * x) * x * x; break; }
