@@ -30,17 +30,18 @@ namespace qg {
 
 namespace {
 
-constexpr int K = 16;           // samples per lane per block
-constexpr int B = 32 * K;       // samples per warp block (2 KB of output)
+// K = samples per lane per block, B = 32*K samples per warp block.  K = 32: one lane = one 128-byte row of the tile,
+// scan and loop overhead amortised over 1,024 samples.
+constexpr int K2_K = 32;
 
-__device__ __forceinline__ void bulk_store_block(float* gdst, const float* ssrc) {
-  // one elected lane: shared -> global bulk async copy of B floats
+__device__ __forceinline__ void bulk_store_block(float* gdst, const float* ssrc, unsigned bytes) {
+  // one elected lane: shared -> global bulk async copy
   unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "n"(B * 4) : "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
-// TMA tensor store of one 16-row x 128-byte box (SWIZZLE_128B layout in shared memory) -> SASS UTMASTG
-__device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, const float* ssrc, int row0) {
+// TMA tensor store of one K-row x 128-byte box (SWIZZLE_128B layout in shared memory) -> SASS UTMASTG
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tmap, const void* ssrc, int row0) {
   unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap), "r"(0), "r"(row0), "r"(s)
                : "memory");
@@ -66,43 +67,54 @@ __device__ __forceinline__ float svf_fma(float x, float& ic1, float& ic2, const 
 }
 
 // same tick fed with the un-scaled noise integer hf (x = hf * 2^-31, an exact power-of-two scaling): the scaling rides on
-// the FMAs that consume x, results are bit-identical to svf_fma(hf * 2^-31)
+// the FMAs that consume x.  Lowpass needs no v1: ic1' = 2 v1 - ic1 = (2 a1 - 1) ic1 + 2 a2 v3 with c11 = 2 a1 - 1 and
+// c12 = 2 a2 both exact in f32 (a1 in [0.5, 1)) -> 6 FP ops per sample instead of 7.
+struct SvfK { float c11, c12, m0s; };
 template <bool LP>
-__device__ __forceinline__ float svf_fma_noise(float hf, float& ic1, float& ic2, const SvfC& c, float m0s) {
-  const float k = 1.0f / 2147483648.0f;
-  float v3 = __fmaf_rn(hf, k, -ic2);
+__device__ __forceinline__ float svf_fma_noise(float hf, float& ic1, float& ic2, const SvfC& c, const SvfK& k) {
+  const float sc = 1.0f / 2147483648.0f;
+  float v3 = __fmaf_rn(hf, sc, -ic2);
+  if (LP) {
+    float v2 = __fmaf_rn(c.a3, v3, __fmaf_rn(c.a2, ic1, ic2));
+    ic1 = __fmaf_rn(k.c12, v3, k.c11 * ic1);
+    ic2 = __fmaf_rn(2.0f, v2, -ic2);
+    return v2;
+  }
   float v1 = __fmaf_rn(c.a2, v3, c.a1 * ic1);
   float v2 = __fmaf_rn(c.a3, v3, __fmaf_rn(c.a2, ic1, ic2));
   ic1 = __fmaf_rn(2.0f, v1, -ic1);
   ic2 = __fmaf_rn(2.0f, v2, -ic2);
-  if (LP) return v2;
-  return __fmaf_rn(c.m2, v2, __fmaf_rn(c.m1, v1, m0s * hf));
+  return __fmaf_rn(c.m2, v2, __fmaf_rn(c.m1, v1, k.m0s * hf));
 }
 // (measured: replacing the hash's SHF with IMAD.HI to unload the half-rate ALU pipe is slower — 13.4 vs 11.8 ms)
 __device__ __forceinline__ float noise_int(uint32_t counter) { return (float)(int32_t)d_hash32x(counter); }
 
-// per-warp shared memory: zero-state outputs [K/4][32 lanes] float4 (conflict-free), two contiguous output blocks for
-// the bulk copies, and the scan matrices A^(K*2^i)
+// Per-warp shared memory.  `tile` holds the block's 32*K samples as float4 chunks: the zero-state outputs are parked in
+// it, corrected IN PLACE and shipped from it, so a warp needs 128*K bytes (+ constants) and 28 warps fit on an SM.
+//   STORE == 2: tile is laid out as the TMA box (K rows x 128 B, SWIZZLE_128B): sample s of the block sits in row s/32,
+//               16-byte chunk ((s%32)/4) ^ (row & 7) — conflict-free for the per-lane float4 accesses;
+//   STORE <= 1: tile is [K/4][32 lanes] float4 (conflict-free); STORE == 1 stages the corrected block linearly in `lin`
+//               for the bulk copy (bank conflicts on that path — it only serves rows that are not 128-byte aligned).
+template <int K, int STORE>
 struct __align__(1024) WarpSmem {
-  float out[B];          // block handed to the bulk copy: linear, or 16 rows x 128 B in the TMA 128-byte swizzle
-  float4 zs[2][K / 4][32];   // zero-state outputs of the current / next block (software pipeline)
+  float4 tile[K / 4 * 32];
   float4 mp[5];          // A^(K*2^i) as (a, b, c, d)
   float4 rc[K / 2];      // homogeneous response rows C*A^i: (r1_i, r2_i, r1_{i+1}, r2_{i+1})
+  float lin[STORE == 1 ? 32 * K : 4];
 };
 
 // MODE 0: write samples; MODE 1: state-only pre-pass (zero start state, no output) for segment chaining
-// STORE (decided on the host from the output alignment): 0 plain scalar stores; 1 linear bulk async copy of the 2 KB block
-// (rows 16-byte aligned); 2 TMA tensor store from a 128-byte-swizzled tile (T % 32 == 0): with 64-byte lane strides the
-// linear layout makes every STS.128 a 4-way bank conflict and the shared-memory pipe becomes the limiter — the swizzled
-// tile is conflict-free.
-template <int MODE, bool LP, int STORE>
+// STORE (decided on the host from the output alignment): 0 plain scalar stores; 1 linear bulk async copy of the block
+// (rows 16-byte aligned); 2 TMA tensor store from the 128-byte-swizzled tile (T % 32 == 0).
+template <int MODE, bool LP, int STORE, int K>
 __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restrict__ params, float* __restrict__ state, int Vp,
                                                            int V, long T, int S, long seg_len, int p_svf, int s_noise,
                                                            int s_svf, float* __restrict__ out, float* __restrict__ seg_state,
                                                            const __grid_constant__ CUtensorMap tmap) {
-  __shared__ WarpSmem sm[4];
+  constexpr int B = 32 * K;
+  __shared__ WarpSmem<K, MODE == 0 ? STORE : 0> sm[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpSmem& W = sm[warp];
+  auto& W = sm[warp];
   const long w = (long)blockIdx.x * 4 + warp;        // warp id = voice * S + segment
   const int v = (int)(w / S), seg = (int)(w % S);
   if (v >= V) return;
@@ -110,11 +122,12 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
   c.a1 = params[(size_t)(p_svf + 0) * Vp + v]; c.a2 = params[(size_t)(p_svf + 1) * Vp + v];
   c.a3 = params[(size_t)(p_svf + 2) * Vp + v]; c.m0 = params[(size_t)(p_svf + 3) * Vp + v];
   c.m1 = params[(size_t)(p_svf + 4) * Vp + v]; c.m2 = params[(size_t)(p_svf + 5) * Vp + v];
+  SvfK kc;
+  kc.c11 = 2.0f * c.a1 - 1.0f; kc.c12 = 2.0f * c.a2; kc.m0s = c.m0 * (1.0f / 2147483648.0f);
   // state-space form of the tick:  s' = A s + B x ; y = C s + D x
   const double a1 = c.a1, a2 = c.a2, a3 = c.a3;
   const double A11 = 2 * a1 - 1, A12 = -2 * a2, A21 = 2 * a2, A22 = 1 - 2 * a3;
   // y_h = m1*v1_h + m2*v2_h with v1_h = a1 s1 - a2 s2, v2_h = a2 s1 + (1 - a3) s2   (row vector C below)
-  const float m0s = c.m0 * (1.0f / 2147483648.0f);
   // per-voice constants in f64, rounded once, kept in shared memory (read as broadcasts):
   //   rc[i] = C * A^i  (the homogeneous output response i samples after a block start state), i < K
   //   mp[i] = A^(K*2^i), i = 0..4  (scan matrices)
@@ -146,88 +159,79 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
   float* orow = MODE == 0 ? out + (size_t)v * T : nullptr;
   constexpr bool can_bulk = MODE == 0 && STORE >= 1;
   constexpr bool swz = MODE == 0 && STORE == 2;
+  // float4 slot of this lane's chunk i4 (samples lane*K + 4*i4 .. +3 of the block) inside the tile
+  auto slot = [&](int i4) -> int {
+    if (!swz) return i4 * 32 + lane;
+    const int s4 = lane * (K / 4) + i4, row = s4 >> 3, ch = s4 & 7;
+    return row * 8 + (ch ^ (row & 7));
+  };
 
   long t = t_begin;
-  // zero-state run of 4 of this lane's samples of the block starting at tb (outputs parked in shared memory)
-  auto zero_state4 = [&](long tb, int i4, int zb, float& z1, float& z2) {
-    const uint32_t cb = counter0 + (uint32_t)tb + (uint32_t)(lane * K) + (uint32_t)(4 * i4);
-    float4 y;
-    y.x = svf_fma_noise<LP>(noise_int(cb + 1u), z1, z2, c, m0s);
-    y.y = svf_fma_noise<LP>(noise_int(cb + 2u), z1, z2, c, m0s);
-    y.z = svf_fma_noise<LP>(noise_int(cb + 3u), z1, z2, c, m0s);
-    y.w = svf_fma_noise<LP>(noise_int(cb + 4u), z1, z2, c, m0s);
-    if (MODE == 0) W.zs[zb][i4][lane] = y;
-  };
-  // one Kogge-Stone step of the affine-map scan (branch-free): e <- A^(K d) e(lane - d) + e
-  auto scan_step = [&](int i, float& e1, float& e2) {
-    const int d = 1 << i;
-    const float4 m = W.mp[i];
-    float r1 = __shfl_up_sync(0xffffffffu, e1, d), r2 = __shfl_up_sync(0xffffffffu, e2, d);
-    r1 = lane >= d ? r1 : 0.0f;
-    r2 = lane >= d ? r2 : 0.0f;
-    e1 = __fmaf_rn(m.x, r1, __fmaf_rn(m.y, r2, e1));
-    e2 = __fmaf_rn(m.z, r1, __fmaf_rn(m.w, r2, e2));
-  };
-  if (t + B <= t_end) {
-    // software pipeline: while block b is being scanned (a chain of 5 dependent shuffles) and corrected, the
-    // zero-state run of block b+1 — independent work — is interleaved between the scan steps
-    int zb = 0;
-    float z1 = 0.0f, z2 = 0.0f;
+  for (; t + B <= t_end; t += B) {
+    if (swz) {   // the previous block's tensor store must have finished reading the tile
+      if (lane == 0) bulk_wait_read_0();
+      __syncwarp();
+    }
+    // ---- 1. zero-state run of this lane's K samples, outputs parked in the tile
+    float e1 = 0.0f, e2 = 0.0f;
+    {
+      const uint32_t cb = counter0 + (uint32_t)t + (uint32_t)(lane * K);
 #pragma unroll
-    for (int i4 = 0; i4 < K / 4; i4++) zero_state4(t, i4, zb, z1, z2);
-    for (; t + B <= t_end; t += B, zb ^= 1) {
-      const bool has_next = t + 2 * B <= t_end;
-      float e1 = z1, e2 = z2;          // zero-state end state of this lane's chunk
-      float n1 = 0.0f, n2 = 0.0f;      // running zero-state of the next block
-      {
-        const float4 m = W.mp[0];
-        const float s1 = lane == 0 ? S1 : 0.0f, s2 = lane == 0 ? S2 : 0.0f;   // only lane 0 inherits the block start state
-        e1 = __fmaf_rn(m.x, s1, __fmaf_rn(m.y, s2, e1));
-        e2 = __fmaf_rn(m.z, s1, __fmaf_rn(m.w, s2, e2));
+      for (int i4 = 0; i4 < K / 4; i4++) {
+        float4 y;
+        y.x = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 1)), e1, e2, c, kc);
+        y.y = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 2)), e1, e2, c, kc);
+        y.z = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 3)), e1, e2, c, kc);
+        y.w = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 4)), e1, e2, c, kc);
+        if (MODE == 0) W.tile[slot(i4)] = y;
       }
-      static_assert(K / 4 == 4, "the pipeline interleaves 4 scan steps with 4 groups of 4 samples");
-      if (has_next) {
+    }
+    // ---- 2. Kogge-Stone scan of the affine maps  e <- A^(K d) e(lane - d) + e ; lane 0 inherits the block start state
+    {
+      const float4 m = W.mp[0];
+      const float s1 = lane == 0 ? S1 : 0.0f, s2 = lane == 0 ? S2 : 0.0f;
+      e1 = __fmaf_rn(m.x, s1, __fmaf_rn(m.y, s2, e1));
+      e2 = __fmaf_rn(m.z, s1, __fmaf_rn(m.w, s2, e2));
+    }
 #pragma unroll
-        for (int i = 0; i < 4; i++) { scan_step(i, e1, e2); zero_state4(t + B, i, zb ^ 1, n1, n2); }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) scan_step(i, e1, e2);
+    for (int i = 0; i < 5; i++) {
+      const int d = 1 << i;
+      const float4 m = W.mp[i];
+      float r1 = __shfl_up_sync(0xffffffffu, e1, d), r2 = __shfl_up_sync(0xffffffffu, e2, d);
+      r1 = lane >= d ? r1 : 0.0f;
+      r2 = lane >= d ? r2 : 0.0f;
+      e1 = __fmaf_rn(m.x, r1, __fmaf_rn(m.y, r2, e1));
+      e2 = __fmaf_rn(m.z, r1, __fmaf_rn(m.w, r2, e2));
+    }
+    float h1 = __shfl_up_sync(0xffffffffu, e1, 1), h2 = __shfl_up_sync(0xffffffffu, e2, 1);
+    if (lane == 0) { h1 = S1; h2 = S2; }
+    S1 = __shfl_sync(0xffffffffu, e1, 31);
+    S2 = __shfl_sync(0xffffffffu, e2, 31);
+    if (MODE == 0) {
+      // ---- 3. homogeneous correction, in place
+      if (STORE == 1) {
+        if (lane == 0) bulk_wait_read_0();          // the previous block's copy has finished reading W.lin
+        __syncwarp();
       }
-      scan_step(4, e1, e2);
-      float h1 = __shfl_up_sync(0xffffffffu, e1, 1), h2 = __shfl_up_sync(0xffffffffu, e2, 1);
-      if (lane == 0) { h1 = S1; h2 = S2; }
-      S1 = __shfl_sync(0xffffffffu, e1, 31);
-      S2 = __shfl_sync(0xffffffffu, e2, 31);
-      z1 = n1; z2 = n2;
-      if (MODE == 0) {
-        // ---- homogeneous correction, written to the contiguous output block
-        if (can_bulk) {
-          if (lane == 0) bulk_wait_read_0();          // the previous block's copy has finished reading W.out
-          __syncwarp();
-        }
-        float4* ob = reinterpret_cast<float4*>(&W.out[lane * K]);
-        // swizzled tile: lane j owns half of row j/2; 16-byte chunk c of row r lives at chunk c ^ (r & 7)
-        const int srow = lane >> 1, sch = (lane & 1) * 4;
 #pragma unroll
-        for (int i4 = 0; i4 < K / 4; i4++) {
-          float4 y = W.zs[zb][i4][lane];
-          const float4 ra = W.rc[2 * i4], rb = W.rc[2 * i4 + 1];
-          y.x = __fmaf_rn(ra.x, h1, __fmaf_rn(ra.y, h2, y.x));
-          y.y = __fmaf_rn(ra.z, h1, __fmaf_rn(ra.w, h2, y.y));
-          y.z = __fmaf_rn(rb.x, h1, __fmaf_rn(rb.y, h2, y.z));
-          y.w = __fmaf_rn(rb.z, h1, __fmaf_rn(rb.w, h2, y.w));
-          if (swz) reinterpret_cast<float4*>(W.out)[srow * 8 + ((sch + i4) ^ (srow & 7))] = y;
-          else if (can_bulk) ob[i4] = y;
-          else { float* g = orow + t + lane * K + 4 * i4; g[0] = y.x; g[1] = y.y; g[2] = y.z; g[3] = y.w; }
-        }
-        // ---- one bulk async copy per block (UBLKCP)
-        if (can_bulk) {
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (swz) tma_store_box(&tmap, &W.out[0], (int)(((long)v * T + t) >> 5));
-            else bulk_store_block(orow + t, &W.out[0]);
-          }
+      for (int i4 = 0; i4 < K / 4; i4++) {
+        float4 y = W.tile[slot(i4)];
+        const float4 ra = W.rc[2 * i4], rb = W.rc[2 * i4 + 1];
+        y.x = __fmaf_rn(ra.x, h1, __fmaf_rn(ra.y, h2, y.x));
+        y.y = __fmaf_rn(ra.z, h1, __fmaf_rn(ra.w, h2, y.y));
+        y.z = __fmaf_rn(rb.x, h1, __fmaf_rn(rb.y, h2, y.z));
+        y.w = __fmaf_rn(rb.z, h1, __fmaf_rn(rb.w, h2, y.w));
+        if (swz) W.tile[slot(i4)] = y;
+        else if (STORE == 1) reinterpret_cast<float4*>(&W.lin[lane * K])[i4] = y;
+        else { float* g = orow + t + lane * K + 4 * i4; g[0] = y.x; g[1] = y.y; g[2] = y.z; g[3] = y.w; }
+      }
+      // ---- 4. one bulk async copy per block (UTMASTG / UBLKCP)
+      if (can_bulk) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (swz) tma_store_box(&tmap, &W.tile[0], (int)(((long)v * T + t) >> 5));
+          else bulk_store_block(orow + t, &W.lin[0], B * 4);
         }
       }
     }
@@ -451,9 +455,9 @@ const char* fused_name(int id) {
   return id == FUSED_NOISE_SVF ? "k_noise_svf_scan" : id == FUSED_SINE_SVF_ENV ? "k_polysynth" : "none";
 }
 
-// 2-D view of a voice-major f32 buffer as rows of 32 samples (128 B); box = 16 rows, shared-memory layout SWIZZLE_128B.
+// 2-D view of a voice-major f32 buffer as rows of 32 samples (128 B); box = K rows, shared-memory layout SWIZZLE_128B.
 // cuTensorMapEncodeTiled is fetched through the runtime's driver entry point (no link-time dependency on libcuda).
-static bool encode_rows32(CUtensorMap* tm, float* base, size_t n_rows) {
+static bool encode_rows32(CUtensorMap* tm, float* base, size_t n_rows, int box_rows) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -469,7 +473,7 @@ static bool encode_rows32(CUtensorMap* tm, float* base, size_t n_rows) {
   if (!fn) return false;
   cuuint64_t dims[2] = {32, (cuuint64_t)n_rows};
   cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {32, 16};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -479,6 +483,8 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
   if (pl.id == FUSED_NOISE_SVF) {
     if (a.group != 1) return cudaErrorNotSupported;
     // segments per voice: enough warps to fill 148 SMs x ~24 warps when the bank is small
+    constexpr int K = K2_K;
+    constexpr int B = 32 * K;
     int S = 1;
     const long target_warps = 148L * 24;
     if (a.V < target_warps) {
@@ -504,8 +510,8 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
       seg = *a.scratch;
       CUtensorMap dummy;
       memset(&dummy, 0, sizeof dummy);
-      if (pl.p[1]) k_noise_svf_scan<1, true, 0><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
-      else k_noise_svf_scan<1, false, 0><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
+      if (pl.p[1]) k_noise_svf_scan<1, true, 0, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
+      else k_noise_svf_scan<1, false, 0, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
       k_chain_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], seg);
       if (launches) *launches += 2;
     }
@@ -514,9 +520,9 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
     if (store == 1 && ((((size_t)(uintptr_t)a.out) & 127) == 0) && (a.T % 32) == 0 && ((size_t)a.V * (size_t)a.T / 32) < 0xffffffffull &&
-        encode_rows32(&tmap, a.out, (size_t)a.V * (size_t)a.T / 32))
+        encode_rows32(&tmap, a.out, (size_t)a.V * (size_t)a.T / 32, K))
       store = 2;
-#define QG_LAUNCH_K2(LPV, SV) k_noise_svf_scan<0, LPV, SV><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg, tmap)
+#define QG_LAUNCH_K2(LPV, SV) k_noise_svf_scan<0, LPV, SV, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg, tmap)
     if (pl.p[1]) { if (store == 2) QG_LAUNCH_K2(true, 2); else if (store == 1) QG_LAUNCH_K2(true, 1); else QG_LAUNCH_K2(true, 0); }
     else { if (store == 2) QG_LAUNCH_K2(false, 2); else if (store == 1) QG_LAUNCH_K2(false, 1); else QG_LAUNCH_K2(false, 0); }
 #undef QG_LAUNCH_K2
