@@ -88,6 +88,17 @@ __device__ __forceinline__ float svf_fma_noise(float hf, float& ic1, float& ic2,
 }
 // (measured: replacing the hash's SHF with IMAD.HI to unload the half-rate ALU pipe is slower — 13.4 vs 11.8 ms)
 __device__ __forceinline__ float noise_int(uint32_t counter) { return (float)(int32_t)d_hash32x(counter); }
+__device__ __forceinline__ uint32_t __umad_opaque(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+// d_hash32x with the caller supplying hi = x >> 16
+__device__ __forceinline__ float noise_int_hi(uint32_t x, uint32_t hi) {
+  x = (x ^ hi) * 0x21f0aaadU;
+  x = (x ^ (x >> 15)) * 0x735a2d97U;
+  return (float)(int32_t)(x ^ (x >> 15));
+}
 
 // Per-warp shared memory.  `tile` holds the block's 32*K samples as float4 chunks: the zero-state outputs are parked in
 // it, corrected IN PLACE and shipped from it, so a warp needs 128*K bytes (+ constants) and 28 warps fit on an SM.
@@ -166,24 +177,45 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
     return row * 8 + (ch ^ (row & 7));
   };
 
+  const uint32_t one = S > 0 ? 1u : 0u;   // always 1; not a compile-time constant
   long t = t_begin;
   for (; t + B <= t_end; t += B) {
     if (swz) {   // the previous block's tensor store must have finished reading the tile
       if (lane == 0) bulk_wait_read_0();
       __syncwarp();
     }
-    // ---- 1. zero-state run of this lane's K samples, outputs parked in the tile
+    // ---- 1. zero-state run of this lane's K samples, outputs parked in the tile.  The hash's first step x ^ (x >> 16)
+    // needs x >> 16, which is constant over the chunk unless its counters cross a multiple of 65,536 (one block in 64):
+    // the common case hoists it (one SHF less per sample), the crossing block takes the plain path (warp-uniform branch)
     float e1 = 0.0f, e2 = 0.0f;
     {
-      const uint32_t cb = counter0 + (uint32_t)t + (uint32_t)(lane * K);
+      const uint32_t base = counter0 + (uint32_t)t + (uint32_t)(lane * K) + 1u;
+      const bool cross = (base & 0xffffu) > (0xffffu - (uint32_t)(K - 1));
+      if (!__any_sync(0xffffffffu, cross)) {
+        const uint32_t hi = base >> 16;
+        // counter + j as IMAD (one * j + base, `one` opaque to ptxas): the add moves from the half-rate ALU pipe, which the
+        // hash's shifts and xors already load, to the FMA pipe
+#define QG_CTR(j) __umad_opaque(one, (uint32_t)(j), base)
 #pragma unroll
-      for (int i4 = 0; i4 < K / 4; i4++) {
-        float4 y;
-        y.x = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 1)), e1, e2, c, kc);
-        y.y = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 2)), e1, e2, c, kc);
-        y.z = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 3)), e1, e2, c, kc);
-        y.w = svf_fma_noise<LP>(noise_int(cb + (uint32_t)(4 * i4 + 4)), e1, e2, c, kc);
-        if (MODE == 0) W.tile[slot(i4)] = y;
+        for (int i4 = 0; i4 < K / 4; i4++) {
+          float4 y;
+          y.x = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 0), hi), e1, e2, c, kc);
+          y.y = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 1), hi), e1, e2, c, kc);
+          y.z = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 2), hi), e1, e2, c, kc);
+          y.w = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 3), hi), e1, e2, c, kc);
+          if (MODE == 0) W.tile[slot(i4)] = y;
+        }
+#undef QG_CTR
+      } else {
+#pragma unroll 2
+        for (int i4 = 0; i4 < K / 4; i4++) {
+          float4 y;
+          y.x = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 0)), e1, e2, c, kc);
+          y.y = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 1)), e1, e2, c, kc);
+          y.z = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 2)), e1, e2, c, kc);
+          y.w = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 3)), e1, e2, c, kc);
+          if (MODE == 0) W.tile[slot(i4)] = y;
+        }
       }
     }
     // ---- 2. Kogge-Stone scan of the affine maps  e <- A^(K d) e(lane - d) + e ; lane 0 inherits the block start state
