@@ -37,8 +37,10 @@ typedef struct qg_bank qg_bank;  /* V voices that share one op tape, resident on
 
 enum { QG_OK = 0, QG_ERR_ARG = 1, QG_ERR_UNSUPPORTED = 2, QG_ERR_CUDA = 3, QG_ERR_ARITY = 4, QG_ERR_MISMATCH = 5 };
 enum { QG_LAYOUT_VOICE_MAJOR = 0, QG_LAYOUT_FRAME_MAJOR = 1 };
-enum { QG_PATH_AUTO = 0, QG_PATH_INTERP = 1, QG_PATH_TV = 2 };   /* kernel selection: AUTO picks a fused kernel when the tape
-   matches, the time-vector interpreter (one CTA per voice) for spectral / small feed-forward banks, else the lane interpreter */
+enum { QG_PATH_AUTO = 0, QG_PATH_INTERP = 1, QG_PATH_TV = 2, QG_PATH_INTERP_SAMPLE = 3 };   /* kernel selection: AUTO picks a
+   fused kernel when the tape matches, the time-vector interpreter (one CTA per voice) for spectral / small feed-forward
+   banks, else the lane interpreter (block mode for feed-forward tapes); INTERP forces the lane interpreter,
+   INTERP_SAMPLE its sample-by-sample kernel */
 
 const char* qg_last_error(void);
 const char* qg_version(void);

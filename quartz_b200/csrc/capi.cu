@@ -47,6 +47,7 @@ struct qg_bank {
   std::vector<float> raw;      // host copy of the per-voice raw parameters [V][R] (empty: every voice = template)
   FusedPlan fused;
   TvPlan tv;
+  bool block_ok = false;   // the tape may run on the block-mode lane interpreter (k_interp_blk)
   int ring_mode = 0;   // 0: rings laid out [pos][voice] (lane kernels); 1: [voice][pos] (time-vector kernel)
 };
 
@@ -292,6 +293,14 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   if ((rc = bank_init_state(b, salts))) return rc;
   b->fused = plan_fused(t);
   b->tv = plan_tv(t, (size_t)180 * 1024);
+  // block mode evaluates an instruction for a whole block of samples before the next one: valid for feed-forward tapes,
+  // and for feedback loops whose delay line is at least one block long
+  b->block_ok = !(t.h.flags & TAPE_DIVERGENT);
+  for (const Instr& i : t.code) {
+    if ((i.op == OP_FB_READ || i.op == OP_FB_WRITE) && t.rings[i.aux].length < (uint32_t)interp_block_len()) b->block_ok = false;
+    // reset()/trig_reset()/reset_v() rewind OTHER ops' state in the middle of a block: sample-by-sample only
+    if (i.op >= OP_KR_BEGIN && i.op <= OP_SEQ_END) b->block_ok = false;
+  }
   return qg_bank_reset(b);
 }
 
@@ -351,7 +360,7 @@ int qg_bank_reset(qg_bank* b) {
 }
 // which kernel family serves voice-major, group-1 renders: 0 lane interpreter, 1 fused, 2 time-vector interpreter
 static int bank_family(const qg_bank* b) {
-  if (b->path == QG_PATH_INTERP) return 0;
+  if (b->path == QG_PATH_INTERP || b->path == QG_PATH_INTERP_SAMPLE) return 0;
   if (b->path == QG_PATH_TV) return b->tv.ok ? 2 : 0;
   if (b->fused.id != FUSED_NONE) return 1;
   if (b->tv.ok && (b->tv.has_fft || b->V <= 2048)) return 2;
@@ -369,7 +378,8 @@ const char* qg_bank_kernel(const qg_bank* b) {
   int f = bank_family(b);
   if (f == 1) return fused_name(b->fused.id);
   if (f == 2) return "k_interp_tv";
-  return (b->tape.h.flags & TAPE_DIVERGENT) ? "k_interp<divergent>" : "k_interp<uniform>";
+  if (b->tape.h.flags & TAPE_DIVERGENT) return "k_interp<divergent>";
+  return (b->block_ok && b->path != QG_PATH_INTERP_SAMPLE) ? "k_interp_blk" : "k_interp<uniform>";
 }
 long qg_bank_out_rows(const qg_bank* b, int group) {
   if (!b) return 0;
@@ -469,7 +479,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   a.in_frame_major = layout == QG_LAYOUT_FRAME_MAJOR; a.out_frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
   a.group = group;
   int l = 0;
-  cudaError_t e = launch_interp(a, (t.h.flags & TAPE_DIVERGENT) != 0, c->stream, &l);
+  cudaError_t e = launch_interp(a, (t.h.flags & TAPE_DIVERGENT) != 0, b->block_ok && b->path != QG_PATH_INTERP_SAMPLE, c->stream, &l);
   c->launches += l;
   if (e == cudaErrorInvalidConfiguration) return fail(QG_ERR_UNSUPPORTED, "tape needs more shared memory per voice than one SM offers");
   CU(e);

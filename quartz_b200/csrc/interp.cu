@@ -32,6 +32,28 @@ struct Lane {
   __device__ __forceinline__ float& ring(uint32_t r, uint32_t pos) const {
     return rings[(size_t)(ring_tab[r].offset + pos) * (size_t)Vp + (size_t)v];
   }
+  // one sample per exec() call
+  __device__ __forceinline__ int first() { return 0; }
+  __device__ __forceinline__ bool more(int k) const { return k < 1; }
+  __device__ __forceinline__ int next(int k) { return k + 1; }
+  __device__ __forceinline__ uint32_t sample() const { return 0u; }
+  __device__ __forceinline__ uint32_t count() const { return 1u; }
+};
+// Block lane (k_interp_blk): one thread = one voice, every instruction is applied to a block of up to BT consecutive
+// samples before the next one is decoded (the tape is feed-forward, so an op only needs its own state and its operands'
+// values for the same sample).  Parameters and state stay scalars; temporary i becomes BT values at
+// x[(PS + (i - PS) * BT + j) * nt].
+template <int BT>
+struct BlockLane : Lane {
+  int PS;          // P + NS: first temporary index
+  int j, n;        // current sample of the block, samples in this block
+  __device__ __forceinline__ float& at(int i) const { return x[(i < PS ? i : PS + (i - PS) * BT + j) * nt]; }
+  __device__ __forceinline__ float& at(int i, int jj) const { return x[(i < PS ? i : PS + (i - PS) * BT + jj) * nt]; }
+  __device__ __forceinline__ int first() { j = 0; return 0; }
+  __device__ __forceinline__ bool more(int k) const { return k < n; }
+  __device__ __forceinline__ int next(int k) { j = k + 1; return k + 1; }
+  __device__ __forceinline__ uint32_t sample() const { return (uint32_t)j; }
+  __device__ __forceinline__ uint32_t count() const { return (uint32_t)n; }
 };
 // Execution context of one SAMPLE of one voice in time-vector mode (one CTA = one voice, threads = samples of a hop):
 // parameters/state are per-voice scalars, temporaries are arrays of H samples.  Only stateless ops go through exec().
@@ -42,15 +64,23 @@ struct TvSample {
   const float* tables;
   __device__ __forceinline__ float& at(int i) const { return i < PS ? ps[i] : tmp[(i - PS) * H]; }
   __device__ __forceinline__ float& ring(uint32_t, uint32_t) const { return ps[0]; }   // never used by stateless ops
+  __device__ __forceinline__ int first() { return 0; }
+  __device__ __forceinline__ bool more(int k) const { return k < 1; }
+  __device__ __forceinline__ int next(int k) { return k + 1; }
+  __device__ __forceinline__ uint32_t sample() const { return 0u; }
+  __device__ __forceinline__ uint32_t count() const { return 1u; }
 };
 
 #define X(i) L.at((int)(i))
+// applies a case body to every sample of the lane's block (exactly once for Lane / TvSample)
+#define QG_EACH for (int k_ = L.first(); L.more(k_); k_ = L.next(k_))
 #define XU(i) __float_as_uint(X(i))
 #define SETU(i, u) X(i) = __uint_as_float(u)
 
 template <class LaneT>
 __device__ __forceinline__ float& ring_at(const LaneT& L, uint32_t ring, uint32_t pos) { return L.ring(ring, pos); }
 __device__ __forceinline__ uint32_t ring_len(const Lane& L, uint32_t r) { return L.ring_tab[r].length; }
+__device__ __forceinline__ uint32_t ring_wrap(uint32_t pos, uint32_t len) { return pos >= len ? pos - len : pos; }
 __device__ __forceinline__ uint32_t ring_len(const TvSample&, uint32_t) { return 1u; }
 
 __device__ __noinline__ void reset_range(const TvSample&, uint32_t) {}
@@ -99,121 +129,117 @@ __device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim,
 
 // Execute one instruction for this lane.  `pc` is only touched by control-flow ops.
 template <class LaneT>
-__device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
+__device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
   switch (I.op) {
     case OP_NOP: break;
-    case OP_MOV: X(I.out) = X(I.in[0]); break;
-    case OP_ZERO: X(I.out) = 0.0f; break;
-    case OP_LD_STATE: X(I.out) = X(I.s); break;
-    case OP_ST_STATE: X(I.s) = X(I.in[0]); break;
-    case OP_ADD: X(I.out) = X(I.in[0]) + X(I.in[1]); break;
-    case OP_SUB: X(I.out) = X(I.in[0]) - X(I.in[1]); break;
-    case OP_MUL: X(I.out) = X(I.in[0]) * X(I.in[1]); break;
-    case OP_GT: X(I.out) = X(I.in[0]) > X(I.in[1]) ? 1.0f : 0.0f; break;
-    case OP_LT: X(I.out) = X(I.in[0]) < X(I.in[1]) ? 1.0f : 0.0f; break;
-    case OP_EQ: X(I.out) = X(I.in[0]) == X(I.in[1]) ? 1.0f : 0.0f; break;
-    case OP_NE: X(I.out) = X(I.in[0]) != X(I.in[1]) ? 1.0f : 0.0f; break;
-    case OP_GE: X(I.out) = X(I.in[0]) >= X(I.in[1]) ? 1.0f : 0.0f; break;
-    case OP_LE: X(I.out) = X(I.in[0]) <= X(I.in[1]) ? 1.0f : 0.0f; break;
-    case OP_MIN: X(I.out) = fminf(X(I.in[0]), X(I.in[1])); break;
-    case OP_MAX: X(I.out) = fmaxf(X(I.in[0]), X(I.in[1])); break;
-    case OP_POW: X(I.out) = d_pow_cr(X(I.in[0]), X(I.in[1])); break;
-    case OP_REM: X(I.out) = d_rem_euclid(X(I.in[0]), X(I.in[1])); break;
-    case OP_LOG: X(I.out) = d_log_cr(X(I.in[0])) / d_log_cr(X(I.in[1])); break;
-    case OP_BITAND: X(I.out) = (float)(d_as_i32(X(I.in[0])) & d_as_i32(X(I.in[1]))); break;
-    case OP_BITOR: X(I.out) = (float)(d_as_i32(X(I.in[0])) | d_as_i32(X(I.in[1]))); break;
-    case OP_BITXOR: X(I.out) = (float)(d_as_i32(X(I.in[0])) ^ d_as_i32(X(I.in[1]))); break;
-    case OP_SHL: X(I.out) = (float)(int32_t)((uint32_t)d_as_i32(X(I.in[0])) << (uint32_t)(d_as_usize(X(I.in[1])) & 31)); break;
-    case OP_SHR: X(I.out) = (float)(d_as_i32(X(I.in[0])) >> (uint32_t)(d_as_usize(X(I.in[1])) & 31)); break;
-    case OP_HYPOT: X(I.out) = hypotf(X(I.in[0]), X(I.in[1])); break;
-    case OP_ATAN2: X(I.out) = atan2f(X(I.in[0]), X(I.in[1])); break;
-    case OP_DISSONANCE: {
+    case OP_MOV: QG_EACH { X(I.out) = X(I.in[0]); } break;
+    case OP_ZERO: QG_EACH { X(I.out) = 0.0f; } break;
+    case OP_LD_STATE: QG_EACH { X(I.out) = X(I.s); } break;
+    case OP_ST_STATE: QG_EACH { X(I.s) = X(I.in[0]); } break;
+    case OP_ADD: QG_EACH { X(I.out) = X(I.in[0]) + X(I.in[1]); } break;
+    case OP_SUB: QG_EACH { X(I.out) = X(I.in[0]) - X(I.in[1]); } break;
+    case OP_MUL: QG_EACH { X(I.out) = X(I.in[0]) * X(I.in[1]); } break;
+    case OP_GT: QG_EACH { X(I.out) = X(I.in[0]) > X(I.in[1]) ? 1.0f : 0.0f; } break;
+    case OP_LT: QG_EACH { X(I.out) = X(I.in[0]) < X(I.in[1]) ? 1.0f : 0.0f; } break;
+    case OP_EQ: QG_EACH { X(I.out) = X(I.in[0]) == X(I.in[1]) ? 1.0f : 0.0f; } break;
+    case OP_NE: QG_EACH { X(I.out) = X(I.in[0]) != X(I.in[1]) ? 1.0f : 0.0f; } break;
+    case OP_GE: QG_EACH { X(I.out) = X(I.in[0]) >= X(I.in[1]) ? 1.0f : 0.0f; } break;
+    case OP_LE: QG_EACH { X(I.out) = X(I.in[0]) <= X(I.in[1]) ? 1.0f : 0.0f; } break;
+    case OP_MIN: QG_EACH { X(I.out) = fminf(X(I.in[0]), X(I.in[1])); } break;
+    case OP_MAX: QG_EACH { X(I.out) = fmaxf(X(I.in[0]), X(I.in[1])); } break;
+    case OP_POW: QG_EACH { X(I.out) = d_pow_cr(X(I.in[0]), X(I.in[1])); } break;
+    case OP_REM: QG_EACH { X(I.out) = d_rem_euclid(X(I.in[0]), X(I.in[1])); } break;
+    case OP_LOG: QG_EACH { X(I.out) = d_log_cr(X(I.in[0])) / d_log_cr(X(I.in[1])); } break;
+    case OP_BITAND: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) & d_as_i32(X(I.in[1]))); } break;
+    case OP_BITOR: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) | d_as_i32(X(I.in[1]))); } break;
+    case OP_BITXOR: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) ^ d_as_i32(X(I.in[1]))); } break;
+    case OP_SHL: QG_EACH { X(I.out) = (float)(int32_t)((uint32_t)d_as_i32(X(I.in[0])) << (uint32_t)(d_as_usize(X(I.in[1])) & 31)); } break;
+    case OP_SHR: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) >> (uint32_t)(d_as_usize(X(I.in[1])) & 31)); } break;
+    case OP_HYPOT: QG_EACH { X(I.out) = hypotf(X(I.in[0]), X(I.in[1])); } break;
+    case OP_ATAN2: QG_EACH { X(I.out) = atan2f(X(I.in[0]), X(I.in[1])); } break;
+    case OP_DISSONANCE: QG_EACH {
       float f0 = X(I.in[0]), f1 = X(I.in[1]);
       float q = fabsf(f0 - f1) / (0.021f * fminf(f0, f1) + 19.0f);
       X(I.out) = 5.531753f * (expf(-0.84f * q) - expf(-1.38f * q));
-      break;
-    }
-    case OP_SIN_HZ: X(I.out) = sinf(X(I.in[1]) * X(I.in[0]) * QG_TAU); break;
-    case OP_COS_HZ: X(I.out) = cosf(X(I.in[1]) * X(I.in[0]) * QG_TAU); break;
-    case OP_SQR_HZ: { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = x < 0.5f ? 1.0f : -1.0f; break; }
-    case OP_TRI_HZ: { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = fabsf(x - 0.5f) * 4.0f - 1.0f; break; }
-    case OP_PDHALF_BI: {   // functions.rs:677-688
+    } break;
+    case OP_SIN_HZ: QG_EACH { X(I.out) = sinf(X(I.in[1]) * X(I.in[0]) * QG_TAU); } break;
+    case OP_COS_HZ: QG_EACH { X(I.out) = cosf(X(I.in[1]) * X(I.in[0]) * QG_TAU); } break;
+    case OP_SQR_HZ: QG_EACH { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = x < 0.5f ? 1.0f : -1.0f; } break;
+    case OP_TRI_HZ: QG_EACH { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = fabsf(x - 0.5f) * 4.0f - 1.0f; } break;
+    case OP_PDHALF_BI: QG_EACH {   // functions.rs:677-688
       float x = X(I.in[0]), mid = d_clamp(X(I.in[1]), -1.0f, 1.0f);
       if (x < mid) { float ls = mid != -1.0f ? 1.0f / (mid + 1.0f) : 0.0f; X(I.out) = ls * x; }
       else { float rs = mid != 1.0f ? 1.0f / (1.0f - mid) : 0.0f; X(I.out) = rs * (x - mid) + 0.5f; }
-      break;
-    }
-    case OP_PDHALF_UNI: {   // functions.rs:689-706
+    } break;
+    case OP_PDHALF_UNI: QG_EACH {   // functions.rs:689-706
       float x = X(I.in[0]), m = X(I.in[1]);
       float mid = m >= 1.0f ? 1.0f : (m <= -1.0f ? 0.0f : (m + 1.0f) / 2.0f);
       if (x < mid) { float ls = mid != 0.0f ? 0.5f / mid : 0.0f; X(I.out) = ls * x; }
       else { float rs = mid != 1.0f ? 0.5f / (1.0f - mid) : 0.0f; X(I.out) = rs * (x - mid) + 0.5f; }
-      break;
-    }
-    case OP_LERP: X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
-    case OP_LERP11: X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); break;
-    case OP_DELERP: X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
-    case OP_DELERP11: X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; break;
-    case OP_XERP: X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
-    case OP_XERP11: X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); break;
-    case OP_DEXERP: X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); break;
-    case OP_DEXERP11: X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; break;
-    case OP_SPLINE: X(I.out) = d_spline(X(I.in[0]), X(I.in[1]), X(I.in[2]), X(I.in[3]), X(I.in[4])); break;
-    case OP_ABS: X(I.out) = fabsf(X(I.in[0])); break;
-    case OP_SIGNUM: X(I.out) = d_signum(X(I.in[0])); break;
-    case OP_FLOOR: X(I.out) = floorf(X(I.in[0])); break;
-    case OP_FRACT: X(I.out) = d_fract(X(I.in[0])); break;
-    case OP_CEIL: X(I.out) = ceilf(X(I.in[0])); break;
-    case OP_ROUND: X(I.out) = roundf(X(I.in[0])); break;
-    case OP_SQRT: X(I.out) = sqrtf(X(I.in[0])); break;
-    case OP_EXP: X(I.out) = d_exp_cr(X(I.in[0])); break;
-    case OP_EXP2: X(I.out) = d_exp2_cr(X(I.in[0])); break;
-    case OP_EXP10: X(I.out) = d_exp10(X(I.in[0])); break;
-    case OP_LN_1P_FN: X(I.out) = log1pf(X(I.in[0])); break;
-    case OP_EXP_M1_FN: X(I.out) = expm1f(X(I.in[0])); break;
-    case OP_LN: X(I.out) = d_log_cr(X(I.in[0])); break;
-    case OP_LOG2: X(I.out) = d_log2_cr(X(I.in[0])); break;
-    case OP_LOG10: X(I.out) = d_log10_cr(X(I.in[0])); break;
-    case OP_SIN: X(I.out) = sinf(X(I.in[0])); break;
-    case OP_COS: X(I.out) = cosf(X(I.in[0])); break;
-    case OP_TAN: X(I.out) = tanf(X(I.in[0])); break;
-    case OP_ASIN: X(I.out) = asinf(X(I.in[0])); break;
-    case OP_ACOS: X(I.out) = acosf(X(I.in[0])); break;
-    case OP_ATAN: X(I.out) = atanf(X(I.in[0])); break;
-    case OP_SINH: X(I.out) = sinhf(X(I.in[0])); break;
-    case OP_COSH: X(I.out) = coshf(X(I.in[0])); break;
-    case OP_TANH: X(I.out) = tanhf(X(I.in[0])); break;
-    case OP_ASINH: X(I.out) = asinhf(X(I.in[0])); break;
-    case OP_ACOSH: X(I.out) = acoshf(X(I.in[0])); break;
-    case OP_ATANH: X(I.out) = atanhf(X(I.in[0])); break;
-    case OP_SQUARED: { float x = X(I.in[0]); X(I.out) = x * x; break; }
-    case OP_CUBED: { float x = X(I.in[0]); X(I.out) = x * x * x; break; }
-    case OP_DB_AMP: X(I.out) = d_exp10(X(I.in[0]) / 20.0f); break;
-    case OP_AMP_DB: X(I.out) = d_log10_cr(X(I.in[0])) * 20.0f; break;
-    case OP_A_WEIGHT: X(I.out) = d_a_weight(X(I.in[0])); break;
-    case OP_SOFTSIGN: { float x = X(I.in[0]); X(I.out) = x / (1.0f + fabsf(x)); break; }
-    case OP_SMOOTH3: { float x = X(I.in[0]); X(I.out) = (3.0f - 2.0f * x) * x * x; break; }
-    case OP_SMOOTH5: X(I.out) = d_smooth5(X(I.in[0])); break;
-    case OP_SMOOTH7: { float x = X(I.in[0]), x2 = x * x; X(I.out) = x2 * x2 * (35.0f - 84.0f * x + (70.0f - 20.0f * x) * x2); break; }
-    case OP_SMOOTH9: {
+    } break;
+    case OP_LERP: QG_EACH { X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
+    case OP_LERP11: QG_EACH { X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); } break;
+    case OP_DELERP: QG_EACH { X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
+    case OP_DELERP11: QG_EACH { X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; } break;
+    case OP_XERP: QG_EACH { X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
+    case OP_XERP11: QG_EACH { X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); } break;
+    case OP_DEXERP: QG_EACH { X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
+    case OP_DEXERP11: QG_EACH { X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; } break;
+    case OP_SPLINE: QG_EACH { X(I.out) = d_spline(X(I.in[0]), X(I.in[1]), X(I.in[2]), X(I.in[3]), X(I.in[4])); } break;
+    case OP_ABS: QG_EACH { X(I.out) = fabsf(X(I.in[0])); } break;
+    case OP_SIGNUM: QG_EACH { X(I.out) = d_signum(X(I.in[0])); } break;
+    case OP_FLOOR: QG_EACH { X(I.out) = floorf(X(I.in[0])); } break;
+    case OP_FRACT: QG_EACH { X(I.out) = d_fract(X(I.in[0])); } break;
+    case OP_CEIL: QG_EACH { X(I.out) = ceilf(X(I.in[0])); } break;
+    case OP_ROUND: QG_EACH { X(I.out) = roundf(X(I.in[0])); } break;
+    case OP_SQRT: QG_EACH { X(I.out) = sqrtf(X(I.in[0])); } break;
+    case OP_EXP: QG_EACH { X(I.out) = d_exp_cr(X(I.in[0])); } break;
+    case OP_EXP2: QG_EACH { X(I.out) = d_exp2_cr(X(I.in[0])); } break;
+    case OP_EXP10: QG_EACH { X(I.out) = d_exp10(X(I.in[0])); } break;
+    case OP_LN_1P_FN: QG_EACH { X(I.out) = log1pf(X(I.in[0])); } break;
+    case OP_EXP_M1_FN: QG_EACH { X(I.out) = expm1f(X(I.in[0])); } break;
+    case OP_LN: QG_EACH { X(I.out) = d_log_cr(X(I.in[0])); } break;
+    case OP_LOG2: QG_EACH { X(I.out) = d_log2_cr(X(I.in[0])); } break;
+    case OP_LOG10: QG_EACH { X(I.out) = d_log10_cr(X(I.in[0])); } break;
+    case OP_SIN: QG_EACH { X(I.out) = sinf(X(I.in[0])); } break;
+    case OP_COS: QG_EACH { X(I.out) = cosf(X(I.in[0])); } break;
+    case OP_TAN: QG_EACH { X(I.out) = tanf(X(I.in[0])); } break;
+    case OP_ASIN: QG_EACH { X(I.out) = asinf(X(I.in[0])); } break;
+    case OP_ACOS: QG_EACH { X(I.out) = acosf(X(I.in[0])); } break;
+    case OP_ATAN: QG_EACH { X(I.out) = atanf(X(I.in[0])); } break;
+    case OP_SINH: QG_EACH { X(I.out) = sinhf(X(I.in[0])); } break;
+    case OP_COSH: QG_EACH { X(I.out) = coshf(X(I.in[0])); } break;
+    case OP_TANH: QG_EACH { X(I.out) = tanhf(X(I.in[0])); } break;
+    case OP_ASINH: QG_EACH { X(I.out) = asinhf(X(I.in[0])); } break;
+    case OP_ACOSH: QG_EACH { X(I.out) = acoshf(X(I.in[0])); } break;
+    case OP_ATANH: QG_EACH { X(I.out) = atanhf(X(I.in[0])); } break;
+    case OP_SQUARED: QG_EACH { float x = X(I.in[0]); X(I.out) = x * x; } break;
+    case OP_CUBED: QG_EACH { float x = X(I.in[0]); X(I.out) = x * x * x; } break;
+    case OP_DB_AMP: QG_EACH { X(I.out) = d_exp10(X(I.in[0]) / 20.0f); } break;
+    case OP_AMP_DB: QG_EACH { X(I.out) = d_log10_cr(X(I.in[0])) * 20.0f; } break;
+    case OP_A_WEIGHT: QG_EACH { X(I.out) = d_a_weight(X(I.in[0])); } break;
+    case OP_SOFTSIGN: QG_EACH { float x = X(I.in[0]); X(I.out) = x / (1.0f + fabsf(x)); } break;
+    case OP_SMOOTH3: QG_EACH { float x = X(I.in[0]); X(I.out) = (3.0f - 2.0f * x) * x * x; } break;
+    case OP_SMOOTH5: QG_EACH { X(I.out) = d_smooth5(X(I.in[0])); } break;
+    case OP_SMOOTH7: QG_EACH { float x = X(I.in[0]), x2 = x * x; X(I.out) = x2 * x2 * (35.0f - 84.0f * x + (70.0f - 20.0f * x) * x2); } break;
+    case OP_SMOOTH9: QG_EACH {
       float x = X(I.in[0]), x2 = x * x;
       X(I.out) = ((((70.0f * x - 315.0f) * x + 540.0f) * x - 420.0f) * x + 126.0f) * x2 * x2 * x;
-      break;
-    }
-    case OP_UPARC: { float x = X(I.in[0]); X(I.out) = 1.0f - sqrtf(fmaxf(0.0f, 1.0f - x * x)); break; }
-    case OP_DOWNARC: { float x = X(I.in[0]); X(I.out) = sqrtf(fmaxf(0.0f, (2.0f - x) * x)); break; }
-    case OP_SINE_EASE: X(I.out) = (1.0f - cosf(X(I.in[0]) * QG_PI)) * 0.5f; break;
-    case OP_SEMITONE_RATIO: X(I.out) = d_exp2_cr(X(I.in[0]) / 12.0f); break;
-    case OP_RND1: X(I.out) = d_rnd1(d_as_usize(X(I.in[0]))); break;
-    case OP_RND2: X(I.out) = d_rnd2(d_as_usize(X(I.in[0]))); break;
-    case OP_DEG: X(I.out) = X(I.in[0]) * 57.2957795130823208767981548141051703f; break;
-    case OP_RAD: X(I.out) = X(I.in[0]) * (QG_PI / 180.0f); break;
-    case OP_RECIP: X(I.out) = 1.0f / X(I.in[0]); break;
-    case OP_NORMAL: { float x = X(I.in[0]); X(I.out) = d_is_normal(x) ? x : 0.0f; break; }
-    case OP_CLIP: X(I.out) = d_clamp(X(I.in[0]), X(I.p), X(I.p + 1)); break;
-    case OP_WRAP2: { float p0 = X(I.p), r = X(I.p + 1); X(I.out) = fmodf(fmodf(X(I.in[0]) - p0, r) + r, r) + p0; break; }
-    case OP_WRAP1: { float x0 = X(I.p), x = X(I.in[0]); X(I.out) = x - x0 * floorf(x / x0); break; }
-    case OP_MIRROR: {   // functions.rs:1167-1180
+    } break;
+    case OP_UPARC: QG_EACH { float x = X(I.in[0]); X(I.out) = 1.0f - sqrtf(fmaxf(0.0f, 1.0f - x * x)); } break;
+    case OP_DOWNARC: QG_EACH { float x = X(I.in[0]); X(I.out) = sqrtf(fmaxf(0.0f, (2.0f - x) * x)); } break;
+    case OP_SINE_EASE: QG_EACH { X(I.out) = (1.0f - cosf(X(I.in[0]) * QG_PI)) * 0.5f; } break;
+    case OP_SEMITONE_RATIO: QG_EACH { X(I.out) = d_exp2_cr(X(I.in[0]) / 12.0f); } break;
+    case OP_RND1: QG_EACH { X(I.out) = d_rnd1(d_as_usize(X(I.in[0]))); } break;
+    case OP_RND2: QG_EACH { X(I.out) = d_rnd2(d_as_usize(X(I.in[0]))); } break;
+    case OP_DEG: QG_EACH { X(I.out) = X(I.in[0]) * 57.2957795130823208767981548141051703f; } break;
+    case OP_RAD: QG_EACH { X(I.out) = X(I.in[0]) * (QG_PI / 180.0f); } break;
+    case OP_RECIP: QG_EACH { X(I.out) = 1.0f / X(I.in[0]); } break;
+    case OP_NORMAL: QG_EACH { float x = X(I.in[0]); X(I.out) = d_is_normal(x) ? x : 0.0f; } break;
+    case OP_CLIP: QG_EACH { X(I.out) = d_clamp(X(I.in[0]), X(I.p), X(I.p + 1)); } break;
+    case OP_WRAP2: QG_EACH { float p0 = X(I.p), r = X(I.p + 1); X(I.out) = fmodf(fmodf(X(I.in[0]) - p0, r) + r, r) + p0; } break;
+    case OP_WRAP1: QG_EACH { float x0 = X(I.p), x = X(I.in[0]); X(I.out) = x - x0 * floorf(x / x0); } break;
+    case OP_MIRROR: QG_EACH {   // functions.rs:1167-1180
       float p0 = X(I.p), p1 = X(I.p + 1), r = X(I.p + 2), x = X(I.in[0]);
       float n = d_is_normal(x) ? x : 0.0f, res;
       if (n >= p0 && n <= p1) res = n;
@@ -224,43 +250,38 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
         else res = p1 - (distance - folds * r);
       }
       X(I.out) = res;
-      break;
-    }
-    case OP_POL: { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = hypotf(a, b); X(I.out + 1) = atan2f(b, a); break; }
-    case OP_CAR: { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = a * cosf(b); X(I.out + 1) = a * sinf(b); break; }
-    case OP_DIVN: X(I.out) = X(I.in[0]) / (float)I.n; break;
-    case OP_PAN: { float x = X(I.in[0]); X(I.out) = X(I.p) * x; X(I.out + 1) = X(I.p + 1) * x; break; }
-    case OP_PAN_VAR: {
+    } break;
+    case OP_POL: QG_EACH { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = hypotf(a, b); X(I.out + 1) = atan2f(b, a); } break;
+    case OP_CAR: QG_EACH { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = a * cosf(b); X(I.out + 1) = a * sinf(b); } break;
+    case OP_DIVN: QG_EACH { X(I.out) = X(I.in[0]) / (float)I.n; } break;
+    case OP_PAN: QG_EACH { float x = X(I.in[0]); X(I.out) = X(I.p) * x; X(I.out + 1) = X(I.p + 1) * x; } break;
+    case OP_PAN_VAR: QG_EACH {
       float x = X(I.in[0]), pan = X(I.in[1]);
       if (pan != X(I.s)) { float l, r; pan_weights(pan, &l, &r); X(I.s) = pan; X(I.s + 1) = l; X(I.s + 2) = r; }
       X(I.out) = X(I.s + 1) * x; X(I.out + 1) = X(I.s + 2) * x;
-      break;
-    }
-    case OP_ROTATE: {
+    } break;
+    case OP_ROTATE: QG_EACH {
       float a = X(I.in[0]), b = X(I.in[1]), c = X(I.p), s = X(I.p + 1);
       X(I.out) = c * a - s * b; X(I.out + 1) = s * a + c * b;
-      break;
-    }
+    } break;
     // ---------------------------------------------------------------- sources
-    case OP_SINE: {
+    case OP_SINE: QG_EACH {
       float ph = X(I.s);
       float np = ph + X(I.in[0]) * X(I.p);
       np -= floorf(np);
       X(I.s) = np;
       X(I.out) = sinf(ph * QG_TAU);
-      break;
-    }
-    case OP_NOISE: { uint32_t c = XU(I.s) + 1u; SETU(I.s, c); X(I.out) = d_noise(c); break; }
-    case OP_IMPULSE: { uint32_t f = XU(I.s); X(I.out) = f ? 0.0f : 1.0f; SETU(I.s, 1u); break; }
-    case OP_RAMP: {   // nodes.rs:476-483
+    } break;
+    case OP_NOISE: QG_EACH { uint32_t c = XU(I.s) + 1u; SETU(I.s, c); X(I.out) = d_noise(c); } break;
+    case OP_IMPULSE: QG_EACH { uint32_t f = XU(I.s); X(I.out) = f ? 0.0f : 1.0f; SETU(I.s, 1u); } break;
+    case OP_RAMP: QG_EACH {   // nodes.rs:476-483
       float val = X(I.s);
       X(I.out) = val;
       val += X(I.in[0]) / X(I.p);
       if (val >= 1.0f) val -= 1.0f;
       X(I.s) = val;
-      break;
-    }
-    case OP_WAVETABLE: {   // FunDSP WaveSynth + Wavetable::read/at (restated, see lower.cpp make_wave)
+    } break;
+    case OP_WAVETABLE: QG_EACH {   // FunDSP WaveSynth + Wavetable::read/at (restated, see lower.cpp make_wave)
       const float* hdr = L.tables + I.aux;
       const uint32_t nt = (uint32_t)hdr[0];
       float f = X(I.in[0]);
@@ -287,24 +308,21 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
       float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
       X(I.out) = (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
-      break;
-    }
-    case OP_WAVE: {
+    } break;
+    case OP_WAVE: QG_EACH {
       uint32_t i = XU(I.s);
       X(I.out) = L.tables[I.aux + i];
       i += 1;
       if (i >= I.aux2) i = 0;
       SETU(I.s, i);
-      break;
-    }
+    } break;
     // ---------------------------------------------------------------- filters
-    case OP_SVF: {
+    case OP_SVF: QG_EACH {
       float ic1 = X(I.s), ic2 = X(I.s + 1);
       X(I.out) = d_svf_tick(X(I.in[0]), ic1, ic2, X(I.p), X(I.p + 1), X(I.p + 2), X(I.p + 3), X(I.p + 4), X(I.p + 5));
       X(I.s) = ic1; X(I.s + 1) = ic2;
-      break;
-    }
-    case OP_SVF_VAR: {
+    } break;
+    case OP_SVF_VAR: QG_EACH {
       int mode = I.n & 0xff, nvar = I.n >> 8;
       float hz = nvar >= 1 ? X(I.in[1]) : X(I.p), q = nvar >= 2 ? X(I.in[2]) : X(I.p + 1), g = nvar >= 3 ? X(I.in[3]) : X(I.p + 2);
       if (hz != X(I.s + 8) || q != X(I.s + 9) || g != X(I.s + 10)) {
@@ -316,16 +334,14 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       float ic1 = X(I.s), ic2 = X(I.s + 1);
       X(I.out) = d_svf_tick(X(I.in[0]), ic1, ic2, X(I.s + 2), X(I.s + 3), X(I.s + 4), X(I.s + 5), X(I.s + 6), X(I.s + 7));
       X(I.s) = ic1; X(I.s + 1) = ic2;
-      break;
-    }
-    case OP_BIQUAD: {
+    } break;
+    case OP_BIQUAD: QG_EACH {
       float x0 = X(I.in[0]), x1 = X(I.s), x2 = X(I.s + 1), y1 = X(I.s + 2), y2 = X(I.s + 3);
       float y0 = X(I.p + 2) * x0 + X(I.p + 3) * x1 + X(I.p + 4) * x2 - X(I.p) * y1 - X(I.p + 1) * y2;
       X(I.s) = x0; X(I.s + 1) = x1; X(I.s + 2) = y0; X(I.s + 3) = y1;
       X(I.out) = y0;
-      break;
-    }
-    case OP_BIQUAD_VAR: {
+    } break;
+    case OP_BIQUAD_VAR: QG_EACH {
       int kind = I.n & 0xff, nvar = I.n >> 8;
       float c0 = X(I.in[1]), c1 = nvar >= 2 ? X(I.in[2]) : X(I.s + 10);
       if (c0 != X(I.s + 9) || c1 != X(I.s + 10)) {
@@ -338,9 +354,8 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       float y0 = X(I.s + 6) * x0 + X(I.s + 7) * x1 + X(I.s + 8) * x2 - X(I.s + 4) * y1 - X(I.s + 5) * y2;
       X(I.s) = x0; X(I.s + 1) = x1; X(I.s + 2) = y0; X(I.s + 3) = y1;
       X(I.out) = y0;
-      break;
-    }
-    case OP_ONEPOLE: case OP_ONEPOLE_VAR: {
+    } break;
+    case OP_ONEPOLE: case OP_ONEPOLE_VAR: QG_EACH {
       float coeff;
       if (I.op == OP_ONEPOLE) coeff = X(I.p);
       else {
@@ -357,9 +372,8 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       }
       X(I.s) = x; X(I.s + 1) = y;
       X(I.out) = y;
-      break;
-    }
-    case OP_PINKPASS: {
+    } break;
+    case OP_PINKPASS: QG_EACH {
       float w = X(I.in[0]);
       float b0 = 0.99886f * X(I.s) + w * 0.0555179f;
       float b1 = 0.99332f * X(I.s + 1) + w * 0.0750759f;
@@ -371,20 +385,18 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       X(I.s) = b0; X(I.s + 1) = b1; X(I.s + 2) = b2; X(I.s + 3) = b3; X(I.s + 4) = b4; X(I.s + 5) = b5;
       X(I.s + 6) = w * 0.115926f;
       X(I.out) = pink * 0.11f;
-      break;
-    }
-    case OP_FIR: {
+    } break;
+    case OP_FIR: QG_EACH {
       int n = I.n;
       for (int k = n - 1; k > 0; k--) X(I.s + k) = X(I.s + k - 1);
       X(I.s) = X(I.in[0]);
       float acc = 0.0f;
       for (int k = 0; k < n; k++) acc += X(I.p + k) * X(I.s + k);
       X(I.out) = acc;
-      break;
-    }
+    } break;
     // ---------------------------------------------------------------- delays
-    case OP_TICK: { float v = X(I.s); X(I.s) = X(I.in[0]); X(I.out) = v; break; }
-    case OP_DELAY: {
+    case OP_TICK: QG_EACH { float v = X(I.s); X(I.s) = X(I.in[0]); X(I.out) = v; } break;
+    case OP_DELAY: QG_EACH {
       uint32_t i = XU(I.s), len = ring_len(L, I.aux);
       float& slot = ring_at(L, I.aux, i);
       float o = slot;
@@ -392,9 +404,8 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       i = i + 1 == len ? 0 : i + 1;
       SETU(I.s, i);
       X(I.out) = o;
-      break;
-    }
-    case OP_TAP: {
+    } break;
+    case OP_TAP: QG_EACH {
       uint32_t idx = XU(I.s), len = ring_len(L, I.aux), mask = len - 1;
       ring_at(L, I.aux, idx) = X(I.in[0]);
       float tap = d_clamp(X(I.in[1]), X(I.p), X(I.p + 1)) * X(I.p + 2);
@@ -410,9 +421,8 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
         X(I.out) = d_lerp(ring_at(L, I.aux, i1), ring_at(L, I.aux, i2), d);
       }
       SETU(I.s, (idx + 1) & mask);
-      break;
-    }
-    case OP_SAMP_DELAY: {   // nodes.rs:726-731: push_front, pop_back, then index from the front
+    } break;
+    case OP_SAMP_DELAY: QG_EACH {   // nodes.rs:726-731: push_front, pop_back, then index from the front
       uint32_t head = XU(I.s), len = ring_len(L, I.aux);
       head = head == 0 ? len - 1 : head - 1;
       ring_at(L, I.aux, head) = X(I.in[0]);
@@ -421,15 +431,15 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       float o = 0.0f;
       if (k < (uint64_t)len) { uint32_t pos = head + (uint32_t)k; if (pos >= len) pos -= len; o = ring_at(L, I.aux, pos); }
       X(I.out) = o;
-      break;
-    }
-    case OP_ENVELOPE: {
+    } break;
+    case OP_ENVELOPE: QG_EACH {
       int shape = I.n & 0xff, nin = I.n >> 8;
       float t = X(I.s), t0 = X(I.s + 1), t1 = X(I.s + 2), v0 = X(I.s + 3), v1 = X(I.s + 4);
       if (t >= t1) {
         float c[4] = {X(I.p), X(I.p + 1), X(I.p + 2), X(I.p + 3)};
-        float in[4] = {0, 0, 0, 0};
-        for (int k = 0; k < nin && k < 4; k++) in[k] = X(I.in[k]);
+        float in[4];
+        in[0] = nin > 0 ? X(I.in[0]) : 0.0f; in[1] = nin > 1 ? X(I.in[1]) : 0.0f;
+        in[2] = nin > 2 ? X(I.in[2]) : 0.0f; in[3] = nin > 3 ? X(I.in[3]) : 0.0f;
         if (XU(I.s + 7)) { v1 = d_env_eval(shape, nin, 0.0f, c, in); SETU(I.s + 7, 0u); }
         uint64_t th = (uint64_t)XU(I.s + 5) | ((uint64_t)XU(I.s + 6) << 32);
         t0 = t1;
@@ -444,29 +454,25 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       float u = d_delerp(t0, t1, t);
       X(I.s) = t + X(I.p + 4);
       X(I.out) = d_lerp(v0, v1, u);
-      break;
-    }
-    case OP_DECLICK: {
+    } break;
+    case OP_DECLICK: QG_EACH {
       float t = X(I.s), dur = X(I.p), x = X(I.in[0]);
       if (t < dur) { X(I.out) = x * d_smooth5(t / dur); X(I.s) = t + X(I.p + 1); }
       else X(I.out) = x;
-      break;
-    }
+    } break;
     // ---------------------------------------------------------------- in-tree stateful nodes
-    case OP_SHIFT_REG: {   // nodes.rs:173-185
+    case OP_SHIFT_REG: QG_EACH {   // nodes.rs:173-185
       if (X(I.in[1]) != 0.0f) {
         for (int k = 7; k > 0; k--) X(I.s + k) = X(I.s + k - 1);
         X(I.s) = X(I.in[0]);
       }
       for (int k = 0; k < 8; k++) X(I.out + k) = X(I.s + k);
-      break;
-    }
-    case OP_SNH: {   // nodes.rs:811-816
+    } break;
+    case OP_SNH: QG_EACH {   // nodes.rs:811-816
       if (X(I.in[1]) != 0.0f) X(I.s) = X(I.in[0]);
       X(I.out) = X(I.s);
-      break;
-    }
-    case OP_QUANTIZE: {   // nodes.rs:213-228
+    } break;
+    case OP_QUANTIZE: QG_EACH {   // nodes.rs:213-228
       float n = X(I.in[0]), range = X(I.p);
       float wrapped = n - range * floorf(n / range);
       float nearest = 0.0f, dist = FLT_MAX;
@@ -476,13 +482,11 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
         if (d < dist) { nearest = v; dist = d; }
       }
       X(I.out) = n + nearest - wrapped;
-      break;
-    }
-    case OP_ARR_GET: {   // nodes.rs:143-149
+    } break;
+    case OP_ARR_GET: QG_EACH {   // nodes.rs:143-149
       uint64_t k = d_as_usize(X(I.in[0]));
       X(I.out) = k < (uint64_t)I.aux2 ? L.tables[I.aux + (uint32_t)k] : 0.0f;
-      break;
-    }
+    } break;
     // ---------------------------------------------------------------- control flow
     case OP_KR_BEGIN: {   // nodes.rs:272-275
       uint32_t c = XU(I.s);
@@ -559,15 +563,17 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       break;
     }
     // ---------------------------------------------------------------- feedback
-    case OP_FB_READ: X(I.out) = X(I.in[0]) + ring_at(L, I.aux, XU(I.s)); break;
+    // block lanes run FB_READ for every sample of the block before FB_WRITE stores any (ring length >= block length is
+    // checked by the launcher), so both address the ring at idx + j and the index advances once per block
+    case OP_FB_READ: QG_EACH { X(I.out) = X(I.in[0]) + ring_at(L, I.aux, ring_wrap(XU(I.s) + L.sample(), ring_len(L, I.aux))); } break;
     case OP_FB_WRITE: {
-      uint32_t i = XU(I.s);
-      ring_at(L, I.aux, i) = X(I.in[0]);
-      if (I.n) { uint32_t len = ring_len(L, I.aux); SETU(I.s, i + 1 == len ? 0 : i + 1); }
+      const uint32_t len = ring_len(L, I.aux), i = XU(I.s);
+      QG_EACH { ring_at(L, I.aux, ring_wrap(i + L.sample(), len)) = X(I.in[0]); }
+      if (I.n) SETU(I.s, ring_wrap(i + L.count(), len));
       break;
     }
     // ---------------------------------------------------------------- spectral nodes (per-lane path)
-    case OP_RFFT: {   // nodes.rs:625-642
+    case OP_RFFT: QG_EACH {   // nodes.rs:625-642
       uint32_t N = 1u << I.n, i = XU(I.s), nx = i + 1 == N ? 0 : i + 1;
       SETU(I.s, nx);
       if (i == 0) {
@@ -577,9 +583,8 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       ring_at(L, I.aux, i) = X(I.in[0]);
       if (i <= N / 2) { X(I.out) = ring_at(L, I.aux + 1, i); X(I.out + 1) = ring_at(L, I.aux + 2, i); }
       else { X(I.out) = ring_at(L, I.aux + 1, N - i); X(I.out + 1) = -ring_at(L, I.aux + 2, N - i); }
-      break;
-    }
-    case OP_IFFT: {   // nodes.rs:681-693
+    } break;
+    case OP_IFFT: QG_EACH {   // nodes.rs:681-693
       uint32_t N = 1u << I.n, i = XU(I.s), nx = i + 1 == N ? 0 : i + 1;
       SETU(I.s, nx);
       if (i == 0) {
@@ -588,8 +593,7 @@ __device__ __forceinline__ void exec(const Instr& I, const LaneT& L, int& pc) {
       }
       ring_at(L, I.aux, i) = X(I.in[0]); ring_at(L, I.aux + 1, i) = X(I.in[1]);
       X(I.out) = ring_at(L, I.aux + 2, i); X(I.out + 1) = ring_at(L, I.aux + 3, i);
-      break;
-    }
+    } break;
     default: break;
   }
 }
@@ -626,14 +630,14 @@ __global__ void __launch_bounds__(128) k_interp(InterpArgs a) {
     }
     if (!DIVERGENT) {
       int pc = 0;
-      for (int i = 0; i < a.n_instr; i++) exec(code[i], L, pc);
+      for (int i = 0; i < a.n_instr; i++) { const Instr I = code[i]; exec(I, L, pc); }
     } else {
       // SIMT-stack emulation: always run the lowest pending instruction; lanes that jumped ahead wait there
       int pc = 0;
       for (;;) {
         int m = __reduce_min_sync(0xffffffffu, pc);
         if (m >= a.n_instr) break;
-        if (pc == m) { pc = m + 1; exec(code[m], L, pc); }
+        if (pc == m) { pc = m + 1; const Instr I = code[m]; exec(I, L, pc); }
       }
     }
     // ---- outputs
@@ -673,6 +677,108 @@ __global__ void __launch_bounds__(128) k_interp(InterpArgs a) {
     }
   }
   for (int s = 0; s < a.NS; s++) a.state[(size_t)s * a.Vp + v] = X(a.P + s);
+}
+
+// K1b — block-mode lane interpreter for feed-forward (uniform) tapes: one lane = one voice, but every instruction is decoded
+// ONCE per block of BT samples and applied to the whole block (FunDSP's `process()` does the same with 64-sample blocks),
+// so the decode / dispatch cost that dominates k_interp is amortised and HBM delay lines are read BT lines at a time
+// (BT independent loads in flight per warp instead of one dependent load per sample).
+template <int BT>
+__global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  Instr* code = reinterpret_cast<Instr*>(smem_raw);
+  float* xs = reinterpret_cast<float*>(smem_raw + (size_t)a.n_instr * sizeof(Instr));
+  const int PS = a.P + a.NS;
+  const int nx = PS + a.NT * BT;
+  float* tiles = xs + (size_t)nx * nt;                       // [n_out][nwarps][32][33]
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.code);
+    uint4* dst = reinterpret_cast<uint4*>(code);
+    for (int i = tid; i < a.n_instr * 2; i += nt) dst[i] = src[i];
+  }
+  const int v = blockIdx.x * nt + tid;
+  BlockLane<BT> L;
+  L.x = xs + tid; L.nt = nt; L.v = v; L.Vp = a.Vp; L.rings = a.rings; L.ring_tab = a.ring_tab; L.tables = a.tables;
+  L.state_init = a.state_init; L.resets = a.resets; L.P = a.P; L.PS = PS; L.j = 0; L.n = BT;
+  for (int p = 0; p < a.P; p++) L.x[p * nt] = a.params[(size_t)p * a.Vp + v];
+  for (int s = 0; s < a.NS; s++) L.x[(a.P + s) * nt] = a.state[(size_t)s * a.Vp + v];
+  for (int k = 0; k < a.NT * BT; k++) L.x[(PS + k) * nt] = 0.0f;
+  __syncthreads();
+
+  const int warp_v0 = blockIdx.x * nt + warp * 32;
+  for (long t0 = 0; t0 < a.T; t0 += BT) {
+    const int n = (a.T - t0) < BT ? (int)(a.T - t0) : BT;
+    L.n = n;
+    for (int c = 0; c < a.n_in; c++)
+      for (int j = 0; j < n; j++) {
+        const long t = t0 + j;
+        size_t idx = a.in_frame_major ? ((size_t)t * a.V + v) * a.n_in + c : ((size_t)v * a.n_in + c) * a.T + t;
+        L.at(PS + c, j) = v < a.V ? a.in[idx] : 0.0f;
+      }
+    for (int i = 0; i < a.n_instr; i++) {
+      const Instr I = code[i];
+      if (I.op == OP_DELAY) {
+        // whole-block delay line access: all reads first (independent loads), then the writes
+        const uint32_t len = ring_len(L, I.aux), idx = __float_as_uint(L.x[I.s * nt]);
+        if (len >= (uint32_t)BT) {
+          float o[BT];
+#pragma unroll
+          for (int j = 0; j < BT; j++) if (j < n) o[j] = ring_at(L, I.aux, ring_wrap(idx + (uint32_t)j, len));
+#pragma unroll
+          for (int j = 0; j < BT; j++) if (j < n) ring_at(L, I.aux, ring_wrap(idx + (uint32_t)j, len)) = L.at(I.in[0], j);
+#pragma unroll
+          for (int j = 0; j < BT; j++) if (j < n) L.at(I.out, j) = o[j];
+          L.x[I.s * nt] = __uint_as_float(ring_wrap(idx + (uint32_t)n, len));
+          continue;
+        }
+      }
+      int pc = 0;
+      exec(I, L, pc);
+    }
+    // ---- outputs
+    if (a.out_frame_major) {
+      if (v < a.V)
+        for (int j = 0; j < n; j++)
+          for (int c = 0; c < a.n_out; c++) a.out[((size_t)(t0 + j) * a.V + v) * a.n_out + c] = L.at(a.out_x[c], j);
+    } else {
+      const int tt0 = (int)(t0 & 31);
+      for (int c = 0; c < a.n_out; c++) {
+        const int ox = a.out_x[c];
+        float* trow = tiles + (((size_t)c * nwarps + warp) * 32 + lane) * 33 + tt0;
+        for (int j = 0; j < n; j++) trow[j] = L.at(ox, j);
+      }
+      const long t = t0 + n - 1;
+      const int tt = (int)(t & 31);
+      if (tt == 31 || t == a.T - 1) {
+        __syncwarp();
+        const long t_base = t - tt;
+        const int ncols = tt + 1;
+        for (int c = 0; c < a.n_out; c++) {
+          const float* tile = tiles + ((size_t)c * nwarps + warp) * 32 * 33;
+          if (a.group <= 1) {
+            for (int r = 0; r < 32; r++) {
+              int vv = warp_v0 + r;
+              if (vv < a.V && lane < ncols) a.out[((size_t)vv * a.n_out + c) * a.T + t_base + lane] = tile[r * 33 + lane];
+            }
+          } else {
+            const int G = a.group;
+            const float inv = 1.0f / (float)G;
+            for (int g0 = 0; g0 < 32; g0 += G) {
+              int gi = (warp_v0 + g0) / G;
+              if (warp_v0 + g0 + G <= a.V && lane < ncols) {
+                float acc = tile[g0 * 33 + lane];
+                for (int r = 1; r < G; r++) acc += tile[(g0 + r) * 33 + lane];
+                a.out[((size_t)gi * a.n_out + c) * a.T + t_base + lane] = acc * inv;
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  for (int s = 0; s < a.NS; s++) a.state[(size_t)s * a.Vp + v] = L.x[(a.P + s) * nt];
 }
 
 // state_init[s][v] = default word, then hash-seeded words (phase / noise seed / envelope hash), salted per voice
@@ -958,9 +1064,32 @@ static size_t interp_smem(const InterpArgs& a, int nt, bool tile) {
   return b;
 }
 
-cudaError_t launch_interp(const InterpArgs& a_in, bool divergent, cudaStream_t stream, int* launches) {
+static size_t blk_smem(const InterpArgs& a, int nt, bool tile, int bt) {
+  size_t b = (size_t)a.n_instr * sizeof(Instr) + (size_t)(a.P + a.NS + a.NT * bt) * nt * sizeof(float);
+  if (tile) b += (size_t)a.n_out * (nt / 32) * 32 * 33 * sizeof(float);
+  return b;
+}
+constexpr int BLK_BT = 8;
+int interp_block_len() { return BLK_BT; }
+
+cudaError_t launch_interp(const InterpArgs& a_in, bool divergent, bool block_ok, cudaStream_t stream, int* launches) {
   InterpArgs a = a_in;
   bool tile = !a.out_frame_major && a.n_out > 0;
+  cudaError_t e;
+  if (!divergent && block_ok && a.T >= 4 * BLK_BT) {
+    // block mode: BT samples per decoded instruction; pick the block width that still leaves >= 8 warps per SM
+    int nt = 128;
+    const size_t per_sm = 220 * 1024;
+    while (nt > 32 && (blk_smem(a, nt, tile, BLK_BT) > per_sm / 4 || (a.Vp / nt) < 148)) nt >>= 1;
+    size_t smem = blk_smem(a, nt, tile, BLK_BT);
+    if (smem <= per_sm / 2) {
+      e = cudaFuncSetAttribute(k_interp_blk<BLK_BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      k_interp_blk<BLK_BT><<<a.Vp / nt, nt, smem, stream>>>(a);
+      if (launches) *launches += 1;
+      return cudaGetLastError();
+    }
+  }
   int nt = 128;
   const size_t limit = 200 * 1024;
   while (nt > 32 && interp_smem(a, nt, tile) > limit) nt >>= 1;
@@ -969,7 +1098,6 @@ cudaError_t launch_interp(const InterpArgs& a_in, bool divergent, cudaStream_t s
   while (nt > 32 && (a.Vp / nt) < 148) nt >>= 1;
   size_t smem = interp_smem(a, nt, tile);
   int blocks = a.Vp / nt;
-  cudaError_t e;
   if (divergent) {
     e = cudaFuncSetAttribute(k_interp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -53,7 +53,9 @@ struct TvArgs {
 size_t tv_smem_bytes(const TvArgs& a);
 cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches);
 
-cudaError_t launch_interp(const InterpArgs& a, bool divergent, cudaStream_t stream, int* launches);
+// block_ok: the tape may run on the block-mode lane interpreter (feed-forward, every feedback ring >= its block length)
+cudaError_t launch_interp(const InterpArgs& a, bool divergent, bool block_ok, cudaStream_t stream, int* launches);
+int interp_block_len();
 cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
                               const uint64_t* salts, cudaStream_t stream);
 cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream);

@@ -12,7 +12,7 @@ from . import _ffi
 from ._ffi import QuartzGpuError, check, lib
 
 LAYOUT_VOICE_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
-PATH_AUTO, PATH_INTERP, PATH_TV = 0, 1, 2
+PATH_AUTO, PATH_INTERP, PATH_TV, PATH_INTERP_SAMPLE = 0, 1, 2, 3
 NODE_LIMIT_DEFAULT = 500   # src/main.rs:72
 
 _CTX = {}

@@ -97,3 +97,44 @@ def test_bank_group_mix_is_left_to_right_sum():
 def test_render_refuses_nets_with_inputs():
     with pytest.raises(qb.QuartzGpuError):
         Net.str_to_net("lowpass(1000,1)").render(8)
+
+
+# ---- every kernel family on the same graphs: AUTO picks per bank, the others are forced
+PATHS = [("auto", qb.PATH_AUTO), ("lane_block", qb.PATH_INTERP), ("lane_sample", qb.PATH_INTERP_SAMPLE)]
+
+
+@pytest.mark.parametrize("pname,path", PATHS[1:], ids=[p[0] for p in PATHS[1:]])
+@pytest.mark.parametrize("name,expr,n,tol", cases.RENDER, ids=[c[0] for c in cases.RENDER])
+def test_render_matches_oracle_on_lane_kernels(name, expr, n, tol, pname, path):
+    net = build(expr, Net)
+    bank = Bank(net, 1).set_path(path)
+    n = n + 3   # not a multiple of the block length: exercises the partial last block
+    got = bank.render(n, layout=qb.LAYOUT_FRAME_MAJOR).reshape(n, net.outputs())
+    ref = build(expr, ONet).render(n)
+    assert_parity(got, ref, tol if tol in ("exact", "float") else "float", f"{name} [{pname}: {bank.kernel()}]")
+
+
+@pytest.mark.parametrize("pname,path", PATHS[1:], ids=[p[0] for p in PATHS[1:]])
+def test_block_kernel_chunked_render_and_voice_major_tiles(pname, path):
+    """state carried across calls of odd lengths; voice-major output tiles with a partial last column block"""
+    V = 70
+    expr = pipe("white()", "delay(0.001)", "lowpole(900)", "tick()")
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    bank = Bank(build(expr, Net), V, salts=salts).set_path(path)
+    parts = np.concatenate([bank.render(k)[:, 0, :] for k in (1, 7, 8, 9, 33, 250, 64, 5)], axis=1)
+    onets = [build(expr, ONet).set_salt(int(s)) for s in salts]
+    ref = render_bank(onets, parts.shape[1])
+    assert_parity(parts, ref, "float", f"chunked [{bank.kernel()}]")
+
+
+@pytest.mark.parametrize("delay,blk", [(None, False), (0.0001, False), (0.001, True)])
+def test_feedback_ring_shorter_than_a_block_stays_sample_by_sample(delay, blk):
+    """FunDSP FeedbackUnit with 1-, 4- and 44-sample loops: only the last may run block-wise (ring >= block length)"""
+    inner = pipe("mul(0.7)", "lowpole(3000)")
+    expr = pipe("white()", {"op": "feedback()", "net": inner, "delay": delay})
+    V, T = 40, 1500
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    bank = Bank(build(expr, Net), V, salts=salts).set_path(qb.PATH_INTERP)
+    assert (bank.kernel() == "k_interp_blk") == blk, bank.kernel()
+    onets = [build(expr, ONet).set_salt(int(s)) for s in salts]
+    assert_parity(bank.render(T)[:, 0, :], render_bank(onets, T), "float", f"feedback delay={delay}")
