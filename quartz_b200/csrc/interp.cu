@@ -55,18 +55,20 @@ struct BlockLane : Lane {
   __device__ __forceinline__ uint32_t sample() const { return (uint32_t)j; }
   __device__ __forceinline__ uint32_t count() const { return (uint32_t)n; }
 };
-// Execution context of one SAMPLE of one voice in time-vector mode (one CTA = one voice, threads = samples of a hop):
-// parameters/state are per-voice scalars, temporaries are arrays of H samples.  Only stateless ops go through exec().
+// Execution context of one THREAD of the time-vector kernel (one CTA = one voice, threads = the samples of a hop):
+// parameters/state are per-voice scalars, temporaries are arrays of H samples.  Only stateless ops go through exec();
+// the thread applies each decoded instruction to its samples j = j0, j0 + stride, ... < n.
 struct TvSample {
   float* ps;       // shared: [P + NS] scalars
-  float* tmp;      // shared: temporaries, already offset by the sample index; stride H
+  float* tmp;      // shared: temporaries, [index][H]
   int PS, H;
   const float* tables;
-  __device__ __forceinline__ float& at(int i) const { return i < PS ? ps[i] : tmp[(i - PS) * H]; }
+  int j0, stride, n, j;
+  __device__ __forceinline__ float& at(int i) const { return i < PS ? ps[i] : tmp[(i - PS) * H + j]; }
   __device__ __forceinline__ float& ring(uint32_t, uint32_t) const { return ps[0]; }   // never used by stateless ops
-  __device__ __forceinline__ int first() { return 0; }
-  __device__ __forceinline__ bool more(int k) const { return k < 1; }
-  __device__ __forceinline__ int next(int k) { return k + 1; }
+  __device__ __forceinline__ int first() { j = j0; return j0; }
+  __device__ __forceinline__ bool more(int k) const { return k < n; }
+  __device__ __forceinline__ int next(int k) { j = k + stride; return k + stride; }
   __device__ __forceinline__ uint32_t sample() const { return 0u; }
   __device__ __forceinline__ uint32_t count() const { return 1u; }
 };
@@ -837,31 +839,61 @@ __global__ void k_mix_rows(const float* rows, int R, long T, float scale, float*
 // are block-copied; rfft/ifft (nodes.rs:601-700) become cooperative shared-memory radix-2 transforms (K3/K4) that run
 // exactly when the node's counter wraps — hops are aligned to the frame grid by construction (H | N, H | start).
 
-// cooperative radix-2 FFT of N = 1 << lg points held in shared memory (re, im); same butterfly arithmetic and
-// twiddle table as the per-lane path, inverse scales by 1/N
+// K3/K4 — cooperative FFT of N = 1 << lg points held in shared memory (re, im), input in bit-reversed order.
+// The arithmetic is the radix-2 decimation-in-time butterfly network of the per-lane path (same twiddle table, same
+// operation order per butterfly, inverse scaled by 1/N), but a thread carries 2^R points through R consecutive stages in
+// registers (R = 3: radix-8 passes), so an N = 2048 transform takes 4 passes / barriers instead of 11 and a quarter of the
+// shared-memory traffic.  Results are bit-identical to the radix-2 schedule.  Buffers are padded by one float per 32 to
+// spread the strided accesses of the first passes over the banks.
+#define FPAD(i) ((i) + ((i) >> 5))
+template <int R>
+__device__ __forceinline__ void tv_fft_pass(float* fr, float* fi, int lg, int s, const float* __restrict__ tw, bool inverse, int tid,
+                                            int nth) {
+  const uint32_t N = 1u << lg, h = 1u << s;
+  for (uint32_t g = tid; g < (N >> R); g += nth) {
+    const uint32_t k = g & (h - 1), base = ((g >> s) << (s + R)) | k;
+    float xr[1 << R], xi[1 << R];
+#pragma unroll
+    for (int m = 0; m < (1 << R); m++) { const uint32_t idx = base + (uint32_t)m * h; xr[m] = fr[FPAD(idx)]; xi[m] = fi[FPAD(idx)]; }
+#pragma unroll
+    for (int q = 0; q < R; q++) {            // stage s + q: partners differ in bit q of m
+      const int hq = 1 << q;
+#pragma unroll
+      for (int m = 0; m < (1 << R); m++) {
+        if (m & hq) continue;
+        const uint32_t kq = k + (uint32_t)(m & (hq - 1)) * h;      // index within the butterfly group of this stage
+        const uint32_t ti = kq << (lg - 1 - (s + q));              // k * (N / len)
+        const float wr = __ldg(tw + 2 * ti);
+        float wi = __ldg(tw + 2 * ti + 1);
+        if (inverse) wi = -wi;
+        const float ur = xr[m], ui = xi[m], vr = xr[m + hq], vi = xi[m + hq];
+        const float tr = vr * wr - vi * wi, tim = vr * wi + vi * wr;
+        xr[m] = ur + tr; xi[m] = ui + tim;
+        xr[m + hq] = ur - tr; xi[m + hq] = ui - tim;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < (1 << R); m++) { const uint32_t idx = base + (uint32_t)m * h; fr[FPAD(idx)] = xr[m]; fi[FPAD(idx)] = xi[m]; }
+  }
+}
 __device__ void tv_fft(float* fr, float* fi, int lg, const float* tw, bool inverse, int tid, int nth) {
   const uint32_t N = 1u << lg;
-  for (uint32_t len = 2; len <= N; len <<= 1) {
-    const uint32_t half = len >> 1, step = N / len;
-    for (uint32_t b = tid; b < N / 2; b += nth) {
-      const uint32_t k = b & (half - 1), i = (b / half) * len + k;
-      float wr = tw[2 * k * step], wi = tw[2 * k * step + 1];
-      if (inverse) wi = -wi;
-      const float ur = fr[i], ui = fi[i], vr = fr[i + half], vi = fi[i + half];
-      const float tr = vr * wr - vi * wi, ti = vr * wi + vi * wr;
-      fr[i] = ur + tr; fi[i] = ui + ti;
-      fr[i + half] = ur - tr; fi[i + half] = ui - ti;
-    }
+  for (int s = 0; s < lg;) {
+    const int r = lg - s >= 3 ? 3 : lg - s;
+    if (r == 3) tv_fft_pass<3>(fr, fi, lg, s, tw, inverse, tid, nth);
+    else if (r == 2) tv_fft_pass<2>(fr, fi, lg, s, tw, inverse, tid, nth);
+    else tv_fft_pass<1>(fr, fi, lg, s, tw, inverse, tid, nth);
+    s += r;
     __syncthreads();
   }
   if (inverse) {
     const float sc = 1.0f / (float)N;
-    for (uint32_t k = tid; k < N; k += nth) { fr[k] *= sc; fi[k] *= sc; }
+    for (uint32_t k = tid; k < N; k += nth) { fr[FPAD(k)] *= sc; fi[FPAD(k)] *= sc; }
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
+__global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nth = blockDim.x, v = blockIdx.x, H = a.H, PS = a.P + a.NS;
   Instr* code = reinterpret_cast<Instr*>(smem_raw);
@@ -869,7 +901,7 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
   float* tmp = ps + ((PS + 3) & ~3);
   float* oldv = tmp + (size_t)a.NT * H;
   float* fr = oldv + H;
-  float* fi = fr + a.fft_n;
+  float* fi = fr + FPAD(a.fft_n);
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.code);
     uint4* dst = reinterpret_cast<uint4*>(code);
@@ -903,11 +935,11 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
         // a run of stateless ops is applied sample by sample without intermediate barriers
         int pe = pc + 1;
         while (pe < a.n_instr && op_is_stateless(code[pe].op)) pe++;
-        for (int j = tid; j < n; j += nth) {
-          TvSample L{ps, tmp + j, PS, H, a.tables};
-          int dummy = 0;
-          for (int q = pc; q < pe; q++) exec(code[q], L, dummy);
-        }
+        // op-outer / sample-inner: every instruction is decoded once per thread and applied to all of the thread's samples;
+        // a thread only ever touches its own sample columns, so the run needs no barrier between ops
+        TvSample L{ps, tmp, PS, H, a.tables, tid, nth, n, tid};
+        int dummy = 0;
+        for (int q = pc; q < pe; q++) { const Instr Iq = code[q]; exec(Iq, L, dummy); }
         pc = pe - 1;
       } else {
         switch (I.op) {
@@ -987,10 +1019,10 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
             float *rin = RING(I.aux), *rre = RING(I.aux + 1), *rim = RING(I.aux + 2);
             __syncthreads();
             if (i0 == 0) {   // K3: the frame is complete -> transform it before this hop's samples are stored
-              for (uint32_t k = tid; k < N; k += nth) { const uint32_t rv = __brev(k) >> (32 - lg); fr[rv] = rin[k]; fi[rv] = 0.0f; }
+              for (uint32_t k = tid; k < N; k += nth) { const uint32_t rv = __brev(k) >> (32 - lg); fr[FPAD(rv)] = rin[k]; fi[FPAD(rv)] = 0.0f; }
               __syncthreads();
               tv_fft(fr, fi, lg, a.tables + I.aux2, false, tid, nth);
-              for (uint32_t k = tid; k < N; k += nth) { rre[k] = fr[k]; rim[k] = fi[k]; }
+              for (uint32_t k = tid; k < N; k += nth) { rre[k] = fr[FPAD(k)]; rim[k] = fi[FPAD(k)]; }
               __syncthreads();
             }
             for (int j = tid; j < n; j += nth) {
@@ -1008,10 +1040,10 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
             float *ire = RING(I.aux), *iim = RING(I.aux + 1), *ore = RING(I.aux + 2), *oim = RING(I.aux + 3);
             __syncthreads();
             if (i0 == 0) {   // K4: full complex inverse transform of the collected bins
-              for (uint32_t k = tid; k < N; k += nth) { const uint32_t rv = __brev(k) >> (32 - lg); fr[rv] = ire[k]; fi[rv] = iim[k]; }
+              for (uint32_t k = tid; k < N; k += nth) { const uint32_t rv = __brev(k) >> (32 - lg); fr[FPAD(rv)] = ire[k]; fi[FPAD(rv)] = iim[k]; }
               __syncthreads();
               tv_fft(fr, fi, lg, a.tables + I.aux2, true, tid, nth);
-              for (uint32_t k = tid; k < N; k += nth) { ore[k] = fr[k]; oim[k] = fi[k]; }
+              for (uint32_t k = tid; k < N; k += nth) { ore[k] = fr[FPAD(k)]; oim[k] = fi[FPAD(k)]; }
               __syncthreads();
             }
             for (int j = tid; j < n; j += nth) {
@@ -1045,7 +1077,7 @@ __global__ void __launch_bounds__(256) k_interp_tv(TvArgs a) {
 
 size_t tv_smem_bytes(const TvArgs& a) {
   return (size_t)a.n_instr * sizeof(Instr) + (size_t)(((a.P + a.NS) + 3) & ~3) * 4 + (size_t)a.NT * a.H * 4 + (size_t)a.H * 4 +
-         (size_t)a.fft_n * 8;
+         (size_t)FPAD(a.fft_n) * 8;
 }
 
 cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches) {

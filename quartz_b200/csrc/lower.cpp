@@ -780,7 +780,7 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
   }
   auto bytes = [&](int h) {
     return (size_t)t.h.n_instr * sizeof(Instr) + (size_t)(t.h.n_params + t.h.n_state + 4) * 4 + (size_t)t.h.n_temps * h * 4 +
-           (size_t)h * 4 + (size_t)fft_n * 8;
+           (size_t)h * 4 + (size_t)(fft_n + fft_n / 32) * 8;
   };
   while (H >= 8 && (bytes(H) > smem_limit || (uint32_t)H > min_tap_ring)) H >>= 1;
   if (H < 8) return pl;
