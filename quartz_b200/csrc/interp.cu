@@ -499,15 +499,15 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
     case OP_KR_END: SETU(I.s, XU(I.s) - 1u); break;
     case OP_RESET_EVERY: {   // nodes.rs:353-358
       uint32_t c = XU(I.s);
-      if (c >= I.aux) { reset_range(L, I.aux2); c = 0; }
+      if (c >= I.aux) { { const LaneT Lc = L; reset_range(Lc, I.aux2); } c = 0; }
       SETU(I.s, c + 1u);
       break;
     }
-    case OP_RESET_IF: if (X(I.in[0]) != 0.0f) reset_range(L, I.aux2); break;
+    case OP_RESET_IF: if (X(I.in[0]) != 0.0f) { const LaneT Lc = L; reset_range(Lc, I.aux2); } break;
     case OP_RESET_V: {   // nodes.rs:435-440
       uint32_t c = XU(I.s);
       uint64_t lim = d_as_usize(roundf(X(I.in[0]) * X(I.p)));
-      if ((uint64_t)c >= lim) { reset_range(L, I.aux2); c = 0; }
+      if ((uint64_t)c >= lim) { { const LaneT Lc = L; reset_range(Lc, I.aux2); } c = 0; }
       SETU(I.s, c + 1u);
       break;
     }
@@ -518,7 +518,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
         const uint64_t k = d_as_usize(X(I.in[1]));
         if (k < (uint64_t)nk) {
           const int b = I.s + 1 + 5 * (int)k;
-          reset_range(L, I.aux2 + (uint32_t)k);
+          { const LaneT Lc = L; reset_range(Lc, I.aux2 + (uint32_t)k); }
           const uint64_t dl = d_as_usize(roundf(X(I.in[2]) * X(I.p))), du = d_as_usize(roundf(X(I.in[3]) * X(I.p)));
           const uint32_t stamp = XU(I.s) + 1u;
           SETU(I.s, stamp);
@@ -580,7 +580,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       SETU(I.s, nx);
       if (i == 0) {
         for (uint32_t k = 0; k < N; k++) { ring_at(L, I.aux + 1, k) = ring_at(L, I.aux, k); ring_at(L, I.aux + 2, k) = 0.0f; }
-        lane_fft(L, I.aux + 1, I.aux + 2, I.n, L.tables + I.aux2, false);
+        { const LaneT Lc = L; lane_fft(Lc, I.aux + 1, I.aux + 2, I.n, L.tables + I.aux2, false); }
       }
       ring_at(L, I.aux, i) = X(I.in[0]);
       if (i <= N / 2) { X(I.out) = ring_at(L, I.aux + 1, i); X(I.out + 1) = ring_at(L, I.aux + 2, i); }
@@ -591,7 +591,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       SETU(I.s, nx);
       if (i == 0) {
         for (uint32_t k = 0; k < N; k++) { ring_at(L, I.aux + 2, k) = ring_at(L, I.aux, k); ring_at(L, I.aux + 3, k) = ring_at(L, I.aux + 1, k); }
-        lane_fft(L, I.aux + 2, I.aux + 3, I.n, L.tables + I.aux2, true);
+        { const LaneT Lc = L; lane_fft(Lc, I.aux + 2, I.aux + 3, I.n, L.tables + I.aux2, true); }
       }
       ring_at(L, I.aux, i) = X(I.in[0]); ring_at(L, I.aux + 1, i) = X(I.in[1]);
       X(I.out) = ring_at(L, I.aux + 2, i); X(I.out + 1) = ring_at(L, I.aux + 3, i);
