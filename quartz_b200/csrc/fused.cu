@@ -378,46 +378,68 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
     v1 = env_ar(t1, e);
     th += 1;
   }
-  // The interpolated envelope lerp(v0, v1, (t - t0) / (t1 - t0)) is advanced incrementally inside a segment
-  // (env += slope per sample, re-anchored at every control point): <= ~120 f32 additions per segment.
+  // The interpolated envelope lerp(v0, v1, (t - t0) / (t1 - t0)) is advanced incrementally (env += slope per sample,
+  // anchored once per control point): <= ~200 f32 additions per anchor.
+  // Two segments are live per lane: the CURRENT one (envC, dC, ends at t1) and the NEXT one (envN, dN, control point
+  // (nt1, nv1) computed ahead of time).  A look-ahead window (look_tiles * 32 samples) is shorter than the shortest lfo
+  // segment, so a lane crosses at most one control point per window: inside the window a sample only SELECTS between
+  // the two running values (et >= t1), and the register rotation + the next look-ahead (hash, powf) happen at the
+  // warp-uniform window boundary.
   float inv = 1.0f / (t1 - t0);
-  float env = __fmaf_rn(v1 - v0, (et - t0) * inv, v0);
-  float denv = (v1 - v0) * inv * esd;
-  float nt1 = 0.0f, nv1 = 0.0f, ninv = 0.0f;
-  int have_next = 0;
+  float envC = __fmaf_rn(v1 - v0, (et - t0) * inv, v0);
+  float dC = (v1 - v0) * inv * esd;
+  float nt1 = 0.0f, nv1 = 0.0f, envN = 0.0f, dN = 0.0f;
+  bool crossed = false;              // the last tested sample of the window was past t1
   uint32_t ncross = 0;               // control points consumed in this launch (added to the 64-bit hash counter at the end)
   float* my_tile = &tile[warp][lane][0];
 
+  // lowpass: ic1' = (2 a1 - 1) ic1 + 2 a2 v3 (both constants exact in f32), no v1 needed: 6 FP ops per tick
+  const float c11 = 2.0f * c.a1 - 1.0f, c12 = 2.0f * c.a2;
   auto sample = [&](int i) {
     // ---- sine (FunDSP Sine::tick): output from the phase before the increment.  The phase recurrence is exact;
-    // sin(2 pi p) uses the SFU (sin.approx, |err| < 2^-20.9 on [-pi, pi]) on the phase folded to [-0.5, 0.5) turns
+    // sin(2 pi p) uses the SFU (MUFU.SIN works on the fractional revolution, so p in [0, 1) needs no folding; the two
+    // roundings of p * 2pi * (1 / 2pi) cost < 5e-7 rad)
     const float p = phase;
     phase = p + inc;
     phase -= floorf(phase);
-    const float pf = p >= 0.5f ? p - 1.0f : p;
-    const float x = __sinf(pf * QG_TAU);
+    const float x = __sinf(p * QG_TAU);
     // ---- SVF
-    const float y = svf_fma<LP>(x, ic1, ic2, c);
-    // ---- envelope (lfo): at most one crossing between two look-ahead points, the body only rotates registers
-    if (et >= t1) {
-      t0 = t1; v0 = v1; t1 = nt1; v1 = nv1; inv = ninv;
-      ncross += 1u;
-      have_next = 0;
-      env = __fmaf_rn(v1 - v0, (et - t0) * inv, v0);
-      denv = (v1 - v0) * inv * esd;
+    float y;
+    if (LP) {
+      const float v3 = x - ic2;
+      y = __fmaf_rn(c.a3, v3, __fmaf_rn(c.a2, ic1, ic2));
+      ic1 = __fmaf_rn(c12, v3, c11 * ic1);
+      ic2 = __fmaf_rn(2.0f, y, -ic2);
+    } else {
+      y = svf_fma<false>(x, ic1, ic2, c);
     }
+    // ---- envelope (lfo)
+    crossed = et >= t1;
     et += esd;
-    my_tile[i] = y * env;
-    env += denv;
+    my_tile[i] = y * (crossed ? envN : envC);
+    envC += dC;
+    envN += dN;
+  };
+  auto rotate = [&]() {              // the lane went past t1 in the window that just ended
+    t0 = t1; v0 = v1; t1 = nt1; v1 = nv1;
+    envC = envN; dC = dN;
+    ncross += 1u;
+    crossed = false;
   };
 
   long tile_idx = 0;
+  bool have_next = false;
   for (long tb = 0; tb < T; tb += 32, tile_idx++) {
-    if ((tile_idx % look_tiles) == 0 && !have_next) {      // warp-uniform point: look one control point ahead
-      nt1 = t1 + d_lerp(0.75f, 1.25f, d_rnd1(th + (uint64_t)ncross)) * 0.002f;
-      nv1 = env_ar(nt1, e);
-      ninv = 1.0f / (nt1 - t1);
-      have_next = 1;
+    if ((tile_idx % look_tiles) == 0) {                    // warp-uniform window boundary
+      if (crossed) { rotate(); have_next = false; }
+      if (!have_next) {                                    // look one control point ahead
+        nt1 = t1 + d_lerp(0.75f, 1.25f, d_rnd1(th + (uint64_t)ncross)) * 0.002f;
+        nv1 = env_ar(nt1, e);
+        const float ninv = 1.0f / (nt1 - t1);
+        envN = __fmaf_rn(nv1 - v1, (et - t1) * ninv, v1);  // the next segment's line, evaluated at the current time
+        dN = (nv1 - v1) * ninv * esd;
+        have_next = true;
+      }
     }
     const int n = (T - tb) < 32 ? (int)(T - tb) : 32;
     if (n == 32) {
@@ -444,6 +466,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
     }
     __syncwarp();
   }
+  if (crossed) rotate();
   th += (uint64_t)ncross;
   if (v < V) {
     ST(s_ph) = phase; ST(s_svf) = ic1; ST(s_svf + 1) = ic2;
