@@ -251,18 +251,45 @@ def main():
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # what the link allows: one large pinned device->host copy, timed alone (explains the e2e number, not part of it)
+        nb = min(out_bytes, 1 << 30)
+        dprobe = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        hprobe = h_out.view(torch.uint8)[:nb]
+        hprobe.copy_(dprobe, non_blocking=True)
+        torch.cuda.synchronize()
+        tp0 = time.perf_counter()
+        hprobe.copy_(dprobe, non_blocking=True)
+        torch.cuda.synchronize()
+        d2h_peak = nb / (time.perf_counter() - tp0) / 1e9
+        del dprobe
         e2e = {"value": world * units / dt, "unit": "voice-samples/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "d2h_gbs": out_bytes / dt / 1e9, "d2h_link_gbs": d2h_peak,
+               "note": "bank build from host tables + render + device->host copy of every output sample (pinned host buffer); "
+                       "bounded by the PCIe link: d2h_gbs vs d2h_link_gbs (one large pinned copy timed alone)",
                "checksum": float(h_np[0, 0, : min(wl.T, 4096)].astype(np.float64).sum())}
 
     if rank == 0:
         peak, peak_src = _peaks()
         alg_bytes = sum(w.V * w.T * w.bytes_per_unit for w in wls)
+        alg_flops = sum(w.V * w.T * w.flops_per_unit for w in wls)
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(f"{wl.name}:{bank.kernel()}")
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": bank.kernel(), "kernel_ms": kern_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "binding_resource": wl.bound}
+        if wl.bound != "hbm" and alg_flops > 0:
+            # compute-bound workload: the binding roofline is the FP32 (non-tensor) pipe, measured here with an FFMA probe
+            fp32_peak = ctx.measure_fp32_tflops()
+            tf = alg_flops / (kern_ms * 1e-3) / 1e12
+            roof = {"bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": traffic,
+                    "peak_source": "measured here (FFMA probe, qg_ctx_measure_fp32_tflops)", "kernel": bank.kernel(),
+                    "kernel_ms": kern_ms, "algorithmic_flops_per_launch": alg_flops, "algorithmic_bytes_per_launch": alg_bytes,
+                    "hbm_frac": achieved / peak, "binding_resource": wl.bound,
+                    "note": "algorithmic flops (SURVEY.md 8d) / kernel time; issue-slot utilisation is in profiles/"}
         line = {
             "metric": "voice-samples/s @48 kHz", "value": value, "unit": "voice-samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -271,10 +298,7 @@ def main():
                        "voices": sum(w.V for w in wls), "samples": wl.T, "sample_rate": 48000, "group": wl.group,
                        "layout": "voice-major [V/G][T] f32", "kernel": "+".join(sorted({b.kernel() for b in banks})), "note": wl.note,
                        "l2": f"each step writes {out_bytes / 1e9:.1f} GB of output (>> 126 MB L2), state re-initialised per step"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": bank.kernel(), "kernel_ms": kern_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "binding_resource": wl.bound},
+            "roofline": roof,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

@@ -77,6 +77,7 @@ int qg_net_tape_info(const qg_net* net, int* n_instr, int* n_params, int* n_stat
 qg_ctx* qg_ctx_create(int device, void* cuda_stream /* cudaStream_t, or NULL for a private stream */);
 void qg_ctx_destroy(qg_ctx* ctx);
 int qg_ctx_synchronize(qg_ctx* ctx);
+double qg_ctx_measure_fp32_tflops(qg_ctx* ctx);               /* FFMA micro-benchmark: the FP32-pipe roofline (TFLOP/s), < 0 on error */
 long qg_ctx_launch_count(const qg_ctx* ctx);                   /* kernels launched by this library so far */
 void* qg_device_alloc(qg_ctx* ctx, size_t bytes);
 void qg_device_free(qg_ctx* ctx, void* p);

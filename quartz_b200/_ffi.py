@@ -43,6 +43,7 @@ SIGNATURES = {
     "qg_ctx_destroy": (None, [vp]),
     "qg_ctx_synchronize": (ci, [vp]),
     "qg_ctx_launch_count": (cl, [vp]),
+    "qg_ctx_measure_fp32_tflops": (cd, [vp]),
     "qg_device_alloc": (vp, [vp, C.c_size_t]),
     "qg_device_free": (None, [vp, vp]),
     "qg_host_alloc_pinned": (vp, [C.c_size_t]),

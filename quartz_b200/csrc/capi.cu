@@ -604,6 +604,34 @@ int qg_mix_rows_device(qg_ctx* c, const float* d_rows, long rows, long n, float 
   return QG_OK;
 }
 
+// Measured FP32 (non-tensor) FFMA peak of this GPU in TFLOP/s: the roofline the compute-bound workloads are compared with.
+double qg_ctx_measure_fp32_tflops(qg_ctx* c) {
+  if (!c) { g_err = "null ctx"; return -1.0; }
+  if (cudaSetDevice(c->device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return -1.0; }
+  float* d = nullptr;
+  if (cudaMalloc((void**)&d, 4) != cudaSuccess) { g_err = "cudaMalloc failed"; return -1.0; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, c->device);
+  const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, c->stream);
+    launch_fp32_peak(d, blocks, iters, c->stream);
+    cudaEventRecord(e1, c->stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { g_err = "fp32 probe failed"; best = -1.0; break; }
+    c->launches++;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
+    if (rep > 0 && ms > 0.0f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+}
+
 // ------------------------------------------------------------------------------------ reference-shaped helpers
 int qg_net_render(qg_ctx* ctx, const qg_net* net, long n, float* h_out) {
   if (!ctx || !net || !h_out) return fail(QG_ERR_ARG, "qg_net_render: bad arguments");

@@ -20,6 +20,7 @@
 
 #include <cuda.h>
 #include <cstring>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -395,13 +396,17 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
 
   // lowpass: ic1' = (2 a1 - 1) ic1 + 2 a2 v3 (both constants exact in f32), no v1 needed: 6 FP ops per tick
   const float c11 = 2.0f * c.a1 - 1.0f, c12 = 2.0f * c.a2;
-  auto sample = [&](int i) {
+  const bool small_inc = __all_sync(0xffffffffu, inc >= 0.0f && inc < 1.0f);   // warp-uniform
+  auto sample = [&](int i, auto small_inc_t) {
     // ---- sine (FunDSP Sine::tick): output from the phase before the increment.  The phase recurrence is exact;
     // sin(2 pi p) uses the SFU (MUFU.SIN works on the fractional revolution, so p in [0, 1) needs no folding; the two
     // roundings of p * 2pi * (1 / 2pi) cost < 5e-7 rad)
     const float p = phase;
     phase = p + inc;
-    phase -= floorf(phase);
+    // p in [0, 1): for 0 <= inc < 1 the sum is in [0, 2) and `phase - floor(phase)` is exactly a conditional `- 1`
+    // (keeps FRND off the quarter-rate XU pipe that MUFU.SIN already uses); other increments take the general form
+    if (decltype(small_inc_t)::value) { if (phase >= 1.0f) phase -= 1.0f; }
+    else phase -= floorf(phase);
     const float x = __sinf(p * QG_TAU);
     // ---- SVF
     float y;
@@ -429,6 +434,8 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
 
   long tile_idx = 0;
   bool have_next = false;
+  const float sc = 1.0f / (float)(G > 0 ? G : 1);
+  const int group0 = G > 1 ? warp_v0 / G : 0;            // first output row of this warp (32 % G == 0)
   for (long tb = 0; tb < T; tb += 32, tile_idx++) {
     if ((tile_idx % look_tiles) == 0) {                    // warp-uniform window boundary
       if (crossed) { rotate(); have_next = false; }
@@ -442,11 +449,14 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
       }
     }
     const int n = (T - tb) < 32 ? (int)(T - tb) : 32;
-    if (n == 32) {
+    if (n == 32 && small_inc) {
 #pragma unroll 8
-      for (int i = 0; i < 32; i++) sample(i);
+      for (int i = 0; i < 32; i++) sample(i, std::true_type{});
+    } else if (n == 32) {
+#pragma unroll 8
+      for (int i = 0; i < 32; i++) sample(i, std::false_type{});
     } else {
-      for (int i = 0; i < n; i++) sample(i);
+      for (int i = 0; i < n; i++) sample(i, std::false_type{});
     }
     __syncwarp();
     if (lane < n) {
@@ -454,12 +464,11 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
         for (int r = 0; r < 32; r++)
           if (warp_v0 + r < V) out[(size_t)(warp_v0 + r) * T + tb + lane] = tile[warp][r][lane];
       } else {
-        const float sc = 1.0f / (float)G;
-        for (int g0 = 0; g0 < 32; g0 += G) {
+        for (int g0 = 0, gi = group0; g0 < 32; g0 += G, gi++) {
           if (warp_v0 + g0 + G <= V) {
             float acc = tile[warp][g0][lane];
             for (int r = 1; r < G; r++) acc += tile[warp][g0 + r][lane];
-            out[(size_t)((warp_v0 + g0) / G) * T + tb + lane] = acc * sc;
+            out[(size_t)gi * T + tb + lane] = acc * sc;
           }
         }
       }

@@ -1089,6 +1089,25 @@ cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches
   return cudaGetLastError();
 }
 
+// FP32 pipe roofline probe: 8 independent FFMA chains per thread, no memory traffic.  bench.py divides the flops by the
+// measured launch time to get the FP32 (non-tensor) peak the compute-bound workloads are compared with.
+__global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+      x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+    }
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456f) out[0] = s;   // keeps the chains alive without a store in the common case
+}
+cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t stream) {
+  k_fp32_peak<<<blocks, 256, 0, stream>>>(out, iters, 0.999f, 0.001f);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 static size_t interp_smem(const InterpArgs& a, int nt, bool tile) {
   size_t b = (size_t)a.n_instr * sizeof(Instr) + (size_t)(a.P + a.NS + a.NT) * nt * sizeof(float);

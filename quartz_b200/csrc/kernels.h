@@ -56,6 +56,8 @@ cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches
 // block_ok: the tape may run on the block-mode lane interpreter (feed-forward, every feedback ring >= its block length)
 cudaError_t launch_interp(const InterpArgs& a, bool divergent, bool block_ok, cudaStream_t stream, int* launches);
 int interp_block_len();
+// 64 flop x iters per thread, blocks x 256 threads
+cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
                               const uint64_t* salts, cudaStream_t stream);
 cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream);

@@ -41,6 +41,13 @@ class Context:
     def launch_count(self):
         return lib().qg_ctx_launch_count(self.h)
 
+    def measure_fp32_tflops(self):
+        """FFMA micro-benchmark on this GPU: the FP32-pipe roofline for compute-bound workloads"""
+        v = lib().qg_ctx_measure_fp32_tflops(self.h)
+        if v < 0:
+            raise QuartzGpuError(_ffi.last_error())
+        return v
+
     def close(self):
         if self.h:
             lib().qg_ctx_destroy(self.h)

@@ -42,10 +42,11 @@ def _sr(g):
 class Workload:
     """name, template graph expression, per-voice raw matrix [V, R], salts [V], samples T, group size G"""
 
-    def __init__(self, name, expr, raw, salts, T, group, voice_expr, bytes_per_unit, bound, note):
+    def __init__(self, name, expr, raw, salts, T, group, voice_expr, bytes_per_unit, bound, note, flops_per_unit=0.0):
         self.name, self.expr, self.raw, self.salts, self.T, self.group = name, expr, raw, salts, T, group
         self.voice_expr = voice_expr          # f(v) -> graph expression of voice v with its own constants
         self.bytes_per_unit = bytes_per_unit  # ALGORITHMIC HBM bytes per voice-sample (DESIGN.md)
+        self.flops_per_unit = flops_per_unit  # ALGORITHMIC f32 flops per voice-sample (SURVEY.md 8d / DESIGN.md)
         self.bound = bound
         self.note = note
         self.V = len(salts)
@@ -73,7 +74,7 @@ def c2_lowpass_bank(V=4096, T=2880000, v0=0):
     expr = _sr(_pipe("white()", "lowpass(1000,1)"))
     return Workload("c2_noise_lowpass_bank", expr, raw, salts_for(voices), T, 1,
                     lambda v: _sr(_pipe("white()", f"lowpass({float(hz[v])!r},{float(q[v])!r})")),
-                    4.0, "hbm", "4 B written per voice-sample")
+                    4.0, "hbm", "4 B written per voice-sample", flops_per_unit=14.0)
 
 
 def c3_polysynth(V=65536, T=480000, G=32, v0=0):
@@ -93,7 +94,8 @@ def c3_polysynth(V=65536, T=480000, G=32, v0=0):
 
     expr = _sr({"op": "*", "n": 0.0, "inputs": [_pipe("sine(440)", "lowpass(1000,1)"), _L("ar(0.01,1,0.5,4)")]})
     return Workload("c3_polysynth_65536", expr, raw, salts_for(voices), T, G, voice, 4.0 / G, "fp32",
-                    "osc->lowpass->envelope, mixed in groups of 32")
+                    "osc->lowpass->envelope, mixed in groups of 32; 32 flop per voice-sample (phase 4, sin 12, SVF 12, "
+                    "envelope 2, gain 1, mix 1)", flops_per_unit=32.0)
 
 
 def hann(n):
@@ -130,8 +132,11 @@ def c4_spectral(V=1024, T=1440000, N=2048, J=4, thr=16.0, v0=0):
     voices = np.arange(v0, v0 + V)
     expr = spectral_graph(N, J, float(thr), hann(N))
     # bytes: 4 B written per channel-sample (input is generated on chip); flops ~ 346 per channel-sample
+    lg = int(np.log2(N))
+    flops = J * (2.5 * N * lg + 5.0 * N * lg) / N + 16.0   # real FFT + complex inverse per instance and sample, windowing
     return Workload(f"c4_spectral_gate_{N}", expr, None, salts_for(voices), T, 1, lambda v: expr, 4.0, "fp32",
-                    f"{J} x [rfft({N}) -> gate -> ifft({N})], hop {N // J}")
+                    f"{J} x [rfft({N}) -> gate -> ifft({N})], hop {N // J}; {flops:.0f} flop per channel-sample for the transforms",
+                    flops_per_unit=flops)
 
 
 MINOR = [0.0, 2.0, 3.0, 5.0, 7.0, 8.0, 10.0, 12.0]
