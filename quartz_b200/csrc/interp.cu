@@ -16,6 +16,12 @@
 
 namespace qg {
 
+// All interpreter kernels carve their dynamic shared memory out of this one symbol.  Addressing it by INDEX (instead of
+// through float* members) lets ptxas emit LDS/STS with plain offsets; generic pointers into shared memory were being
+// re-materialised (S2UR CgaCtaId + ULEA) at every use.
+extern __shared__ __align__(16) unsigned char qg_smem[];
+#define QG_SMEM_F (reinterpret_cast<float*>(qg_smem))
+
 // Execution context of one voice in lane mode (one thread = one voice).
 struct Lane {
   float* x;        // shared: X[i] at x[i * nt]
@@ -59,13 +65,12 @@ struct BlockLane : Lane {
 // parameters/state are per-voice scalars, temporaries are arrays of H samples.  Only stateless ops go through exec();
 // the thread applies each decoded instruction to its samples j = j0, j0 + stride, ... < n.
 struct TvSample {
-  float* ps;       // shared: [P + NS] scalars
-  float* tmp;      // shared: temporaries, [index][H]
+  int ps_off, tmp_off;   // float offsets into the CTA's shared memory: [P + NS] scalars, temporaries [index][H]
   int PS, H;
   const float* tables;
   int j0, stride, n, j;
-  __device__ __forceinline__ float& at(int i) const { return i < PS ? ps[i] : tmp[(i - PS) * H + j]; }
-  __device__ __forceinline__ float& ring(uint32_t, uint32_t) const { return ps[0]; }   // never used by stateless ops
+  __device__ __forceinline__ float& at(int i) const { return QG_SMEM_F[i < PS ? ps_off + i : tmp_off + (i - PS) * H + j]; }
+  __device__ __forceinline__ float& ring(uint32_t, uint32_t) const { return QG_SMEM_F[ps_off]; }   // never used by stateless ops
   __device__ __forceinline__ int first() { j = j0; return j0; }
   __device__ __forceinline__ bool more(int k) const { return k < n; }
   __device__ __forceinline__ int next(int k) { j = k + stride; return k + stride; }
@@ -603,10 +608,9 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
 // ------------------------------------------------------------------------------------------------ kernels
 template <bool DIVERGENT>
 __global__ void __launch_bounds__(128) k_interp(InterpArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  Instr* code = reinterpret_cast<Instr*>(smem_raw);
-  float* xs = reinterpret_cast<float*>(smem_raw + (size_t)a.n_instr * sizeof(Instr));
+  Instr* code = reinterpret_cast<Instr*>(qg_smem);
+  float* xs = reinterpret_cast<float*>(qg_smem + (size_t)a.n_instr * sizeof(Instr));
   const int nx = a.P + a.NS + a.NT;
   float* tiles = xs + (size_t)nx * nt;                       // [n_out][nwarps][32][33] when a.tile
   {   // stage the tape
@@ -687,10 +691,9 @@ __global__ void __launch_bounds__(128) k_interp(InterpArgs a) {
 // (BT independent loads in flight per warp instead of one dependent load per sample).
 template <int BT>
 __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  Instr* code = reinterpret_cast<Instr*>(smem_raw);
-  float* xs = reinterpret_cast<float*>(smem_raw + (size_t)a.n_instr * sizeof(Instr));
+  Instr* code = reinterpret_cast<Instr*>(qg_smem);
+  float* xs = reinterpret_cast<float*>(qg_smem + (size_t)a.n_instr * sizeof(Instr));
   const int PS = a.P + a.NS;
   const int nx = PS + a.NT * BT;
   float* tiles = xs + (size_t)nx * nt;                       // [n_out][nwarps][32][33]
@@ -893,15 +896,23 @@ __device__ void tv_fft(float* fr, float* fi, int lg, const float* tw, bool inver
   }
 }
 
+// (idx + j) mod len for idx < len: one conditional subtract in the common case (ring at least one hop long)
+__device__ __forceinline__ uint32_t tv_wrap(uint32_t p, uint32_t len) {
+  if (p >= len) { p -= len; if (p >= len) p %= len; }
+  return p;
+}
+
 __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nth = blockDim.x, v = blockIdx.x, H = a.H, PS = a.P + a.NS;
-  Instr* code = reinterpret_cast<Instr*>(smem_raw);
-  float* ps = reinterpret_cast<float*>(smem_raw + (size_t)a.n_instr * sizeof(Instr));
-  float* tmp = ps + ((PS + 3) & ~3);
-  float* oldv = tmp + (size_t)a.NT * H;
-  float* fr = oldv + H;
-  float* fi = fr + FPAD(a.fft_n);
+  Instr* code = reinterpret_cast<Instr*>(qg_smem);
+  // float offsets of the regions behind the tape: scalars, temporaries, tap scratch, transform buffers
+  const int ps_off = a.n_instr * (int)(sizeof(Instr) / 4), tmp_off = ps_off + ((PS + 3) & ~3);
+  const int oldv_off = tmp_off + a.NT * H, fr_off = oldv_off + H, fi_off = fr_off + (int)FPAD(a.fft_n);
+#define ps (QG_SMEM_F + ps_off)
+#define tmp (QG_SMEM_F + tmp_off)
+#define oldv (QG_SMEM_F + oldv_off)
+#define fr (QG_SMEM_F + fr_off)
+#define fi (QG_SMEM_F + fi_off)
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.code);
     uint4* dst = reinterpret_cast<uint4*>(code);
@@ -909,11 +920,11 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
   }
   for (int p = tid; p < a.P; p += nth) ps[p] = a.params[(size_t)p * a.Vp + v];
   for (int s = tid; s < a.NS; s += nth) ps[a.P + s] = a.state[(size_t)s * a.Vp + v];
-  for (size_t k = tid; k < (size_t)a.NT * H; k += nth) tmp[k] = 0.0f;
+  for (int k = tid; k < a.NT * H; k += nth) tmp[k] = 0.0f;
   float* rg = a.rings + (size_t)v * a.ring_floats;        // voice-major rings in this mode
 #define RING(r) (rg + a.ring_tab[r].offset)
-#define TMP(i) (tmp + (size_t)((int)(i) - PS) * H)         // temporaries only
-#define SRC(i, j) ((int)(i) < PS ? ps[(int)(i)] : tmp[(size_t)((int)(i) - PS) * H + (j)])
+#define TMP(i) (tmp + ((int)(i) - PS) * H)                 // temporaries only
+#define SRC(i, j) ((int)(i) < PS ? ps[(int)(i)] : tmp[((int)(i) - PS) * H + (j)])
   __syncthreads();
   // a previous call may have stopped in the middle of a hop: the first pass only completes that hop, so that
   // transform frames stay aligned with hop boundaries (all rfft/ifft counters are congruent modulo H)
@@ -933,11 +944,10 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
       const Instr I = code[pc];
       if (op_is_stateless(I.op)) {
         // a run of stateless ops is applied sample by sample without intermediate barriers
-        int pe = pc + 1;
-        while (pe < a.n_instr && op_is_stateless(code[pe].op)) pe++;
+        const int pe = (int)I.pad;   // end of the run, precomputed by lower()
         // op-outer / sample-inner: every instruction is decoded once per thread and applied to all of the thread's samples;
         // a thread only ever touches its own sample columns, so the run needs no barrier between ops
-        TvSample L{ps, tmp, PS, H, a.tables, tid, nth, n, tid};
+        TvSample L{ps_off, tmp_off, PS, H, a.tables, tid, nth, n, tid};
         int dummy = 0;
         for (int q = pc; q < pe; q++) { const Instr Iq = code[q]; exec(Iq, L, dummy); }
         pc = pe - 1;
@@ -953,8 +963,8 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
           case OP_WAVE: {
             const uint32_t idx = __float_as_uint(ps[I.s]);
             __syncthreads();
-            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = a.tables[I.aux + (idx + (uint32_t)j) % I.aux2];
-            if (tid == 0) ps[I.s] = __uint_as_float((idx + (uint32_t)n) % I.aux2);
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = a.tables[I.aux + tv_wrap(idx + (uint32_t)j, I.aux2)];
+            if (tid == 0) ps[I.s] = __uint_as_float(tv_wrap(idx + (uint32_t)n, I.aux2));
             break;
           }
           case OP_IMPULSE: {
@@ -976,11 +986,11 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             float* r = RING(I.aux);
             __syncthreads();
             for (int j = tid; j < n; j += nth)
-              TMP(I.out)[j] = (uint32_t)j < Lr ? r[(idx + (uint32_t)j) % Lr] : SRC(I.in[0], j - (int)Lr);
+              TMP(I.out)[j] = (uint32_t)j < Lr ? r[tv_wrap(idx + (uint32_t)j, Lr)] : SRC(I.in[0], j - (int)Lr);
             __syncthreads();
             const int jlo = n > (int)Lr ? n - (int)Lr : 0;
-            for (int j = jlo + tid; j < n; j += nth) r[(idx + (uint32_t)j) % Lr] = SRC(I.in[0], j);
-            if (tid == 0) ps[I.s] = __uint_as_float((idx + (uint32_t)n) % Lr);
+            for (int j = jlo + tid; j < n; j += nth) r[tv_wrap(idx + (uint32_t)j, Lr)] = SRC(I.in[0], j);
+            if (tid == 0) ps[I.s] = __uint_as_float(tv_wrap(idx + (uint32_t)n, Lr));
             break;
           }
           case OP_TAP: {   // write-then-read per sample; `oldv` keeps what the hop overwrites (ring length >= H)
@@ -1073,6 +1083,11 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
 #undef RING
 #undef TMP
 #undef SRC
+#undef ps
+#undef tmp
+#undef oldv
+#undef fr
+#undef fi
 }
 
 size_t tv_smem_bytes(const TvArgs& a) {

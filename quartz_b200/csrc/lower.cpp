@@ -860,6 +860,11 @@ bool lower(const Graph& g, Tape* out, std::string* err) {
   }
   for (ResetRange& r : t.resets) { r.s_lo = (uint16_t)(P + r.s_lo); r.s_hi = (uint16_t)(P + r.s_hi); }
   for (uint16_t o : outs) t.out_x.push_back(fix(o));
+  // stateless runs (time-vector kernel): `pad` of a stateless instruction = index of the first stateful one after it
+  for (int k = (int)t.code.size() - 1, end = (int)t.code.size(); k >= 0; k--) {
+    if (op_is_stateless(t.code[k].op)) t.code[k].pad = (uint32_t)end;
+    else { t.code[k].pad = 0; end = k; }
+  }
   t.h.magic = TAPE_MAGIC; t.h.version = TAPE_VERSION;
   t.h.n_instr = (uint32_t)t.code.size();
   t.h.n_params = (uint32_t)P; t.h.n_state = (uint32_t)NS; t.h.n_temps = (uint32_t)L.n_temps;

@@ -121,7 +121,7 @@ struct Instr {
   uint16_t n;        // small immediate (tap count, mode, period, ...)
   uint32_t aux;      // table offset / ring id / jump target / sample count
   uint32_t aux2;     // reset range id
-  uint32_t pad;
+  uint32_t pad;      // stateless instructions: end (exclusive) of the run of stateless instructions they belong to
 };
 static_assert(sizeof(Instr) == 32, "Instr must stay 32 bytes");
 
