@@ -220,7 +220,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         n_e2e = max(1, min(args.steps, 3))
-        h_out = torch.empty(rows * T, dtype=torch.float32).pin_memory()
+        pinned = True
+        try:
+            h_out = torch.empty(rows * T, dtype=torch.float32).pin_memory()
+        except RuntimeError:   # not enough lockable host memory on this box (N ranks x 47 GB): pageable buffer, noted below
+            h_out, pinned = torch.empty(rows * T, dtype=torch.float32), False
         h_all = h_out.numpy()
         h_views = [h_all[int(o) // 4: int(o) // 4 + r * T].reshape(w.V // w.group, t.outputs(), T)
                    for o, r, w, t in zip(offs, rows_l, wls, tmpls)]
@@ -264,7 +268,7 @@ def main():
         del dprobe
         e2e = {"value": world * units / dt, "unit": "voice-samples/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": dt * 1e3, "steps": n_e2e,
-               "d2h_gbs": out_bytes / dt / 1e9, "d2h_link_gbs": d2h_peak,
+               "d2h_gbs": out_bytes / dt / 1e9, "d2h_link_gbs": d2h_peak, "host_buffer": "pinned" if pinned else "pageable",
                "note": "bank build from host tables + render + device->host copy of every output sample (pinned host buffer); "
                        "bounded by the PCIe link: d2h_gbs vs d2h_link_gbs (one large pinned copy timed alone)",
                "checksum": float(h_np[0, 0, : min(wl.T, 4096)].astype(np.float64).sum())}
