@@ -35,6 +35,10 @@ struct Lane {
   const ResetRange* resets;
   int P;
   __device__ __forceinline__ float& at(int i) const { return x[i * nt]; }
+  // operand access by role (exec() uses these): k-th output of an instruction, an input operand, a parameter/state scalar
+  __device__ __forceinline__ float& out(int base, int k) const { return x[(base + k) * nt]; }
+  __device__ __forceinline__ float& in(int f) const { return x[f * nt]; }
+  __device__ __forceinline__ float& sc(int i) const { return x[i * nt]; }
   __device__ __forceinline__ float& ring(uint32_t r, uint32_t pos) const {
     return rings[(size_t)(ring_tab[r].offset + pos) * (size_t)Vp + (size_t)v];
   }
@@ -53,14 +57,23 @@ template <int BT>
 struct BlockLane : Lane {
   int PS;          // P + NS: first temporary index
   int j, n;        // current sample of the block, samples in this block
-  __device__ __forceinline__ float& at(int i) const { return x[(i < PS ? i : PS + (i - PS) * BT + j) * nt]; }
-  __device__ __forceinline__ float& at(int i, int jj) const { return x[(i < PS ? i : PS + (i - PS) * BT + jj) * nt]; }
+  // k_interp_blk rewrites the temporary indices of the staged tape to block layout (i' = PS + (i - PS) * BT, see blk_index),
+  // so an access is one add and one multiply; outputs are always temporaries, parameters/state always scalars, only input
+  // operands can be either
+  __device__ __forceinline__ float& out(int base, int k) const { return x[(base + k * BT + j) * nt]; }
+  __device__ __forceinline__ float& in(int f) const { return x[(f + (f >= PS ? j : 0)) * nt]; }
+  __device__ __forceinline__ float& sc(int i) const { return x[i * nt]; }
+  __device__ __forceinline__ float& tr(int f, int jj) const { return x[(f + (f >= PS ? jj : 0)) * nt]; }   // translated index, sample jj
   __device__ __forceinline__ int first() { j = 0; return 0; }
   __device__ __forceinline__ bool more(int k) const { return k < n; }
   __device__ __forceinline__ int next(int k) { j = k + 1; return k + 1; }
   __device__ __forceinline__ uint32_t sample() const { return (uint32_t)j; }
   __device__ __forceinline__ uint32_t count() const { return (uint32_t)n; }
 };
+template <int BT>
+__device__ __forceinline__ uint16_t blk_index(uint16_t i, int PS) {
+  return (i == 0xffffu || (int)i < PS) ? i : (uint16_t)(PS + ((int)i - PS) * BT);
+}
 // Execution context of one THREAD of the time-vector kernel (one CTA = one voice, threads = the samples of a hop):
 // parameters/state are per-voice scalars, temporaries are arrays of H samples.  Only stateless ops go through exec();
 // the thread applies each decoded instruction to its samples j = j0, j0 + stride, ... < n.
@@ -70,6 +83,9 @@ struct TvSample {
   const float* tables;
   int j0, stride, n, j;
   __device__ __forceinline__ float& at(int i) const { return QG_SMEM_F[i < PS ? ps_off + i : tmp_off + (i - PS) * H + j]; }
+  __device__ __forceinline__ float& out(int base, int k) const { return QG_SMEM_F[tmp_off + (base + k - PS) * H + j]; }
+  __device__ __forceinline__ float& in(int f) const { return QG_SMEM_F[f < PS ? ps_off + f : tmp_off + (f - PS) * H + j]; }
+  __device__ __forceinline__ float& sc(int i) const { return QG_SMEM_F[ps_off + i]; }
   __device__ __forceinline__ float& ring(uint32_t, uint32_t) const { return QG_SMEM_F[ps_off]; }   // never used by stateless ops
   __device__ __forceinline__ int first() { j = j0; return j0; }
   __device__ __forceinline__ bool more(int k) const { return k < n; }
@@ -83,6 +99,12 @@ struct TvSample {
 #define QG_EACH for (int k_ = L.first(); L.more(k_); k_ = L.next(k_))
 #define XU(i) __float_as_uint(X(i))
 #define SETU(i, u) X(i) = __uint_as_float(u)
+// operand access by role inside exec(): k-th output, k-th input operand, parameter/state scalar
+#define XO(k) L.out((int)I.out, (int)(k))
+#define XI(k) L.in((int)I.in[k])
+#define XS(i) L.sc((int)(i))
+#define XSU(i) __float_as_uint(XS(i))
+#define SETSU(i, u) XS(i) = __uint_as_float(u)
 
 template <class LaneT>
 __device__ __forceinline__ float& ring_at(const LaneT& L, uint32_t ring, uint32_t pos) { return L.ring(ring, pos); }
@@ -139,115 +161,115 @@ template <class LaneT>
 __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
   switch (I.op) {
     case OP_NOP: break;
-    case OP_MOV: QG_EACH { X(I.out) = X(I.in[0]); } break;
-    case OP_ZERO: QG_EACH { X(I.out) = 0.0f; } break;
-    case OP_LD_STATE: QG_EACH { X(I.out) = X(I.s); } break;
-    case OP_ST_STATE: QG_EACH { X(I.s) = X(I.in[0]); } break;
-    case OP_ADD: QG_EACH { X(I.out) = X(I.in[0]) + X(I.in[1]); } break;
-    case OP_SUB: QG_EACH { X(I.out) = X(I.in[0]) - X(I.in[1]); } break;
-    case OP_MUL: QG_EACH { X(I.out) = X(I.in[0]) * X(I.in[1]); } break;
-    case OP_GT: QG_EACH { X(I.out) = X(I.in[0]) > X(I.in[1]) ? 1.0f : 0.0f; } break;
-    case OP_LT: QG_EACH { X(I.out) = X(I.in[0]) < X(I.in[1]) ? 1.0f : 0.0f; } break;
-    case OP_EQ: QG_EACH { X(I.out) = X(I.in[0]) == X(I.in[1]) ? 1.0f : 0.0f; } break;
-    case OP_NE: QG_EACH { X(I.out) = X(I.in[0]) != X(I.in[1]) ? 1.0f : 0.0f; } break;
-    case OP_GE: QG_EACH { X(I.out) = X(I.in[0]) >= X(I.in[1]) ? 1.0f : 0.0f; } break;
-    case OP_LE: QG_EACH { X(I.out) = X(I.in[0]) <= X(I.in[1]) ? 1.0f : 0.0f; } break;
-    case OP_MIN: QG_EACH { X(I.out) = fminf(X(I.in[0]), X(I.in[1])); } break;
-    case OP_MAX: QG_EACH { X(I.out) = fmaxf(X(I.in[0]), X(I.in[1])); } break;
-    case OP_POW: QG_EACH { X(I.out) = d_pow_cr(X(I.in[0]), X(I.in[1])); } break;
-    case OP_REM: QG_EACH { X(I.out) = d_rem_euclid(X(I.in[0]), X(I.in[1])); } break;
-    case OP_LOG: QG_EACH { X(I.out) = d_log_cr(X(I.in[0])) / d_log_cr(X(I.in[1])); } break;
-    case OP_BITAND: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) & d_as_i32(X(I.in[1]))); } break;
-    case OP_BITOR: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) | d_as_i32(X(I.in[1]))); } break;
-    case OP_BITXOR: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) ^ d_as_i32(X(I.in[1]))); } break;
-    case OP_SHL: QG_EACH { X(I.out) = (float)(int32_t)((uint32_t)d_as_i32(X(I.in[0])) << (uint32_t)(d_as_usize(X(I.in[1])) & 31)); } break;
-    case OP_SHR: QG_EACH { X(I.out) = (float)(d_as_i32(X(I.in[0])) >> (uint32_t)(d_as_usize(X(I.in[1])) & 31)); } break;
-    case OP_HYPOT: QG_EACH { X(I.out) = hypotf(X(I.in[0]), X(I.in[1])); } break;
-    case OP_ATAN2: QG_EACH { X(I.out) = atan2f(X(I.in[0]), X(I.in[1])); } break;
+    case OP_MOV: QG_EACH { XO(0) = XI(0); } break;
+    case OP_ZERO: QG_EACH { XO(0) = 0.0f; } break;
+    case OP_LD_STATE: QG_EACH { XO(0) = XS(I.s); } break;
+    case OP_ST_STATE: QG_EACH { XS(I.s) = XI(0); } break;
+    case OP_ADD: QG_EACH { XO(0) = XI(0) + XI(1); } break;
+    case OP_SUB: QG_EACH { XO(0) = XI(0) - XI(1); } break;
+    case OP_MUL: QG_EACH { XO(0) = XI(0) * XI(1); } break;
+    case OP_GT: QG_EACH { XO(0) = XI(0) > XI(1) ? 1.0f : 0.0f; } break;
+    case OP_LT: QG_EACH { XO(0) = XI(0) < XI(1) ? 1.0f : 0.0f; } break;
+    case OP_EQ: QG_EACH { XO(0) = XI(0) == XI(1) ? 1.0f : 0.0f; } break;
+    case OP_NE: QG_EACH { XO(0) = XI(0) != XI(1) ? 1.0f : 0.0f; } break;
+    case OP_GE: QG_EACH { XO(0) = XI(0) >= XI(1) ? 1.0f : 0.0f; } break;
+    case OP_LE: QG_EACH { XO(0) = XI(0) <= XI(1) ? 1.0f : 0.0f; } break;
+    case OP_MIN: QG_EACH { XO(0) = fminf(XI(0), XI(1)); } break;
+    case OP_MAX: QG_EACH { XO(0) = fmaxf(XI(0), XI(1)); } break;
+    case OP_POW: QG_EACH { XO(0) = d_pow_cr(XI(0), XI(1)); } break;
+    case OP_REM: QG_EACH { XO(0) = d_rem_euclid(XI(0), XI(1)); } break;
+    case OP_LOG: QG_EACH { XO(0) = d_log_cr(XI(0)) / d_log_cr(XI(1)); } break;
+    case OP_BITAND: QG_EACH { XO(0) = (float)(d_as_i32(XI(0)) & d_as_i32(XI(1))); } break;
+    case OP_BITOR: QG_EACH { XO(0) = (float)(d_as_i32(XI(0)) | d_as_i32(XI(1))); } break;
+    case OP_BITXOR: QG_EACH { XO(0) = (float)(d_as_i32(XI(0)) ^ d_as_i32(XI(1))); } break;
+    case OP_SHL: QG_EACH { XO(0) = (float)(int32_t)((uint32_t)d_as_i32(XI(0)) << (uint32_t)(d_as_usize(XI(1)) & 31)); } break;
+    case OP_SHR: QG_EACH { XO(0) = (float)(d_as_i32(XI(0)) >> (uint32_t)(d_as_usize(XI(1)) & 31)); } break;
+    case OP_HYPOT: QG_EACH { XO(0) = hypotf(XI(0), XI(1)); } break;
+    case OP_ATAN2: QG_EACH { XO(0) = atan2f(XI(0), XI(1)); } break;
     case OP_DISSONANCE: QG_EACH {
-      float f0 = X(I.in[0]), f1 = X(I.in[1]);
+      float f0 = XI(0), f1 = XI(1);
       float q = fabsf(f0 - f1) / (0.021f * fminf(f0, f1) + 19.0f);
-      X(I.out) = 5.531753f * (expf(-0.84f * q) - expf(-1.38f * q));
+      XO(0) = 5.531753f * (expf(-0.84f * q) - expf(-1.38f * q));
     } break;
-    case OP_SIN_HZ: QG_EACH { X(I.out) = sinf(X(I.in[1]) * X(I.in[0]) * QG_TAU); } break;
-    case OP_COS_HZ: QG_EACH { X(I.out) = cosf(X(I.in[1]) * X(I.in[0]) * QG_TAU); } break;
-    case OP_SQR_HZ: QG_EACH { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = x < 0.5f ? 1.0f : -1.0f; } break;
-    case OP_TRI_HZ: QG_EACH { float x = X(I.in[1]) * X(I.in[0]); x = x - floorf(x); X(I.out) = fabsf(x - 0.5f) * 4.0f - 1.0f; } break;
+    case OP_SIN_HZ: QG_EACH { XO(0) = sinf(XI(1) * XI(0) * QG_TAU); } break;
+    case OP_COS_HZ: QG_EACH { XO(0) = cosf(XI(1) * XI(0) * QG_TAU); } break;
+    case OP_SQR_HZ: QG_EACH { float x = XI(1) * XI(0); x = x - floorf(x); XO(0) = x < 0.5f ? 1.0f : -1.0f; } break;
+    case OP_TRI_HZ: QG_EACH { float x = XI(1) * XI(0); x = x - floorf(x); XO(0) = fabsf(x - 0.5f) * 4.0f - 1.0f; } break;
     case OP_PDHALF_BI: QG_EACH {   // functions.rs:677-688
-      float x = X(I.in[0]), mid = d_clamp(X(I.in[1]), -1.0f, 1.0f);
-      if (x < mid) { float ls = mid != -1.0f ? 1.0f / (mid + 1.0f) : 0.0f; X(I.out) = ls * x; }
-      else { float rs = mid != 1.0f ? 1.0f / (1.0f - mid) : 0.0f; X(I.out) = rs * (x - mid) + 0.5f; }
+      float x = XI(0), mid = d_clamp(XI(1), -1.0f, 1.0f);
+      if (x < mid) { float ls = mid != -1.0f ? 1.0f / (mid + 1.0f) : 0.0f; XO(0) = ls * x; }
+      else { float rs = mid != 1.0f ? 1.0f / (1.0f - mid) : 0.0f; XO(0) = rs * (x - mid) + 0.5f; }
     } break;
     case OP_PDHALF_UNI: QG_EACH {   // functions.rs:689-706
-      float x = X(I.in[0]), m = X(I.in[1]);
+      float x = XI(0), m = XI(1);
       float mid = m >= 1.0f ? 1.0f : (m <= -1.0f ? 0.0f : (m + 1.0f) / 2.0f);
-      if (x < mid) { float ls = mid != 0.0f ? 0.5f / mid : 0.0f; X(I.out) = ls * x; }
-      else { float rs = mid != 1.0f ? 0.5f / (1.0f - mid) : 0.0f; X(I.out) = rs * (x - mid) + 0.5f; }
+      if (x < mid) { float ls = mid != 0.0f ? 0.5f / mid : 0.0f; XO(0) = ls * x; }
+      else { float rs = mid != 1.0f ? 0.5f / (1.0f - mid) : 0.0f; XO(0) = rs * (x - mid) + 0.5f; }
     } break;
-    case OP_LERP: QG_EACH { X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
-    case OP_LERP11: QG_EACH { X(I.out) = d_lerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); } break;
-    case OP_DELERP: QG_EACH { X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
-    case OP_DELERP11: QG_EACH { X(I.out) = d_delerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; } break;
-    case OP_XERP: QG_EACH { X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
-    case OP_XERP11: QG_EACH { X(I.out) = d_xerp(X(I.in[0]), X(I.in[1]), X(I.in[2]) * 0.5f + 0.5f); } break;
-    case OP_DEXERP: QG_EACH { X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])); } break;
-    case OP_DEXERP11: QG_EACH { X(I.out) = d_dexerp(X(I.in[0]), X(I.in[1]), X(I.in[2])) * 2.0f - 1.0f; } break;
-    case OP_SPLINE: QG_EACH { X(I.out) = d_spline(X(I.in[0]), X(I.in[1]), X(I.in[2]), X(I.in[3]), X(I.in[4])); } break;
-    case OP_ABS: QG_EACH { X(I.out) = fabsf(X(I.in[0])); } break;
-    case OP_SIGNUM: QG_EACH { X(I.out) = d_signum(X(I.in[0])); } break;
-    case OP_FLOOR: QG_EACH { X(I.out) = floorf(X(I.in[0])); } break;
-    case OP_FRACT: QG_EACH { X(I.out) = d_fract(X(I.in[0])); } break;
-    case OP_CEIL: QG_EACH { X(I.out) = ceilf(X(I.in[0])); } break;
-    case OP_ROUND: QG_EACH { X(I.out) = roundf(X(I.in[0])); } break;
-    case OP_SQRT: QG_EACH { X(I.out) = sqrtf(X(I.in[0])); } break;
-    case OP_EXP: QG_EACH { X(I.out) = d_exp_cr(X(I.in[0])); } break;
-    case OP_EXP2: QG_EACH { X(I.out) = d_exp2_cr(X(I.in[0])); } break;
-    case OP_EXP10: QG_EACH { X(I.out) = d_exp10(X(I.in[0])); } break;
-    case OP_LN_1P_FN: QG_EACH { X(I.out) = log1pf(X(I.in[0])); } break;
-    case OP_EXP_M1_FN: QG_EACH { X(I.out) = expm1f(X(I.in[0])); } break;
-    case OP_LN: QG_EACH { X(I.out) = d_log_cr(X(I.in[0])); } break;
-    case OP_LOG2: QG_EACH { X(I.out) = d_log2_cr(X(I.in[0])); } break;
-    case OP_LOG10: QG_EACH { X(I.out) = d_log10_cr(X(I.in[0])); } break;
-    case OP_SIN: QG_EACH { X(I.out) = sinf(X(I.in[0])); } break;
-    case OP_COS: QG_EACH { X(I.out) = cosf(X(I.in[0])); } break;
-    case OP_TAN: QG_EACH { X(I.out) = tanf(X(I.in[0])); } break;
-    case OP_ASIN: QG_EACH { X(I.out) = asinf(X(I.in[0])); } break;
-    case OP_ACOS: QG_EACH { X(I.out) = acosf(X(I.in[0])); } break;
-    case OP_ATAN: QG_EACH { X(I.out) = atanf(X(I.in[0])); } break;
-    case OP_SINH: QG_EACH { X(I.out) = sinhf(X(I.in[0])); } break;
-    case OP_COSH: QG_EACH { X(I.out) = coshf(X(I.in[0])); } break;
-    case OP_TANH: QG_EACH { X(I.out) = tanhf(X(I.in[0])); } break;
-    case OP_ASINH: QG_EACH { X(I.out) = asinhf(X(I.in[0])); } break;
-    case OP_ACOSH: QG_EACH { X(I.out) = acoshf(X(I.in[0])); } break;
-    case OP_ATANH: QG_EACH { X(I.out) = atanhf(X(I.in[0])); } break;
-    case OP_SQUARED: QG_EACH { float x = X(I.in[0]); X(I.out) = x * x; } break;
-    case OP_CUBED: QG_EACH { float x = X(I.in[0]); X(I.out) = x * x * x; } break;
-    case OP_DB_AMP: QG_EACH { X(I.out) = d_exp10(X(I.in[0]) / 20.0f); } break;
-    case OP_AMP_DB: QG_EACH { X(I.out) = d_log10_cr(X(I.in[0])) * 20.0f; } break;
-    case OP_A_WEIGHT: QG_EACH { X(I.out) = d_a_weight(X(I.in[0])); } break;
-    case OP_SOFTSIGN: QG_EACH { float x = X(I.in[0]); X(I.out) = x / (1.0f + fabsf(x)); } break;
-    case OP_SMOOTH3: QG_EACH { float x = X(I.in[0]); X(I.out) = (3.0f - 2.0f * x) * x * x; } break;
-    case OP_SMOOTH5: QG_EACH { X(I.out) = d_smooth5(X(I.in[0])); } break;
-    case OP_SMOOTH7: QG_EACH { float x = X(I.in[0]), x2 = x * x; X(I.out) = x2 * x2 * (35.0f - 84.0f * x + (70.0f - 20.0f * x) * x2); } break;
+    case OP_LERP: QG_EACH { XO(0) = d_lerp(XI(0), XI(1), XI(2)); } break;
+    case OP_LERP11: QG_EACH { XO(0) = d_lerp(XI(0), XI(1), XI(2) * 0.5f + 0.5f); } break;
+    case OP_DELERP: QG_EACH { XO(0) = d_delerp(XI(0), XI(1), XI(2)); } break;
+    case OP_DELERP11: QG_EACH { XO(0) = d_delerp(XI(0), XI(1), XI(2)) * 2.0f - 1.0f; } break;
+    case OP_XERP: QG_EACH { XO(0) = d_xerp(XI(0), XI(1), XI(2)); } break;
+    case OP_XERP11: QG_EACH { XO(0) = d_xerp(XI(0), XI(1), XI(2) * 0.5f + 0.5f); } break;
+    case OP_DEXERP: QG_EACH { XO(0) = d_dexerp(XI(0), XI(1), XI(2)); } break;
+    case OP_DEXERP11: QG_EACH { XO(0) = d_dexerp(XI(0), XI(1), XI(2)) * 2.0f - 1.0f; } break;
+    case OP_SPLINE: QG_EACH { XO(0) = d_spline(XI(0), XI(1), XI(2), XI(3), XI(4)); } break;
+    case OP_ABS: QG_EACH { XO(0) = fabsf(XI(0)); } break;
+    case OP_SIGNUM: QG_EACH { XO(0) = d_signum(XI(0)); } break;
+    case OP_FLOOR: QG_EACH { XO(0) = floorf(XI(0)); } break;
+    case OP_FRACT: QG_EACH { XO(0) = d_fract(XI(0)); } break;
+    case OP_CEIL: QG_EACH { XO(0) = ceilf(XI(0)); } break;
+    case OP_ROUND: QG_EACH { XO(0) = roundf(XI(0)); } break;
+    case OP_SQRT: QG_EACH { XO(0) = sqrtf(XI(0)); } break;
+    case OP_EXP: QG_EACH { XO(0) = d_exp_cr(XI(0)); } break;
+    case OP_EXP2: QG_EACH { XO(0) = d_exp2_cr(XI(0)); } break;
+    case OP_EXP10: QG_EACH { XO(0) = d_exp10(XI(0)); } break;
+    case OP_LN_1P_FN: QG_EACH { XO(0) = log1pf(XI(0)); } break;
+    case OP_EXP_M1_FN: QG_EACH { XO(0) = expm1f(XI(0)); } break;
+    case OP_LN: QG_EACH { XO(0) = d_log_cr(XI(0)); } break;
+    case OP_LOG2: QG_EACH { XO(0) = d_log2_cr(XI(0)); } break;
+    case OP_LOG10: QG_EACH { XO(0) = d_log10_cr(XI(0)); } break;
+    case OP_SIN: QG_EACH { XO(0) = sinf(XI(0)); } break;
+    case OP_COS: QG_EACH { XO(0) = cosf(XI(0)); } break;
+    case OP_TAN: QG_EACH { XO(0) = tanf(XI(0)); } break;
+    case OP_ASIN: QG_EACH { XO(0) = asinf(XI(0)); } break;
+    case OP_ACOS: QG_EACH { XO(0) = acosf(XI(0)); } break;
+    case OP_ATAN: QG_EACH { XO(0) = atanf(XI(0)); } break;
+    case OP_SINH: QG_EACH { XO(0) = sinhf(XI(0)); } break;
+    case OP_COSH: QG_EACH { XO(0) = coshf(XI(0)); } break;
+    case OP_TANH: QG_EACH { XO(0) = tanhf(XI(0)); } break;
+    case OP_ASINH: QG_EACH { XO(0) = asinhf(XI(0)); } break;
+    case OP_ACOSH: QG_EACH { XO(0) = acoshf(XI(0)); } break;
+    case OP_ATANH: QG_EACH { XO(0) = atanhf(XI(0)); } break;
+    case OP_SQUARED: QG_EACH { float x = XI(0); XO(0) = x * x; } break;
+    case OP_CUBED: QG_EACH { float x = XI(0); XO(0) = x * x * x; } break;
+    case OP_DB_AMP: QG_EACH { XO(0) = d_exp10(XI(0) / 20.0f); } break;
+    case OP_AMP_DB: QG_EACH { XO(0) = d_log10_cr(XI(0)) * 20.0f; } break;
+    case OP_A_WEIGHT: QG_EACH { XO(0) = d_a_weight(XI(0)); } break;
+    case OP_SOFTSIGN: QG_EACH { float x = XI(0); XO(0) = x / (1.0f + fabsf(x)); } break;
+    case OP_SMOOTH3: QG_EACH { float x = XI(0); XO(0) = (3.0f - 2.0f * x) * x * x; } break;
+    case OP_SMOOTH5: QG_EACH { XO(0) = d_smooth5(XI(0)); } break;
+    case OP_SMOOTH7: QG_EACH { float x = XI(0), x2 = x * x; XO(0) = x2 * x2 * (35.0f - 84.0f * x + (70.0f - 20.0f * x) * x2); } break;
     case OP_SMOOTH9: QG_EACH {
-      float x = X(I.in[0]), x2 = x * x;
-      X(I.out) = ((((70.0f * x - 315.0f) * x + 540.0f) * x - 420.0f) * x + 126.0f) * x2 * x2 * x;
+      float x = XI(0), x2 = x * x;
+      XO(0) = ((((70.0f * x - 315.0f) * x + 540.0f) * x - 420.0f) * x + 126.0f) * x2 * x2 * x;
     } break;
-    case OP_UPARC: QG_EACH { float x = X(I.in[0]); X(I.out) = 1.0f - sqrtf(fmaxf(0.0f, 1.0f - x * x)); } break;
-    case OP_DOWNARC: QG_EACH { float x = X(I.in[0]); X(I.out) = sqrtf(fmaxf(0.0f, (2.0f - x) * x)); } break;
-    case OP_SINE_EASE: QG_EACH { X(I.out) = (1.0f - cosf(X(I.in[0]) * QG_PI)) * 0.5f; } break;
-    case OP_SEMITONE_RATIO: QG_EACH { X(I.out) = d_exp2_cr(X(I.in[0]) / 12.0f); } break;
-    case OP_RND1: QG_EACH { X(I.out) = d_rnd1(d_as_usize(X(I.in[0]))); } break;
-    case OP_RND2: QG_EACH { X(I.out) = d_rnd2(d_as_usize(X(I.in[0]))); } break;
-    case OP_DEG: QG_EACH { X(I.out) = X(I.in[0]) * 57.2957795130823208767981548141051703f; } break;
-    case OP_RAD: QG_EACH { X(I.out) = X(I.in[0]) * (QG_PI / 180.0f); } break;
-    case OP_RECIP: QG_EACH { X(I.out) = 1.0f / X(I.in[0]); } break;
-    case OP_NORMAL: QG_EACH { float x = X(I.in[0]); X(I.out) = d_is_normal(x) ? x : 0.0f; } break;
-    case OP_CLIP: QG_EACH { X(I.out) = d_clamp(X(I.in[0]), X(I.p), X(I.p + 1)); } break;
-    case OP_WRAP2: QG_EACH { float p0 = X(I.p), r = X(I.p + 1); X(I.out) = fmodf(fmodf(X(I.in[0]) - p0, r) + r, r) + p0; } break;
-    case OP_WRAP1: QG_EACH { float x0 = X(I.p), x = X(I.in[0]); X(I.out) = x - x0 * floorf(x / x0); } break;
+    case OP_UPARC: QG_EACH { float x = XI(0); XO(0) = 1.0f - sqrtf(fmaxf(0.0f, 1.0f - x * x)); } break;
+    case OP_DOWNARC: QG_EACH { float x = XI(0); XO(0) = sqrtf(fmaxf(0.0f, (2.0f - x) * x)); } break;
+    case OP_SINE_EASE: QG_EACH { XO(0) = (1.0f - cosf(XI(0) * QG_PI)) * 0.5f; } break;
+    case OP_SEMITONE_RATIO: QG_EACH { XO(0) = d_exp2_cr(XI(0) / 12.0f); } break;
+    case OP_RND1: QG_EACH { XO(0) = d_rnd1(d_as_usize(XI(0))); } break;
+    case OP_RND2: QG_EACH { XO(0) = d_rnd2(d_as_usize(XI(0))); } break;
+    case OP_DEG: QG_EACH { XO(0) = XI(0) * 57.2957795130823208767981548141051703f; } break;
+    case OP_RAD: QG_EACH { XO(0) = XI(0) * (QG_PI / 180.0f); } break;
+    case OP_RECIP: QG_EACH { XO(0) = 1.0f / XI(0); } break;
+    case OP_NORMAL: QG_EACH { float x = XI(0); XO(0) = d_is_normal(x) ? x : 0.0f; } break;
+    case OP_CLIP: QG_EACH { XO(0) = d_clamp(XI(0), XS(I.p), XS(I.p + 1)); } break;
+    case OP_WRAP2: QG_EACH { float p0 = XS(I.p), r = XS(I.p + 1); XO(0) = fmodf(fmodf(XI(0) - p0, r) + r, r) + p0; } break;
+    case OP_WRAP1: QG_EACH { float x0 = XS(I.p), x = XI(0); XO(0) = x - x0 * floorf(x / x0); } break;
     case OP_MIRROR: QG_EACH {   // functions.rs:1167-1180
-      float p0 = X(I.p), p1 = X(I.p + 1), r = X(I.p + 2), x = X(I.in[0]);
+      float p0 = XS(I.p), p1 = XS(I.p + 1), r = XS(I.p + 2), x = XI(0);
       float n = d_is_normal(x) ? x : 0.0f, res;
       if (n >= p0 && n <= p1) res = n;
       else {
@@ -256,50 +278,50 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
         if ((n > p1 && fmodf(folds, 2.0f) == 0.0f) || (n < p0 && fmodf(folds, 2.0f) != 0.0f)) res = p0 + (distance - folds * r);
         else res = p1 - (distance - folds * r);
       }
-      X(I.out) = res;
+      XO(0) = res;
     } break;
-    case OP_POL: QG_EACH { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = hypotf(a, b); X(I.out + 1) = atan2f(b, a); } break;
-    case OP_CAR: QG_EACH { float a = X(I.in[0]), b = X(I.in[1]); X(I.out) = a * cosf(b); X(I.out + 1) = a * sinf(b); } break;
-    case OP_DIVN: QG_EACH { X(I.out) = X(I.in[0]) / (float)I.n; } break;
-    case OP_PAN: QG_EACH { float x = X(I.in[0]); X(I.out) = X(I.p) * x; X(I.out + 1) = X(I.p + 1) * x; } break;
+    case OP_POL: QG_EACH { float a = XI(0), b = XI(1); XO(0) = hypotf(a, b); XO(1) = atan2f(b, a); } break;
+    case OP_CAR: QG_EACH { float a = XI(0), b = XI(1); XO(0) = a * cosf(b); XO(1) = a * sinf(b); } break;
+    case OP_DIVN: QG_EACH { XO(0) = XI(0) / (float)I.n; } break;
+    case OP_PAN: QG_EACH { float x = XI(0); XO(0) = XS(I.p) * x; XO(1) = XS(I.p + 1) * x; } break;
     case OP_PAN_VAR: QG_EACH {
-      float x = X(I.in[0]), pan = X(I.in[1]);
-      if (pan != X(I.s)) { float l, r; pan_weights(pan, &l, &r); X(I.s) = pan; X(I.s + 1) = l; X(I.s + 2) = r; }
-      X(I.out) = X(I.s + 1) * x; X(I.out + 1) = X(I.s + 2) * x;
+      float x = XI(0), pan = XI(1);
+      if (pan != XS(I.s)) { float l, r; pan_weights(pan, &l, &r); XS(I.s) = pan; XS(I.s + 1) = l; XS(I.s + 2) = r; }
+      XO(0) = XS(I.s + 1) * x; XO(1) = XS(I.s + 2) * x;
     } break;
     case OP_ROTATE: QG_EACH {
-      float a = X(I.in[0]), b = X(I.in[1]), c = X(I.p), s = X(I.p + 1);
-      X(I.out) = c * a - s * b; X(I.out + 1) = s * a + c * b;
+      float a = XI(0), b = XI(1), c = XS(I.p), s = XS(I.p + 1);
+      XO(0) = c * a - s * b; XO(1) = s * a + c * b;
     } break;
     // ---------------------------------------------------------------- sources
     case OP_SINE: QG_EACH {
-      float ph = X(I.s);
-      float np = ph + X(I.in[0]) * X(I.p);
+      float ph = XS(I.s);
+      float np = ph + XI(0) * XS(I.p);
       np -= floorf(np);
-      X(I.s) = np;
-      X(I.out) = sinf(ph * QG_TAU);
+      XS(I.s) = np;
+      XO(0) = sinf(ph * QG_TAU);
     } break;
-    case OP_NOISE: QG_EACH { uint32_t c = XU(I.s) + 1u; SETU(I.s, c); X(I.out) = d_noise(c); } break;
-    case OP_IMPULSE: QG_EACH { uint32_t f = XU(I.s); X(I.out) = f ? 0.0f : 1.0f; SETU(I.s, 1u); } break;
+    case OP_NOISE: QG_EACH { uint32_t c = XSU(I.s) + 1u; SETSU(I.s, c); XO(0) = d_noise(c); } break;
+    case OP_IMPULSE: QG_EACH { uint32_t f = XSU(I.s); XO(0) = f ? 0.0f : 1.0f; SETSU(I.s, 1u); } break;
     case OP_RAMP: QG_EACH {   // nodes.rs:476-483
-      float val = X(I.s);
-      X(I.out) = val;
-      val += X(I.in[0]) / X(I.p);
+      float val = XS(I.s);
+      XO(0) = val;
+      val += XI(0) / XS(I.p);
       if (val >= 1.0f) val -= 1.0f;
-      X(I.s) = val;
+      XS(I.s) = val;
     } break;
     case OP_WAVETABLE: QG_EACH {   // FunDSP WaveSynth + Wavetable::read/at (restated, see lower.cpp make_wave)
       const float* hdr = L.tables + I.aux;
       const uint32_t nt = (uint32_t)hdr[0];
-      float f = X(I.in[0]);
-      float ph = X(I.s) + f * X(I.p);
+      float f = XI(0);
+      float ph = XS(I.s) + f * XS(I.p);
       ph -= floorf(ph);
-      X(I.s) = ph;
+      XS(I.s) = ph;
       float af = fabsf(f);
-      uint32_t hint = XU(I.s + 1);
+      uint32_t hint = XSU(I.s + 1);
       while (hint + 1 < nt && af >= hdr[1 + 3 * hint]) hint++;
       while (hint > 0 && af < hdr[1 + 3 * (hint - 1)]) hint--;
-      SETU(I.s + 1, hint);
+      SETSU(I.s + 1, hint);
       const uint32_t off = __float_as_uint(hdr[2 + 3 * hint]), len = __float_as_uint(hdr[3 + 3 * hint]), mask = len - 1;
       const float* tb = hdr + off;
       float pp = (float)len * ph;
@@ -314,173 +336,173 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       float c2 = even1 * -0.25194210134021744f + even2 * 0.25194744935939062f;
       float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
       float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
-      X(I.out) = (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
+      XO(0) = (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
     } break;
     case OP_WAVE: QG_EACH {
-      uint32_t i = XU(I.s);
-      X(I.out) = L.tables[I.aux + i];
+      uint32_t i = XSU(I.s);
+      XO(0) = L.tables[I.aux + i];
       i += 1;
       if (i >= I.aux2) i = 0;
-      SETU(I.s, i);
+      SETSU(I.s, i);
     } break;
     // ---------------------------------------------------------------- filters
     case OP_SVF: QG_EACH {
-      float ic1 = X(I.s), ic2 = X(I.s + 1);
-      X(I.out) = d_svf_tick(X(I.in[0]), ic1, ic2, X(I.p), X(I.p + 1), X(I.p + 2), X(I.p + 3), X(I.p + 4), X(I.p + 5));
-      X(I.s) = ic1; X(I.s + 1) = ic2;
+      float ic1 = XS(I.s), ic2 = XS(I.s + 1);
+      XO(0) = d_svf_tick(XI(0), ic1, ic2, XS(I.p), XS(I.p + 1), XS(I.p + 2), XS(I.p + 3), XS(I.p + 4), XS(I.p + 5));
+      XS(I.s) = ic1; XS(I.s + 1) = ic2;
     } break;
     case OP_SVF_VAR: QG_EACH {
       int mode = I.n & 0xff, nvar = I.n >> 8;
-      float hz = nvar >= 1 ? X(I.in[1]) : X(I.p), q = nvar >= 2 ? X(I.in[2]) : X(I.p + 1), g = nvar >= 3 ? X(I.in[3]) : X(I.p + 2);
-      if (hz != X(I.s + 8) || q != X(I.s + 9) || g != X(I.s + 10)) {
+      float hz = nvar >= 1 ? XI(1) : XS(I.p), q = nvar >= 2 ? XI(2) : XS(I.p + 1), g = nvar >= 3 ? XI(3) : XS(I.p + 2);
+      if (hz != XS(I.s + 8) || q != XS(I.s + 9) || g != XS(I.s + 10)) {
         float c[6];
-        svf_coefs(mode, hz, q, g, X(I.p + 3), c);
-        for (int k = 0; k < 6; k++) X(I.s + 2 + k) = c[k];
-        X(I.s + 8) = hz; X(I.s + 9) = q; X(I.s + 10) = g;
+        svf_coefs(mode, hz, q, g, XS(I.p + 3), c);
+        for (int k = 0; k < 6; k++) XS(I.s + 2 + k) = c[k];
+        XS(I.s + 8) = hz; XS(I.s + 9) = q; XS(I.s + 10) = g;
       }
-      float ic1 = X(I.s), ic2 = X(I.s + 1);
-      X(I.out) = d_svf_tick(X(I.in[0]), ic1, ic2, X(I.s + 2), X(I.s + 3), X(I.s + 4), X(I.s + 5), X(I.s + 6), X(I.s + 7));
-      X(I.s) = ic1; X(I.s + 1) = ic2;
+      float ic1 = XS(I.s), ic2 = XS(I.s + 1);
+      XO(0) = d_svf_tick(XI(0), ic1, ic2, XS(I.s + 2), XS(I.s + 3), XS(I.s + 4), XS(I.s + 5), XS(I.s + 6), XS(I.s + 7));
+      XS(I.s) = ic1; XS(I.s + 1) = ic2;
     } break;
     case OP_BIQUAD: QG_EACH {
-      float x0 = X(I.in[0]), x1 = X(I.s), x2 = X(I.s + 1), y1 = X(I.s + 2), y2 = X(I.s + 3);
-      float y0 = X(I.p + 2) * x0 + X(I.p + 3) * x1 + X(I.p + 4) * x2 - X(I.p) * y1 - X(I.p + 1) * y2;
-      X(I.s) = x0; X(I.s + 1) = x1; X(I.s + 2) = y0; X(I.s + 3) = y1;
-      X(I.out) = y0;
+      float x0 = XI(0), x1 = XS(I.s), x2 = XS(I.s + 1), y1 = XS(I.s + 2), y2 = XS(I.s + 3);
+      float y0 = XS(I.p + 2) * x0 + XS(I.p + 3) * x1 + XS(I.p + 4) * x2 - XS(I.p) * y1 - XS(I.p + 1) * y2;
+      XS(I.s) = x0; XS(I.s + 1) = x1; XS(I.s + 2) = y0; XS(I.s + 3) = y1;
+      XO(0) = y0;
     } break;
     case OP_BIQUAD_VAR: QG_EACH {
       int kind = I.n & 0xff, nvar = I.n >> 8;
-      float c0 = X(I.in[1]), c1 = nvar >= 2 ? X(I.in[2]) : X(I.s + 10);
-      if (c0 != X(I.s + 9) || c1 != X(I.s + 10)) {
+      float c0 = XI(1), c1 = nvar >= 2 ? XI(2) : XS(I.s + 10);
+      if (c0 != XS(I.s + 9) || c1 != XS(I.s + 10)) {
         float c[5];
-        biquad_coefs(kind, c0, c1, X(I.p), c);
-        for (int k = 0; k < 5; k++) X(I.s + 4 + k) = c[k];
-        X(I.s + 9) = c0; X(I.s + 10) = c1;
+        biquad_coefs(kind, c0, c1, XS(I.p), c);
+        for (int k = 0; k < 5; k++) XS(I.s + 4 + k) = c[k];
+        XS(I.s + 9) = c0; XS(I.s + 10) = c1;
       }
-      float x0 = X(I.in[0]), x1 = X(I.s), x2 = X(I.s + 1), y1 = X(I.s + 2), y2 = X(I.s + 3);
-      float y0 = X(I.s + 6) * x0 + X(I.s + 7) * x1 + X(I.s + 8) * x2 - X(I.s + 4) * y1 - X(I.s + 5) * y2;
-      X(I.s) = x0; X(I.s + 1) = x1; X(I.s + 2) = y0; X(I.s + 3) = y1;
-      X(I.out) = y0;
+      float x0 = XI(0), x1 = XS(I.s), x2 = XS(I.s + 1), y1 = XS(I.s + 2), y2 = XS(I.s + 3);
+      float y0 = XS(I.s + 6) * x0 + XS(I.s + 7) * x1 + XS(I.s + 8) * x2 - XS(I.s + 4) * y1 - XS(I.s + 5) * y2;
+      XS(I.s) = x0; XS(I.s + 1) = x1; XS(I.s + 2) = y0; XS(I.s + 3) = y1;
+      XO(0) = y0;
     } break;
     case OP_ONEPOLE: case OP_ONEPOLE_VAR: QG_EACH {
       float coeff;
-      if (I.op == OP_ONEPOLE) coeff = X(I.p);
+      if (I.op == OP_ONEPOLE) coeff = XS(I.p);
       else {
-        float p = X(I.in[1]);
-        if (p != X(I.s + 3)) { X(I.s + 3) = p; X(I.s + 2) = onepole_coef(I.n, p, X(I.p)); }
-        coeff = X(I.s + 2);
+        float p = XI(1);
+        if (p != XS(I.s + 3)) { XS(I.s + 3) = p; XS(I.s + 2) = onepole_coef(I.n, p, XS(I.p)); }
+        coeff = XS(I.s + 2);
       }
-      float x = X(I.in[0]), x1 = X(I.s), y1 = X(I.s + 1), y;
+      float x = XI(0), x1 = XS(I.s), y1 = XS(I.s + 1), y;
       switch (I.n) {
         case 0: y = (1.0f - coeff) * x + coeff * y1; break;
         case 1: y = coeff * (y1 + x - x1); break;
         case 2: y = x - x1 + coeff * y1; break;
         default: y = coeff * (x - y1) + x1; break;
       }
-      X(I.s) = x; X(I.s + 1) = y;
-      X(I.out) = y;
+      XS(I.s) = x; XS(I.s + 1) = y;
+      XO(0) = y;
     } break;
     case OP_PINKPASS: QG_EACH {
-      float w = X(I.in[0]);
-      float b0 = 0.99886f * X(I.s) + w * 0.0555179f;
-      float b1 = 0.99332f * X(I.s + 1) + w * 0.0750759f;
-      float b2 = 0.96900f * X(I.s + 2) + w * 0.1538520f;
-      float b3 = 0.86650f * X(I.s + 3) + w * 0.3104856f;
-      float b4 = 0.55000f * X(I.s + 4) + w * 0.5329522f;
-      float b5 = -0.7616f * X(I.s + 5) - w * 0.0168980f;
-      float pink = b0 + b1 + b2 + b3 + b4 + b5 + X(I.s + 6) + w * 0.5362f;
-      X(I.s) = b0; X(I.s + 1) = b1; X(I.s + 2) = b2; X(I.s + 3) = b3; X(I.s + 4) = b4; X(I.s + 5) = b5;
-      X(I.s + 6) = w * 0.115926f;
-      X(I.out) = pink * 0.11f;
+      float w = XI(0);
+      float b0 = 0.99886f * XS(I.s) + w * 0.0555179f;
+      float b1 = 0.99332f * XS(I.s + 1) + w * 0.0750759f;
+      float b2 = 0.96900f * XS(I.s + 2) + w * 0.1538520f;
+      float b3 = 0.86650f * XS(I.s + 3) + w * 0.3104856f;
+      float b4 = 0.55000f * XS(I.s + 4) + w * 0.5329522f;
+      float b5 = -0.7616f * XS(I.s + 5) - w * 0.0168980f;
+      float pink = b0 + b1 + b2 + b3 + b4 + b5 + XS(I.s + 6) + w * 0.5362f;
+      XS(I.s) = b0; XS(I.s + 1) = b1; XS(I.s + 2) = b2; XS(I.s + 3) = b3; XS(I.s + 4) = b4; XS(I.s + 5) = b5;
+      XS(I.s + 6) = w * 0.115926f;
+      XO(0) = pink * 0.11f;
     } break;
     case OP_FIR: QG_EACH {
       int n = I.n;
-      for (int k = n - 1; k > 0; k--) X(I.s + k) = X(I.s + k - 1);
-      X(I.s) = X(I.in[0]);
+      for (int k = n - 1; k > 0; k--) XS(I.s + k) = XS(I.s + k - 1);
+      XS(I.s) = XI(0);
       float acc = 0.0f;
-      for (int k = 0; k < n; k++) acc += X(I.p + k) * X(I.s + k);
-      X(I.out) = acc;
+      for (int k = 0; k < n; k++) acc += XS(I.p + k) * XS(I.s + k);
+      XO(0) = acc;
     } break;
     // ---------------------------------------------------------------- delays
-    case OP_TICK: QG_EACH { float v = X(I.s); X(I.s) = X(I.in[0]); X(I.out) = v; } break;
+    case OP_TICK: QG_EACH { float v = XS(I.s); XS(I.s) = XI(0); XO(0) = v; } break;
     case OP_DELAY: QG_EACH {
-      uint32_t i = XU(I.s), len = ring_len(L, I.aux);
+      uint32_t i = XSU(I.s), len = ring_len(L, I.aux);
       float& slot = ring_at(L, I.aux, i);
       float o = slot;
-      slot = X(I.in[0]);
+      slot = XI(0);
       i = i + 1 == len ? 0 : i + 1;
-      SETU(I.s, i);
-      X(I.out) = o;
+      SETSU(I.s, i);
+      XO(0) = o;
     } break;
     case OP_TAP: QG_EACH {
-      uint32_t idx = XU(I.s), len = ring_len(L, I.aux), mask = len - 1;
-      ring_at(L, I.aux, idx) = X(I.in[0]);
-      float tap = d_clamp(X(I.in[1]), X(I.p), X(I.p + 1)) * X(I.p + 2);
+      uint32_t idx = XSU(I.s), len = ring_len(L, I.aux), mask = len - 1;
+      ring_at(L, I.aux, idx) = XI(0);
+      float tap = d_clamp(XI(1), XS(I.p), XS(I.p + 1)) * XS(I.p + 2);
       if (tap != tap) tap = 0.0f;
       uint32_t fl = (uint32_t)d_as_usize(tap);
       float d = tap - (float)fl;
       uint32_t i1 = (idx + len - fl) & mask;
       if (I.n) {
         uint32_t i0 = (i1 + 1) & mask, i2 = (i1 + len - 1) & mask, i3 = (i1 + len - 2) & mask;
-        X(I.out) = d_spline(ring_at(L, I.aux, i0), ring_at(L, I.aux, i1), ring_at(L, I.aux, i2), ring_at(L, I.aux, i3), d);
+        XO(0) = d_spline(ring_at(L, I.aux, i0), ring_at(L, I.aux, i1), ring_at(L, I.aux, i2), ring_at(L, I.aux, i3), d);
       } else {
         uint32_t i2 = (i1 + len - 1) & mask;
-        X(I.out) = d_lerp(ring_at(L, I.aux, i1), ring_at(L, I.aux, i2), d);
+        XO(0) = d_lerp(ring_at(L, I.aux, i1), ring_at(L, I.aux, i2), d);
       }
-      SETU(I.s, (idx + 1) & mask);
+      SETSU(I.s, (idx + 1) & mask);
     } break;
     case OP_SAMP_DELAY: QG_EACH {   // nodes.rs:726-731: push_front, pop_back, then index from the front
-      uint32_t head = XU(I.s), len = ring_len(L, I.aux);
+      uint32_t head = XSU(I.s), len = ring_len(L, I.aux);
       head = head == 0 ? len - 1 : head - 1;
-      ring_at(L, I.aux, head) = X(I.in[0]);
-      SETU(I.s, head);
-      uint64_t k = d_as_usize(X(I.in[1]));
+      ring_at(L, I.aux, head) = XI(0);
+      SETSU(I.s, head);
+      uint64_t k = d_as_usize(XI(1));
       float o = 0.0f;
       if (k < (uint64_t)len) { uint32_t pos = head + (uint32_t)k; if (pos >= len) pos -= len; o = ring_at(L, I.aux, pos); }
-      X(I.out) = o;
+      XO(0) = o;
     } break;
     case OP_ENVELOPE: QG_EACH {
       int shape = I.n & 0xff, nin = I.n >> 8;
-      float t = X(I.s), t0 = X(I.s + 1), t1 = X(I.s + 2), v0 = X(I.s + 3), v1 = X(I.s + 4);
+      float t = XS(I.s), t0 = XS(I.s + 1), t1 = XS(I.s + 2), v0 = XS(I.s + 3), v1 = XS(I.s + 4);
       if (t >= t1) {
-        float c[4] = {X(I.p), X(I.p + 1), X(I.p + 2), X(I.p + 3)};
+        float c[4] = {XS(I.p), XS(I.p + 1), XS(I.p + 2), XS(I.p + 3)};
         float in[4];
-        in[0] = nin > 0 ? X(I.in[0]) : 0.0f; in[1] = nin > 1 ? X(I.in[1]) : 0.0f;
-        in[2] = nin > 2 ? X(I.in[2]) : 0.0f; in[3] = nin > 3 ? X(I.in[3]) : 0.0f;
-        if (XU(I.s + 7)) { v1 = d_env_eval(shape, nin, 0.0f, c, in); SETU(I.s + 7, 0u); }
-        uint64_t th = (uint64_t)XU(I.s + 5) | ((uint64_t)XU(I.s + 6) << 32);
+        in[0] = nin > 0 ? XI(0) : 0.0f; in[1] = nin > 1 ? XI(1) : 0.0f;
+        in[2] = nin > 2 ? XI(2) : 0.0f; in[3] = nin > 3 ? XI(3) : 0.0f;
+        if (XSU(I.s + 7)) { v1 = d_env_eval(shape, nin, 0.0f, c, in); SETSU(I.s + 7, 0u); }
+        uint64_t th = (uint64_t)XSU(I.s + 5) | ((uint64_t)XSU(I.s + 6) << 32);
         t0 = t1;
         v0 = v1;
         float next = d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
         t1 = t0 + next;
         v1 = d_env_eval(shape, nin, t1, c, in);
         th += 1;
-        SETU(I.s + 5, (uint32_t)th); SETU(I.s + 6, (uint32_t)(th >> 32));
-        X(I.s + 1) = t0; X(I.s + 2) = t1; X(I.s + 3) = v0; X(I.s + 4) = v1;
+        SETSU(I.s + 5, (uint32_t)th); SETSU(I.s + 6, (uint32_t)(th >> 32));
+        XS(I.s + 1) = t0; XS(I.s + 2) = t1; XS(I.s + 3) = v0; XS(I.s + 4) = v1;
       }
       float u = d_delerp(t0, t1, t);
-      X(I.s) = t + X(I.p + 4);
-      X(I.out) = d_lerp(v0, v1, u);
+      XS(I.s) = t + XS(I.p + 4);
+      XO(0) = d_lerp(v0, v1, u);
     } break;
     case OP_DECLICK: QG_EACH {
-      float t = X(I.s), dur = X(I.p), x = X(I.in[0]);
-      if (t < dur) { X(I.out) = x * d_smooth5(t / dur); X(I.s) = t + X(I.p + 1); }
-      else X(I.out) = x;
+      float t = XS(I.s), dur = XS(I.p), x = XI(0);
+      if (t < dur) { XO(0) = x * d_smooth5(t / dur); XS(I.s) = t + XS(I.p + 1); }
+      else XO(0) = x;
     } break;
     // ---------------------------------------------------------------- in-tree stateful nodes
     case OP_SHIFT_REG: QG_EACH {   // nodes.rs:173-185
-      if (X(I.in[1]) != 0.0f) {
-        for (int k = 7; k > 0; k--) X(I.s + k) = X(I.s + k - 1);
-        X(I.s) = X(I.in[0]);
+      if (XI(1) != 0.0f) {
+        for (int k = 7; k > 0; k--) XS(I.s + k) = XS(I.s + k - 1);
+        XS(I.s) = XI(0);
       }
-      for (int k = 0; k < 8; k++) X(I.out + k) = X(I.s + k);
+      for (int k = 0; k < 8; k++) XO(k) = XS(I.s + k);
     } break;
     case OP_SNH: QG_EACH {   // nodes.rs:811-816
-      if (X(I.in[1]) != 0.0f) X(I.s) = X(I.in[0]);
-      X(I.out) = X(I.s);
+      if (XI(1) != 0.0f) XS(I.s) = XI(0);
+      XO(0) = XS(I.s);
     } break;
     case OP_QUANTIZE: QG_EACH {   // nodes.rs:213-228
-      float n = X(I.in[0]), range = X(I.p);
+      float n = XI(0), range = XS(I.p);
       float wrapped = n - range * floorf(n / range);
       float nearest = 0.0f, dist = FLT_MAX;
       for (uint32_t k = 0; k < I.aux2; k++) {
@@ -488,45 +510,45 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
         float d = fabsf(wrapped - v);
         if (d < dist) { nearest = v; dist = d; }
       }
-      X(I.out) = n + nearest - wrapped;
+      XO(0) = n + nearest - wrapped;
     } break;
     case OP_ARR_GET: QG_EACH {   // nodes.rs:143-149
-      uint64_t k = d_as_usize(X(I.in[0]));
-      X(I.out) = k < (uint64_t)I.aux2 ? L.tables[I.aux + (uint32_t)k] : 0.0f;
+      uint64_t k = d_as_usize(XI(0));
+      XO(0) = k < (uint64_t)I.aux2 ? L.tables[I.aux + (uint32_t)k] : 0.0f;
     } break;
     // ---------------------------------------------------------------- control flow
     case OP_KR_BEGIN: {   // nodes.rs:272-275
-      uint32_t c = XU(I.s);
-      if (c == 0) SETU(I.s, I.aux2);
+      uint32_t c = XSU(I.s);
+      if (c == 0) SETSU(I.s, I.aux2);
       else pc = (int)I.aux;
       break;
     }
-    case OP_KR_END: SETU(I.s, XU(I.s) - 1u); break;
+    case OP_KR_END: SETSU(I.s, XSU(I.s) - 1u); break;
     case OP_RESET_EVERY: {   // nodes.rs:353-358
-      uint32_t c = XU(I.s);
+      uint32_t c = XSU(I.s);
       if (c >= I.aux) { { const LaneT Lc = L; reset_range(Lc, I.aux2); } c = 0; }
-      SETU(I.s, c + 1u);
+      SETSU(I.s, c + 1u);
       break;
     }
-    case OP_RESET_IF: if (X(I.in[0]) != 0.0f) { const LaneT Lc = L; reset_range(Lc, I.aux2); } break;
+    case OP_RESET_IF: if (XI(0) != 0.0f) { const LaneT Lc = L; reset_range(Lc, I.aux2); } break;
     case OP_RESET_V: {   // nodes.rs:435-440
-      uint32_t c = XU(I.s);
-      uint64_t lim = d_as_usize(roundf(X(I.in[0]) * X(I.p)));
+      uint32_t c = XSU(I.s);
+      uint64_t lim = d_as_usize(roundf(XI(0) * XS(I.p)));
       if ((uint64_t)c >= lim) { { const LaneT Lc = L; reset_range(Lc, I.aux2); } c = 0; }
-      SETU(I.s, c + 1u);
+      SETSU(I.s, c + 1u);
       break;
     }
-    case OP_JNE_IDX: if (d_as_usize(X(I.in[0])) != (uint64_t)I.aux2) pc = (int)I.aux; break;
+    case OP_JNE_IDX: if (d_as_usize(XI(0)) != (uint64_t)I.aux2) pc = (int)I.aux; break;
     case OP_SEQ_TRIG: {   // nodes.rs:76-91
       const int nk = I.n;
-      if (X(I.in[0]) != 0.0f) {
-        const uint64_t k = d_as_usize(X(I.in[1]));
+      if (XI(0) != 0.0f) {
+        const uint64_t k = d_as_usize(XI(1));
         if (k < (uint64_t)nk) {
           const int b = I.s + 1 + 5 * (int)k;
           { const LaneT Lc = L; reset_range(Lc, I.aux2 + (uint32_t)k); }
-          const uint64_t dl = d_as_usize(roundf(X(I.in[2]) * X(I.p))), du = d_as_usize(roundf(X(I.in[3]) * X(I.p)));
-          const uint32_t stamp = XU(I.s) + 1u;
-          SETU(I.s, stamp);
+          const uint64_t dl = d_as_usize(roundf(XI(2) * XS(I.p))), du = d_as_usize(roundf(XI(3) * XS(I.p)));
+          const uint32_t stamp = XSU(I.s) + 1u;
+          SETSU(I.s, stamp);
           SETU(b, 1u);
           SETU(b + 1, dl > 0xffffffffull ? 0xffffffffu : (uint32_t)dl);
           SETU(b + 2, du > 0xffffffffull ? 0xffffffffu : (uint32_t)du);
@@ -566,40 +588,40 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
         acc += X(I.in[0] + best);
         done = bs;
       }
-      X(I.out) = acc;
+      XO(0) = acc;
       break;
     }
     // ---------------------------------------------------------------- feedback
     // block lanes run FB_READ for every sample of the block before FB_WRITE stores any (ring length >= block length is
     // checked by the launcher), so both address the ring at idx + j and the index advances once per block
-    case OP_FB_READ: QG_EACH { X(I.out) = X(I.in[0]) + ring_at(L, I.aux, ring_wrap(XU(I.s) + L.sample(), ring_len(L, I.aux))); } break;
+    case OP_FB_READ: QG_EACH { XO(0) = XI(0) + ring_at(L, I.aux, ring_wrap(XSU(I.s) + L.sample(), ring_len(L, I.aux))); } break;
     case OP_FB_WRITE: {
-      const uint32_t len = ring_len(L, I.aux), i = XU(I.s);
-      QG_EACH { ring_at(L, I.aux, ring_wrap(i + L.sample(), len)) = X(I.in[0]); }
-      if (I.n) SETU(I.s, ring_wrap(i + L.count(), len));
+      const uint32_t len = ring_len(L, I.aux), i = XSU(I.s);
+      QG_EACH { ring_at(L, I.aux, ring_wrap(i + L.sample(), len)) = XI(0); }
+      if (I.n) SETSU(I.s, ring_wrap(i + L.count(), len));
       break;
     }
     // ---------------------------------------------------------------- spectral nodes (per-lane path)
     case OP_RFFT: QG_EACH {   // nodes.rs:625-642
-      uint32_t N = 1u << I.n, i = XU(I.s), nx = i + 1 == N ? 0 : i + 1;
-      SETU(I.s, nx);
+      uint32_t N = 1u << I.n, i = XSU(I.s), nx = i + 1 == N ? 0 : i + 1;
+      SETSU(I.s, nx);
       if (i == 0) {
         for (uint32_t k = 0; k < N; k++) { ring_at(L, I.aux + 1, k) = ring_at(L, I.aux, k); ring_at(L, I.aux + 2, k) = 0.0f; }
         { const LaneT Lc = L; lane_fft(Lc, I.aux + 1, I.aux + 2, I.n, L.tables + I.aux2, false); }
       }
-      ring_at(L, I.aux, i) = X(I.in[0]);
-      if (i <= N / 2) { X(I.out) = ring_at(L, I.aux + 1, i); X(I.out + 1) = ring_at(L, I.aux + 2, i); }
-      else { X(I.out) = ring_at(L, I.aux + 1, N - i); X(I.out + 1) = -ring_at(L, I.aux + 2, N - i); }
+      ring_at(L, I.aux, i) = XI(0);
+      if (i <= N / 2) { XO(0) = ring_at(L, I.aux + 1, i); XO(1) = ring_at(L, I.aux + 2, i); }
+      else { XO(0) = ring_at(L, I.aux + 1, N - i); XO(1) = -ring_at(L, I.aux + 2, N - i); }
     } break;
     case OP_IFFT: QG_EACH {   // nodes.rs:681-693
-      uint32_t N = 1u << I.n, i = XU(I.s), nx = i + 1 == N ? 0 : i + 1;
-      SETU(I.s, nx);
+      uint32_t N = 1u << I.n, i = XSU(I.s), nx = i + 1 == N ? 0 : i + 1;
+      SETSU(I.s, nx);
       if (i == 0) {
         for (uint32_t k = 0; k < N; k++) { ring_at(L, I.aux + 2, k) = ring_at(L, I.aux, k); ring_at(L, I.aux + 3, k) = ring_at(L, I.aux + 1, k); }
         { const LaneT Lc = L; lane_fft(Lc, I.aux + 2, I.aux + 3, I.n, L.tables + I.aux2, true); }
       }
-      ring_at(L, I.aux, i) = X(I.in[0]); ring_at(L, I.aux + 1, i) = X(I.in[1]);
-      X(I.out) = ring_at(L, I.aux + 2, i); X(I.out + 1) = ring_at(L, I.aux + 3, i);
+      ring_at(L, I.aux, i) = XI(0); ring_at(L, I.aux + 1, i) = XI(1);
+      XO(0) = ring_at(L, I.aux + 2, i); XO(1) = ring_at(L, I.aux + 3, i);
     } break;
     default: break;
   }
@@ -697,10 +719,11 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
   const int PS = a.P + a.NS;
   const int nx = PS + a.NT * BT;
   float* tiles = xs + (size_t)nx * nt;                       // [n_out][nwarps][32][33]
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.code);
-    uint4* dst = reinterpret_cast<uint4*>(code);
-    for (int i = tid; i < a.n_instr * 2; i += nt) dst[i] = src[i];
+  for (int i = tid; i < a.n_instr; i += nt) {   // stage the tape with its temporary indices rewritten to block layout
+    Instr I = a.code[i];
+    I.out = blk_index<BT>(I.out, PS);
+    for (int k = 0; k < 5; k++) I.in[k] = blk_index<BT>(I.in[k], PS);
+    code[i] = I;
   }
   const int v = blockIdx.x * nt + tid;
   BlockLane<BT> L;
@@ -719,7 +742,7 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
       for (int j = 0; j < n; j++) {
         const long t = t0 + j;
         size_t idx = a.in_frame_major ? ((size_t)t * a.V + v) * a.n_in + c : ((size_t)v * a.n_in + c) * a.T + t;
-        L.at(PS + c, j) = v < a.V ? a.in[idx] : 0.0f;
+        L.tr(PS + c * BT, j) = v < a.V ? a.in[idx] : 0.0f;
       }
     for (int i = 0; i < a.n_instr; i++) {
       const Instr I = code[i];
@@ -731,9 +754,9 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
 #pragma unroll
           for (int j = 0; j < BT; j++) if (j < n) o[j] = ring_at(L, I.aux, ring_wrap(idx + (uint32_t)j, len));
 #pragma unroll
-          for (int j = 0; j < BT; j++) if (j < n) ring_at(L, I.aux, ring_wrap(idx + (uint32_t)j, len)) = L.at(I.in[0], j);
+          for (int j = 0; j < BT; j++) if (j < n) ring_at(L, I.aux, ring_wrap(idx + (uint32_t)j, len)) = L.tr(I.in[0], j);
 #pragma unroll
-          for (int j = 0; j < BT; j++) if (j < n) L.at(I.out, j) = o[j];
+          for (int j = 0; j < BT; j++) if (j < n) L.tr(I.out, j) = o[j];
           L.x[I.s * nt] = __uint_as_float(ring_wrap(idx + (uint32_t)n, len));
           continue;
         }
@@ -745,13 +768,13 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
     if (a.out_frame_major) {
       if (v < a.V)
         for (int j = 0; j < n; j++)
-          for (int c = 0; c < a.n_out; c++) a.out[((size_t)(t0 + j) * a.V + v) * a.n_out + c] = L.at(a.out_x[c], j);
+          for (int c = 0; c < a.n_out; c++) a.out[((size_t)(t0 + j) * a.V + v) * a.n_out + c] = L.tr(blk_index<BT>(a.out_x[c], PS), j);
     } else {
       const int tt0 = (int)(t0 & 31);
       for (int c = 0; c < a.n_out; c++) {
-        const int ox = a.out_x[c];
+        const int ox = blk_index<BT>(a.out_x[c], PS);
         float* trow = tiles + (((size_t)c * nwarps + warp) * 32 + lane) * 33 + tt0;
-        for (int j = 0; j < n; j++) trow[j] = L.at(ox, j);
+        for (int j = 0; j < n; j++) trow[j] = L.tr(ox, j);
       }
       const long t = t0 + n - 1;
       const int tt = (int)(t & 31);
