@@ -363,7 +363,7 @@ static int bank_family(const qg_bank* b) {
   if (b->path == QG_PATH_INTERP || b->path == QG_PATH_INTERP_SAMPLE) return 0;
   if (b->path == QG_PATH_TV) return b->tv.ok ? 2 : 0;
   if (b->fused.id != FUSED_NONE) return 1;
-  if (b->tv.ok && (b->tv.has_fft || b->V <= 2048)) return 2;
+  if (b->tv.ok && (b->tv.has_fft || b->V <= (b->tv.sequential ? 256 : 2048))) return 2;
   return 0;
 }
 int qg_bank_set_path(qg_bank* b, int path) {
@@ -451,7 +451,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     ta.n_in = (int)t.h.n_inputs; ta.n_out = (int)t.h.n_outputs; ta.out_x = b->d_out_x;
     ta.params = b->d_params; ta.state = b->d_state; ta.rings = b->d_rings; ta.ring_floats = t.h.ring_floats;
     ta.ring_tab = b->d_ring_tab; ta.tables = b->d_tables; ta.in = d_in; ta.out = d_out;
-    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n; ta.align_s = b->tv.align_s; ta.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
+    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n; ta.align_s = b->tv.align_s; ta.n_lti = b->tv.n_lti; ta.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
     int l = 0;
     CU(launch_interp_tv(ta, c->stream, &l));
     c->launches += l;

@@ -931,6 +931,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
   // float offsets of the regions behind the tape: scalars, temporaries, tap scratch, transform buffers
   const int ps_off = a.n_instr * (int)(sizeof(Instr) / 4), tmp_off = ps_off + ((PS + 3) & ~3);
   const int oldv_off = tmp_off + a.NT * H, fr_off = oldv_off + H, fi_off = fr_off + (int)FPAD(a.fft_n);
+  const int lti_off = fi_off + (int)FPAD(a.fft_n), scan_off = lti_off + a.n_lti * TV_LTI_FLOATS;   // scan scratch: 2 x 2 x 8 warps
 #define ps (QG_SMEM_F + ps_off)
 #define tmp (QG_SMEM_F + tmp_off)
 #define oldv (QG_SMEM_F + oldv_off)
@@ -944,6 +945,42 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
   for (int p = tid; p < a.P; p += nth) ps[p] = a.params[(size_t)p * a.Vp + v];
   for (int s = tid; s < a.NS; s += nth) ps[a.P + s] = a.state[(size_t)s * a.Vp + v];
   for (int k = tid; k < a.NT * H; k += nth) tmp[k] = 0.0f;
+  __syncthreads();
+  // ---- scan matrices of the fixed-coefficient LTI filters (one thread per filter, f64, rounded once):
+  // a thread advances CPT consecutive samples, so the per-thread map is s -> M s + e with M = A^CPT
+  const int CPT = (H + nth - 1) / nth;                    // samples per thread in the LTI scans (<= 2)
+  for (int pc = tid; pc < a.n_instr; pc += nth) {
+    const Instr I = code[pc];
+    if (!op_is_lti(I.op)) continue;
+    double A11, A12, A21, A22;
+    if (I.op == OP_SVF) {
+      const double a1 = ps[I.p], a2 = ps[I.p + 1], a3 = ps[I.p + 2];
+      A11 = 2 * a1 - 1; A12 = -2 * a2; A21 = 2 * a2; A22 = 1 - 2 * a3;
+    } else if (I.op == OP_BIQUAD) {
+      A11 = -(double)ps[I.p]; A12 = -(double)ps[I.p + 1]; A21 = 1; A22 = 0;
+    } else {
+      const double c = ps[I.p];
+      A11 = I.n == 3 ? -c : c; A12 = 0; A21 = 0; A22 = 0;
+    }
+    double m11 = 1, m12 = 0, m21 = 0, m22 = 1;
+    for (int k = 0; k < CPT; k++) {
+      const double n11 = A11 * m11 + A12 * m21, n12 = A11 * m12 + A12 * m22, n21 = A21 * m11 + A22 * m21, n22 = A21 * m12 + A22 * m22;
+      m11 = n11; m12 = n12; m21 = n21; m22 = n22;
+    }
+    float4* tab = reinterpret_cast<float4*>(QG_SMEM_F + lti_off + (int)I.aux * TV_LTI_FLOATS);
+    double p11 = 1, p12 = 0, p21 = 0, p22 = 1;             // M^l, l = 0..32
+    for (int l = 0; l <= 32; l++) {
+      if (l < 32) tab[5 + l] = make_float4((float)p11, (float)p12, (float)p21, (float)p22);
+      else tab[37] = make_float4((float)p11, (float)p12, (float)p21, (float)p22);
+      if (l == 1) tab[0] = tab[5 + l];
+      if (l == 2) tab[1] = tab[5 + l];
+      if (l == 4) tab[2] = tab[5 + l];
+      if (l == 8) tab[3] = tab[5 + l];
+      if (l == 16) tab[4] = tab[5 + l];
+      const double n11 = m11 * p11 + m12 * p21, n12 = m11 * p12 + m12 * p22, n21 = m21 * p11 + m22 * p21, n22 = m21 * p12 + m22 * p22;
+      p11 = n11; p12 = n12; p21 = n21; p22 = n22;
+    }
+  }
   float* rg = a.rings + (size_t)v * a.ring_floats;        // voice-major rings in this mode
 #define RING(r) (rg + a.ring_tab[r].offset)
 #define TMP(i) (tmp + ((int)(i) - PS) * H)                 // temporaries only
@@ -995,6 +1032,118 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             __syncthreads();
             for (int j = tid; j < n; j += nth) TMP(I.out)[j] = (f == 0u && j == 0) ? 1.0f : 0.0f;
             if (tid == 0) ps[I.s] = __uint_as_float(1u);
+            break;
+          }
+          case OP_SVF: case OP_BIQUAD: case OP_ONEPOLE: {
+            // Block-level parallel linear-recurrence scan over the hop.  Thread t owns samples [t*CPT, t*CPT + cnt):
+            //   1. zero-state run of its samples (real inputs, zero filter state) -> e_t;
+            //   2. scan of the affine maps s -> M s + e_t: Kogge-Stone inside a warp (M^(2^i)), warp totals chained by
+            //      one thread (M^32), start state of lane l = M^l P_warp + E_(l-1);
+            //   3. the samples are re-run from the true start state with the op's own arithmetic (same code as exec()).
+            const float4* tab = reinterpret_cast<const float4*>(QG_SMEM_F + lti_off + (int)I.aux * TV_LTI_FLOATS);
+            float* wtot = QG_SMEM_F + scan_off;             // [nwarps][2] warp totals, then [nwarps][2] warp start states
+            float* wsta = wtot + 2 * (nth >> 5);
+            const int j0 = tid * CPT;
+            const int cnt = j0 >= n ? 0 : (n - j0 < CPT ? n - j0 : CPT);
+            const int lane = tid & 31, wid = tid >> 5;
+            // inputs and the two previous inputs (history comes from the hop or from the persisted state)
+            float xin[2] = {0.0f, 0.0f}, xm1 = 0.0f, xm2 = 0.0f;
+            for (int k = 0; k < cnt; k++) xin[k] = SRC(I.in[0], j0 + k);
+            if (I.op == OP_BIQUAD) {
+              xm1 = j0 >= 1 ? SRC(I.in[0], j0 - 1) : ps[I.s];
+              xm2 = j0 >= 2 ? SRC(I.in[0], j0 - 2) : (j0 == 1 ? ps[I.s] : ps[I.s + 1]);
+            } else if (I.op == OP_ONEPOLE) {
+              xm1 = j0 >= 1 ? SRC(I.in[0], j0 - 1) : ps[I.s];
+            }
+            float S1, S2;                                   // hop start state
+            if (I.op == OP_SVF) { S1 = ps[I.s]; S2 = ps[I.s + 1]; }
+            else if (I.op == OP_BIQUAD) { S1 = ps[I.s + 2]; S2 = ps[I.s + 3]; }
+            else { S1 = ps[I.s + 1]; S2 = 0.0f; }
+            float c0 = ps[I.p], c1 = 0.0f, c2 = 0.0f, c3 = 0.0f, c4 = 0.0f, c5 = 0.0f;
+            if (I.op != OP_ONEPOLE) { c1 = ps[I.p + 1]; c2 = ps[I.p + 2]; c3 = ps[I.p + 3]; c4 = ps[I.p + 4]; }
+            if (I.op == OP_SVF) c5 = ps[I.p + 5];
+            const int kind = I.n;
+            // one tick with the op's own arithmetic; (s1, s2) is the scanned state, (h1, h2) the input history
+            auto tick = [&](float x, float& s1, float& s2, float& h1, float& h2) -> float {
+              if (I.op == OP_SVF) return d_svf_tick(x, s1, s2, c0, c1, c2, c3, c4, c5);
+              if (I.op == OP_BIQUAD) {
+                const float y0 = c2 * x + c3 * h1 + c4 * h2 - c0 * s1 - c1 * s2;
+                h2 = h1; h1 = x; s2 = s1; s1 = y0;
+                return y0;
+              }
+              float y;
+              switch (kind) {
+                case 0: y = (1.0f - c0) * x + c0 * s1; break;
+                case 1: y = c0 * (s1 + x - h1); break;
+                case 2: y = x - h1 + c0 * s1; break;
+                default: y = c0 * (x - s1) + h1; break;
+              }
+              h1 = x; s1 = y;
+              return y;
+            };
+            float e1 = 0.0f, e2 = 0.0f;
+            { float h1 = xm1, h2 = xm2; for (int k = 0; k < cnt; k++) tick(xin[k], e1, e2, h1, h2); }
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+              const int d = 1 << i;
+              const float4 m = tab[i];
+              float r1 = __shfl_up_sync(0xffffffffu, e1, d), r2 = __shfl_up_sync(0xffffffffu, e2, d);
+              if (lane >= d) { e1 += m.x * r1 + m.y * r2; e2 += m.z * r1 + m.w * r2; }
+            }
+            float p1 = __shfl_up_sync(0xffffffffu, e1, 1), p2 = __shfl_up_sync(0xffffffffu, e2, 1);
+            if (lane == 0) { p1 = 0.0f; p2 = 0.0f; }
+            if (lane == 31) { wtot[2 * wid] = e1; wtot[2 * wid + 1] = e2; }
+            __syncthreads();                                 // also: every thread has read its inputs and the old state
+            if (tid == 0) {
+              const float4 m32 = tab[37];
+              float q1 = S1, q2 = S2;
+              for (int w = 0; w < (nth >> 5); w++) {
+                wsta[2 * w] = q1; wsta[2 * w + 1] = q2;
+                const float t1 = m32.x * q1 + m32.y * q2 + wtot[2 * w], t2 = m32.z * q1 + m32.w * q2 + wtot[2 * w + 1];
+                q1 = t1; q2 = t2;
+              }
+            }
+            __syncthreads();
+            {
+              const float4 ml = tab[5 + lane];
+              const float q1 = wsta[2 * wid], q2 = wsta[2 * wid + 1];
+              float s1 = ml.x * q1 + ml.y * q2 + p1, s2 = ml.z * q1 + ml.w * q2 + p2;
+              float h1 = xm1, h2 = xm2;
+              for (int k = 0; k < cnt; k++) TMP(I.out)[j0 + k] = tick(xin[k], s1, s2, h1, h2);
+              if (cnt > 0 && j0 + cnt == n) {              // owner of the hop's last sample persists the state
+                if (I.op == OP_SVF) { ps[I.s] = s1; ps[I.s + 1] = s2; }
+                else if (I.op == OP_BIQUAD) { ps[I.s] = h1; ps[I.s + 1] = h2; ps[I.s + 2] = s1; ps[I.s + 3] = s2; }
+                else { ps[I.s] = h1; ps[I.s + 1] = s1; }
+              }
+            }
+            break;
+          }
+          case OP_SINE: {   // exec(): out = sin(phase * TAU) from the phase BEFORE the increment; phase += f * (1/sr), wrapped
+            const float isr = ps[I.p];
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = SRC(I.in[0], j) * isr;     // increments, in parallel
+            __syncthreads();
+            if (tid == 0) {                                  // the exact f32 recurrence, sequential
+              float ph = ps[I.s];
+              float* o = TMP(I.out);
+              for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = ph; ph += inc; ph -= floorf(ph); }
+              ps[I.s] = ph;
+            }
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = sinf(TMP(I.out)[j] * QG_TAU);
+            break;
+          }
+          case OP_RAMP: {   // nodes.rs:476-483: out = val; val += f / sr; if (val >= 1) val -= 1
+            const float sr = ps[I.p];
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = SRC(I.in[0], j) / sr;
+            __syncthreads();
+            if (tid == 0) {
+              float val = ps[I.s];
+              float* o = TMP(I.out);
+              for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = val; val += inc; if (val >= 1.0f) val -= 1.0f; }
+              ps[I.s] = val;
+            }
             break;
           }
           case OP_TICK: {
@@ -1115,7 +1264,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
 
 size_t tv_smem_bytes(const TvArgs& a) {
   return (size_t)a.n_instr * sizeof(Instr) + (size_t)(((a.P + a.NS) + 3) & ~3) * 4 + (size_t)a.NT * a.H * 4 + (size_t)a.H * 4 +
-         (size_t)FPAD(a.fft_n) * 8;
+         (size_t)FPAD(a.fft_n) * 8 + (size_t)a.n_lti * TV_LTI_FLOATS * 4 + 4 * 2 * 8 * 4;
 }
 
 cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches) {

@@ -763,6 +763,8 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
     if (op_is_stateless(i.op)) continue;
     switch (i.op) {
       case OP_NOISE: case OP_WAVE: case OP_IMPULSE: case OP_TICK: case OP_DELAY: break;
+      case OP_SVF: case OP_BIQUAD: case OP_ONEPOLE: pl.n_lti++; break;       // block-level scan over the hop
+      case OP_SINE: case OP_RAMP: pl.sequential = true; break;              // exact phase recurrence on one thread
       case OP_TAP: min_tap_ring = std::min(min_tap_ring, t.rings[i.aux].length); break;
       case OP_RFFT: case OP_IFFT: {
         int N = 1 << i.n;
@@ -780,7 +782,7 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
   }
   auto bytes = [&](int h) {
     return (size_t)t.h.n_instr * sizeof(Instr) + (size_t)(t.h.n_params + t.h.n_state + 4) * 4 + (size_t)t.h.n_temps * h * 4 +
-           (size_t)h * 4 + (size_t)(fft_n + fft_n / 32) * 8;
+           (size_t)h * 4 + (size_t)(fft_n + fft_n / 32) * 8 + (size_t)pl.n_lti * TV_LTI_FLOATS * 4 + 1024;
   };
   while (H >= 8 && (bytes(H) > smem_limit || (uint32_t)H > min_tap_ring)) H >>= 1;
   if (H < 8) return pl;
@@ -865,6 +867,9 @@ bool lower(const Graph& g, Tape* out, std::string* err) {
     if (op_is_stateless(t.code[k].op)) t.code[k].pad = (uint32_t)end;
     else { t.code[k].pad = 0; end = k; }
   }
+  // fixed-coefficient LTI filters get an index into the time-vector kernel's table of scan matrices
+  t.h.n_lti = 0;
+  for (Instr& i : t.code) if (op_is_lti(i.op)) i.aux = t.h.n_lti++;
   t.h.magic = TAPE_MAGIC; t.h.version = TAPE_VERSION;
   t.h.n_instr = (uint32_t)t.code.size();
   t.h.n_params = (uint32_t)P; t.h.n_state = (uint32_t)NS; t.h.n_temps = (uint32_t)L.n_temps;

@@ -58,7 +58,10 @@ struct TvPlan {
   int H = 0;
   int fft_n = 0;
   int align_s = -1;   // X index of one rfft/ifft counter
+  int n_lti = 0;      // fixed-coefficient LTI filters evaluated by block-level scans
+  bool sequential = false;   // the tape has phase accumulators that one thread steps through: only worth it for small banks
 };
+
 TvPlan plan_tv(const Tape& t, size_t smem_limit);
 
 // Lower a graph.  Returns false (and fills `err`) when the graph contains something that has no GPU lowering —

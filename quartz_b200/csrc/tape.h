@@ -107,6 +107,11 @@ enum Op : uint16_t {
 #define QG_TAPE_HD
 #endif
 // ops that read only the current sample's operands (no per-voice memory): they can be applied to any sample of a hop
+// fixed-coefficient linear recurrences: the time-vector kernel evaluates them with a block-level scan over the hop
+QG_TAPE_HD inline bool op_is_lti(uint16_t op) { return op == OP_SVF || op == OP_BIQUAD || op == OP_ONEPOLE; }
+// phase accumulators: exact f32 sequential recurrences; the time-vector kernel runs the recurrence on one thread and the
+// per-sample function (sin, table lookup) on all of them
+QG_TAPE_HD inline bool op_is_phasor(uint16_t op) { return op == OP_SINE || op == OP_RAMP; }
 QG_TAPE_HD inline bool op_is_stateless(uint16_t op) {
   return op == OP_NOP || op == OP_MOV || op == OP_ZERO || (op >= OP_ADD && op <= OP_PAN) || op == OP_ROTATE ||
          op == OP_QUANTIZE || op == OP_ARR_GET;
@@ -164,10 +169,13 @@ struct TapeHeader {
   uint32_t n_raw;      // raw (op-string) parameters of the graph, in order of appearance
   uint32_t fused_id;   // FUSED_* when the tape matches a hand-fused kernel shape, else 0
   float sample_rate;
-  uint32_t reserved[7];
+  uint32_t n_lti;      // fixed-coefficient LTI filters (OP_SVF / OP_BIQUAD / OP_ONEPOLE): their `aux` is an index < n_lti
+  uint32_t reserved[6];
 };
 static const uint32_t TAPE_MAGIC = 0x50544751u;
 static const uint32_t TAPE_VERSION = 1;
 static const uint32_t TAPE_DIVERGENT = 1u;
+// floats of scan-matrix table per LTI filter in the time-vector kernel: M^(2^i) for i < 5, M^l for l < 32, M^32
+static const int TV_LTI_FLOATS = (5 + 32 + 1) * 4;
 
 }  // namespace qg

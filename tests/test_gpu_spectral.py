@@ -36,13 +36,10 @@ def test_spectral_gate_matches_oracle(N, J, V, T):
     assert_parity(both, ref, "float", "two-call render")
 
 
-TV_CASES = ["white", "wave", "impulse", "tick", "delay", "tap_noise", "tap_zero_delay", "tap_linear_noise", "quantize", "arr_get", "rfft_ifft_roundtrip",
-            "rfft_start", "spectral_gate_small", "split_join", "chan_pan", "rotate", "dc3", "live_io"]
-
-
-@pytest.mark.parametrize("name", TV_CASES)
-def test_time_vector_interpreter_on_generic_cases(name):
-    _, expr, n, tol = next(c for c in cases.RENDER if c[0] == name)
+@pytest.mark.parametrize("name,expr,n,tol", cases.RENDER, ids=[c[0] for c in cases.RENDER])
+def test_time_vector_interpreter_on_generic_cases(name, expr, n, tol):
+    """every render case whose tape is time-vector capable (feed-forward; stateless ops, counter sources, delay lines,
+    transforms, fixed LTI filters as block-level scans, phase accumulators stepped by one thread)"""
     net = build(expr, Net)
     bank = Bank(net, 3).set_path(qb.PATH_TV)
     if bank.kernel() != "k_interp_tv":
@@ -51,6 +48,32 @@ def test_time_vector_interpreter_on_generic_cases(name):
     ref = build(expr, ONet).render(n).T
     for v in range(3):
         assert_parity(got[v], ref, tol if tol in ("exact", "float") else "float", name)
+
+
+def test_time_vector_covers_filters_and_oscillators():
+    capable = {name for name, expr, n, tol in cases.RENDER if Bank(build(expr, Net), 1).set_path(qb.PATH_TV).kernel() == "k_interp_tv"}
+    for must in ("white_lowpass", "biquad", "butterpass", "resonator", "lowpole", "highpole", "dcblock", "allpole", "white_bell"):
+        assert must in capable, must
+
+
+@pytest.mark.parametrize("expr", [
+    pipe("white()", "lowpass(300,6)", "highpole(40)", "butterpass(2500)"),
+    pipe("sine(220.5)", "resonator(900,30)", "allpole(0.3)"),
+    pipe(pipe("dc(3.3)", "ramp()", "mul(TAU)", "sin()", "mul(300)", "add(500)"), "sine()", "dcblock()", "lowpole(1200)"),
+], ids=["noise_svf_onepole_biquad", "sine_resonator_allpole", "fm_sine_dcblock_lowpole"])
+def test_time_vector_scans_persist_state_across_odd_chunks(expr):
+    """block-level scans + one-thread phase recurrences: hop-partial renders (1, 7, 511, 513 ...) continue exactly where the
+    previous call stopped, for every voice of a salted bank"""
+    V = 5
+    salts = np.arange(11, 11 + V, dtype=np.uint64)
+    bank = Bank(build(expr, Net), V, salts=salts).set_path(qb.PATH_TV)
+    assert bank.kernel() == "k_interp_tv"
+    chunks = (1, 7, 511, 513, 2, 1024, 700, 3000)
+    parts = np.concatenate([bank.render(k)[:, 0, :] for k in chunks], axis=1)
+    ref = render_bank([build(expr, ONet).set_salt(int(s)) for s in salts], sum(chunks))
+    assert_parity(parts, ref, "float", "time-vector chunked")
+    lane = Bank(build(expr, Net), V, salts=salts).set_path(qb.PATH_INTERP_SAMPLE)
+    assert_parity(lane.render(sum(chunks))[:, 0, :], ref, "float", "lane path")
 
 
 def test_round_trip_property_full_frame_size():
