@@ -1236,7 +1236,17 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             if (tid == 0) ps[I.s] = __uint_as_float((i0 + (uint32_t)n) & (N - 1));
             break;
           }
-          default: break;
+          default: {
+            // scalar-state op without a block form (variable filters, envelopes, sample-and-hold, wavetable phase ...):
+            // one thread steps it through the hop with the generic per-sample code; plan_tv() admits only ring-free ops here
+            __syncthreads();
+            if (tid == 0) {
+              TvSample L{ps_off, tmp_off, PS, H, a.tables, 0, 1, n, 0};
+              int dummy = 0;
+              exec(I, L, dummy);
+            }
+            break;
+          }
         }
       }
       __syncthreads();

@@ -765,6 +765,10 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
       case OP_NOISE: case OP_WAVE: case OP_IMPULSE: case OP_TICK: case OP_DELAY: break;
       case OP_SVF: case OP_BIQUAD: case OP_ONEPOLE: pl.n_lti++; break;       // block-level scan over the hop
       case OP_SINE: case OP_RAMP: pl.sequential = true; break;              // exact phase recurrence on one thread
+      // scalar-state ops without a block form: one thread steps them through the hop with the generic per-sample code
+      case OP_SVF_VAR: case OP_BIQUAD_VAR: case OP_ONEPOLE_VAR: case OP_PINKPASS: case OP_FIR: case OP_ENVELOPE:
+      case OP_DECLICK: case OP_SHIFT_REG: case OP_SNH: case OP_PAN_VAR: case OP_WAVETABLE:
+        pl.sequential = true; break;
       case OP_TAP: min_tap_ring = std::min(min_tap_ring, t.rings[i.aux].length); break;
       case OP_RFFT: case OP_IFFT: {
         int N = 1 << i.n;
