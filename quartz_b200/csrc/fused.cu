@@ -583,7 +583,7 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     int store = ((((size_t)(uintptr_t)a.out) & 15) == 0) && ((a.T & 3) == 0) ? 1 : 0;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof tmap);
-    if (store == 1 && ((((size_t)(uintptr_t)a.out) & 127) == 0) && (a.T % 32) == 0 && ((size_t)a.V * (size_t)a.T / 32) < 0xffffffffull &&
+    if (store == 1 && ((((size_t)(uintptr_t)a.out) & 127) == 0) && (a.T % 32) == 0 && ((size_t)a.V * (size_t)a.T / 32) < 0x7fffffffull &&
         encode_rows32(&tmap, a.out, (size_t)a.V * (size_t)a.T / 32, K))
       store = 2;
 #define QG_LAUNCH_K2(LPV, SV) k_noise_svf_scan<0, LPV, SV, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg, tmap)

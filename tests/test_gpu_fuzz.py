@@ -1,0 +1,184 @@
+"""Randomised graph parity: seeded random feed-forward graphs built from the supported op vocabulary are rendered by
+every kernel family (auto selection, block-mode lane interpreter, sample-by-sample lane interpreter, time-vector kernel
+when the tape is capable) for a small salted bank and compared with the CPU oracle.  Two families:
+  * exact: only operations that round identically on both sides (IEEE add/mul/div/floor/compare, table lookups,
+    in-tree nodes) -> bit-exact, including through delay lines, sample-and-hold and shift registers;
+  * float: smooth DSP chains (oscillators, noise, LTI filters, waveshapers, delay taps) -> f32 audio tolerance.
+The generator exercises what the fixed case list cannot enumerate: temporary reuse in lowering, in-place operands in
+the block / time-vector kernels, diamonds (split -> parallel branches -> join), sums and products of sub-graphs."""
+import numpy as np
+import pytest
+
+import quartz_b200 as qb
+from quartz_b200 import Bank, Net
+from tests.graphs import L, add, branch, build, bus, mul, pipe, stack
+from tests.oracle_ffi import ONet
+from tests.util import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+MINOR = [0.0, 2.0, 3.0, 5.0, 7.0, 8.0, 10.0, 12.0]
+
+
+def _c(rng, lo, hi, nd=3):
+    return round(float(rng.uniform(lo, hi)), nd)
+
+
+# ---------------------------------------------------------------- exact family
+def exact_source(rng):
+    k = rng.integers(0, 5)
+    if k == 0:
+        return pipe(f"dc({_c(rng, 20, 900)})", "ramp()")
+    if k == 1:
+        return L("white()")
+    if k == 2:
+        return {"op": "wave()", "arr": [round(float(x), 3) for x in rng.uniform(-2, 2, int(rng.integers(3, 40)))]}
+    if k == 3:
+        return pipe(f"dc({_c(rng, 1, 50)})", "ramp()", f"mul({_c(rng, 2, 24)})", {"op": "quantize()", "arr": MINOR})
+    return pipe("impulse()", f"add({_c(rng, -1, 1)})")
+
+
+def exact_stage(rng):
+    k = rng.integers(0, 16)
+    if k == 0:
+        return L(f"add({_c(rng, -3, 3)})")
+    if k == 1:
+        return L(f"mul({_c(rng, -3, 3)})")
+    if k == 2:
+        return L("abs()")
+    if k == 3:
+        return L("floor()")
+    if k == 4:
+        return L(f">({_c(rng, -0.5, 0.8)})")
+    if k == 5:
+        return L(f"min({_c(rng, -1, 1)})")
+    if k == 6:
+        return L(f"clip({_c(rng, -1, 0)},{_c(rng, 0.1, 1)})")
+    if k == 7:
+        return L(f"wrap({_c(rng, -2, 0)},{_c(rng, 0.5, 3)})")
+    if k == 8:
+        return L("tick()")
+    if k == 9:
+        return L(f"delay({_c(rng, 0.0001, 0.01, 5)})")
+    if k == 10:   # sample-and-hold clocked by an edge detector
+        clock = pipe(f"dc({_c(rng, 30, 700)})", "ramp()", "<(0.5)", "rise()")
+        return pipe(stack("pass()", clock), "snh()")
+    if k == 11:   # shift register, a few taps summed
+        clock = pipe(f"dc({_c(rng, 30, 700)})", "ramp()", "<(0.5)", "rise()")
+        return pipe(stack("pass()", clock), "shift_reg()", "join(8)")
+    if k == 12:   # diamond
+        return pipe("split(2)", stack(exact_stage(rng), exact_stage(rng)), "join(2)")
+    if k == 13:
+        return L("squared()")
+    if k == 14:
+        return L("mirror(-1,1)")
+    return L("round()")
+
+
+def exact_graph(rng):
+    g = exact_source(rng)
+    for _ in range(int(rng.integers(1, 6))):
+        g = pipe(g, exact_stage(rng))
+    if rng.uniform() < 0.4:
+        other = exact_source(rng)
+        for _ in range(int(rng.integers(0, 3))):
+            other = pipe(other, exact_stage(rng))
+        g = (add if rng.uniform() < 0.5 else mul)(g, other)
+    return g
+
+
+# ---------------------------------------------------------------- float family
+def float_source(rng):
+    k = rng.integers(0, 6)
+    if k == 0:
+        return L("white()")
+    if k == 1:
+        return L(f"sine({_c(rng, 30, 3000)})")
+    if k == 2:
+        return L(f"saw({_c(rng, 30, 1500)})")
+    if k == 3:
+        return L("pink()")
+    if k == 4:   # FM pair
+        return pipe(pipe(f"sine({_c(rng, 0.5, 8)})", f"mul({_c(rng, 5, 80)})", f"add({_c(rng, 200, 900)})"), "sine()")
+    return pipe(f"dc({_c(rng, 40, 800)})", "ramp()", "mul(TAU)", "sin()")
+
+
+def float_stage(rng):
+    k = rng.integers(0, 17)
+    f, q = _c(rng, 80, 6000), _c(rng, 0.5, 5)
+    if k == 0:
+        return L(f"lowpass({f},{q})")
+    if k == 1:
+        return L(f"highpass({f},{q})")
+    if k == 2:
+        return L(f"bell({f},{q},{_c(rng, 0.5, 2)})")
+    if k == 3:
+        return L(f"butterpass({f})")
+    if k == 4:
+        return L(f"resonator({f},{_c(rng, 20, 300)})")
+    if k == 5:
+        return L(f"lowpole({f})")
+    if k == 6:
+        return L(f"highpole({_c(rng, 5, 400)})")
+    if k == 7:
+        return L("dcblock()")
+    if k == 8:
+        return L(f"allpole({_c(rng, 0.1, 0.9)})")
+    if k == 9:
+        return L("tanh()")
+    if k == 10:
+        return L(f"mul({_c(rng, 0.2, 1.5)})")
+    if k == 11:
+        return L(f"delay({_c(rng, 0.0002, 0.02, 5)})")
+    if k == 12:   # modulated delay tap
+        return pipe(stack("pass()", pipe(f"sine({_c(rng, 0.2, 5)})", "mul(0.002)", "add(0.004)")), "tap(0.001,0.01)")
+    if k == 13:   # parallel filters summed
+        return bus(float_stage(rng), float_stage(rng))
+    if k == 14:   # diamond through branch
+        return pipe(branch(float_stage(rng), "pass()"), "join(2)")
+    if k == 15:
+        return L("fir(0.2,0.5,0.2,0.1)")
+    return L(f"lowpass({q})") if False else L("softsign()")
+
+
+def float_graph(rng):
+    g = float_source(rng)
+    for _ in range(int(rng.integers(1, 6))):
+        g = pipe(g, float_stage(rng))
+    if rng.uniform() < 0.35:
+        g = add(g, pipe(float_source(rng), float_stage(rng)))
+    if rng.uniform() < 0.3:
+        g = mul(g, L(f"xd({_c(rng, 1, 20)})"))
+    return g
+
+
+PATHS = [("auto", qb.PATH_AUTO), ("lane_block", qb.PATH_INTERP), ("lane_sample", qb.PATH_INTERP_SAMPLE), ("time_vector", qb.PATH_TV)]
+
+
+def _check(expr, tol, n, seed):
+    V = 3
+    salts = np.arange(1, V + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15 + seed)
+    net = build(expr, Net)
+    assert net.inputs() == 0 and net.outputs() == 1, (net.inputs(), net.outputs(), expr)
+    ref = np.stack([build(expr, ONet).set_salt(int(s)).render(n)[:, 0] for s in salts])
+    seen = set()
+    for pname, path in PATHS:
+        bank = Bank(net, V, salts=salts).set_path(path)
+        if (pname == "time_vector" and bank.kernel() != "k_interp_tv") or bank.kernel() in seen and pname != "auto":
+            continue
+        seen.add(bank.kernel())
+        # two calls of uneven length: state, rings and counters carry over
+        got = np.concatenate([bank.render(n // 3 + 1)[:, 0, :], bank.render(n - n // 3 - 1)[:, 0, :]], axis=1)
+        assert_parity(got, ref, tol, f"seed {seed} [{pname}: {bank.kernel()}] {expr}")
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_exact_graphs(seed):
+    rng = np.random.default_rng(1000 + seed)
+    _check(exact_graph(rng), "exact", 2500, seed)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_float_graphs(seed):
+    rng = np.random.default_rng(5000 + seed)
+    _check(float_graph(rng), "float", 3000, seed)

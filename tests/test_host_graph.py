@@ -112,3 +112,18 @@ def test_device_entry_points_fail_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(qb.QuartzGpuError):
         Net.str_to_net("sine(440)").render(16)
+
+
+@pytest.mark.parametrize("family,base", [("exact", 1000), ("float", 5000)])
+def test_random_graphs_agree_with_oracle_on_shape(family, base):
+    """the generator of tests/test_gpu_fuzz.py, host side only: parser, connective algebra and lowering accept every
+    graph, and the product and the oracle agree on inputs / outputs / size"""
+    import numpy as np
+    from tests import test_gpu_fuzz as fz
+    gen = fz.exact_graph if family == "exact" else fz.float_graph
+    for seed in range(40):
+        e = gen(np.random.default_rng(base + seed))
+        a, b = build(e, Net), build(e, ONet)
+        assert (a.inputs(), a.outputs(), a.size()) == (b.inputs(), b.outputs(), b.size()) and a.outputs() == 1, e
+        assert a.unsupported() is None
+        assert a.tape_info()["n_instr"] > 0
