@@ -156,6 +156,30 @@ __device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim,
   }
 }
 
+// Band-limited wavetable lookup: pick the table for |f| (search from `hint`, which is only a starting point), read it at
+// phase `ph` with the 4-point optimal interpolator.
+__device__ __forceinline__ float d_wavetable_read(const float* hdr, float f, float ph, uint32_t& hint) {
+  const uint32_t nt = (uint32_t)hdr[0];
+  const float af = fabsf(f);
+  while (hint + 1 < nt && af >= hdr[1 + 3 * hint]) hint++;
+  while (hint > 0 && af < hdr[1 + 3 * (hint - 1)]) hint--;
+  const uint32_t off = __float_as_uint(hdr[2 + 3 * hint]), len = __float_as_uint(hdr[3 + 3 * hint]), mask = len - 1;
+  const float* tb = hdr + off;
+  float pp = (float)len * ph;
+  uint32_t i1 = (uint32_t)pp;
+  float w = pp - (float)i1;
+  uint32_t i0 = (i1 + len - 1) & mask;
+  i1 &= mask;
+  float a0 = tb[i0], a1 = tb[i1], a2 = tb[(i1 + 1) & mask], a3 = tb[(i1 + 2) & mask];
+  float z = w - 0.5f, even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
+  float c0 = even1 * 0.46567255120778489f + even2 * 0.03432729708429672f;
+  float c1 = odd1 * 0.53743830753560162f + odd2 * 0.15429462557307461f;
+  float c2 = even1 * -0.25194210134021744f + even2 * 0.25194744935939062f;
+  float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
+  float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
+  return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
+}
+
 // Execute one instruction for this lane.  `pc` is only touched by control-flow ops.
 template <class LaneT>
 __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
@@ -311,32 +335,13 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       XS(I.s) = val;
     } break;
     case OP_WAVETABLE: QG_EACH {   // FunDSP WaveSynth + Wavetable::read/at (restated, see lower.cpp make_wave)
-      const float* hdr = L.tables + I.aux;
-      const uint32_t nt = (uint32_t)hdr[0];
       float f = XI(0);
       float ph = XS(I.s) + f * XS(I.p);
       ph -= floorf(ph);
       XS(I.s) = ph;
-      float af = fabsf(f);
       uint32_t hint = XSU(I.s + 1);
-      while (hint + 1 < nt && af >= hdr[1 + 3 * hint]) hint++;
-      while (hint > 0 && af < hdr[1 + 3 * (hint - 1)]) hint--;
+      XO(0) = d_wavetable_read(L.tables + I.aux, f, ph, hint);
       SETSU(I.s + 1, hint);
-      const uint32_t off = __float_as_uint(hdr[2 + 3 * hint]), len = __float_as_uint(hdr[3 + 3 * hint]), mask = len - 1;
-      const float* tb = hdr + off;
-      float pp = (float)len * ph;
-      uint32_t i1 = (uint32_t)pp;
-      float w = pp - (float)i1;
-      uint32_t i0 = (i1 + len - 1) & mask;
-      i1 &= mask;
-      float a0 = tb[i0], a1 = tb[i1], a2 = tb[(i1 + 1) & mask], a3 = tb[(i1 + 2) & mask];
-      float z = w - 0.5f, even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
-      float c0 = even1 * 0.46567255120778489f + even2 * 0.03432729708429672f;
-      float c1 = odd1 * 0.53743830753560162f + odd2 * 0.15429462557307461f;
-      float c2 = even1 * -0.25194210134021744f + even2 * 0.25194744935939062f;
-      float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
-      float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
-      XO(0) = (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
     } break;
     case OP_WAVE: QG_EACH {
       uint32_t i = XSU(I.s);
@@ -919,6 +924,7 @@ __device__ void tv_fft(float* fr, float* fi, int lg, const float* tw, bool inver
   }
 }
 
+constexpr int TV_SEGCAP = 72;   // lfo segments a 512-sample hop can cross when a segment is at least 8 samples long
 // (idx + j) mod len for idx < len: one conditional subtract in the common case (ring at least one hop long)
 __device__ __forceinline__ uint32_t tv_wrap(uint32_t p, uint32_t len) {
   if (p >= len) { p -= len; if (p >= len) p %= len; }
@@ -931,7 +937,8 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
   // float offsets of the regions behind the tape: scalars, temporaries, tap scratch, transform buffers
   const int ps_off = a.n_instr * (int)(sizeof(Instr) / 4), tmp_off = ps_off + ((PS + 3) & ~3);
   const int oldv_off = tmp_off + a.NT * H, fr_off = oldv_off + H, fi_off = fr_off + (int)FPAD(a.fft_n);
-  const int lti_off = fi_off + (int)FPAD(a.fft_n), scan_off = lti_off + a.n_lti * TV_LTI_FLOATS;   // scan scratch: 2 x 2 x 8 warps
+  const int lti_off = (fi_off + (int)FPAD(a.fft_n) + 3) & ~3, scan_off = lti_off + a.n_lti * TV_LTI_FLOATS;   // scan scratch: 2 x 2 x 8 warps
+  const int segi_off = scan_off + 32, segt_off = segi_off + H;   // envelope: per-sample segment index, segment table [TV_SEGCAP][4]
 #define ps (QG_SMEM_F + ps_off)
 #define tmp (QG_SMEM_F + tmp_off)
 #define oldv (QG_SMEM_F + oldv_off)
@@ -1146,6 +1153,67 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             }
             break;
           }
+          case OP_WAVETABLE: {   // phase recurrence on one thread (phase AFTER the increment is what is read), lookups on all
+            const float isr = ps[I.p];
+            __syncthreads();
+            if (tid == 0) {
+              float ph = ps[I.s];
+              for (int j = 0; j < n; j++) { ph += SRC(I.in[0], j) * isr; ph -= floorf(ph); oldv[j] = ph; }
+              ps[I.s] = ph;
+            }
+            __syncthreads();
+            const uint32_t hint0 = __float_as_uint(ps[I.s + 1]);
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) {
+              uint32_t hint = hint0;
+              TMP(I.out)[j] = d_wavetable_read(a.tables + I.aux, SRC(I.in[0], j), oldv[j], hint);
+              if (j == n - 1) ps[I.s + 1] = __uint_as_float(hint);
+            }
+            break;
+          }
+          case OP_ENVELOPE: {   // lfo()/lfo_in(): control points every ~2 ms, linear interpolation in between
+            const float dt = ps[I.p + 4];
+            if (!(0.0015f / dt >= 9.0f)) {                   // segments shorter than 8 samples: no room in the segment table
+              if (tid == 0) { TvSample L{ps_off, tmp_off, PS, H, a.tables, 0, 1, n, 0}; int dummy = 0; exec(I, L, dummy); }
+              break;
+            }
+            float* segi = QG_SMEM_F + segi_off;
+            float4* segt = reinterpret_cast<float4*>(QG_SMEM_F + segt_off);
+            __syncthreads();
+            if (tid == 0) {                                  // time accumulation + control-point updates, exactly like exec()
+              const int shape = I.n & 0xff, nin = I.n >> 8;
+              float t = ps[I.s], t0 = ps[I.s + 1], t1 = ps[I.s + 2], v0 = ps[I.s + 3], v1 = ps[I.s + 4];
+              int ns = 0;
+              segt[0] = make_float4(t0, t1, v0, v1);
+              for (int j = 0; j < n; j++) {
+                if (t >= t1) {
+                  float c[4] = {ps[I.p], ps[I.p + 1], ps[I.p + 2], ps[I.p + 3]};
+                  float in[4];
+                  in[0] = nin > 0 ? SRC(I.in[0], j) : 0.0f; in[1] = nin > 1 ? SRC(I.in[1], j) : 0.0f;
+                  in[2] = nin > 2 ? SRC(I.in[2], j) : 0.0f; in[3] = nin > 3 ? SRC(I.in[3], j) : 0.0f;
+                  if (__float_as_uint(ps[I.s + 7])) { v1 = d_env_eval(shape, nin, 0.0f, c, in); ps[I.s + 7] = __uint_as_float(0u); }
+                  uint64_t th = (uint64_t)__float_as_uint(ps[I.s + 5]) | ((uint64_t)__float_as_uint(ps[I.s + 6]) << 32);
+                  t0 = t1; v0 = v1;
+                  t1 = t0 + d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
+                  v1 = d_env_eval(shape, nin, t1, c, in);
+                  th += 1;
+                  ps[I.s + 5] = __uint_as_float((uint32_t)th); ps[I.s + 6] = __uint_as_float((uint32_t)(th >> 32));
+                  ns = ns + 1 < TV_SEGCAP ? ns + 1 : ns;
+                  segt[ns] = make_float4(t0, t1, v0, v1);
+                }
+                oldv[j] = t;
+                segi[j] = __int_as_float(ns);
+                t += dt;
+              }
+              ps[I.s] = t; ps[I.s + 1] = t0; ps[I.s + 2] = t1; ps[I.s + 3] = v0; ps[I.s + 4] = v1;
+            }
+            __syncthreads();
+            for (int j = tid; j < n; j += nth) {
+              const float4 sg = segt[__float_as_int(segi[j])];
+              TMP(I.out)[j] = d_lerp(sg.z, sg.w, d_delerp(sg.x, sg.y, oldv[j]));
+            }
+            break;
+          }
           case OP_TICK: {
             const float prev = ps[I.s];
             __syncthreads();
@@ -1274,7 +1342,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
 
 size_t tv_smem_bytes(const TvArgs& a) {
   return (size_t)a.n_instr * sizeof(Instr) + (size_t)(((a.P + a.NS) + 3) & ~3) * 4 + (size_t)a.NT * a.H * 4 + (size_t)a.H * 4 +
-         (size_t)FPAD(a.fft_n) * 8 + (size_t)a.n_lti * TV_LTI_FLOATS * 4 + 4 * 2 * 8 * 4;
+         (size_t)FPAD(a.fft_n) * 8 + (size_t)a.n_lti * TV_LTI_FLOATS * 4 + 16 + 32 * 4 + (size_t)a.H * 4 + TV_SEGCAP * 16;
 }
 
 cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches) {

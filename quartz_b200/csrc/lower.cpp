@@ -786,7 +786,7 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
   }
   auto bytes = [&](int h) {
     return (size_t)t.h.n_instr * sizeof(Instr) + (size_t)(t.h.n_params + t.h.n_state + 4) * 4 + (size_t)t.h.n_temps * h * 4 +
-           (size_t)h * 4 + (size_t)(fft_n + fft_n / 32) * 8 + (size_t)pl.n_lti * TV_LTI_FLOATS * 4 + 1024;
+           (size_t)h * 4 + (size_t)(fft_n + fft_n / 32) * 8 + (size_t)pl.n_lti * TV_LTI_FLOATS * 4 + (size_t)h * 4 + 2560;
   };
   while (H >= 8 && (bytes(H) > smem_limit || (uint32_t)H > min_tap_ring)) H >>= 1;
   if (H < 8) return pl;
