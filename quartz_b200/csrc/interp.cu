@@ -1126,18 +1126,37 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             break;
           }
           case OP_SINE: {   // exec(): out = sin(phase * TAU) from the phase BEFORE the increment; phase += f * (1/sr), wrapped
-            const float isr = ps[I.p];
-            __syncthreads();
-            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = SRC(I.in[0], j) * isr;     // increments, in parallel
-            __syncthreads();
-            if (tid == 0) {                                  // the exact f32 recurrence, sequential
-              float ph = ps[I.s];
-              float* o = TMP(I.out);
-              for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = ph; ph += inc; ph -= floorf(ph); }
-              ps[I.s] = ph;
+            // A run of consecutive, mutually independent oscillators (chords, additive banks: `sine(f0) + sine(f1) + ...`)
+            // is stepped concurrently: one warp leader per oscillator runs that oscillator's exact f32 phase recurrence.
+            int pe = pc + 1;
+            while (pe < a.n_instr && code[pe].op == OP_SINE) {
+              bool dep = false;
+              for (int q = pc; q < pe; q++) dep = dep || code[pe].in[0] == code[q].out;
+              if (dep) break;
+              pe++;
             }
             __syncthreads();
-            for (int j = tid; j < n; j += nth) TMP(I.out)[j] = sinf(TMP(I.out)[j] * QG_TAU);
+            for (int q = pc; q < pe; q++) {                  // increments, in parallel
+              const Instr Q = code[q];
+              const float isr = ps[Q.p];
+              for (int j = tid; j < n; j += nth) TMP(Q.out)[j] = SRC(Q.in[0], j) * isr;
+            }
+            __syncthreads();
+            if ((tid & 31) == 0) {
+              for (int q = pc + (tid >> 5); q < pe; q += nth >> 5) {
+                const Instr Q = code[q];
+                float ph = ps[Q.s];
+                float* o = TMP(Q.out);
+                for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = ph; ph += inc; ph -= floorf(ph); }
+                ps[Q.s] = ph;
+              }
+            }
+            __syncthreads();
+            for (int q = pc; q < pe; q++) {
+              float* o = TMP(code[q].out);
+              for (int j = tid; j < n; j += nth) o[j] = sinf(o[j] * QG_TAU);
+            }
+            pc = pe - 1;
             break;
           }
           case OP_RAMP: {   // nodes.rs:476-483: out = val; val += f / sr; if (val >= 1) val -= 1
