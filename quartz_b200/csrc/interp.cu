@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
   __syncthreads();
   // ---- scan matrices of the fixed-coefficient LTI filters (one thread per filter, f64, rounded once):
   // a thread advances CPT consecutive samples, so the per-thread map is s -> M s + e with M = A^CPT
-  const int CPT = (H + nth - 1) / nth;                    // samples per thread in the LTI scans (<= 2)
+  const int CPT = (H + nth - 1) / nth;                    // samples per thread in the LTI scans (<= 4: H <= 512, >= 128 threads)
   for (int pc = tid; pc < a.n_instr; pc += nth) {
     const Instr I = code[pc];
     if (!op_is_lti(I.op)) continue;
@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             const int cnt = j0 >= n ? 0 : (n - j0 < CPT ? n - j0 : CPT);
             const int lane = tid & 31, wid = tid >> 5;
             // inputs and the two previous inputs (history comes from the hop or from the persisted state)
-            float xin[2] = {0.0f, 0.0f}, xm1 = 0.0f, xm2 = 0.0f;
+            float xin[4] = {0.0f, 0.0f, 0.0f, 0.0f}, xm1 = 0.0f, xm2 = 0.0f;
             for (int k = 0; k < cnt; k++) xin[k] = SRC(I.in[0], j0 + k);
             if (I.op == OP_BIQUAD) {
               xm1 = j0 >= 1 ? SRC(I.in[0], j0 - 1) : ps[I.s];
@@ -1368,6 +1368,8 @@ cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches
   size_t smem = tv_smem_bytes(a);
   cudaError_t e = cudaFuncSetAttribute(k_interp_tv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  // 256 threads: 2 samples per thread and hop.  (128 threads = 4 samples per thread halves the per-op decode work but was
+  // measured 35 % slower on configs[3]: the kernel is latency-bound, it wants the warps.)
   k_interp_tv<<<a.V, 256, smem, stream>>>(a);
   if (launches) *launches += 1;
   return cudaGetLastError();
