@@ -33,3 +33,25 @@ def test_structural_parameters_must_match_across_voices():
     raw[1, 0] *= 2      # a different delay time changes the ring length: not batchable
     with pytest.raises(qb.QuartzGpuError):
         Bank(build(wl.expr, Net), wl.V, raw=raw, salts=wl.salts)
+
+
+def test_single_process_sharded_render_matches_one_bank():
+    """quartz is one process: render_sharded() drives one context + bank per device from host threads (no collective).
+    With one GPU the device list repeats it — the sharding, row placement and thread safety are what is under test;
+    with several GPUs every device is used."""
+    import torch
+    from quartz_b200 import workloads
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0, 0]
+    wl = workloads.c3_polysynth(V=96 * len(devices) + 32, T=3000, G=32)
+    tmpl = build(wl.expr, Net)
+    one = Bank(tmpl, wl.V, raw=wl.raw, salts=wl.salts).render(wl.T, group=wl.group)
+    got = qb.render_sharded(tmpl, wl.V, wl.T, raw=wl.raw, salts=wl.salts, group=wl.group, devices=devices)
+    assert got.shape == one.shape
+    assert_parity(got[:, 0, :], one[:, 0, :], "exact", "sharded vs single bank")
+    # per-voice rows of a tape that only the interpreters serve, uneven split
+    wl2 = workloads.c5_mixed(V=4 * 1000, T=700)[3]
+    t2 = build(wl2.expr, Net)
+    one2 = Bank(t2, wl2.V, raw=wl2.raw, salts=wl2.salts).render(wl2.T)
+    got2 = qb.render_sharded(t2, wl2.V, wl2.T, raw=wl2.raw, salts=wl2.salts, devices=devices)
+    assert_parity(got2[:, 0, :], one2[:, 0, :], "exact", "sharded delay/lowpole voices")
