@@ -106,3 +106,24 @@ def test_hello_440_full_length():
     n = np.arange(len(x))
     amp = 2 * abs(np.sum(x * np.exp(-2j * np.pi * 440.0 * n / 48000.0))) / len(x)
     assert abs(amp - 1.0) < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["lowpass", "bandpass", "highshelf"])
+def test_noise_svf_fused_extreme_parameters(mode):
+    """poles almost on the unit circle (5 Hz, Q = 200), cutoffs next to Nyquist, over-damped filters: the scan matrices
+    A^(32 * 2^i) and the chained segment states must stay within the audio tolerance of the sequential oracle"""
+    hz = np.array([5, 5, 20, 20, 80, 300, 1000, 6000, 20000, 23000, 23900, 50], dtype=np.float32)
+    q = np.array([0.1, 200, 50, 0.5, 200, 100, 0.05, 30, 2, 0.7, 5, 1000], dtype=np.float32)
+    V, T = len(hz), 300000
+    extra = ",2" if mode == "highshelf" else ""
+    tmpl = build({"op": "sr()", "n": 48000.0, "net": {"op": ">>", "n": 0, "inputs": [{"op": "white()"}, {"op": f"{mode}(1000,1{extra})"}]}}, Net)
+    raw = np.stack([hz, q] + ([np.full(V, 2.0, np.float32)] if extra else []), 1)
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    bank = Bank(tmpl, V, raw=raw, salts=salts)
+    assert bank.kernel() == "k_noise_svf_scan"
+    got = bank.render(T)[:, 0, :]
+    onets = [build({"op": "sr()", "n": 48000.0, "net": {"op": ">>", "n": 0, "inputs": [
+        {"op": "white()"}, {"op": f"{mode}({float(hz[v])!r},{float(q[v])!r}{extra})"}]}}, ONet).set_salt(v + 1) for v in range(V)]
+    ref = render_bank(onets, T, threads=8)
+    for v in range(V):   # per voice: the resonant gains differ by orders of magnitude
+        assert_parity(got[v:v + 1], ref[v:v + 1], "float", f"{mode} hz={hz[v]} q={q[v]}")
