@@ -723,7 +723,10 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
   float* xs = reinterpret_cast<float*>(qg_smem + (size_t)a.n_instr * sizeof(Instr));
   const int PS = a.P + a.NS;
   const int nx = PS + a.NT * BT;
-  float* tiles = xs + (size_t)nx * nt;                       // [n_out][nwarps][32][33]
+  // output staging: a [32 voices][BT + 1] tile per warp and output — one block of samples wide, so that the kernel's shared
+  // memory is dominated by X and more warps fit (the lane kernels are latency-bound); rows leave as BT*4-byte segments
+  constexpr int TW = BT + 1;
+  float* tiles = xs + (size_t)nx * nt;                       // [n_out][nwarps][32][TW]
   for (int i = tid; i < a.n_instr; i += nt) {   // stage the tape with its temporary indices rewritten to block layout
     Instr I = a.code[i];
     I.out = blk_index<BT>(I.out, PS);
@@ -775,40 +778,38 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
         for (int j = 0; j < n; j++)
           for (int c = 0; c < a.n_out; c++) a.out[((size_t)(t0 + j) * a.V + v) * a.n_out + c] = L.tr(blk_index<BT>(a.out_x[c], PS), j);
     } else {
-      const int tt0 = (int)(t0 & 31);
       for (int c = 0; c < a.n_out; c++) {
         const int ox = blk_index<BT>(a.out_x[c], PS);
-        float* trow = tiles + (((size_t)c * nwarps + warp) * 32 + lane) * 33 + tt0;
+        float* trow = tiles + (((size_t)c * nwarps + warp) * 32 + lane) * TW;
         for (int j = 0; j < n; j++) trow[j] = L.tr(ox, j);
       }
-      const long t = t0 + n - 1;
-      const int tt = (int)(t & 31);
-      if (tt == 31 || t == a.T - 1) {
-        __syncwarp();
-        const long t_base = t - tt;
-        const int ncols = tt + 1;
-        for (int c = 0; c < a.n_out; c++) {
-          const float* tile = tiles + ((size_t)c * nwarps + warp) * 32 * 33;
-          if (a.group <= 1) {
-            for (int r = 0; r < 32; r++) {
-              int vv = warp_v0 + r;
-              if (vv < a.V && lane < ncols) a.out[((size_t)vv * a.n_out + c) * a.T + t_base + lane] = tile[r * 33 + lane];
-            }
-          } else {
-            const int G = a.group;
-            const float inv = 1.0f / (float)G;
-            for (int g0 = 0; g0 < 32; g0 += G) {
-              int gi = (warp_v0 + g0) / G;
-              if (warp_v0 + g0 + G <= a.V && lane < ncols) {
-                float acc = tile[g0 * 33 + lane];
-                for (int r = 1; r < G; r++) acc += tile[(g0 + r) * 33 + lane];
-                a.out[((size_t)gi * a.n_out + c) * a.T + t_base + lane] = acc * inv;
-              }
+      __syncwarp();
+      for (int c = 0; c < a.n_out; c++) {
+        const float* tile = tiles + ((size_t)c * nwarps + warp) * 32 * TW;
+        if (a.group <= 1) {
+          // lane -> (voice row, sample): 32 / BT rows per pass, each row a contiguous run of BT samples
+          constexpr int RP = 32 / BT;
+          const int jj = lane % BT, rr = lane / BT;
+          for (int r0 = 0; r0 < 32; r0 += RP) {
+            const int r = r0 + rr, vv = warp_v0 + r;
+            if (vv < a.V && jj < n) a.out[((size_t)vv * a.n_out + c) * a.T + t0 + jj] = tile[r * TW + jj];
+          }
+        } else {
+          // K6 group mix: voices of a group are summed left to right, then scaled by 1/G; lane -> (group, sample)
+          const int G = a.group, per_pass = 32 / BT;         // groups handled per pass
+          const float inv = 1.0f / (float)G;
+          const int jj = lane % BT;
+          for (int gp = 0; gp * G < 32; gp += per_pass) {
+            const int g0 = (gp + lane / BT) * G;
+            if (g0 < 32 && warp_v0 + g0 + G <= a.V && jj < n) {
+              float acc = tile[g0 * TW + jj];
+              for (int r = 1; r < G; r++) acc += tile[(g0 + r) * TW + jj];
+              a.out[((size_t)((warp_v0 + g0) / G) * a.n_out + c) * a.T + t0 + jj] = acc * inv;
             }
           }
         }
-        __syncwarp();
       }
+      __syncwarp();
     }
   }
   for (int s = 0; s < a.NS; s++) a.state[(size_t)s * a.Vp + v] = L.x[(a.P + s) * nt];
@@ -1403,7 +1404,7 @@ static size_t interp_smem(const InterpArgs& a, int nt, bool tile) {
 
 static size_t blk_smem(const InterpArgs& a, int nt, bool tile, int bt) {
   size_t b = (size_t)a.n_instr * sizeof(Instr) + (size_t)(a.P + a.NS + a.NT * bt) * nt * sizeof(float);
-  if (tile) b += (size_t)a.n_out * (nt / 32) * 32 * 33 * sizeof(float);
+  if (tile) b += (size_t)a.n_out * (nt / 32) * 32 * (bt + 1) * sizeof(float);
   return b;
 }
 constexpr int BLK_BT = 8;
