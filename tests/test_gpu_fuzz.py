@@ -182,3 +182,54 @@ def test_random_exact_graphs(seed):
 def test_random_float_graphs(seed):
     rng = np.random.default_rng(5000 + seed)
     _check(float_graph(rng), "float", 3000, seed)
+
+
+# ---------------------------------------------------------------- control-flow family (nested nets: nodes.rs:10-453)
+def _clock(rng):
+    return pipe(f"dc({_c(rng, 20, 400)})", "ramp()", "<(0.5)", "rise()")
+
+
+def _gen0(rng, depth):
+    """a 0-input, 1-output exact sub-graph, possibly wrapped in nested-net control nodes"""
+    if depth <= 0 or rng.uniform() < 0.35:
+        g = exact_source(rng)
+        for _ in range(int(rng.integers(0, 3))):
+            g = pipe(g, exact_stage(rng))
+        return g
+    k = rng.integers(0, 7)
+    if k == 0:     # kr(): tick the inner net every n-th sample, hold in between
+        return {"op": "kr()", "net": _gen0(rng, depth - 1), "n": float(rng.integers(2, 9))}
+    if k == 1:     # s(): same, inner net runs at sr / n
+        return {"op": "s()", "net": _gen0(rng, depth - 1), "n": float(rng.integers(2, 6))}
+    if k == 2:     # reset(): periodic reset of the inner net
+        return {"op": "reset()", "net": _gen0(rng, depth - 1), "n": _c(rng, 0.001, 0.02, 4)}
+    if k == 3:     # trig_reset(): reset on a trigger input
+        return pipe(_clock(rng), {"op": "trig_reset()", "net": _gen0(rng, depth - 1)})
+    if k == 4:     # reset_v(): reset period read from an input
+        return pipe(f"dc({_c(rng, 0.002, 0.02, 4)})", {"op": "reset_v()", "net": _gen0(rng, depth - 1)})
+    if k == 5:     # select(): index input picks one of the nets
+        kids = [_gen0(rng, depth - 1) for _ in range(int(rng.integers(2, 4)))]
+        return pipe(f"dc({_c(rng, 5, 60)})", "ramp()", f"mul({len(kids)})", {"op": "select()", "inputs": kids})
+    kids = [_gen0(rng, depth - 1) for _ in range(int(rng.integers(2, 4)))]   # seq(): triggered, possibly overlapping events
+    ctl = stack(_clock(rng), pipe(f"dc({_c(rng, 3, 40)})", "ramp()", f"mul({len(kids)})"), f"dc({_c(rng, 0, 0.004, 4)})",
+                f"dc({_c(rng, 0.002, 0.03, 4)})")
+    return pipe(ctl, {"op": "seq()", "inputs": kids})
+
+
+def control_graph(rng):
+    g = _gen0(rng, 2)
+    if rng.uniform() < 0.5:     # a 1-in/1-out feedback loop around exact stages (1-sample or longer delay line)
+        inner = pipe(f"mul({_c(rng, -0.9, 0.9)})", exact_stage(rng))
+        delay = None if rng.uniform() < 0.5 else _c(rng, 0.0001, 0.004, 5)
+        g = pipe(g, {"op": "feedback()", "net": inner, "delay": delay})
+    if rng.uniform() < 0.4:
+        g = add(g, _gen0(rng, 1))
+    return g
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_control_flow_graphs(seed):
+    """kr / s / reset / trig_reset / reset_v / select / seq / feedback nested up to two levels around exact sub-graphs:
+    the SIMT-stack interpreter must reproduce the oracle's nested-net semantics bit for bit"""
+    rng = np.random.default_rng(9000 + seed)
+    _check(control_graph(rng), "exact", 3000, seed)

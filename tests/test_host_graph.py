@@ -114,13 +114,13 @@ def test_device_entry_points_fail_loudly_without_gpu():
         Net.str_to_net("sine(440)").render(16)
 
 
-@pytest.mark.parametrize("family,base", [("exact", 1000), ("float", 5000)])
+@pytest.mark.parametrize("family,base", [("exact", 1000), ("float", 5000), ("control", 9000)])
 def test_random_graphs_agree_with_oracle_on_shape(family, base):
     """the generator of tests/test_gpu_fuzz.py, host side only: parser, connective algebra and lowering accept every
     graph, and the product and the oracle agree on inputs / outputs / size"""
     import numpy as np
     from tests import test_gpu_fuzz as fz
-    gen = fz.exact_graph if family == "exact" else fz.float_graph
+    gen = {"exact": fz.exact_graph, "float": fz.float_graph, "control": fz.control_graph}[family]
     for seed in range(40):
         e = gen(np.random.default_rng(base + seed))
         a, b = build(e, Net), build(e, ONet)
