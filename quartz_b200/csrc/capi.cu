@@ -47,6 +47,7 @@ struct qg_bank {
   std::vector<float> raw;      // host copy of the per-voice raw parameters [V][R] (empty: every voice = template)
   FusedPlan fused;
   TvPlan tv;
+  bool biquad_scan_ok = true;   // every direct-form biquad of every voice may be re-associated (scans) within the tolerance
   bool block_ok = false;   // the tape may run on the block-mode lane interpreter (k_interp_blk)
   int ring_mode = 0;   // 0: rings laid out [pos][voice] (lane kernels); 1: [voice][pos] (time-vector kernel)
 };
@@ -84,6 +85,24 @@ static int upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
   CU(cudaMalloc((void**)dst, src.size() * sizeof(T)));
   CU(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   return QG_OK;
+}
+
+// K2 and the time-vector kernel's block scans re-associate recurrences (zero-state runs + scan).  A direct-form biquad with poles close to z = 1 amplifies any
+// rounding difference by its round-off noise gain; when that gain is large even a perfect evaluation differs from the
+// reference's own f32 rounding by more than the parity tolerance, so such banks stay on the interpreter, which performs
+// the reference's operations in the reference's order.  Power gain of 1 / (1 + a1 z^-1 + a2 z^-2):
+//   (1 + a2) / ((1 - a2) ((1 + a2)^2 - a1^2))
+template <typename ParamAt>
+static bool biquads_well_conditioned(const Tape& t, ParamAt param, long V) {
+  for (const Instr& i : t.code) {
+    if (i.op != OP_BIQUAD) continue;
+    for (long v = 0; v < V; v++) {
+      const double a1 = param(i.p, v), a2 = param(i.p + 1, v);
+      const double den = (1.0 - a2) * ((1.0 + a2) * (1.0 + a2) - a1 * a1);
+      if (!(den > 0.0) || (1.0 + a2) / den > 1.0e4) return false;
+    }
+  }
+  return true;
 }
 
 extern "C" {
@@ -282,6 +301,7 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
     }
     CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    b->biquad_scan_ok = biquads_well_conditioned(t, [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V);
   } else if (P > 0) {
     float* d_tmpl = nullptr;
     if ((rc = upload(&d_tmpl, t.params, c->stream))) return rc;
@@ -291,8 +311,11 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
     cudaFree(d_tmpl);
   }
   if ((rc = bank_init_state(b, salts))) return rc;
+  if (!(raw_matrix && R > 0 && P > 0)) b->biquad_scan_ok = biquads_well_conditioned(t, [&](int p, long) { return t.params[p]; }, 1);
   b->fused = plan_fused(t);
+  if (b->fused.id == FUSED_NOISE_SVF && b->fused.p[1] == 2 && !b->biquad_scan_ok) b->fused.id = FUSED_NONE;
   b->tv = plan_tv(t, (size_t)180 * 1024);
+  if (!b->biquad_scan_ok) b->tv.sequential = true;   // those biquads are stepped by one thread in the reference's operation order
   // block mode evaluates an instruction for a whole block of samples before the next one: valid for feed-forward tapes,
   // and for feedback loops whose delay line is at least one block long
   b->block_ok = !(t.h.flags & TAPE_DIVERGENT);
@@ -451,7 +474,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     ta.n_in = (int)t.h.n_inputs; ta.n_out = (int)t.h.n_outputs; ta.out_x = b->d_out_x;
     ta.params = b->d_params; ta.state = b->d_state; ta.rings = b->d_rings; ta.ring_floats = t.h.ring_floats;
     ta.ring_tab = b->d_ring_tab; ta.tables = b->d_tables; ta.in = d_in; ta.out = d_out;
-    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n; ta.align_s = b->tv.align_s; ta.n_lti = b->tv.n_lti; ta.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
+    ta.V = (int)b->V; ta.Vp = b->Vp; ta.T = T; ta.H = b->tv.H; ta.fft_n = b->tv.fft_n; ta.align_s = b->tv.align_s; ta.n_lti = b->tv.n_lti; ta.biquad_scan = b->biquad_scan_ok ? 1 : 0; ta.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
     int l = 0;
     CU(launch_interp_tv(ta, c->stream, &l));
     c->launches += l;

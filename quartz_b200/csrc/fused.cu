@@ -101,6 +101,83 @@ __device__ __forceinline__ float noise_int_hi(uint32_t x, uint32_t hi) {
   return (float)(int32_t)(x ^ (x >> 15));
 }
 
+// ---- filter families K2 serves (template parameter F).  Every one is a linear recurrence with at most two state words
+// that are scanned; the previous INPUT samples some of them use (biquad x1, x2; one-poles x1) are not state for the scan:
+// noise is counter-based, so a lane recomputes the two samples before its chunk.
+//   F_SVF / F_SVF_LP  Simper SVF, state (ic1, ic2); LP = lowpass mix known at plan time (6 FP ops per tick)
+//   F_BIQUAD          direct form I (FunDSP Biquad): y0 = b0 x0 + b1 x1 + b2 x2 - a1 y1 - a2 y2, scanned state (y1, y2)
+//   F_ONEPOLE         lowpole / highpole / dcblock / allpole (kind 0..3, as OP_ONEPOLE), scanned state (y1)
+enum : int { F_SVF = 0, F_SVF_LP = 1, F_BIQUAD = 2, F_ONEPOLE = 3 };
+struct FiltC {
+  SvfC c;          // SVF: a1 a2 a3 m0 m1 m2 ; BIQUAD: a1 a2 (c.a1, c.a2), b0 b1 b2 scaled by 2^-31 (c.a3, c.m0, c.m1) ; ONEPOLE: coeff (c.a1)
+  SvfK k;          // SVF only
+  int kind;        // ONEPOLE kind
+};
+// one tick fed with the un-scaled noise integer hf (x = hf * 2^-31); (s1, s2) scanned state, (h1, h2) previous hf values
+template <int F>
+__device__ __forceinline__ float filt_tick(float hf, float& s1, float& s2, float& h1, float& h2, const FiltC& f) {
+  const float sc = 1.0f / 2147483648.0f;
+  if (F == F_SVF) return svf_fma_noise<false>(hf, s1, s2, f.c, f.k);
+  if (F == F_SVF_LP) return svf_fma_noise<true>(hf, s1, s2, f.c, f.k);
+  if (F == F_BIQUAD) {
+    const float fb = __fmaf_rn(f.c.a1, s1, f.c.a2 * s2);
+    const float y0 = __fmaf_rn(f.c.a3, hf, __fmaf_rn(f.c.m0, h1, __fmaf_rn(f.c.m1, h2, -fb)));
+    h2 = h1; h1 = hf; s2 = s1; s1 = y0;
+    return y0;
+  }
+  const float c = f.c.a1;
+  float y;
+  switch (f.kind) {
+    case 0: y = __fmaf_rn(c, s1, ((1.0f - c) * sc) * hf); break;                    // (1 - c) x + c y1
+    case 1: y = c * __fmaf_rn(sc, hf - h1, s1); break;                              // c (y1 + x - x1)
+    case 2: y = __fmaf_rn(c, s1, sc * (hf - h1)); break;                            // x - x1 + c y1
+    default: y = __fmaf_rn(c, __fmaf_rn(sc, hf, -s1), sc * h1); break;              // c (x - y1) + x1
+  }
+  h1 = hf; s1 = y;
+  return y;
+}
+// state transition matrix A and the row (c1, c2) with y_h(i) = (c1, c2) A^i s_start for the homogeneous output response
+template <int F>
+__device__ __forceinline__ void filt_matrices(const FiltC& f, double& A11, double& A12, double& A21, double& A22, double& c1, double& c2) {
+  if (F == F_SVF || F == F_SVF_LP) {
+    const double a1 = f.c.a1, a2 = f.c.a2, a3 = f.c.a3;
+    A11 = 2 * a1 - 1; A12 = -2 * a2; A21 = 2 * a2; A22 = 1 - 2 * a3;
+    // y_h = m1*v1_h + m2*v2_h with v1_h = a1 s1 - a2 s2, v2_h = a2 s1 + (1 - a3) s2
+    c1 = (double)f.c.m1 * a1 + (double)f.c.m2 * a2; c2 = -(double)f.c.m1 * a2 + (double)f.c.m2 * (1 - a3);
+  } else if (F == F_BIQUAD) {
+    A11 = -(double)f.c.a1; A12 = -(double)f.c.a2; A21 = 1; A22 = 0;
+    c1 = A11; c2 = A12;                                                             // y0 is the first component of A s
+  } else {
+    A11 = f.kind == 3 ? -(double)f.c.a1 : (double)f.c.a1; A12 = 0; A21 = 0; A22 = 0;
+    c1 = A11; c2 = 0;
+  }
+}
+template <int F>
+__device__ __forceinline__ FiltC filt_load(const float* __restrict__ params, int Vp, int v, int p0, int kind) {
+  FiltC f;
+  f.kind = kind;
+  const float sc = 1.0f / 2147483648.0f;
+#define QG_P(i) params[(size_t)(p0 + (i)) * Vp + v]
+  if (F == F_SVF || F == F_SVF_LP) {
+    f.c.a1 = QG_P(0); f.c.a2 = QG_P(1); f.c.a3 = QG_P(2); f.c.m0 = QG_P(3); f.c.m1 = QG_P(4); f.c.m2 = QG_P(5);
+    f.k.c11 = 2.0f * f.c.a1 - 1.0f; f.k.c12 = 2.0f * f.c.a2; f.k.m0s = f.c.m0 * sc;
+  } else if (F == F_BIQUAD) {
+    f.c.a1 = QG_P(0); f.c.a2 = QG_P(1); f.c.a3 = QG_P(2) * sc; f.c.m0 = QG_P(3) * sc; f.c.m1 = QG_P(4) * sc; f.c.m2 = 0.0f;
+    f.k.c11 = f.k.c12 = f.k.m0s = 0.0f;
+  } else {
+    f.c.a1 = QG_P(0); f.c.a2 = f.c.a3 = f.c.m0 = f.c.m1 = f.c.m2 = 0.0f;
+    f.k.c11 = f.k.c12 = f.k.m0s = 0.0f;
+  }
+#undef QG_P
+  return f;
+}
+// where the scanned state words and the input history live in the bank's state table (relative to the op's first state word)
+template <int F> struct FiltState {
+  static constexpr int s1 = F == F_BIQUAD ? 2 : (F == F_ONEPOLE ? 1 : 0);   // first scanned word
+  static constexpr int n_s = F == F_ONEPOLE ? 1 : 2;                          // scanned words
+  static constexpr int n_h = F == F_BIQUAD ? 2 : (F == F_ONEPOLE ? 1 : 0);    // history words (x1[, x2]) at offset 0
+};
+
 // Per-warp shared memory.  `tile` holds the block's 32*K samples as float4 chunks: the zero-state outputs are parked in
 // it, corrected IN PLACE and shipped from it, so a warp needs 128*K bytes (+ constants) and 28 warps fit on an SM.
 //   STORE == 2: tile is laid out as the TMA box (K rows x 128 B, SWIZZLE_128B): sample s of the block sits in row s/32,
@@ -118,33 +195,27 @@ struct __align__(1024) WarpSmem {
 // MODE 0: write samples; MODE 1: state-only pre-pass (zero start state, no output) for segment chaining
 // STORE (decided on the host from the output alignment): 0 plain scalar stores; 1 linear bulk async copy of the block
 // (rows 16-byte aligned); 2 TMA tensor store from the 128-byte-swizzled tile (T % 32 == 0).
-template <int MODE, bool LP, int STORE, int K>
+template <int MODE, int F, int STORE, int K>
 __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restrict__ params, float* __restrict__ state, int Vp,
                                                            int V, long T, int S, long seg_len, int p_svf, int s_noise,
-                                                           int s_svf, float* __restrict__ out, float* __restrict__ seg_state,
-                                                           const __grid_constant__ CUtensorMap tmap) {
+                                                           int s_svf, int kind, float* __restrict__ out,
+                                                           float* __restrict__ seg_state, const __grid_constant__ CUtensorMap tmap) {
   constexpr int B = 32 * K;
+  using FS = FiltState<F>;
   __shared__ WarpSmem<K, MODE == 0 ? STORE : 0> sm[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto& W = sm[warp];
   const long w = (long)blockIdx.x * 4 + warp;        // warp id = voice * S + segment
   const int v = (int)(w / S), seg = (int)(w % S);
   if (v >= V) return;
-  SvfC c;
-  c.a1 = params[(size_t)(p_svf + 0) * Vp + v]; c.a2 = params[(size_t)(p_svf + 1) * Vp + v];
-  c.a3 = params[(size_t)(p_svf + 2) * Vp + v]; c.m0 = params[(size_t)(p_svf + 3) * Vp + v];
-  c.m1 = params[(size_t)(p_svf + 4) * Vp + v]; c.m2 = params[(size_t)(p_svf + 5) * Vp + v];
-  SvfK kc;
-  kc.c11 = 2.0f * c.a1 - 1.0f; kc.c12 = 2.0f * c.a2; kc.m0s = c.m0 * (1.0f / 2147483648.0f);
+  const FiltC fc = filt_load<F>(params, Vp, v, p_svf, kind);
   // state-space form of the tick:  s' = A s + B x ; y = C s + D x
-  const double a1 = c.a1, a2 = c.a2, a3 = c.a3;
-  const double A11 = 2 * a1 - 1, A12 = -2 * a2, A21 = 2 * a2, A22 = 1 - 2 * a3;
-  // y_h = m1*v1_h + m2*v2_h with v1_h = a1 s1 - a2 s2, v2_h = a2 s1 + (1 - a3) s2   (row vector C below)
+  double A11, A12, A21, A22, c1, c2;
+  filt_matrices<F>(fc, A11, A12, A21, A22, c1, c2);
   // per-voice constants in f64, rounded once, kept in shared memory (read as broadcasts):
   //   rc[i] = C * A^i  (the homogeneous output response i samples after a block start state), i < K
   //   mp[i] = A^(K*2^i), i = 0..4  (scan matrices)
   if (lane == 0) {
-    const double c1 = (double)c.m1 * a1 + (double)c.m2 * a2, c2 = -(double)c.m1 * a2 + (double)c.m2 * (1 - a3);
     double m11 = 1, m12 = 0, m21 = 0, m22 = 1;
     float* rcf = reinterpret_cast<float*>(W.rc);
     for (int i = 0; i < K; i++) {
@@ -167,7 +238,16 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
   if (MODE == 1 || seg > 0) {
     if (MODE == 1) { S1 = 0.0f; S2 = 0.0f; }
     else { S1 = seg_state[((size_t)v * (S + 1) + seg) * 2]; S2 = seg_state[((size_t)v * (S + 1) + seg) * 2 + 1]; }
-  } else { S1 = state[(size_t)s_svf * Vp + v]; S2 = state[(size_t)(s_svf + 1) * Vp + v]; }
+  } else { S1 = state[(size_t)(s_svf + FS::s1) * Vp + v]; S2 = FS::n_s > 1 ? state[(size_t)(s_svf + FS::s1 + 1) * Vp + v] : 0.0f; }
+  // input history of the voice's first sample of this launch comes from the persisted state (x = hf * 2^-31 exactly)
+  const float xp1 = FS::n_h >= 1 ? state[(size_t)s_svf * Vp + v] * 2147483648.0f : 0.0f;
+  const float xp2 = FS::n_h >= 2 ? state[(size_t)(s_svf + 1) * Vp + v] * 2147483648.0f : 0.0f;
+  // hf of the two samples before absolute sample index ta (counter of sample ta is counter0 + ta + 1)
+  auto history = [&](long ta, float& h1, float& h2) {
+    if (FS::n_h == 0) { h1 = 0.0f; h2 = 0.0f; return; }
+    h1 = ta >= 1 ? noise_int(counter0 + (uint32_t)ta) : xp1;
+    h2 = FS::n_h < 2 ? 0.0f : (ta >= 2 ? noise_int(counter0 + (uint32_t)ta - 1u) : (ta == 1 ? xp1 : xp2));
+  };
   float* orow = MODE == 0 ? out + (size_t)v * T : nullptr;
   constexpr bool can_bulk = MODE == 0 && STORE >= 1;
   constexpr bool swz = MODE == 0 && STORE == 2;
@@ -190,6 +270,8 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
     // the common case hoists it (one SHF less per sample), the crossing block takes the plain path (warp-uniform branch)
     float e1 = 0.0f, e2 = 0.0f;
     {
+      float h1, h2;
+      history(t + (long)lane * K, h1, h2);
       const uint32_t base = counter0 + (uint32_t)t + (uint32_t)(lane * K) + 1u;
       const bool cross = (base & 0xffffu) > (0xffffu - (uint32_t)(K - 1));
       if (!__any_sync(0xffffffffu, cross)) {
@@ -200,10 +282,10 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
 #pragma unroll
         for (int i4 = 0; i4 < K / 4; i4++) {
           float4 y;
-          y.x = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 0), hi), e1, e2, c, kc);
-          y.y = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 1), hi), e1, e2, c, kc);
-          y.z = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 2), hi), e1, e2, c, kc);
-          y.w = svf_fma_noise<LP>(noise_int_hi(QG_CTR(4 * i4 + 3), hi), e1, e2, c, kc);
+          y.x = filt_tick<F>(noise_int_hi(QG_CTR(4 * i4 + 0), hi), e1, e2, h1, h2, fc);
+          y.y = filt_tick<F>(noise_int_hi(QG_CTR(4 * i4 + 1), hi), e1, e2, h1, h2, fc);
+          y.z = filt_tick<F>(noise_int_hi(QG_CTR(4 * i4 + 2), hi), e1, e2, h1, h2, fc);
+          y.w = filt_tick<F>(noise_int_hi(QG_CTR(4 * i4 + 3), hi), e1, e2, h1, h2, fc);
           if (MODE == 0) W.tile[slot(i4)] = y;
         }
 #undef QG_CTR
@@ -211,10 +293,10 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
 #pragma unroll 2
         for (int i4 = 0; i4 < K / 4; i4++) {
           float4 y;
-          y.x = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 0)), e1, e2, c, kc);
-          y.y = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 1)), e1, e2, c, kc);
-          y.z = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 2)), e1, e2, c, kc);
-          y.w = svf_fma_noise<LP>(noise_int(base + (uint32_t)(4 * i4 + 3)), e1, e2, c, kc);
+          y.x = filt_tick<F>(noise_int(base + (uint32_t)(4 * i4 + 0)), e1, e2, h1, h2, fc);
+          y.y = filt_tick<F>(noise_int(base + (uint32_t)(4 * i4 + 1)), e1, e2, h1, h2, fc);
+          y.z = filt_tick<F>(noise_int(base + (uint32_t)(4 * i4 + 2)), e1, e2, h1, h2, fc);
+          y.w = filt_tick<F>(noise_int(base + (uint32_t)(4 * i4 + 3)), e1, e2, h1, h2, fc);
           if (MODE == 0) W.tile[slot(i4)] = y;
         }
       }
@@ -271,9 +353,10 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
   }
   // ---- tail (< B samples): sequential on every lane (redundant), lane 0 stores
   {
-    float s1 = S1, s2 = S2;
+    float s1 = S1, s2 = S2, h1, h2;
+    history(t, h1, h2);
     for (long tt = t; tt < t_end; tt++) {
-      float yv = svf_fma<LP>(d_noise(counter0 + (uint32_t)tt + 1u), s1, s2, c);
+      float yv = filt_tick<F>(noise_int(counter0 + (uint32_t)tt + 1u), s1, s2, h1, h2, fc);
       if (MODE == 0 && lane == 0) orow[tt] = yv;
     }
     S1 = s1; S2 = s2;
@@ -284,8 +367,14 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
     if (can_bulk && lane == 0) bulk_wait_all();
     if (seg == S - 1 && lane == 0) {
       if (S == 1) {
-        state[(size_t)s_svf * Vp + v] = S1;
-        state[(size_t)(s_svf + 1) * Vp + v] = S2;
+        state[(size_t)(s_svf + FS::s1) * Vp + v] = S1;
+        if (FS::n_s > 1) state[(size_t)(s_svf + FS::s1 + 1) * Vp + v] = S2;
+        if (FS::n_h >= 1) {   // the last inputs of this launch become the persisted history
+          float h1, h2;
+          history(T, h1, h2);
+          state[(size_t)s_svf * Vp + v] = h1 * (1.0f / 2147483648.0f);
+          if (FS::n_h >= 2) state[(size_t)(s_svf + 1) * Vp + v] = h2 * (1.0f / 2147483648.0f);
+        }
         state[(size_t)s_noise * Vp + v] = __uint_as_float(counter0 + (uint32_t)T);
       } else {
         // other segments of this voice may not have read the persisted state yet: publish through slot S,
@@ -297,24 +386,34 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
   }
 }
 
+template <int F>
 __global__ void k_finalize_segments(float* __restrict__ state, int Vp, int V, long T, int S, int s_noise, int s_svf,
                                     const float* __restrict__ seg_state) {
+  using FS = FiltState<F>;
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
-  state[(size_t)s_svf * Vp + v] = seg_state[((size_t)v * (S + 1) + S) * 2];
-  state[(size_t)(s_svf + 1) * Vp + v] = seg_state[((size_t)v * (S + 1) + S) * 2 + 1];
-  state[(size_t)s_noise * Vp + v] = __uint_as_float(__float_as_uint(state[(size_t)s_noise * Vp + v]) + (uint32_t)T);
+  const uint32_t counter0 = __float_as_uint(state[(size_t)s_noise * Vp + v]);
+  if (FS::n_h >= 1) {   // last inputs of the launch -> persisted history (x1[, x2]); T >= 2 whenever time is segmented
+    state[(size_t)s_svf * Vp + v] = d_noise(counter0 + (uint32_t)T);
+    if (FS::n_h >= 2) state[(size_t)(s_svf + 1) * Vp + v] = d_noise(counter0 + (uint32_t)T - 1u);
+  }
+  state[(size_t)(s_svf + FS::s1) * Vp + v] = seg_state[((size_t)v * (S + 1) + S) * 2];
+  if (FS::n_s > 1) state[(size_t)(s_svf + FS::s1 + 1) * Vp + v] = seg_state[((size_t)v * (S + 1) + S) * 2 + 1];
+  state[(size_t)s_noise * Vp + v] = __uint_as_float(counter0 + (uint32_t)T);
 }
 
 // Chain the segment start states: start_0 = persisted state, start_{g+1} = A^len_g start_g + zs_end_g.
 // One thread per voice; A^len by square-and-multiply in f64.
+template <int F>
 __global__ void k_chain_segments(const float* __restrict__ params, const float* __restrict__ state, int Vp, int V, long T, int S,
-                                 long seg_len, int p_svf, int s_svf, float* __restrict__ seg_state) {
+                                 long seg_len, int p_svf, int s_svf, int kind, float* __restrict__ seg_state) {
+  using FS = FiltState<F>;
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
-  const double a1 = params[(size_t)(p_svf + 0) * Vp + v], a2 = params[(size_t)(p_svf + 1) * Vp + v], a3 = params[(size_t)(p_svf + 2) * Vp + v];
-  const double A11 = 2 * a1 - 1, A12 = -2 * a2, A21 = 2 * a2, A22 = 1 - 2 * a3;
-  double s1 = state[(size_t)s_svf * Vp + v], s2 = state[(size_t)(s_svf + 1) * Vp + v];
+  const FiltC fc = filt_load<F>(params, Vp, v, p_svf, kind);
+  double A11, A12, A21, A22, c1, c2;
+  filt_matrices<F>(fc, A11, A12, A21, A22, c1, c2);
+  double s1 = state[(size_t)(s_svf + FS::s1) * Vp + v], s2 = FS::n_s > 1 ? state[(size_t)(s_svf + FS::s1 + 1) * Vp + v] : 0.0;
   for (int g = 0; g < S; g++) {
     float z1 = seg_state[((size_t)v * (S + 1) + g) * 2], z2 = seg_state[((size_t)v * (S + 1) + g) * 2 + 1];
     seg_state[((size_t)v * (S + 1) + g) * 2] = (float)s1;
@@ -492,14 +591,23 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
 FusedPlan plan_fused(const Tape& t) {
   FusedPlan pl;
   const auto& c = t.code;
-  if (t.h.n_inputs == 0 && t.h.n_outputs == 1 && c.size() == 2 && c[0].op == OP_NOISE && c[1].op == OP_SVF &&
-      c[1].in[0] == c[0].out && t.out_x.size() == 1 && t.out_x[0] == c[1].out) {
+  // white() >> <fixed linear filter>: K2
+  if (t.h.n_inputs == 0 && t.h.n_outputs == 1 && c.size() == 2 && c[0].op == OP_NOISE &&
+      (c[1].op == OP_SVF || c[1].op == OP_BIQUAD || c[1].op == OP_ONEPOLE) && c[1].in[0] == c[0].out && t.out_x.size() == 1 &&
+      t.out_x[0] == c[1].out) {
     pl.id = FUSED_NOISE_SVF;
-    pl.p[0] = c[1].p;                                   // a1 a2 a3 m0 m1 m2 (X index == parameter index)
+    pl.p[0] = c[1].p;                                   // first coefficient (X index == parameter index)
     pl.s[0] = c[0].s - (int)t.h.n_params;               // noise counter
-    pl.s[1] = c[1].s - (int)t.h.n_params;               // ic1, ic2
-    // the mix (m0, m1, m2) is a function of the filter mode alone for lowpass: identical for every voice
-    pl.p[1] = (t.params[c[1].p + 3] == 0.0f && t.params[c[1].p + 4] == 0.0f && t.params[c[1].p + 5] == 1.0f) ? 1 : 0;
+    pl.s[1] = c[1].s - (int)t.h.n_params;               // first state word of the filter
+    if (c[1].op == OP_SVF) {
+      // the mix (m0, m1, m2) is a function of the filter mode alone for lowpass: identical for every voice
+      pl.p[1] = (t.params[c[1].p + 3] == 0.0f && t.params[c[1].p + 4] == 0.0f && t.params[c[1].p + 5] == 1.0f) ? 1 : 0;
+    } else if (c[1].op == OP_BIQUAD) {
+      pl.p[1] = 2;
+    } else {
+      pl.p[1] = 3;
+      pl.p[2] = c[1].n;                                 // one-pole kind
+    }
     return pl;
   }
   // sine(f) >> svf(fixed)  *  ar(a,ak,r,rk)
@@ -561,7 +669,12 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     if (S < 1) S = 1;
     long warps = (long)a.V * S;
     unsigned blocks = (unsigned)((warps + 3) / 4);
+    const int filt = pl.p[1], kind = filt == 3 ? pl.p[2] : 0;
     float* seg = nullptr;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+#define QG_K2(MODEV, FV, SV) k_noise_svf_scan<MODEV, FV, SV, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], kind, MODEV == 0 ? a.out : nullptr, seg, tmap)
+#define QG_K2_F(MODEV, SV) do { if (filt == 1) QG_K2(MODEV, F_SVF_LP, SV); else if (filt == 0) QG_K2(MODEV, F_SVF, SV); else if (filt == 2) QG_K2(MODEV, F_BIQUAD, SV); else QG_K2(MODEV, F_ONEPOLE, SV); } while (0)
     if (S > 1) {
       size_t need = (size_t)a.V * (S + 1) * 2 * sizeof(float);
       if (need > *a.scratch_bytes) {
@@ -572,27 +685,27 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
         *a.scratch_bytes = need;
       }
       seg = *a.scratch;
-      CUtensorMap dummy;
-      memset(&dummy, 0, sizeof dummy);
-      if (pl.p[1]) k_noise_svf_scan<1, true, 0, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
-      else k_noise_svf_scan<1, false, 0, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], nullptr, seg, dummy);
-      k_chain_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], seg);
+      QG_K2_F(1, 0);
+      const unsigned cb = (a.V + 127) / 128;
+      if (filt == 2) k_chain_segments<F_BIQUAD><<<cb, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], kind, seg);
+      else if (filt == 3) k_chain_segments<F_ONEPOLE><<<cb, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], kind, seg);
+      else k_chain_segments<F_SVF><<<cb, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[1], kind, seg);
       if (launches) *launches += 2;
     }
     // output path: TMA tensor store needs 32-sample rows on 128-byte boundaries; linear bulk copies need 16-byte rows
     int store = ((((size_t)(uintptr_t)a.out) & 15) == 0) && ((a.T & 3) == 0) ? 1 : 0;
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof tmap);
     if (store == 1 && ((((size_t)(uintptr_t)a.out) & 127) == 0) && (a.T % 32) == 0 && ((size_t)a.V * (size_t)a.T / 32) < 0x7fffffffull &&
         encode_rows32(&tmap, a.out, (size_t)a.V * (size_t)a.T / 32, K))
       store = 2;
-#define QG_LAUNCH_K2(LPV, SV) k_noise_svf_scan<0, LPV, SV, K><<<blocks, 128, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, S, seg_len, pl.p[0], pl.s[0], pl.s[1], a.out, seg, tmap)
-    if (pl.p[1]) { if (store == 2) QG_LAUNCH_K2(true, 2); else if (store == 1) QG_LAUNCH_K2(true, 1); else QG_LAUNCH_K2(true, 0); }
-    else { if (store == 2) QG_LAUNCH_K2(false, 2); else if (store == 1) QG_LAUNCH_K2(false, 1); else QG_LAUNCH_K2(false, 0); }
-#undef QG_LAUNCH_K2
+    if (store == 2) QG_K2_F(0, 2); else if (store == 1) QG_K2_F(0, 1); else QG_K2_F(0, 0);
+#undef QG_K2_F
+#undef QG_K2
     if (launches) *launches += 1;
     if (S > 1) {
-      k_finalize_segments<<<(a.V + 127) / 128, 128, 0, stream>>>(a.state, a.Vp, a.V, a.T, S, pl.s[0], pl.s[1], seg);
+      const unsigned cb = (a.V + 127) / 128;
+      if (filt == 2) k_finalize_segments<F_BIQUAD><<<cb, 128, 0, stream>>>(a.state, a.Vp, a.V, a.T, S, pl.s[0], pl.s[1], seg);
+      else if (filt == 3) k_finalize_segments<F_ONEPOLE><<<cb, 128, 0, stream>>>(a.state, a.Vp, a.V, a.T, S, pl.s[0], pl.s[1], seg);
+      else k_finalize_segments<F_SVF><<<cb, 128, 0, stream>>>(a.state, a.Vp, a.V, a.T, S, pl.s[0], pl.s[1], seg);
       if (launches) *launches += 1;
     }
     return cudaGetLastError();

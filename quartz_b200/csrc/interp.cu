@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
         for (int q = pc; q < pe; q++) { const Instr Iq = code[q]; exec(Iq, L, dummy); }
         pc = pe - 1;
       } else {
-        switch (I.op) {
+        switch (I.op == OP_BIQUAD && !a.biquad_scan ? (uint16_t)OP_COUNT_ : I.op) {   // OP_COUNT_ -> the generic one-thread path
           case OP_NOISE: {
             const uint32_t c = __float_as_uint(ps[I.s]);
             __syncthreads();

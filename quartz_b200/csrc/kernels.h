@@ -50,6 +50,7 @@ struct TvArgs {
   int frame_major;            // 1: in/out are frame-major [T][V][ch] instead of voice-major [V][ch][T]
   int align_s;                // X index of one rfft/ifft counter (hop alignment across calls), -1 if none
   int n_lti;                  // fixed-coefficient LTI filters in the tape (scan-matrix table in shared memory)
+  int biquad_scan;            // 0: some voice's direct-form biquad is too ill-conditioned to re-associate -> one-thread exact order
 };
 size_t tv_smem_bytes(const TvArgs& a);
 cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches);

@@ -127,3 +127,61 @@ def test_noise_svf_fused_extreme_parameters(mode):
     ref = render_bank(onets, T, threads=8)
     for v in range(V):   # per voice: the resonant gains differ by orders of magnitude
         assert_parity(got[v:v + 1], ref[v:v + 1], "float", f"{mode} hz={hz[v]} q={q[v]}")
+
+
+LTI_OPS = {
+    # op name -> (template op string, per-voice raw parameter generator, op string for voice v)
+    "butterpass": ("butterpass(1000)", lambda rng, V: np.exp(rng.uniform(np.log(500), np.log(15000), (V, 1))), lambda r: f"butterpass({r[0]!r})"),
+    "resonator": ("resonator(1000,50)", lambda rng, V: np.stack([np.exp(rng.uniform(np.log(600), np.log(9000), V)), rng.uniform(60, 400, V)], 1),
+                  lambda r: f"resonator({r[0]!r},{r[1]!r})"),
+    "biquad": ("biquad(-1.2,0.5,0.2,0.3,0.2)", lambda rng, V: np.stack([rng.uniform(-1.7, 1.7, V), rng.uniform(0.1, 0.95, V) * 0 + 0.8, rng.uniform(0.1, 1, V),
+                                                                         rng.uniform(-1, 1, V), rng.uniform(-1, 1, V)], 1),
+               lambda r: f"biquad({r[0]!r},{r[1]!r},{r[2]!r},{r[3]!r},{r[4]!r})"),
+    "lowpole": ("lowpole(500)", lambda rng, V: np.exp(rng.uniform(np.log(5), np.log(15000), (V, 1))), lambda r: f"lowpole({r[0]!r})"),
+    "highpole": ("highpole(500)", lambda rng, V: np.exp(rng.uniform(np.log(5), np.log(15000), (V, 1))), lambda r: f"highpole({r[0]!r})"),
+    "dcblock": ("dcblock(10)", lambda rng, V: rng.uniform(1, 200, (V, 1)), lambda r: f"dcblock({r[0]!r})"),
+    "allpole": ("allpole(0.4)", lambda rng, V: rng.uniform(0.05, 3.0, (V, 1)), lambda r: f"allpole({r[0]!r})"),
+}
+
+
+@pytest.mark.parametrize("V,T", [(37, 5000), (3, 200000)])
+@pytest.mark.parametrize("op", sorted(LTI_OPS))
+def test_noise_lti_fused_families(op, V, T):
+    """K2 on the other linear recurrences (one-pole family, direct-form biquads): one wave (V = 37) and chained time
+    segments (V = 3, 200,000 samples), then a continuation call that has to pick up filter state AND input history"""
+    tmpl_op, gen, fmt = LTI_OPS[op]
+    rng = np.random.default_rng(abs(hash(op)) % 1000 + V)
+    raw = gen(rng, V).astype(np.float32)
+    if op == "biquad":   # keep |a1| < 1 + a2 (stable)
+        raw[:, 0] = np.clip(raw[:, 0], -1.7, 1.7)
+    sr = lambda g: {"op": "sr()", "n": 48000.0, "net": g}
+    tmpl = build(sr({"op": ">>", "n": 0, "inputs": [{"op": "white()"}, {"op": tmpl_op}]}), Net)
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    bank = Bank(tmpl, V, raw=raw, salts=salts)
+    assert bank.kernel() == "k_noise_svf_scan"
+    got = np.concatenate([bank.render(T)[:, 0, :], bank.render(777)[:, 0, :]], axis=1)
+    onets = [build(sr({"op": ">>", "n": 0, "inputs": [{"op": "white()"}, {"op": fmt([float(x) for x in raw[v]])}]}), ONet).set_salt(v + 1)
+             for v in range(V)]
+    ref = render_bank(onets, T + 777, threads=8)
+    for v in range(V):
+        assert_parity(got[v:v + 1], ref[v:v + 1], "float", f"{op} raw={raw[v]}")
+
+
+def test_ill_conditioned_biquads_stay_on_the_op_order_exact_path():
+    """a direct-form biquad with poles next to z = 1 amplifies ANY rounding difference by its round-off noise gain (here
+    ~4e2 in amplitude): re-associating it cannot stay inside the parity tolerance, so the bank is refused by K2 and runs on
+    an interpreter that performs the reference's operations in the reference's order"""
+    V, T = 9, 20000
+    sr = lambda g: {"op": "sr()", "n": 48000.0, "net": g}
+    hz = np.array([97.5, 800, 50, 2000, 30, 5000, 120, 60, 1000], dtype=np.float32)
+    bw = np.array([169.4, 100, 20, 300, 10, 50, 40, 300, 80], dtype=np.float32)
+    tmpl = build(sr({"op": ">>", "n": 0, "inputs": [{"op": "white()"}, {"op": "resonator(1000,50)"}]}), Net)
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    bank = Bank(tmpl, V, raw=np.stack([hz, bw], 1), salts=salts)
+    assert bank.kernel() != "k_noise_svf_scan", bank.kernel()
+    onets = [build(sr({"op": ">>", "n": 0, "inputs": [{"op": "white()"}, {"op": f"resonator({float(hz[v])!r},{float(bw[v])!r})"}]}), ONet)
+             .set_salt(v + 1) for v in range(V)]
+    ref = render_bank(onets, T, threads=4)
+    got = bank.render(T)[:, 0, :]
+    for v in range(V):
+        assert_parity(got[v:v + 1], ref[v:v + 1], "float", f"resonator hz={hz[v]} bw={bw[v]} [{bank.kernel()}]")
