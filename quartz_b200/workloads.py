@@ -77,6 +77,17 @@ def c2_lowpass_bank(V=4096, T=2880000, v0=0):
                     4.0, "hbm", "4 B written per voice-sample", flops_per_unit=14.0)
 
 
+def c2_lti_bank(kind="butterpass", V=4096, T=2880000, v0=0):
+    """noise -> butterpass(hz_v) / lowpole(hz_v): configs[1]'s shape with the other linear recurrences K2 serves
+    (not a BASELINE config: used to time the biquad / one-pole instantiations of the scan kernel)"""
+    voices = np.arange(v0, v0 + V)
+    hz = _loguniform(uniform01(voices, 1), 500.0 if kind == "butterpass" else 20.0, 12000.0).astype(np.float32)
+    expr = _sr(_pipe("white()", f"{kind}(1000)"))
+    return Workload(f"c2_noise_{kind}_bank", expr, hz[:, None], salts_for(voices), T, 1,
+                    lambda v: _sr(_pipe("white()", f"{kind}({float(hz[v])!r})")), 4.0, "hbm", "4 B written per voice-sample",
+                    flops_per_unit=10.0)
+
+
 def c3_polysynth(V=65536, T=480000, G=32, v0=0):
     """sine(f_v) -> lowpass(hz_v, q_v) -> * ar(a_v, 1, r_v, 4) -> groups of G voices, scaled 1/G (configs[2])"""
     voices = np.arange(v0, v0 + V)
@@ -187,4 +198,5 @@ def c5_mixed(V=1048576, T=96000, G=32, v0=0):
     return out
 
 
-WORKLOADS = {"c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth, "c4": c4_spectral, "c5": c5_mixed}
+WORKLOADS = {"c2_butterpass": lambda **kw: c2_lti_bank("butterpass", **kw), "c2_lowpole": lambda **kw: c2_lti_bank("lowpole", **kw),
+             "c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth, "c4": c4_spectral, "c5": c5_mixed}
