@@ -2,6 +2,7 @@
 // str_to_net restated from /root/reference/src/functions.rs:111-1226 (grammar :112-127, constants :47-109).
 // Ops whose FunDSP implementation is not restated return status 1 ("exists in the reference, unsupported
 // here") instead of the reference's silent Net::new(0,0), so that a gap is never mistaken for parity.
+#include <mutex>
 #include <cstdlib>
 #include <map>
 
@@ -81,16 +82,18 @@ static std::vector<float> make_wave(double pitch, int shape) {
   return wave;
 }
 const WaveTableSet& wavetable_set(int shape) {
+  // built once per shape; render_bank() ticks voices from several threads, so the lazy build must be thread-safe
   static WaveTableSet sets[4];
+  static std::once_flag once[4];
   WaveTableSet& ts = sets[shape & 3];
-  if (ts.table.empty()) {
+  std::call_once(once[shape & 3], [&ts, shape] {
     for (int i = 0;; i++) {
       double pn = 20.0 * std::pow(2.0, (double)(i + 1) / 4.0);
       ts.limit.push_back((float)pn);
       ts.table.push_back(make_wave(pn, shape));
       if (pn >= 20000.0) break;
     }
-  }
+  });
   return ts;
 }
 

@@ -486,10 +486,14 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     FusedArgs fa;
     fa.params = b->d_params; fa.state = b->d_state; fa.V = (int)b->V; fa.Vp = b->Vp; fa.T = T; fa.group = group; fa.out = d_out;
     fa.scratch = &b->d_fused_scratch; fa.scratch_bytes = &b->fused_scratch_bytes; fa.sample_rate = t.h.sample_rate;
+    fa.tables = b->d_tables;
     int l = 0;
-    CU(launch_fused(b->fused, fa, c->stream, &l));
+    cudaError_t fe = launch_fused(b->fused, fa, c->stream, &l);
     c->launches += l;
-    return QG_OK;
+    if (fe == cudaSuccess) return QG_OK;
+    if (fe != cudaErrorNotSupported) CU(fe);
+    // the fused kernel does not serve this call (group mix on K2, sample rate too low for the envelope look-ahead ...):
+    // the interpreters below do
   }
   InterpArgs a;
   memset(&a, 0, sizeof a);

@@ -81,6 +81,40 @@ __device__ __forceinline__ float d_a_weight(float f) {
   return c4 * c0 * f2 * f2 / ((f2 + c1) * sqrtf((f2 + c2) * (f2 + c3)) * (f2 + c0));
 }
 
+// Band-limited wavetable oscillators (FunDSP WaveSynth + Wavetable::read/at, restated; table blob built by lower.cpp
+// make_wave): header = [n][n x (limit, offset(bits), length(bits))][samples...].
+// Table for |f|: search from `hint`, which is only a starting point.
+__device__ __forceinline__ const float* d_wavetable_select(const float* hdr, float f, uint32_t& hint, uint32_t& len) {
+  const uint32_t nt = (uint32_t)hdr[0];
+  const float af = fabsf(f);
+  while (hint + 1 < nt && af >= hdr[1 + 3 * hint]) hint++;
+  while (hint > 0 && af < hdr[1 + 3 * (hint - 1)]) hint--;
+  len = __float_as_uint(hdr[3 + 3 * hint]);
+  return hdr + __float_as_uint(hdr[2 + 3 * hint]);
+}
+// read a table (length a power of two) at phase ph in [0, 1) with the 4-point optimal interpolator
+__device__ __forceinline__ float d_wavetable_interp(const float* tb, uint32_t len, float ph) {
+  const uint32_t mask = len - 1;
+  float pp = (float)len * ph;
+  uint32_t i1 = (uint32_t)pp;
+  float w = pp - (float)i1;
+  uint32_t i0 = (i1 + len - 1) & mask;
+  i1 &= mask;
+  float a0 = tb[i0], a1 = tb[i1], a2 = tb[(i1 + 1) & mask], a3 = tb[(i1 + 2) & mask];
+  float z = w - 0.5f, even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
+  float c0 = even1 * 0.46567255120778489f + even2 * 0.03432729708429672f;
+  float c1 = odd1 * 0.53743830753560162f + odd2 * 0.15429462557307461f;
+  float c2 = even1 * -0.25194210134021744f + even2 * 0.25194744935939062f;
+  float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
+  float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
+  return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
+}
+__device__ __forceinline__ float d_wavetable_read(const float* hdr, float f, float ph, uint32_t& hint) {
+  uint32_t len;
+  const float* tb = d_wavetable_select(hdr, f, hint, len);
+  return d_wavetable_interp(tb, len, ph);
+}
+
 // Simper SVF tick (FunDSP Svf): updates (ic1, ic2), returns m0*v0 + m1*v1 + m2*v2
 __device__ __forceinline__ float d_svf_tick(float v0, float& ic1, float& ic2, float a1, float a2, float a3, float m0,
                                             float m1, float m2) {

@@ -20,6 +20,7 @@
 
 #include <cuda.h>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -444,18 +445,18 @@ __global__ void k_chain_segments(const float* __restrict__ params, const float* 
 //        per-sample crossing only rotates registers;
 //      * SVF / envelope interpolation use FMA and a per-segment reciprocal: f32 audio tolerance, not bits;
 //      * group mix (K6): a 32x33 shared tile per warp, lane j adds column j over the group's voices left to right.
-struct EnvC { float c0, c1, c2, c3; };
-__device__ __forceinline__ float env_ar(float tt, const EnvC& e) {   // functions.rs:547-555
-  if (tt < e.c0) return powf(tt / e.c0, e.c1);
-  if (tt < e.c0 + e.c2) return powf((e.c2 - (tt - e.c0)) / e.c2, e.c3);
-  return 0.0f;
-}
+// lfo control functions with constant parameters: xd(t) = exp(-t p), xD, ar (functions.rs:505-507, 517-540, 547-555)
+struct EnvC { float c[4]; int shape; };
+__device__ __forceinline__ float env_eval(float tt, const EnvC& e) { return d_env_eval(e.shape, 0, tt, e.c, e.c); }
 
 constexpr int PS_THREADS = 64;   // 2 warps per block: 1024 blocks for 65,536 voices spread evenly (6.9 per SM)
-template <bool LP>
+// OSC 0: sine(f) (SFU); OSC 1: band-limited wavetable oscillator saw / square / triangle / soft_saw (f fixed per voice: the
+// table is chosen once, a sample costs the phase step + a 4-point interpolated read)
+template <bool LP, int OSC>
 __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restrict__ params, float* __restrict__ state, int Vp, int V,
                                                    long T, int G, int look_tiles, int p_f, int p_sd, int p_svf, int p_env,
-                                                   int s_ph, int s_svf, int s_env, float* __restrict__ out) {
+                                                   int s_ph, int s_svf, int s_env, int env_shape, const float* __restrict__ wt_hdr,
+                                                   float* __restrict__ out) {
   __shared__ float tile[PS_THREADS / 32][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v = blockIdx.x * PS_THREADS + threadIdx.x;   // < Vp (padded voices run on copies of the last voice)
@@ -464,18 +465,21 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
 #define ST(i) state[(size_t)(i) * Vp + v]
   const float inc = PRM(p_f) * PRM(p_sd);                // input[0] * sample_duration
   const SvfC c = {PRM(p_svf), PRM(p_svf + 1), PRM(p_svf + 2), PRM(p_svf + 3), PRM(p_svf + 4), PRM(p_svf + 5)};
-  const EnvC e = {PRM(p_env), PRM(p_env + 1), PRM(p_env + 2), PRM(p_env + 3)};
+  const EnvC e = {{PRM(p_env), PRM(p_env + 1), PRM(p_env + 2), PRM(p_env + 3)}, env_shape};
   const float esd = PRM(p_env + 4);
+  // wavetable oscillator: the frequency is a per-voice constant, so is the table
+  uint32_t wt_hint = OSC == 1 ? __float_as_uint(ST(s_ph + 1)) : 0u, wt_len = 2;
+  const float* wt_tb = OSC == 1 ? d_wavetable_select(wt_hdr, PRM(p_f), wt_hint, wt_len) : nullptr;
   float phase = ST(s_ph), ic1 = ST(s_svf), ic2 = ST(s_svf + 1);
   float et = ST(s_env), t0 = ST(s_env + 1), t1 = ST(s_env + 2), v0 = ST(s_env + 3), v1 = ST(s_env + 4);
   uint64_t th = (uint64_t)__float_as_uint(ST(s_env + 5)) | ((uint64_t)__float_as_uint(ST(s_env + 6)) << 32);
   uint32_t first = __float_as_uint(ST(s_env + 7));
   // prologue: bring the envelope "inside a segment" exactly like the per-sample code would on its first tick
   if (et >= t1) {
-    if (first) { v1 = env_ar(0.0f, e); first = 0u; }
+    if (first) { v1 = env_eval(0.0f, e); first = 0u; }
     t0 = t1; v0 = v1;
     t1 = t0 + d_lerp(0.75f, 1.25f, d_rnd1(th)) * 0.002f;
-    v1 = env_ar(t1, e);
+    v1 = env_eval(t1, e);
     th += 1;
   }
   // The interpolated envelope lerp(v0, v1, (t - t0) / (t1 - t0)) is advanced incrementally (env += slope per sample,
@@ -506,7 +510,8 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
     // (keeps FRND off the quarter-rate XU pipe that MUFU.SIN already uses); other increments take the general form
     if (decltype(small_inc_t)::value) { if (phase >= 1.0f) phase -= 1.0f; }
     else phase -= floorf(phase);
-    const float x = __sinf(p * QG_TAU);
+    // sine reads the phase BEFORE the step, the wavetable oscillators the phase AFTER it (FunDSP Sine / WaveSynth)
+    const float x = OSC == 0 ? __sinf(p * QG_TAU) : d_wavetable_interp(wt_tb, wt_len, phase);
     // ---- SVF
     float y;
     if (LP) {
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
       if (crossed) { rotate(); have_next = false; }
       if (!have_next) {                                    // look one control point ahead
         nt1 = t1 + d_lerp(0.75f, 1.25f, d_rnd1(th + (uint64_t)ncross)) * 0.002f;
-        nv1 = env_ar(nt1, e);
+        nv1 = env_eval(nt1, e);
         const float ninv = 1.0f / (nt1 - t1);
         envN = __fmaf_rn(nv1 - v1, (et - t1) * ninv, v1);  // the next segment's line, evaluated at the current time
         dN = (nv1 - v1) * ninv * esd;
@@ -578,6 +583,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
   th += (uint64_t)ncross;
   if (v < V) {
     ST(s_ph) = phase; ST(s_svf) = ic1; ST(s_svf + 1) = ic2;
+    if (OSC == 1) ST(s_ph + 1) = __uint_as_float(wt_hint);
     ST(s_env) = et; ST(s_env + 1) = t0; ST(s_env + 2) = t1; ST(s_env + 3) = v0; ST(s_env + 4) = v1;
     ST(s_env + 5) = __uint_as_float((uint32_t)th); ST(s_env + 6) = __uint_as_float((uint32_t)(th >> 32));
     ST(s_env + 7) = __uint_as_float(first);
@@ -612,13 +618,17 @@ FusedPlan plan_fused(const Tape& t) {
   }
   // sine(f) >> svf(fixed)  *  ar(a,ak,r,rk)
   const int P = (int)t.h.n_params;
-  if (t.h.n_inputs == 0 && t.h.n_outputs == 1 && c.size() == 4 && c[0].op == OP_SINE && c[0].in[0] < P && c[1].op == OP_SVF &&
-      c[1].in[0] == c[0].out && c[2].op == OP_ENVELOPE && c[2].n == 2 && c[3].op == OP_MUL && c[3].in[0] == c[1].out &&
-      c[3].in[1] == c[2].out && t.out_x.size() == 1 && t.out_x[0] == c[3].out) {
+  // <sine | saw | square | triangle | soft_saw>(f) >> svf(fixed)  *  <xd(p) | xD(d,k) | ar(a,ak,r,rk)>   (constant parameters)
+  if (t.h.n_inputs == 0 && t.h.n_outputs == 1 && c.size() == 4 && (c[0].op == OP_SINE || c[0].op == OP_WAVETABLE) && c[0].in[0] < P &&
+      c[1].op == OP_SVF && c[1].in[0] == c[0].out && c[2].op == OP_ENVELOPE && (c[2].n >> 8) == 0 && (c[2].n & 0xff) <= 2 &&
+      c[3].op == OP_MUL && c[3].in[0] == c[1].out && c[3].in[1] == c[2].out && t.out_x.size() == 1 && t.out_x[0] == c[3].out) {
     pl.id = FUSED_SINE_SVF_ENV;
     pl.p[0] = c[0].in[0]; pl.p[1] = c[0].p; pl.p[2] = c[1].p; pl.p[3] = c[2].p;
     pl.s[0] = c[0].s - P; pl.s[1] = c[1].s - P; pl.s[2] = c[2].s - P;
     pl.p[4] = (t.params[c[1].p + 3] == 0.0f && t.params[c[1].p + 4] == 0.0f && t.params[c[1].p + 5] == 1.0f) ? 1 : 0;
+    pl.p[5] = c[0].op == OP_WAVETABLE ? 1 : 0;          // oscillator kind
+    pl.p[6] = (int)c[0].aux;                            // wavetable: table-set header offset
+    pl.p[7] = c[2].n & 0xff;                            // envelope shape
   }
   return pl;
 }
@@ -634,14 +644,13 @@ static bool encode_rows32(CUtensorMap* tm, float* base, size_t n_rows, int box_r
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
       fn = (EncodeFn)p;
-  }
+  });
   if (!fn) return false;
   cuuint64_t dims[2] = {32, (cuuint64_t)n_rows};
   cuuint64_t strides[1] = {128};
@@ -717,8 +726,11 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     const double min_seg = 0.0015 * (double)a.sample_rate - 2.0;
     int look_tiles = min_seg >= 64.0 ? 2 : (min_seg >= 32.0 ? 1 : 0);
     if (look_tiles == 0) return cudaErrorNotSupported;
-    if (pl.p[4]) k_polysynth<true><<<a.Vp / PS_THREADS, PS_THREADS, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, look_tiles, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], a.out);
-    else k_polysynth<false><<<a.Vp / PS_THREADS, PS_THREADS, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, look_tiles, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], a.out);
+#define QG_PS(LPV, OSCV) k_polysynth<LPV, OSCV><<<a.Vp / PS_THREADS, PS_THREADS, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, look_tiles, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], pl.p[7], a.tables ? a.tables + pl.p[6] : nullptr, a.out)
+    if (pl.p[5] && !a.tables) return cudaErrorNotSupported;
+    if (pl.p[4]) { if (pl.p[5]) QG_PS(true, 1); else QG_PS(true, 0); }
+    else { if (pl.p[5]) QG_PS(false, 1); else QG_PS(false, 0); }
+#undef QG_PS
     if (launches) *launches += 1;
     return cudaGetLastError();
   }

@@ -25,6 +25,7 @@ struct FusedArgs {
   float** scratch;        // bank-owned scratch buffer (segment states), grown on demand
   size_t* scratch_bytes;
   float sample_rate;
+  const float* tables;    // the bank's table region (wavetable sets)
 };
 
 FusedPlan plan_fused(const Tape& t);

@@ -156,30 +156,6 @@ __device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim,
   }
 }
 
-// Band-limited wavetable lookup: pick the table for |f| (search from `hint`, which is only a starting point), read it at
-// phase `ph` with the 4-point optimal interpolator.
-__device__ __forceinline__ float d_wavetable_read(const float* hdr, float f, float ph, uint32_t& hint) {
-  const uint32_t nt = (uint32_t)hdr[0];
-  const float af = fabsf(f);
-  while (hint + 1 < nt && af >= hdr[1 + 3 * hint]) hint++;
-  while (hint > 0 && af < hdr[1 + 3 * (hint - 1)]) hint--;
-  const uint32_t off = __float_as_uint(hdr[2 + 3 * hint]), len = __float_as_uint(hdr[3 + 3 * hint]), mask = len - 1;
-  const float* tb = hdr + off;
-  float pp = (float)len * ph;
-  uint32_t i1 = (uint32_t)pp;
-  float w = pp - (float)i1;
-  uint32_t i0 = (i1 + len - 1) & mask;
-  i1 &= mask;
-  float a0 = tb[i0], a1 = tb[i1], a2 = tb[(i1 + 1) & mask], a3 = tb[(i1 + 2) & mask];
-  float z = w - 0.5f, even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
-  float c0 = even1 * 0.46567255120778489f + even2 * 0.03432729708429672f;
-  float c1 = odd1 * 0.53743830753560162f + odd2 * 0.15429462557307461f;
-  float c2 = even1 * -0.25194210134021744f + even2 * 0.25194744935939062f;
-  float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
-  float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
-  return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
-}
-
 // Execute one instruction for this lane.  `pc` is only touched by control-flow ops.
 template <class LaneT>
 __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {

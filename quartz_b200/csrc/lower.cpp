@@ -4,6 +4,7 @@
 // predicated / jumped-over instruction ranges.
 #include "lower.h"
 
+#include <mutex>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -77,9 +78,11 @@ std::vector<float> make_wave(double pitch, int shape) {
 }
 // table-set blob: [n][n x (limit, offset(bits), length(bits))][samples...]; offsets are relative to the blob start
 const std::vector<float>& wavetable_blob(int shape) {
+  // built once per shape; banks may be created from several host threads (one per GPU), so the lazy build is guarded
   static std::vector<float> blobs[4];
+  static std::once_flag once[4];
   std::vector<float>& b = blobs[shape & 3];
-  if (b.empty()) {
+  std::call_once(once[shape & 3], [&b, shape] {
     std::vector<float> limits;
     std::vector<std::vector<float>> tabs;
     for (int i = 0;; i++) {
@@ -99,7 +102,7 @@ const std::vector<float>& wavetable_blob(int shape) {
       off += tabs[i].size();
     }
     for (auto& tb : tabs) b.insert(b.end(), tb.begin(), tb.end());
-  }
+  });
   return b;
 }
 

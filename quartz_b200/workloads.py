@@ -88,8 +88,9 @@ def c2_lti_bank(kind="butterpass", V=4096, T=2880000, v0=0):
                     flops_per_unit=10.0)
 
 
-def c3_polysynth(V=65536, T=480000, G=32, v0=0):
-    """sine(f_v) -> lowpass(hz_v, q_v) -> * ar(a_v, 1, r_v, 4) -> groups of G voices, scaled 1/G (configs[2])"""
+def c3_polysynth(V=65536, T=480000, G=32, v0=0, osc="sine"):
+    """sine(f_v) -> lowpass(hz_v, q_v) -> * ar(a_v, 1, r_v, 4) -> groups of G voices, scaled 1/G (configs[2]);
+    osc = saw / square / triangle / soft_saw gives the same voice with a band-limited wavetable oscillator"""
     voices = np.arange(v0, v0 + V)
     f = _loguniform(uniform01(voices, 3), 55.0, 3520.0).astype(np.float32)
     hz = _loguniform(uniform01(voices, 4), 200.0, 8000.0).astype(np.float32)
@@ -100,11 +101,11 @@ def c3_polysynth(V=65536, T=480000, G=32, v0=0):
     raw = np.stack([f, hz, q, a, one, r, four], axis=1)
 
     def voice(v):
-        osc = _pipe(f"sine({float(f[v])!r})", f"lowpass({float(hz[v])!r},{float(q[v])!r})")
-        return _sr({"op": "*", "n": 0.0, "inputs": [osc, _L(f"ar({float(a[v])!r},1,{float(r[v])!r},4)")]})
+        o = _pipe(f"{osc}({float(f[v])!r})", f"lowpass({float(hz[v])!r},{float(q[v])!r})")
+        return _sr({"op": "*", "n": 0.0, "inputs": [o, _L(f"ar({float(a[v])!r},1,{float(r[v])!r},4)")]})
 
-    expr = _sr({"op": "*", "n": 0.0, "inputs": [_pipe("sine(440)", "lowpass(1000,1)"), _L("ar(0.01,1,0.5,4)")]})
-    return Workload("c3_polysynth_65536", expr, raw, salts_for(voices), T, G, voice, 4.0 / G, "fp32",
+    expr = _sr({"op": "*", "n": 0.0, "inputs": [_pipe(f"{osc}(440)", "lowpass(1000,1)"), _L("ar(0.01,1,0.5,4)")]})
+    return Workload("c3_polysynth_65536" if osc == "sine" else f"c3_polysynth_{osc}_65536", expr, raw, salts_for(voices), T, G, voice, 4.0 / G, "fp32",
                     "osc->lowpass->envelope, mixed in groups of 32; 32 flop per voice-sample (phase 4, sin 12, SVF 12, "
                     "envelope 2, gain 1, mix 1)", flops_per_unit=32.0)
 
@@ -198,5 +199,5 @@ def c5_mixed(V=1048576, T=96000, G=32, v0=0):
     return out
 
 
-WORKLOADS = {"c2_butterpass": lambda **kw: c2_lti_bank("butterpass", **kw), "c2_lowpole": lambda **kw: c2_lti_bank("lowpole", **kw),
+WORKLOADS = {"c3_saw": lambda **kw: c3_polysynth(osc="saw", **kw), "c2_butterpass": lambda **kw: c2_lti_bank("butterpass", **kw), "c2_lowpole": lambda **kw: c2_lti_bank("lowpole", **kw),
              "c1": c1_hello, "c2": c2_lowpass_bank, "c3": c3_polysynth, "c4": c4_spectral, "c5": c5_mixed}

@@ -150,7 +150,7 @@ def test_noise_lti_fused_families(op, V, T):
     """K2 on the other linear recurrences (one-pole family, direct-form biquads): one wave (V = 37) and chained time
     segments (V = 3, 200,000 samples), then a continuation call that has to pick up filter state AND input history"""
     tmpl_op, gen, fmt = LTI_OPS[op]
-    rng = np.random.default_rng(abs(hash(op)) % 1000 + V)
+    rng = np.random.default_rng(sum(map(ord, op)) + V)
     raw = gen(rng, V).astype(np.float32)
     if op == "biquad":   # keep |a1| < 1 + a2 (stable)
         raw[:, 0] = np.clip(raw[:, 0], -1.7, 1.7)
@@ -185,3 +185,38 @@ def test_ill_conditioned_biquads_stay_on_the_op_order_exact_path():
     got = bank.render(T)[:, 0, :]
     for v in range(V):
         assert_parity(got[v:v + 1], ref[v:v + 1], "float", f"resonator hz={hz[v]} bw={bw[v]} [{bank.kernel()}]")
+
+
+@pytest.mark.parametrize("env", ["ar", "xd", "xD"])
+@pytest.mark.parametrize("osc", ["sine", "saw", "square", "triangle", "soft_saw"])
+def test_polysynth_fused_oscillator_and_envelope_variants(osc, env):
+    """K1f serves <sine | band-limited wavetable oscillator>(f) >> <fixed SVF> * <xd | xD | ar> with per-voice constants:
+    parity with the oracle, with the interpreter on the same bank, group mix, and a continuation call"""
+    V, T, G = 64, 6000, 32
+    rng = np.random.default_rng(sum(map(ord, osc + env)))
+    f = np.exp(rng.uniform(np.log(40), np.log(5000), V)).astype(np.float32)
+    hz = np.exp(rng.uniform(np.log(200), np.log(8000), V)).astype(np.float32)
+    q = rng.uniform(0.5, 4, V).astype(np.float32)
+    if env == "ar":
+        ep = np.stack([rng.uniform(0.002, 0.05, V), np.ones(V), rng.uniform(0.02, 0.3, V), np.full(V, 4.0)], 1).astype(np.float32)
+    elif env == "xd":
+        ep = rng.uniform(2, 60, (V, 1)).astype(np.float32)
+    else:
+        ep = np.stack([rng.uniform(0.02, 0.4, V), rng.uniform(0.5, 4, V)], 1).astype(np.float32)
+    sr = lambda g: {"op": "sr()", "n": 48000.0, "net": g}
+
+    def voice(fv, hv, qv, e):
+        osc_g = {"op": ">>", "n": 0.0, "inputs": [{"op": f"{osc}({fv!r})"}, {"op": f"highpass({hv!r},{qv!r})"}]}
+        return sr({"op": "*", "n": 0.0, "inputs": [osc_g, {"op": f"{env}(" + ",".join(repr(float(x)) for x in e) + ")"}]})
+
+    tmpl = build(voice(440.0, 1000.0, 1.0, ep[0]), Net)
+    raw = np.concatenate([f[:, None], hz[:, None], q[:, None], ep], axis=1)
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    bank = Bank(tmpl, V, raw=raw, salts=salts)
+    assert bank.kernel() == "k_polysynth"
+    got = np.concatenate([bank.render(T, group=G)[:, 0, :], bank.render(999, group=G)[:, 0, :]], axis=1)
+    onets = [build(voice(float(f[v]), float(hz[v]), float(q[v]), ep[v]), ONet).set_salt(v + 1) for v in range(V)]
+    ref = render_bank(onets, T + 999, group=G, threads=8)
+    assert_parity(got, ref, "float", f"{osc} * {env}")
+    interp = Bank(tmpl, V, raw=raw, salts=salts).set_path(qb.PATH_INTERP)
+    assert_parity(interp.render(T + 999, group=G)[:, 0, :], ref, "float", "interp")
