@@ -34,6 +34,8 @@ struct qg_bank {
   float* d_params = nullptr;
   float* d_state = nullptr;
   float* d_state_init = nullptr;
+  uint8_t* d_state_keep = nullptr;
+  bool state_ready = false;   // d_state holds a valid state (the first reset is a plain copy of the init table)
   float* d_rings = nullptr;
   Ring* d_ring_tab = nullptr;
   ResetRange* d_resets = nullptr;
@@ -228,7 +230,7 @@ void qg_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 static void bank_release(qg_bank* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
-  cudaFree(b->d_code); cudaFree(b->d_out_x); cudaFree(b->d_params); cudaFree(b->d_state); cudaFree(b->d_state_init);
+  cudaFree(b->d_code); cudaFree(b->d_out_x); cudaFree(b->d_params); cudaFree(b->d_state); cudaFree(b->d_state_init); cudaFree(b->d_state_keep);
   cudaFree(b->d_rings); cudaFree(b->d_ring_tab); cudaFree(b->d_resets); cudaFree(b->d_tables); cudaFree(b->d_scratch);
   cudaFree(b->d_in); cudaFree(b->d_fused_scratch);
   delete b;
@@ -278,6 +280,7 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   if ((rc = upload(&b->d_ring_tab, t.rings, c->stream))) return rc;
   if ((rc = upload(&b->d_resets, t.resets, c->stream))) return rc;
   if ((rc = upload(&b->d_tables, t.tables, c->stream))) return rc;
+  if ((rc = upload(&b->d_state_keep, t.state_keep, c->stream))) return rc;
   CU(cudaMalloc((void**)&b->d_params, std::max<size_t>(1, (size_t)P * b->Vp) * sizeof(float)));
   CU(cudaMalloc((void**)&b->d_state, std::max<size_t>(1, (size_t)NS * b->Vp) * sizeof(float)));
   CU(cudaMalloc((void**)&b->d_state_init, std::max<size_t>(1, (size_t)NS * b->Vp) * sizeof(float)));
@@ -376,7 +379,15 @@ int qg_bank_reset(qg_bank* b) {
   qg_ctx* c = b->ctx;
   CU(cudaSetDevice(c->device));
   size_t ns = (size_t)b->tape.h.n_state * b->Vp * sizeof(float);
-  if (ns) CU(cudaMemcpyAsync(b->d_state, b->d_state_init, ns, cudaMemcpyDeviceToDevice, c->stream));
+  bool any_keep = false;
+  for (uint8_t k : b->tape.state_keep) any_keep = any_keep || k;
+  if (ns && b->state_ready && any_keep) {   // Seq::reset leaves the event list alone (nodes.rs:116-120)
+    CU(launch_reset_state(b->d_state, b->d_state_init, b->d_state_keep, (int)b->tape.h.n_state, b->Vp, c->stream));
+    c->launches++;
+  } else if (ns) {
+    CU(cudaMemcpyAsync(b->d_state, b->d_state_init, ns, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  b->state_ready = true;
   size_t rb = (size_t)b->tape.h.ring_floats * b->Vp * sizeof(float);
   if (rb) CU(cudaMemsetAsync(b->d_rings, 0, rb, c->stream));
   return QG_OK;
@@ -500,7 +511,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   a.code = b->d_code; a.n_instr = (int)t.h.n_instr;
   a.P = (int)t.h.n_params; a.NS = (int)t.h.n_state; a.NT = (int)t.h.n_temps;
   a.n_in = (int)t.h.n_inputs; a.n_out = (int)t.h.n_outputs; a.out_x = b->d_out_x;
-  a.params = b->d_params; a.state = b->d_state; a.state_init = b->d_state_init; a.rings = b->d_rings;
+  a.params = b->d_params; a.state = b->d_state; a.state_init = b->d_state_init; a.state_keep = b->d_state_keep; a.rings = b->d_rings;
   a.ring_tab = b->d_ring_tab; a.resets = b->d_resets; a.tables = b->d_tables;
   a.in = d_in; a.out = d_out; a.V = (int)b->V; a.Vp = b->Vp; a.T = T;
   a.in_frame_major = layout == QG_LAYOUT_FRAME_MAJOR; a.out_frame_major = layout == QG_LAYOUT_FRAME_MAJOR;

@@ -32,6 +32,7 @@ struct Lane {
   const Ring* ring_tab;
   const float* tables;
   const float* state_init;
+  const uint8_t* state_keep;
   const ResetRange* resets;
   int P;
   __device__ __forceinline__ float& at(int i) const { return x[i * nt]; }
@@ -115,7 +116,8 @@ __device__ __forceinline__ uint32_t ring_len(const TvSample&, uint32_t) { return
 __device__ __noinline__ void reset_range(const TvSample&, uint32_t) {}
 __device__ __noinline__ void reset_range(const Lane& L, uint32_t id) {
   ResetRange r = L.resets[id];
-  for (int s = r.s_lo; s < r.s_hi; s++) X(s) = L.state_init[(size_t)(s - L.P) * L.Vp + L.v];
+  for (int s = r.s_lo; s < r.s_hi; s++)
+    if (!L.state_keep[s - L.P]) X(s) = L.state_init[(size_t)(s - L.P) * L.Vp + L.v];   // a nested seq() keeps its event list
   for (int g = r.ring_lo; g < r.ring_hi; g++) {
     uint32_t len = L.ring_tab[g].length;
     for (uint32_t k = 0; k < len; k++) ring_at(L, g, k) = 0.0f;
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(128) k_interp(InterpArgs a) {
   const int v = blockIdx.x * nt + tid;                       // padded voice index, always < Vp
   Lane L;
   L.x = xs + tid; L.nt = nt; L.v = v; L.Vp = a.Vp; L.rings = a.rings; L.ring_tab = a.ring_tab; L.tables = a.tables;
-  L.state_init = a.state_init; L.resets = a.resets; L.P = a.P;
+  L.state_init = a.state_init; L.state_keep = a.state_keep; L.resets = a.resets; L.P = a.P;
   for (int p = 0; p < a.P; p++) X(p) = a.params[(size_t)p * a.Vp + v];
   for (int s = 0; s < a.NS; s++) X(a.P + s) = a.state[(size_t)s * a.Vp + v];
   for (int k = 0; k < a.NT; k++) X(a.P + a.NS + k) = 0.0f;
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
   const int v = blockIdx.x * nt + tid;
   BlockLane<BT> L;
   L.x = xs + tid; L.nt = nt; L.v = v; L.Vp = a.Vp; L.rings = a.rings; L.ring_tab = a.ring_tab; L.tables = a.tables;
-  L.state_init = a.state_init; L.resets = a.resets; L.P = a.P; L.PS = PS; L.j = 0; L.n = BT;
+  L.state_init = a.state_init; L.state_keep = a.state_keep; L.resets = a.resets; L.P = a.P; L.PS = PS; L.j = 0; L.n = BT;
   for (int p = 0; p < a.P; p++) L.x[p * nt] = a.params[(size_t)p * a.Vp + v];
   for (int s = 0; s < a.NS; s++) L.x[(a.P + s) * nt] = a.state[(size_t)s * a.Vp + v];
   for (int k = 0; k < a.NT * BT; k++) L.x[(PS + k) * nt] = 0.0f;
@@ -810,6 +812,11 @@ __global__ void k_init_state(float* state_init, const uint32_t* defaults, int NS
     }
     state_init[(size_t)hi[k].state * Vp + v] = __uint_as_float(w);
   }
+}
+
+__global__ void k_reset_state(float* state, const float* __restrict__ state_init, const uint8_t* __restrict__ keep, int NS, int Vp) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)NS * Vp && !keep[i / Vp]) state[i] = state_init[i];
 }
 
 __global__ void k_broadcast_params(float* params, const float* tmpl, int P, int Vp) {
@@ -1428,6 +1435,12 @@ cudaError_t launch_interp(const InterpArgs& a_in, bool divergent, bool block_ok,
 cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
                               const uint64_t* salts, cudaStream_t stream) {
   k_init_state<<<(Vp + 127) / 128, 128, 0, stream>>>(state_init, defaults, NS, Vp, hi, n_hi, salts);
+  return cudaGetLastError();
+}
+cudaError_t launch_reset_state(float* state, const float* state_init, const uint8_t* keep, int NS, int Vp, cudaStream_t stream) {
+  size_t n = (size_t)NS * Vp;
+  if (n == 0) return cudaSuccess;
+  k_reset_state<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(state, state_init, keep, NS, Vp);
   return cudaGetLastError();
 }
 cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream) {

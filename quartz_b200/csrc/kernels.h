@@ -16,6 +16,7 @@ struct InterpArgs {
   const float* params;        // [P][Vp]
   float* state;               // [NS][Vp]
   const float* state_init;    // [NS][Vp]
+  const uint8_t* state_keep;  // [NS] 1: word survives a reset of the nested net it belongs to
   float* rings;               // [ring_floats][Vp]
   const Ring* ring_tab;
   const ResetRange* resets;
@@ -62,6 +63,8 @@ int interp_block_len();
 cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int NS, int Vp, const HashInit* hi, int n_hi,
                               const uint64_t* salts, cudaStream_t stream);
+// AudioUnit::reset for every voice: state <- state_init except the words marked in `keep`
+cudaError_t launch_reset_state(float* state, const float* state_init, const uint8_t* keep, int NS, int Vp, cudaStream_t stream);
 cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream);
 cudaError_t launch_stereo_frames(const float* src, int n_ch, long n, float* frames, cudaStream_t stream);
 cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream);

@@ -120,6 +120,7 @@ struct Lower {
   uint16_t state(int n = 1, uint32_t init = 0) {
     uint16_t b = (uint16_t)t.state_init.size();
     t.state_init.resize(t.state_init.size() + n, init);
+    t.state_keep.resize(t.state_init.size(), 0);
     return (uint16_t)(R_STATE | b);
   }
   uint16_t zero() { if (zero_p < 0) zero_p = param(0.0f); return (uint16_t)zero_p; }
@@ -658,6 +659,7 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
       uint16_t p = params(1);
       deriver(D_RAMP_SR, 0, 0, p, 1, 0, 0, n.sr);
       uint16_t st = state(1 + 5 * nk);
+      for (int k = 0; k < 1 + 5 * nk; k++) t.state_keep[(st & 0x3fff) + k] = 1;   // the event list is not touched by reset()
       uint16_t vals = temp(nk);
       uint32_t first_range = (uint32_t)t.resets.size();
       t.resets.resize(t.resets.size() + nk);           // one reset range per net, filled in below

@@ -36,6 +36,8 @@ struct Tape {
   std::vector<Instr> code;
   std::vector<float> params;          // template parameter values (P)
   std::vector<uint32_t> state_init;   // default state words (bit patterns)
+  std::vector<uint8_t> state_keep;    // 1: the word survives reset() — Seq::reset only resets its nets, the event list stays
+                                      // (/root/reference/src/nodes.rs:116-120)
   std::vector<Ring> rings;
   std::vector<ResetRange> resets;
   std::vector<HashInit> hash_init;

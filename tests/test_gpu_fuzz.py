@@ -6,6 +6,8 @@ when the tape is capable) for a small salted bank and compared with the CPU orac
   * float: smooth DSP chains (oscillators, noise, LTI filters, waveshapers, delay taps) -> f32 audio tolerance.
 The generator exercises what the fixed case list cannot enumerate: temporary reuse in lowering, in-place operands in
 the block / time-vector kernels, diamonds (split -> parallel branches -> join), sums and products of sub-graphs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -18,6 +20,7 @@ from tests.util import assert_parity
 pytestmark = pytest.mark.gpu
 
 MINOR = [0.0, 2.0, 3.0, 5.0, 7.0, 8.0, 10.0, 12.0]
+N_SEEDS = int(os.environ.get("QG_FUZZ_SEEDS", "40"))   # soak runs: QG_FUZZ_SEEDS=400
 
 
 def _c(rng, lo, hi, nd=3):
@@ -172,13 +175,13 @@ def _check(expr, tol, n, seed):
         assert_parity(got, ref, tol, f"seed {seed} [{pname}: {bank.kernel()}] {expr}")
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(N_SEEDS))
 def test_random_exact_graphs(seed):
     rng = np.random.default_rng(1000 + seed)
     _check(exact_graph(rng), "exact", 2500, seed)
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(N_SEEDS))
 def test_random_float_graphs(seed):
     rng = np.random.default_rng(5000 + seed)
     _check(float_graph(rng), "float", 3000, seed)
@@ -227,7 +230,7 @@ def control_graph(rng):
     return g
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(N_SEEDS))
 def test_random_control_flow_graphs(seed):
     """kr / s / reset / trig_reset / reset_v / select / seq / feedback nested up to two levels around exact sub-graphs:
     the SIMT-stack interpreter must reproduce the oracle's nested-net semantics bit for bit"""
