@@ -42,7 +42,7 @@ def exact_source(rng):
 
 
 def exact_stage(rng):
-    k = rng.integers(0, 16)
+    k = rng.integers(0, 20)
     if k == 0:
         return L(f"add({_c(rng, -3, 3)})")
     if k == 1:
@@ -75,6 +75,15 @@ def exact_stage(rng):
         return L("squared()")
     if k == 14:
         return L("mirror(-1,1)")
+    if k == 16:   # variable sample delay (nodes.rs:707-738), index from a slow ramp
+        return pipe(stack("pass()", pipe(f"dc({_c(rng, 1, 40)})", "ramp()", f"mul({int(rng.integers(2, 60))})")), f"samp_delay({int(rng.integers(8, 64))})")
+    if k == 17:   # table lookup (nodes.rs:127-150) of a scaled, folded index
+        arr = [round(float(x), 3) for x in rng.uniform(-1, 1, int(rng.integers(4, 24)))]
+        return pipe("abs()", f"mul({_c(rng, 1, 30)})", {"op": "get()", "arr": arr})
+    if k == 18:
+        return pipe(f"mul({_c(rng, 2, 200)})", f"bitand({int(rng.integers(1, 255))})")
+    if k == 19:   # equal-power pan to stereo and back (FunDSP pan / join)
+        return pipe(f"mul({_c(rng, 0.1, 2)})", "split(2)", stack("pass()", "tick()"), "reverse(2)", "join(2)")
     return L("round()")
 
 
@@ -92,7 +101,13 @@ def exact_graph(rng):
 
 # ---------------------------------------------------------------- float family
 def float_source(rng):
-    k = rng.integers(0, 6)
+    k = rng.integers(0, 9)
+    if k == 6:
+        return L(f"{rng.choice(['square', 'triangle', 'soft_saw'])}({_c(rng, 30, 2500)})")
+    if k == 7:   # oscillator swept by an exponential map of a slow ramp
+        return pipe(f"dc({_c(rng, 0.2, 3)})", "ramp()", f"xerp({_c(rng, 40, 200)},{_c(rng, 400, 6000)})", str(rng.choice(["sine()", "saw()"])))
+    if k == 8:
+        return L("brown()")
     if k == 0:
         return L("white()")
     if k == 1:
@@ -107,7 +122,7 @@ def float_source(rng):
 
 
 def float_stage(rng):
-    k = rng.integers(0, 17)
+    k = rng.integers(0, 23)
     f, q = _c(rng, 80, 6000), _c(rng, 0.5, 5)
     if k == 0:
         return L(f"lowpass({f},{q})")
@@ -141,7 +156,19 @@ def float_stage(rng):
         return pipe(branch(float_stage(rng), "pass()"), "join(2)")
     if k == 15:
         return L("fir(0.2,0.5,0.2,0.1)")
-    return L(f"lowpass({q})") if False else L("softsign()")
+    if k == 17:   # spectral round trip (nodes.rs:601-700): real part of ifft(rfft(x)), 2N samples late
+        n, st = int(rng.choice([16, 64, 256])), 0
+        st = int(rng.integers(0, n))
+        return pipe(f"rfft({n},{st})", f"ifft({n},{st})", "chan(1,0)")
+    if k == 18:   # stereo detour: pan, rotate, back to mono
+        return pipe(f"pan({_c(rng, -1, 1)})", f"rotate({_c(rng, -3, 3)},{_c(rng, 0.5, 1.2)})", "join(2)")
+    if k == 19:   # variable-cutoff lowpass driven by an lfo
+        return pipe(stack("pass()", pipe(f"sine({_c(rng, 0.3, 9)})", f"mul({_c(rng, 50, 400)})", f"add({_c(rng, 600, 3000)})")), f"lowpass({q})")
+    if k == 20:
+        return L("pinkpass()")
+    if k == 21:
+        return pipe(f"mul({_c(rng, 0.5, 3)})", "atan()")
+    return L("softsign()")
 
 
 def float_graph(rng):
