@@ -263,3 +263,35 @@ def test_random_control_flow_graphs(seed):
     the SIMT-stack interpreter must reproduce the oracle's nested-net semantics bit for bit"""
     rng = np.random.default_rng(9000 + seed)
     _check(control_graph(rng), "exact", 3000, seed)
+
+
+# ---------------------------------------------------------------- block path with inputs (AudioUnit::process, audio.rs:85-118)
+@pytest.mark.parametrize("seed", range(N_SEEDS))
+def test_random_process_chains(seed):
+    """1-input chains driven with external buffers through qg_bank_process, voice-major and frame-major, two calls"""
+    rng = np.random.default_rng(13000 + seed)
+    exact = bool(seed % 2)
+    stage = exact_stage if exact else float_stage
+    g = stage(rng)
+    for _ in range(int(rng.integers(0, 4))):
+        g = pipe(g, stage(rng))
+    net = build(g, Net)
+    assert (net.inputs(), net.outputs()) == (1, 1), g
+    V, n = 3, 1800
+    x = rng.uniform(-1, 1, (V, 1, n)).astype(np.float32)
+    onets = [build(g, ONet).set_salt(v + 1) for v in range(V)]
+    ref = np.stack([o.process(x[v, 0][:, None])[:, 0] for v, o in enumerate(onets)])
+    tol = "exact" if exact else "float"
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    seen = set()
+    for pname, path in PATHS:
+        bank = Bank(net, V, salts=salts).set_path(path)
+        if (pname == "time_vector" and bank.kernel() != "k_interp_tv") or bank.kernel() in seen and pname != "auto":
+            continue
+        seen.add(bank.kernel())
+        a = bank.process(x[:, :, :700], 700)[:, 0, :]
+        b = bank.process(np.ascontiguousarray(x[:, :, 700:]), n - 700)[:, 0, :]
+        assert_parity(np.concatenate([a, b], axis=1), ref, tol, f"seed {seed} voice-major [{pname}: {bank.kernel()}] {g}")
+        bank.reset()
+        fm = bank.process(np.ascontiguousarray(x.transpose(2, 0, 1)), n, layout=qb.LAYOUT_FRAME_MAJOR)[:, :, 0].T
+        assert_parity(fm, ref, tol, f"seed {seed} frame-major [{pname}: {bank.kernel()}] {g}")
