@@ -916,13 +916,20 @@ __device__ __forceinline__ uint32_t tv_wrap(uint32_t p, uint32_t len) {
 }
 
 __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
-  const int tid = threadIdx.x, nth = blockDim.x, v = blockIdx.x, H = a.H, PS = a.P + a.NS;
+  const int tid = threadIdx.x, nth = blockDim.x, v = blockIdx.x;
   Instr* code = reinterpret_cast<Instr*>(qg_smem);
-  // float offsets of the regions behind the tape: scalars, temporaries, tap scratch, transform buffers
-  const int ps_off = a.n_instr * (int)(sizeof(Instr) / 4), tmp_off = ps_off + ((PS + 3) & ~3);
-  const int oldv_off = tmp_off + a.NT * H, fr_off = oldv_off + H, fi_off = fr_off + (int)FPAD(a.fft_n);
-  const int lti_off = (fi_off + (int)FPAD(a.fft_n) + 3) & ~3, scan_off = lti_off + a.n_lti * TV_LTI_FLOATS;   // scan scratch: 2 x 2 x 8 warps
-  const int segi_off = scan_off + 32, segt_off = segi_off + H;   // envelope: per-sample segment index, segment table [TV_SEGCAP][4]
+  // region offsets (floats) come precomputed as kernel parameters (tv_layout)
+#define H a.H
+#define PS a.PS
+#define ps_off a.ps_off
+#define tmp_off a.tmp_off
+#define oldv_off a.oldv_off
+#define fr_off a.fr_off
+#define fi_off a.fi_off
+#define lti_off a.lti_off
+#define scan_off a.scan_off
+#define segi_off a.segi_off
+#define segt_off a.segt_off
 #define ps (QG_SMEM_F + ps_off)
 #define tmp (QG_SMEM_F + tmp_off)
 #define oldv (QG_SMEM_F + oldv_off)
@@ -993,7 +1000,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
     __syncthreads();
     for (int pc = 0; pc < a.n_instr; pc++) {
       const Instr I = code[pc];
-      if (op_is_stateless(I.op)) {
+      if (I.pad != 0) {   // stateless op: lower() stored the end of its run in `pad` (0 for stateful ops)
         // a run of stateless ops is applied sample by sample without intermediate barriers
         const int pe = (int)I.pad;   // end of the run, precomputed by lower()
         // op-outer / sample-inner: every instruction is decoded once per thread and applied to all of the thread's samples;
@@ -1341,15 +1348,42 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
 #undef oldv
 #undef fr
 #undef fi
+#undef H
+#undef PS
+#undef ps_off
+#undef tmp_off
+#undef oldv_off
+#undef fr_off
+#undef fi_off
+#undef lti_off
+#undef scan_off
+#undef segi_off
+#undef segt_off
 }
 
-size_t tv_smem_bytes(const TvArgs& a) {
-  return (size_t)a.n_instr * sizeof(Instr) + (size_t)(((a.P + a.NS) + 3) & ~3) * 4 + (size_t)a.NT * a.H * 4 + (size_t)a.H * 4 +
-         (size_t)FPAD(a.fft_n) * 8 + (size_t)a.n_lti * TV_LTI_FLOATS * 4 + 16 + 32 * 4 + (size_t)a.H * 4 + TV_SEGCAP * 16;
+// shared-memory layout of k_interp_tv, in floats: tape | scalars | temporaries | tap scratch | transform buffers | LTI scan
+// matrices | scan scratch (2 x 2 x 8 warps) | envelope segment indices | envelope segment table
+static size_t tv_layout(TvArgs& a) {
+  a.PS = a.P + a.NS;
+  a.ps_off = a.n_instr * (int)(sizeof(Instr) / 4);
+  a.tmp_off = a.ps_off + ((a.PS + 3) & ~3);
+  a.oldv_off = a.tmp_off + a.NT * a.H;
+  a.fr_off = a.oldv_off + a.H;
+  a.fi_off = a.fr_off + (int)FPAD(a.fft_n);
+  a.lti_off = (a.fi_off + (int)FPAD(a.fft_n) + 3) & ~3;
+  a.scan_off = a.lti_off + a.n_lti * TV_LTI_FLOATS;
+  a.segi_off = a.scan_off + 32;
+  a.segt_off = a.segi_off + a.H;
+  return (size_t)(a.segt_off + TV_SEGCAP * 4) * sizeof(float);
+}
+size_t tv_smem_bytes(const TvArgs& a_in) {
+  TvArgs a = a_in;
+  return tv_layout(a);
 }
 
-cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches) {
-  size_t smem = tv_smem_bytes(a);
+cudaError_t launch_interp_tv(const TvArgs& a_in, cudaStream_t stream, int* launches) {
+  TvArgs a = a_in;
+  size_t smem = tv_layout(a);
   cudaError_t e = cudaFuncSetAttribute(k_interp_tv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   // 256 threads: 2 samples per thread and hop.  (128 threads = 4 samples per thread halves the per-op decode work but was

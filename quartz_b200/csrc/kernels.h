@@ -52,6 +52,9 @@ struct TvArgs {
   int align_s;                // X index of one rfft/ifft counter (hop alignment across calls), -1 if none
   int n_lti;                  // fixed-coefficient LTI filters in the tape (scan-matrix table in shared memory)
   int biquad_scan;            // 0: some voice's direct-form biquad is too ill-conditioned to re-associate -> one-thread exact order
+  // shared-memory layout in floats, filled by launch_interp_tv(): kernel parameters live in the constant bank and fold into
+  // the consuming instructions, whereas values derived in the kernel were being re-materialised at every use
+  int PS, ps_off, tmp_off, oldv_off, fr_off, fi_off, lti_off, scan_off, segi_off, segt_off;
 };
 size_t tv_smem_bytes(const TvArgs& a);
 cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches);
