@@ -706,7 +706,9 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     if (store == 1 && ((((size_t)(uintptr_t)a.out) & 127) == 0) && (a.T % 32) == 0 && ((size_t)a.V * (size_t)a.T / 32) < 0x7fffffffull &&
         encode_rows32(&tmap, a.out, (size_t)a.V * (size_t)a.T / 32, K))
       store = 2;
-    if (store == 2) QG_K2_F(0, 2); else if (store == 1) QG_K2_F(0, 1); else QG_K2_F(0, 0);
+    // rows that are 16-byte but not 128-byte aligned could use the linear bulk copy (STORE == 1, kept in the kernel template);
+    // it is not instantiated: the case is rare and the scalar-store variant serves it
+    if (store == 2) QG_K2_F(0, 2); else QG_K2_F(0, 0);
 #undef QG_K2_F
 #undef QG_K2
     if (launches) *launches += 1;

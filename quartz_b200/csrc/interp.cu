@@ -908,6 +908,13 @@ __device__ void tv_fft(float* fr, float* fi, int lg, const float* tw, bool inver
   }
 }
 
+// one out-of-line copy of the generic per-sample code for the time-vector kernel's one-thread paths (keeps the hot loop's
+// instruction footprint small)
+__device__ __noinline__ void exec_one_thread(const Instr& I, TvSample& L) {
+  int dummy = 0;
+  exec(I, L, dummy);
+}
+
 constexpr int TV_SEGCAP = 72;   // lfo segments a 512-sample hop can cross when a segment is at least 8 samples long
 // (idx + j) mod len for idx < len: one conditional subtract in the common case (ring at least one hop long)
 __device__ __forceinline__ uint32_t tv_wrap(uint32_t p, uint32_t len) {
@@ -1184,7 +1191,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
           case OP_ENVELOPE: {   // lfo()/lfo_in(): control points every ~2 ms, linear interpolation in between
             const float dt = ps[I.p + 4];
             if (!(0.0015f / dt >= 9.0f)) {                   // segments shorter than 8 samples: no room in the segment table
-              if (tid == 0) { TvSample L{ps_off, tmp_off, PS, H, a.tables, 0, 1, n, 0}; int dummy = 0; exec(I, L, dummy); }
+              if (tid == 0) { TvSample L{ps_off, tmp_off, PS, H, a.tables, 0, 1, n, 0}; exec_one_thread(I, L); }
               break;
             }
             float* segi = QG_SMEM_F + segi_off;
@@ -1320,8 +1327,7 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             __syncthreads();
             if (tid == 0) {
               TvSample L{ps_off, tmp_off, PS, H, a.tables, 0, 1, n, 0};
-              int dummy = 0;
-              exec(I, L, dummy);
+              exec_one_thread(I, L);
             }
             break;
           }
