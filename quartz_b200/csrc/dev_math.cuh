@@ -100,7 +100,7 @@ __device__ __forceinline__ float d_wavetable_interp(const float* tb, uint32_t le
   float w = pp - (float)i1;
   uint32_t i0 = (i1 + len - 1) & mask;
   i1 &= mask;
-  float a0 = tb[i0], a1 = tb[i1], a2 = tb[(i1 + 1) & mask], a3 = tb[(i1 + 2) & mask];
+  float a0 = __ldg(tb + i0), a1 = __ldg(tb + i1), a2 = __ldg(tb + ((i1 + 1) & mask)), a3 = __ldg(tb + ((i1 + 2) & mask));   // read-only path
   float z = w - 0.5f, even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
   float c0 = even1 * 0.46567255120778489f + even2 * 0.03432729708429672f;
   float c1 = odd1 * 0.53743830753560162f + odd2 * 0.15429462557307461f;
@@ -108,6 +108,24 @@ __device__ __forceinline__ float d_wavetable_interp(const float* tb, uint32_t le
   float c3 = odd1 * -0.46896069955075126f + odd2 * 0.15578800670302476f;
   float c4 = even1 * 0.00986988334359864f + even2 * -0.00989340017126506f;
   return (((c4 * z + c3) * z + c2) * z + c1) * z + c0;
+}
+// same read with contracted arithmetic (14 FMA-pipe ops instead of 27) for the fused kernels, which are held to the f32 audio
+// tolerance rather than to the interpreters' operation order
+__device__ __forceinline__ float d_wavetable_interp_fma(const float* __restrict__ tb, uint32_t len, float flen, float ph) {
+  const uint32_t mask = len - 1;
+  const float pp = flen * ph;
+  uint32_t i1 = (uint32_t)pp;
+  const float z = (pp - (float)i1) - 0.5f;
+  const uint32_t i0 = (i1 + len - 1) & mask;
+  i1 &= mask;
+  const float a0 = __ldg(tb + i0), a1 = __ldg(tb + i1), a2 = __ldg(tb + ((i1 + 1) & mask)), a3 = __ldg(tb + ((i1 + 2) & mask));
+  const float even1 = a2 + a1, odd1 = a2 - a1, even2 = a3 + a0, odd2 = a3 - a0;
+  const float c0 = __fmaf_rn(even1, 0.46567255120778489f, even2 * 0.03432729708429672f);
+  const float c1 = __fmaf_rn(odd1, 0.53743830753560162f, odd2 * 0.15429462557307461f);
+  const float c2 = __fmaf_rn(even1, -0.25194210134021744f, even2 * 0.25194744935939062f);
+  const float c3 = __fmaf_rn(odd1, -0.46896069955075126f, odd2 * 0.15578800670302476f);
+  const float c4 = __fmaf_rn(even1, 0.00986988334359864f, even2 * -0.00989340017126506f);
+  return __fmaf_rn(__fmaf_rn(__fmaf_rn(__fmaf_rn(c4, z, c3), z, c2), z, c1), z, c0);
 }
 __device__ __forceinline__ float d_wavetable_read(const float* hdr, float f, float ph, uint32_t& hint) {
   uint32_t len;

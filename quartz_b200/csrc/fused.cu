@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
   // wavetable oscillator: the frequency is a per-voice constant, so is the table
   uint32_t wt_hint = OSC == 1 ? __float_as_uint(ST(s_ph + 1)) : 0u, wt_len = 2;
   const float* wt_tb = OSC == 1 ? d_wavetable_select(wt_hdr, PRM(p_f), wt_hint, wt_len) : nullptr;
+  const float wt_flen = (float)wt_len;
   float phase = ST(s_ph), ic1 = ST(s_svf), ic2 = ST(s_svf + 1);
   float et = ST(s_env), t0 = ST(s_env + 1), t1 = ST(s_env + 2), v0 = ST(s_env + 3), v1 = ST(s_env + 4);
   uint64_t th = (uint64_t)__float_as_uint(ST(s_env + 5)) | ((uint64_t)__float_as_uint(ST(s_env + 6)) << 32);
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(PS_THREADS) k_polysynth(const float* __restric
     if (decltype(small_inc_t)::value) { if (phase >= 1.0f) phase -= 1.0f; }
     else phase -= floorf(phase);
     // sine reads the phase BEFORE the step, the wavetable oscillators the phase AFTER it (FunDSP Sine / WaveSynth)
-    const float x = OSC == 0 ? __sinf(p * QG_TAU) : d_wavetable_interp(wt_tb, wt_len, phase);
+    const float x = OSC == 0 ? __sinf(p * QG_TAU) : d_wavetable_interp_fma(wt_tb, wt_len, wt_flen, phase);
     // ---- SVF
     float y;
     if (LP) {
