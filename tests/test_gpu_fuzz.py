@@ -20,7 +20,8 @@ from tests.util import assert_parity
 pytestmark = pytest.mark.gpu
 
 MINOR = [0.0, 2.0, 3.0, 5.0, 7.0, 8.0, 10.0, 12.0]
-N_SEEDS = int(os.environ.get("QG_FUZZ_SEEDS", "40"))   # soak runs: QG_FUZZ_SEEDS=400
+N_SEEDS = int(os.environ.get("QG_FUZZ_SEEDS", "40"))   # soak runs: QG_FUZZ_SEEDS=400 [QG_FUZZ_OFFSET=1000 for fresh graphs]
+OFFSET = int(os.environ.get("QG_FUZZ_OFFSET", "0"))
 
 
 def _c(rng, lo, hi, nd=3):
@@ -202,13 +203,13 @@ def _check(expr, tol, n, seed):
         assert_parity(got, ref, tol, f"seed {seed} [{pname}: {bank.kernel()}] {expr}")
 
 
-@pytest.mark.parametrize("seed", range(N_SEEDS))
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
 def test_random_exact_graphs(seed):
     rng = np.random.default_rng(1000 + seed)
     _check(exact_graph(rng), "exact", 2500, seed)
 
 
-@pytest.mark.parametrize("seed", range(N_SEEDS))
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
 def test_random_float_graphs(seed):
     rng = np.random.default_rng(5000 + seed)
     _check(float_graph(rng), "float", 3000, seed)
@@ -257,7 +258,7 @@ def control_graph(rng):
     return g
 
 
-@pytest.mark.parametrize("seed", range(N_SEEDS))
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
 def test_random_control_flow_graphs(seed):
     """kr / s / reset / trig_reset / reset_v / select / seq / feedback nested up to two levels around exact sub-graphs:
     the SIMT-stack interpreter must reproduce the oracle's nested-net semantics bit for bit"""
@@ -266,7 +267,7 @@ def test_random_control_flow_graphs(seed):
 
 
 # ---------------------------------------------------------------- block path with inputs (AudioUnit::process, audio.rs:85-118)
-@pytest.mark.parametrize("seed", range(N_SEEDS))
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
 def test_random_process_chains(seed):
     """1-input chains driven with external buffers through qg_bank_process, voice-major and frame-major, two calls"""
     rng = np.random.default_rng(13000 + seed)
