@@ -228,9 +228,14 @@ Graph make_seq_select(bool is_seq, const std::vector<const Graph*>& nets) {   //
   n.kind = is_seq ? NK_SEQ : NK_SELECT;
   n.n_in = is_seq ? 4 : 1;
   n.n_out = 1;
-  for (const Graph* g : nets)
+  std::string unsup;
+  for (const Graph* g : nets) {
+    if (g && !g->unsupported.empty() && unsup.empty()) unsup = g->unsupported;
     if (g && g->inputs() == 0 && g->outputs() == 1) n.kids.push_back(*g);
-  return wrap_node(n, is_seq ? ID_SEQ : ID_SELECT);
+  }
+  Graph r = wrap_node(n, is_seq ? ID_SEQ : ID_SELECT);
+  if (r.unsupported.empty()) r.unsupported = unsup;
+  return r;
 }
 Graph make_var(float value) {   // var(): a Shared-backed constant (process.rs:1373-1385), value = the circle's Number
   Node n;
@@ -253,17 +258,28 @@ Graph make_live_io(const std::string& name) {
 Graph connect(const std::string& op, const std::vector<const Graph*>& nets, double number, int node_limit) {
   if (op == "!") {   // process.rs:1868-1873
     Graph g = (!nets.empty() && nets[0]) ? *nets[0] : Graph(0, 0);
-    return Graph::thru(g);
+    std::string u = g.unsupported;
+    Graph r = Graph::thru(g);
+    if (r.unsupported.empty()) r.unsupported = u;
+    return r;
   }
   if (op == "-") {   // process.rs:1787-1797
+    std::string u;
+    for (const Graph* np : nets) if (np && !np->unsupported.empty() && u.empty()) u = np->unsupported;
     if (nets.size() >= 2 && nets[0] && nets[1] && nets[0]->outputs() == nets[1]->outputs()) {
       Graph g = Graph::combine('-', *nets[0], *nets[1]);
+      if (g.unsupported.empty()) g.unsupported = u;
       if (g.size() < node_limit) return g;
     }
-    return Graph(0, 0);
+    Graph e(0, 0);
+    e.unsupported = u;
+    return e;
   }
   Graph graph(0, 0);
   bool empty = true;
+  // an input that mentions an op without a GPU lowering marks the result even when an arity guard skips it
+  std::string unsup;
+  for (const Graph* np : nets) if (np && !np->unsupported.empty() && unsup.empty()) unsup = np->unsupported;
   int reps = as_i32(std::fmax((float)number, 1.0f));   // `.max(1.) as i32` (process.rs:1744, 1825)
   for (int r = 0; r < reps; r++) {
     for (const Graph* np : nets) {
@@ -284,6 +300,7 @@ Graph connect(const std::string& op, const std::vector<const Graph*>& nets, doub
       }
     }
   }
+  if (graph.unsupported.empty()) graph.unsupported = unsup;
   return graph;
 }
 
@@ -322,6 +339,7 @@ Graph array_op(const std::string& kind, const std::string& op_str, const std::ve
     else if (kind == "stack()") graph = Graph::combine('|', std::move(graph), net);
     else if (kind == "sum()") { if (go == no) graph = Graph::combine('+', std::move(graph), net); }
     else if (kind == "product()") { if (go == no) graph = Graph::combine('*', std::move(graph), net); }
+    if (!net.unsupported.empty() && graph.unsupported.empty()) graph.unsupported = net.unsupported;
   }
   return graph;
 }

@@ -122,8 +122,12 @@ static Graph single(uint64_t id, uint16_t kind, int n_in, int n_out, std::vector
   b.N(i).devop = devop; b.N(i).mode = mode; b.N(i).aux = aux;
   return b.finish(n_in, outs_of(i, n_out));
 }
-static Graph unsupported(const std::string& name) {
-  Graph g(0, 0);
+// An op the reference has but whose FunDSP implementation is not restated here.  The placeholder carries the op's real
+// arity (FunDSP's documented signature), so composition — arity guards, stacking, node counts — proceeds exactly as in the
+// reference, and the `unsupported` mark travels with the graph: lowering refuses it by name instead of rendering
+// something else.
+static Graph unsupported(const std::string& name, int n_in, int n_out) {
+  Graph g = single(ID_MAP, NK_ZERO_SRC, n_in, n_out);
   g.unsupported = name;
   return g;
 }
@@ -232,10 +236,12 @@ Graph str_to_net(const std::string& op_in) {
     }
     return single(ID_WAVESYNTH, NK_WAVETABLE, 1, 1, {}, 0, shape);
   }
-  if (name == "organ" || name == "hammond" || name == "pulse" || name == "lorenz" || name == "rossler" || name == "dsf_saw" ||
-      name == "dsf_square" || name == "mls")
-    return unsupported(name);
-  if (name == "pluck") return has(3) ? unsupported(name) : EMPTY;
+  if (name == "organ" || name == "hammond") return unsupported(name, has(1) ? 0 : 1, 1);      // organ_hz(f) / organ()
+  if (name == "pulse") return unsupported(name, 2, 1);                                          // frequency, duty cycle
+  if (name == "lorenz" || name == "rossler") return unsupported(name, 1, 1);                    // frequency
+  if (name == "dsf_saw" || name == "dsf_square") return unsupported(name, has(1) ? 1 : 2, 1);   // dsf_saw_r(r) / dsf_saw()
+  if (name == "mls") return unsupported(name, 0, 1);
+  if (name == "pluck") return has(3) ? unsupported(name, 1, 1) : EMPTY;
 
   // -------------------- filters (functions.rs:233-430)
   if (name == "lowpass") return svf(0, p);
@@ -269,8 +275,10 @@ Graph str_to_net(const std::string& op_in) {
     float alpha = (p[0] + 1.0f) / 2.0f, beta = (1.0f - alpha) / 2.0f;
     return single(ID_FIR, NK_FIR, 1, 1, {beta, alpha, beta});
   }
-  if (name == "follow") return has(1) ? unsupported(name) : EMPTY;
-  if (name == "moog" || name == "morph" || name == "lowrez" || name == "bandrez") return unsupported(name);
+  if (name == "follow") return has(1) ? unsupported(name, 1, 1) : EMPTY;                        // follow(t) / afollow(a, r)
+  if (name == "moog" || name == "lowrez" || name == "bandrez")                                  // x_hz(f, q) / x_q(q) / x()
+    return unsupported(name, has(2) ? 1 : (has(1) ? 2 : 3), 1);
+  if (name == "morph") return unsupported(name, has(3) ? 1 : 4, 1);                             // morph_hz(f, q, m) / morph()
 
   // -------------------- channels (functions.rs:433-494)
   if (name == "sink") return single(ID_SINK, NK_SINK, 1, 0);
@@ -295,7 +303,7 @@ Graph str_to_net(const std::string& op_in) {
   }
 
   // -------------------- envelopes (functions.rs:497-578): mode = shape (0 xd, 1 xD, 2 ar, 3 t)
-  if (name == "adsr") return has(4) ? unsupported(name) : EMPTY;
+  if (name == "adsr") return has(4) ? unsupported(name, 1, 1) : EMPTY;                          // adsr_live: gate in
   if (name == "xd")
     return has(1) ? single(ID_ENVELOPE, NK_ENVELOPE, 0, 1, {p[0]}, 0, 0) : single(ID_ENVELOPE_IN, NK_ENVELOPE, 1, 1, {}, 0, 0);
   if (name == "xD") {
@@ -313,9 +321,16 @@ Graph str_to_net(const std::string& op_in) {
   if (name == "tick") return single(ID_TICK, NK_TICK, 1, 1);
   if (name == "shift_reg") return single(ID_SHIFTREG, NK_SHIFT_REG, 2, 8);
   if (name == "snh") return single(ID_SNH, NK_SNH, 2, 1);
-  if (name == "meter" || name == "chorus" || name == "hold" || name == "limiter" || name == "limiter_stereo" ||
-      name == "reverb_stereo" || name == "reverb_mono")
-    return has(1) ? unsupported(name) : EMPTY;
+  if (name == "meter") {   // meter(peak|rms, t): the mode word is not a number, the time is (functions.rs:584-592)
+    const bool mode = args[1].rfind("peak", 0) == 0 || args[1].rfind("rms", 0) == 0;
+    return (mode && has(1)) ? unsupported(name, 1, 1) : EMPTY;
+  }
+  if (name == "chorus") return has(4) ? unsupported(name, 1, 1) : EMPTY;
+  if (name == "hold") return has(2) ? unsupported(name, 1, 1) : (has(1) ? unsupported(name, 2, 1) : EMPTY);   // hold_hz / hold
+  if (name == "limiter") return has(2) ? unsupported(name, 1, 1) : EMPTY;
+  if (name == "limiter_stereo") return has(2) ? unsupported(name, 2, 2) : EMPTY;
+  if (name == "reverb_stereo") return has(1) ? unsupported(name, 2, 2) : EMPTY;
+  if (name == "reverb_mono") return has(1) ? unsupported(name, 1, 1) : EMPTY;
   if (name == "clip") {
     float lo = -1.0f, hi = 1.0f;
     if (has(2)) { lo = p[0] < p[1] ? p[0] : p[1]; hi = p[0] < p[1] ? p[1] : p[0]; }
@@ -394,9 +409,11 @@ Graph str_to_net(const std::string& op_in) {
     if (it != bin2.end()) return single(ID_MAP, NK_BIN, 2, 1, {}, it->second);
   }
   if (name == "spline") return single(ID_MAP, NK_SPLINE, 5, 1);
-  if (name == "dissonance_max" || name == "m_weight" || name == "spline_mono" || name == "softexp" ||
-      name == "softmix" || name == "spline_noise" || name == "fractal_noise")
-    return unsupported(name);
+  if (name == "dissonance_max" || name == "m_weight" || name == "softexp") return unsupported(name, 1, 1);
+  if (name == "spline_mono") return unsupported(name, 5, 1);
+  if (name == "softmix") return unsupported(name, 3, 1);
+  if (name == "spline_noise") return unsupported(name, 2, 1);
+  if (name == "fractal_noise") return unsupported(name, 4, 1);
   if (name == "wrap") {
     if (has(2)) return single(ID_MAP, NK_WRAP2, 1, 1, {p[0], p[1]});
     if (has(1)) return single(ID_MAP, NK_WRAP1, 1, 1, {p[0]});

@@ -88,6 +88,42 @@ def test_unsupported_ops_fail_loudly_not_silently():
         assert g.unsupported() is not None
 
 
+UNSUPPORTED_ARITY = [   # FunDSP's documented signatures, per parameter count as functions.rs dispatches them
+    ("organ()", 1, 1), ("organ(220)", 0, 1), ("hammond()", 1, 1), ("pulse()", 2, 1), ("lorenz()", 1, 1), ("rossler()", 1, 1),
+    ("dsf_saw()", 2, 1), ("dsf_saw(0.5)", 1, 1), ("dsf_square()", 2, 1), ("dsf_square(0.4)", 1, 1), ("mls()", 0, 1), ("mls(12)", 0, 1),
+    ("pluck(220,0.5,0.5)", 1, 1), ("follow(0.1)", 1, 1), ("follow(0.01,0.2)", 1, 1),
+    ("moog()", 3, 1), ("moog(0.5)", 2, 1), ("moog(1000,0.5)", 1, 1), ("lowrez(0.3)", 2, 1), ("bandrez(800,0.3)", 1, 1),
+    ("morph()", 4, 1), ("morph(1000,1,0)", 1, 1), ("adsr(0.1,0.1,0.5,0.2)", 1, 1), ("meter(peak,0.1)", 1, 1), ("meter(rms,0.1)", 1, 1),
+    ("chorus(0,0.015,0.005,0.2)", 1, 1), ("hold(0.5)", 2, 1), ("hold(200,0.5)", 1, 1), ("limiter(0.01,0.1)", 1, 1),
+    ("limiter_stereo(0.01,0.1)", 2, 2), ("reverb_stereo(10)", 2, 2), ("reverb_stereo(10,2,0.5)", 2, 2), ("reverb_mono(10,2)", 1, 1),
+    ("dissonance_max()", 1, 1), ("m_weight()", 1, 1), ("softexp()", 1, 1), ("spline_mono()", 5, 1), ("softmix()", 3, 1),
+    ("spline_noise()", 2, 1), ("fractal_noise()", 4, 1),
+]
+
+
+@pytest.mark.parametrize("op,ni,no", UNSUPPORTED_ARITY, ids=[u[0] for u in UNSUPPORTED_ARITY])
+def test_unsupported_ops_keep_the_reference_arity_and_mark_every_graph_they_touch(op, ni, no):
+    """an op without a GPU lowering composes like the reference's unit would (same arity, one vertex) and the mark travels
+    through every connective, array op and nested-net constructor: the patch fails by name instead of rendering without it"""
+    n = Net.str_to_net(op)
+    assert (n.inputs(), n.outputs(), n.size()) == (ni, no, 1)
+    name = op.split("(")[0]
+    assert n.unsupported() == name
+    src = Net.str_to_net("dc(" + ",".join(["0.5"] * ni) + ")") if ni else None
+    g = Net.connect(">>", [src, n]) if src is not None else n
+    assert (g.inputs(), g.outputs()) == (0, no) and g.unsupported() == name
+    # arity guards that SKIP the net still carry the mark (here: stacking is fine, piping into a 7-input net is not)
+    for combo in (Net.connect("|", [Net.str_to_net("sine(220)"), g]), Net.connect(">>", [g, Net.str_to_net("join(7)")]),
+                  Net.connect("+", [Net.str_to_net("dc(1,2,3)"), g]), Net.connect("!", [g]), Net.connect("-", [Net.str_to_net("dc(1,2,3)"), g])):
+        assert combo.unsupported() == name
+        with pytest.raises(qb.QuartzGpuError):
+            combo.tape_info()
+    if (g.inputs(), g.outputs()) == (0, 1):
+        for wrapped in (Net.kr(g, 4), Net.reset_every(g, 0.1), Net.trig_reset(g), Net.select([Net.str_to_net("white()"), g]),
+                        Net.seq([g, Net.str_to_net("white()")])):
+            assert wrapped.unsupported() == name
+
+
 def test_raw_parameters_and_signature():
     a = build(pipe("sine(220)", "lowpass(800,2)"), Net)
     b = build(pipe("sine(330)", "lowpass(1200,0.7)"), Net)
