@@ -77,7 +77,8 @@ impl Drop for GpuContext {
 
 /// `render` op replacement (src/process.rs:1345-1351): `len` ticks of a 0-input, 1-output net.
 pub fn render(ctx: &GpuContext, net: &GpuNet, len: usize) -> Result<Vec<f32>, String> {
-    if net.inputs() != 0 || net.outputs() != 1 { return Ok(Vec::new()); }   // the reference's arity guard
+    if net.inputs() != 0 || net.outputs() != 1 { return Ok(Vec::new()); }   // the reference's arity guard (process.rs:1345)
+    let len = len.min(10_000_000);                                          // and its length cap (process.rs:1341-1342)
     let bank = unsafe { qg_bank_create(ctx.0, net.0, 1, std::ptr::null(), std::ptr::null()) };
     if bank.is_null() { return Err(last_error()); }
     let mut out = vec![0f32; len];
