@@ -1,21 +1,23 @@
 // Hand-fused kernels for hot tape shapes (see fused.h).
 //
-// K2  k_noise_svf_scan — `white() >> <fixed SVF>` banks (BASELINE configs[1]): ONE WARP PER VOICE, time-parallel.
-//     The SVF with fixed coefficients is LTI:  s' = A s + B x,  y = C s + D x  with s = (ic1, ic2).  A block of
-//     32*K consecutive samples (K = 16) is split over the 32 lanes (K contiguous samples each):
-//       1. every lane runs its K samples from zero state (noise is counter-based, so lane j just starts its
-//          counter at base + j*K) and parks the K zero-state outputs in shared memory (conflict-free float4 rows);
+// K2  k_noise_svf_scan — `white() >> <fixed linear filter>` banks (BASELINE configs[1]): ONE WARP PER VOICE, time-parallel.
+//     A filter with fixed coefficients is LTI:  s' = A s + B x,  y = C s + D x  with at most two scanned state words
+//     (SVF: ic1, ic2; direct-form biquad: y1, y2; one-poles: y1 — the filter family is a template parameter).  A block of
+//     32*K consecutive samples (K = 32) is split over the 32 lanes (K contiguous samples each = one 128-byte output row):
+//       1. every lane runs its K samples from zero filter state (noise is counter-based, so lane j just starts its
+//          counter at base + j*K and recomputes the two inputs before its chunk) and parks the K zero-state outputs in a
+//          shared tile laid out as the TMA box (SWIZZLE_128B, conflict-free float4 accesses);
 //       2. the per-lane end states are combined with a 5-step warp-shuffle scan of the affine maps
 //          s -> A^K s + c_j  (Kogge-Stone, matrices A^K, A^2K, ... A^16K precomputed per voice in f64);
-//       3. every lane adds the homogeneous response (C A^i) s_start to its K outputs (rows C A^i precomputed per voice);
-//       4. the 32*K outputs (one contiguous 2 KB run of the voice's row) are staged in shared memory and written
-//          with ONE bulk async copy (cp.async.bulk.global.shared::cta -> UBLKCP);
-//       the zero-state run of block b+1 is software-pipelined into the shuffle chain of block b.
+//       3. every lane adds the homogeneous response (C A^i) s_start to its K outputs IN PLACE (rows C A^i precomputed);
+//       4. the 32*K outputs (one contiguous 4 KB run of the voice's row) leave with ONE TMA tensor store
+//          (cp.async.bulk.tensor.2d -> UTMASTG).
 //     Small banks use S time segments per voice: a state-only pre-pass computes each segment's zero-state end
-//     state, the segment start states are chained on the fly (block-level scan), then every segment renders.
+//     state, the segment start states are chained (f64 square-and-multiply of A^len), then every segment renders.
 //     Arithmetic uses explicit FMAs and a re-associated recurrence: parity is the f32 audio tolerance
-//     (<= 1e-4 abs, <= -90 dBFS), demonstrated at full length in tests/test_gpu_fused.py; noise samples and the
-//     persisted counter are bit-exact.
+//     (<= 1e-4 abs, <= -90 dBFS), demonstrated at full length and on extreme parameters in tests/test_gpu_fused.py;
+//     noise samples and the persisted counter are bit-exact.  Ill-conditioned direct-form biquads are refused by the
+//     bank (capi.cu: biquads_well_conditioned) and run in the reference's operation order instead.
 #include "fused.h"
 
 #include <cuda.h>

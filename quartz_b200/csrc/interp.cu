@@ -1,11 +1,17 @@
-// K1 — fused op-tape interpreter: one lane = one voice, the whole render loop runs inside the kernel.
+// The general paths: every kernel here evaluates an arbitrary lowered op tape through the same exec().
 //
-// Replaces the reference's per-sample virtual dispatch (`for _ in 0..len { net.tick(&[], &mut s) }`,
-// /root/reference/src/process.rs:1347-1351 -> FunDSP Net::tick -> Box<dyn AudioUnit>::tick per vertex).
+// K1  k_interp<uniform | divergent>  one lane = one voice, the whole render loop runs inside the kernel, sample by sample;
+//     tapes with nested nets (kr / select / seq / reset ...) run a SIMT-stack emulation.  Replaces the reference's
+//     per-sample virtual dispatch (`for _ in 0..len { net.tick(&[], &mut s) }`, /root/reference/src/process.rs:1347-1351
+//     -> FunDSP Net::tick -> Box<dyn AudioUnit>::tick per vertex).
+// K1b k_interp_blk<8>  same layout, every instruction decoded once per block of 8 samples (feed-forward tapes).
+// K3/K4 + time-parallel path  k_interp_tv  one CTA per voice, threads = the samples of a hop: stateless ops on all threads,
+//     block-level linear-recurrence scans for fixed LTI filters, cooperative shared-memory FFTs for rfft / ifft, exact
+//     phase recurrences stepped by one thread.
 // Data layout (DESIGN.md "HBM layout"): every per-voice table is [index][voice] so the 32 lanes of a warp read
 // one 128-byte line; per-lane working values X live in shared memory as X[index][thread] (bank = thread, so
-// every access is conflict-free); outputs are staged through a per-warp 32x33 shared tile and written as
-// 128-byte rows (voice-major) or, for group mixes, summed left-to-right over the voices of a group (K6).
+// every access is conflict-free); outputs are staged through per-warp shared tiles and written as full sectors
+// (voice-major) or, for group mixes, summed left-to-right over the voices of a group (K6).
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
