@@ -186,12 +186,12 @@ def float_graph(rng):
 PATHS = [("auto", qb.PATH_AUTO), ("lane_block", qb.PATH_INTERP), ("lane_sample", qb.PATH_INTERP_SAMPLE), ("time_vector", qb.PATH_TV)]
 
 
-def _check(expr, tol, n, seed):
+def _check(expr, tol, n, seed, n_out=1):
     V = 3
     salts = np.arange(1, V + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15 + seed)
     net = build(expr, Net)
-    assert net.inputs() == 0 and net.outputs() == 1, (net.inputs(), net.outputs(), expr)
-    ref = np.stack([build(expr, ONet).set_salt(int(s)).render(n)[:, 0] for s in salts])
+    assert net.inputs() == 0 and net.outputs() == n_out, (net.inputs(), net.outputs(), expr)
+    ref = np.stack([build(expr, ONet).set_salt(int(s)).render(n).T for s in salts])     # [V, outputs, n]
     seen = set()
     for pname, path in PATHS:
         bank = Bank(net, V, salts=salts).set_path(path)
@@ -199,8 +199,12 @@ def _check(expr, tol, n, seed):
             continue
         seen.add(bank.kernel())
         # two calls of uneven length: state, rings and counters carry over
-        got = np.concatenate([bank.render(n // 3 + 1)[:, 0, :], bank.render(n - n // 3 - 1)[:, 0, :]], axis=1)
+        got = np.concatenate([bank.render(n // 3 + 1), bank.render(n - n // 3 - 1)], axis=2)
         assert_parity(got, ref, tol, f"seed {seed} [{pname}: {bank.kernel()}] {expr}")
+        if n_out > 1:   # the frame-major interleave of audio.rs:113-117
+            bank.reset()
+            fm = bank.render(n, layout=qb.LAYOUT_FRAME_MAJOR)                              # [n, V, outputs]
+            assert_parity(fm.transpose(1, 2, 0), ref, tol, f"seed {seed} frame-major [{pname}: {bank.kernel()}]")
 
 
 @pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
@@ -296,3 +300,19 @@ def test_random_process_chains(seed):
         bank.reset()
         fm = bank.process(np.ascontiguousarray(x.transpose(2, 0, 1)), n, layout=qb.LAYOUT_FRAME_MAJOR)[:, :, 0].T
         assert_parity(fm, ref, tol, f"seed {seed} frame-major [{pname}: {bank.kernel()}] {g}")
+
+
+# ---------------------------------------------------------------- multi-output graphs (stereo patches end in out())
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
+def test_random_stereo_graphs(seed):
+    """two float chains stacked, cross-fed through pan / rotate / reverse: 2 outputs, voice-major and frame-major"""
+    rng = np.random.default_rng(17000 + seed)
+    g = stack(float_graph(rng), float_graph(rng))
+    k = rng.integers(0, 4)
+    if k == 0:
+        g = pipe(g, f"rotate({_c(rng, -3, 3)},{_c(rng, 0.5, 1.1)})")
+    elif k == 1:
+        g = pipe(g, "reverse(2)", stack(float_stage(rng), "pass()"))
+    elif k == 2:
+        g = pipe(g, "join(2)", f"pan({_c(rng, -1, 1)})")
+    _check(g, "float", 2400, seed, n_out=2)
