@@ -316,3 +316,22 @@ def test_random_stereo_graphs(seed):
     elif k == 2:
         g = pipe(g, "join(2)", f"pan({_c(rng, -1, 1)})")
     _check(g, "float", 2400, seed, n_out=2)
+
+
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + max(8, N_SEEDS // 5)))
+def test_random_graphs_in_ragged_banks(seed):
+    """banks whose voice count is not a multiple of a warp / CTA (130 voices), rows and pairwise group mixes, salted voices:
+    padding lanes, partial tiles and the left-to-right mix on the lane kernels"""
+    from tests.oracle_ffi import render_bank
+    rng = np.random.default_rng(21000 + seed)
+    exact = bool(seed % 2)
+    g = exact_graph(rng) if exact else float_graph(rng)
+    V, n = 130, 1100
+    salts = (np.arange(V, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+    net = build(g, Net)
+    for G in (1, 2):
+        ref = render_bank([build(g, ONet).set_salt(int(s)) for s in salts], n, group=G, threads=4)
+        for pname, path in (("lane_block", qb.PATH_INTERP), ("lane_sample", qb.PATH_INTERP_SAMPLE)):
+            bank = Bank(net, V, salts=salts).set_path(path)
+            got = np.concatenate([bank.render(401, group=G)[:, 0, :], bank.render(n - 401, group=G)[:, 0, :]], axis=1)
+            assert_parity(got, ref, "exact" if exact else "float", f"seed {seed} G={G} [{pname}: {bank.kernel()}] {g}")
