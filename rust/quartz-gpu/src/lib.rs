@@ -21,6 +21,22 @@ extern "C" {
     fn qg_net_size(n: *const qg_net) -> c_int;
     fn qg_net_set_sample_rate(n: *mut qg_net, sr: c_double) -> c_int;
     fn qg_connect(op: *const c_char, nets: *const *const qg_net, n: c_int, number: c_double, node_limit: c_int) -> *mut qg_net;
+    fn qg_array_op(kind: *const c_char, op_str: *const c_char, arr: *const c_float, n: c_int) -> *mut qg_net;
+    fn qg_get(arr: *const c_float, n: c_int) -> *mut qg_net;
+    fn qg_quantize(arr: *const c_float, n: c_int) -> *mut qg_net;
+    fn qg_wave(arr: *const c_float, n: c_int) -> *mut qg_net;
+    fn qg_feedback(net: *const qg_net, has_delay: c_int, delay_seconds: c_double) -> *mut qg_net;
+    fn qg_kr(net: *const qg_net, n: c_double, preserve_time: c_int) -> *mut qg_net;
+    fn qg_reset_every(net: *const qg_net, seconds: c_double) -> *mut qg_net;
+    fn qg_trig_reset(net: *const qg_net, variable: c_int) -> *mut qg_net;
+    fn qg_seq_select(is_seq: c_int, nets: *const *const qg_net, n: c_int) -> *mut qg_net;
+    fn qg_live_io(name: *const c_char) -> *mut qg_net;
+    fn qg_var(value: c_float) -> *mut qg_net;
+    fn qg_net_unsupported(n: *const qg_net) -> *const c_char;
+    fn qg_net_tick(c: *mut qg_ctx, n: *const qg_net, input: *const c_float, n_in: c_int, out: *mut c_float, n_out: c_int) -> c_int;
+    fn qg_bank_from_nets(c: *mut qg_ctx, nets: *const *const qg_net, n: c_long, salts: *const u64) -> *mut qg_bank;
+    fn qg_bank_set_raw(b: *mut qg_bank, raw_index: c_int, value: c_float) -> c_int;
+    fn qg_bank_render_stereo(b: *mut qg_bank, n_frames: c_long, frames: *mut c_float) -> c_int;
     fn qg_ctx_create(device: c_int, stream: *mut c_void) -> *mut qg_ctx;
     fn qg_ctx_destroy(c: *mut qg_ctx);
     fn qg_bank_create(c: *mut qg_ctx, t: *const qg_net, v: c_long, raw: *const c_float, salts: *const u64) -> *mut qg_bank;
@@ -55,6 +71,48 @@ impl GpuNet {
         GpuNet(unsafe { qg_connect(c.as_ptr(), ptrs.as_ptr(), ptrs.len() as c_int, number as c_double, node_limit as c_int) })
     }
 }
+/// graph-level constructors of the patch interpreter (src/process.rs:1450-1667); `arr` is the linked circle's `Arr`
+impl GpuNet {
+    fn wrap(p: *mut qg_net) -> GpuNet { GpuNet(p) }
+    fn ptrs(nets: &[&GpuNet]) -> Vec<*const qg_net> { nets.iter().map(|n| n.0 as *const qg_net).collect() }
+    pub fn get(arr: &[f32]) -> GpuNet { Self::wrap(unsafe { qg_get(arr.as_ptr(), arr.len() as c_int) }) }                 // :1455
+    pub fn quantize(arr: &[f32]) -> GpuNet { Self::wrap(unsafe { qg_quantize(arr.as_ptr(), arr.len() as c_int) }) }       // :1468-1471
+    pub fn wave(arr: &[f32]) -> GpuNet { Self::wrap(unsafe { qg_wave(arr.as_ptr(), arr.len() as c_int) }) }               // :1658-1662
+    pub fn feedback(net: &GpuNet, delay: Option<f32>) -> GpuNet {                                                         // :1500-1507
+        Self::wrap(unsafe { qg_feedback(net.0, delay.is_some() as c_int, delay.unwrap_or(0.) as c_double) })
+    }
+    pub fn kr(net: &GpuNet, n: f32, preserve_time: bool) -> GpuNet {                                                      // :1562-1566
+        Self::wrap(unsafe { qg_kr(net.0, n as c_double, preserve_time as c_int) })
+    }
+    pub fn reset(net: &GpuNet, seconds: f32) -> GpuNet { Self::wrap(unsafe { qg_reset_every(net.0, seconds as c_double) }) }   // :1568-1569
+    pub fn trig_reset(net: &GpuNet) -> GpuNet { Self::wrap(unsafe { qg_trig_reset(net.0, 0) }) }                          // :1602-1606
+    pub fn reset_v(net: &GpuNet) -> GpuNet { Self::wrap(unsafe { qg_trig_reset(net.0, 1) }) }
+    pub fn seq(nets: &[&GpuNet]) -> GpuNet {                                                                              // :1636-1647
+        let p = Self::ptrs(nets);
+        Self::wrap(unsafe { qg_seq_select(1, p.as_ptr(), p.len() as c_int) })
+    }
+    pub fn select(nets: &[&GpuNet]) -> GpuNet {
+        let p = Self::ptrs(nets);
+        Self::wrap(unsafe { qg_seq_select(0, p.as_ptr(), p.len() as c_int) })
+    }
+    /// branch() bus() pipe() stack() sum() product() with `#` substitution (src/process.rs:1669-1717)
+    pub fn array_op(kind: &str, op_str: &str, arr: &[f32]) -> GpuNet {
+        let (k, o) = (CString::new(kind).unwrap_or_default(), CString::new(op_str).unwrap_or_default());
+        Self::wrap(unsafe { qg_array_op(k.as_ptr(), o.as_ptr(), arr.as_ptr(), arr.len() as c_int) })
+    }
+    /// var(): a constant the control plane rewrites (src/process.rs:1373-1385); see GpuRender::set_var
+    pub fn var(value: f32) -> GpuNet { Self::wrap(unsafe { qg_var(value) }) }
+    /// in() adc() buffin() buffout() monitor(): offline equivalents of the live-I/O units
+    pub fn live_io(name: &str) -> GpuNet {
+        let c = CString::new(name).unwrap_or_default();
+        Self::wrap(unsafe { qg_live_io(c.as_ptr()) })
+    }
+    /// Some(op) when the graph mentions an op that has no GPU lowering: the caller keeps the CPU Net for this circle
+    pub fn unsupported(&self) -> Option<String> {
+        let p = unsafe { qg_net_unsupported(self.0) };
+        if p.is_null() { None } else { Some(unsafe { CStr::from_ptr(p) }.to_string_lossy().into_owned()) }
+    }
+}
 impl Clone for GpuNet {
     fn clone(&self) -> Self { GpuNet(unsafe { qg_net_clone(self.0) }) }
 }
@@ -87,6 +145,27 @@ pub fn render(ctx: &GpuContext, net: &GpuNet, len: usize) -> Result<Vec<f32>, St
     if rc != 0 { Err(last_error()) } else { Ok(out) }
 }
 
+/// `apply` op replacement (src/process.rs:1311-1330): one frame through the graph
+pub fn apply(ctx: &GpuContext, net: &GpuNet, input: &[f32]) -> Result<Vec<f32>, String> {
+    if net.inputs() != input.len() { return Ok(Vec::new()); }              // the reference's arity guard (process.rs:1322)
+    let mut out = vec![0f32; net.outputs()];
+    let rc = unsafe { qg_net_tick(ctx.0, net.0, input.as_ptr(), input.len() as c_int, out.as_mut_ptr(), out.len() as c_int) };
+    if rc != 0 { Err(last_error()) } else { Ok(out) }
+}
+
+/// Many `render` circles whose graphs differ only in their constants: one bank, one launch.  `salts` re-seeds the
+/// hash-derived state (sine phase, noise seed) per voice; returns voice-major rows [nets.len()][len].
+pub fn render_many(ctx: &GpuContext, nets: &[&GpuNet], salts: Option<&[u64]>, len: usize) -> Result<Vec<f32>, String> {
+    let len = len.min(10_000_000);
+    let p: Vec<*const qg_net> = nets.iter().map(|n| n.0 as *const qg_net).collect();
+    let bank = unsafe { qg_bank_from_nets(ctx.0, p.as_ptr(), p.len() as c_long, salts.map_or(std::ptr::null(), |s| s.as_ptr())) };
+    if bank.is_null() { return Err(last_error()); }
+    let mut out = vec![0f32; nets.len() * len];
+    let rc = unsafe { qg_bank_render(bank, len as c_long, 0, 1, out.as_mut_ptr()) };
+    unsafe { qg_bank_free(bank) };
+    if rc != 0 { Err(last_error()) } else { Ok(out) }
+}
+
 /// AudioUnit served from GPU-rendered blocks (0 inputs, C outputs); what `slot.set(.., Box::new(..))`
 /// (src/process.rs:1897) receives instead of the CPU Net.
 pub struct GpuRender {
@@ -105,6 +184,15 @@ impl GpuRender {
         if bank.is_null() { return Err(last_error()); }
         let outputs = net.outputs();
         Ok(GpuRender { bank, outputs, block: vec![0.0; outputs * BLOCK], pos: BLOCK })
+    }
+    /// var() update from the control plane (src/process.rs:1382-1385): takes effect at the next block
+    pub fn set_var(&mut self, raw_index: usize, value: f32) -> Result<(), String> {
+        if unsafe { qg_bank_set_raw(self.bank, raw_index as c_int, value) } != 0 { Err(last_error()) } else { Ok(()) }
+    }
+    /// `n` sanitised, clamped, interleaved stereo frames straight from the device (src/audio.rs:85-118)
+    pub fn stereo_frames(&mut self, n: usize) -> Result<Vec<f32>, String> {
+        let mut frames = vec![0f32; 2 * n];
+        if unsafe { qg_bank_render_stereo(self.bank, n as c_long, frames.as_mut_ptr()) } != 0 { Err(last_error()) } else { Ok(frames) }
     }
     fn refill(&mut self) {
         unsafe { qg_bank_render(self.bank, BLOCK as c_long, 0, 1, self.block.as_mut_ptr()); }
