@@ -163,3 +163,18 @@ def test_random_graphs_agree_with_oracle_on_shape(family, base):
         assert (a.inputs(), a.outputs(), a.size()) == (b.inputs(), b.outputs(), b.size()) and a.outputs() == 1, e
         assert a.unsupported() is None
         assert a.tape_info()["n_instr"] > 0
+
+
+def test_rust_binding_declares_only_exported_entry_points():
+    """rust/quartz-gpu cannot be compiled here (no cargo): at least every `extern "C"` name it binds must be declared in
+    include/quartz_gpu.h and exported by the built library"""
+    src = open(os.path.join(ROOT, "rust", "quartz-gpu", "src", "lib.rs")).read()
+    block = src[src.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    names = re.findall(r"\bfn (qg_\w+)\(", block)
+    assert len(names) >= 25
+    header = open(os.path.join(ROOT, "include", "quartz_gpu.h")).read()
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    for n in names:
+        assert re.search(r"\b%s\(" % n, header), n
+        assert hasattr(lib, n), n
