@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/quartz_gpu.h"
@@ -94,6 +95,34 @@ static int upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
 // reference's own f32 rounding by more than the parity tolerance, so such banks stay on the interpreter, which performs
 // the reference's operations in the reference's order.  Power gain of 1 / (1 + a1 z^-1 + a2 z^-2):
 //   (1 + a2) / ((1 - a2) ((1 + a2)^2 - a1^2))
+// Per-voice parameter derivation (coefficients through the host libm, exactly like the reference at construction) for
+// banks of up to a million voices: voices are independent, so the table is filled by all host threads.
+static void derive_table(const Tape& t, const float* raw_matrix, int R, long V, int Vp, std::vector<float>* host) {
+  const int P = (int)t.h.n_params;
+  host->assign((size_t)P * Vp, 0.0f);
+  auto work = [&](long lo, long hi) {
+    std::vector<float> pv(P);
+    for (long v = lo; v < hi; v++) {
+      const long src = v < V ? v : V - 1;
+      for (int p = 0; p < P; p++) pv[p] = t.params[p];
+      t.derive(raw_matrix + (size_t)src * R, pv.data());
+      for (int p = 0; p < P; p++) (*host)[(size_t)p * Vp + v] = pv[p];
+    }
+  };
+  unsigned nthr = std::thread::hardware_concurrency();
+  if (nthr == 0) nthr = 1;
+  const long chunk = 8192;
+  if (Vp <= chunk || nthr == 1) { work(0, Vp); return; }
+  nthr = (unsigned)std::min<long>(nthr, (Vp + chunk - 1) / chunk);
+  std::vector<std::thread> pool;
+  const long per = (Vp + nthr - 1) / nthr;
+  for (unsigned k = 0; k < nthr; k++) {
+    const long lo = (long)k * per, hi = std::min<long>(Vp, lo + per);
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (std::thread& th : pool) th.join();
+}
+
 template <typename ParamAt>
 static bool biquads_well_conditioned(const Tape& t, ParamAt param, long V) {
   for (const Instr& i : t.code) {
@@ -294,14 +323,8 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
         if (memcmp(&raw_matrix[(size_t)v * R + r], &t.raw[r], 4) != 0)
           return fail(QG_ERR_MISMATCH, "raw parameter " + std::to_string(r) + " shapes the tape (delay length / reset period) and must be equal for every voice");
     }
-    std::vector<float> host((size_t)P * b->Vp);
-    std::vector<float> pv(P);
-    for (long v = 0; v < b->Vp; v++) {
-      long src = v < b->V ? v : b->V - 1;
-      for (int p = 0; p < P; p++) pv[p] = t.params[p];
-      t.derive(raw_matrix + (size_t)src * R, pv.data());
-      for (int p = 0; p < P; p++) host[(size_t)p * b->Vp + v] = pv[p];
-    }
+    std::vector<float> host;
+    derive_table(t, raw_matrix, R, b->V, b->Vp, &host);
     CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     b->biquad_scan_ok = biquads_well_conditioned(t, [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V);
@@ -445,14 +468,9 @@ int qg_bank_set_raw(qg_bank* b, int raw_index, float value) {
     CU(cudaStreamSynchronize(c->stream));
     cudaFree(d_tmpl);
   } else {
-    std::vector<float> host((size_t)P * b->Vp), pv(P);
+    std::vector<float> host;
     for (long v = 0; v < b->V; v++) b->raw[(size_t)v * R + raw_index] = value;
-    for (long v = 0; v < b->Vp; v++) {
-      long src = v < b->V ? v : b->V - 1;
-      for (int p = 0; p < P; p++) pv[p] = t.params[p];
-      t.derive(b->raw.data() + (size_t)src * R, pv.data());
-      for (int p = 0; p < P; p++) host[(size_t)p * b->Vp + v] = pv[p];
-    }
+    derive_table(t, b->raw.data(), R, b->V, b->Vp, &host);
     CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
