@@ -220,3 +220,28 @@ def test_polysynth_fused_oscillator_and_envelope_variants(osc, env):
     assert_parity(got, ref, "float", f"{osc} * {env}")
     interp = Bank(tmpl, V, raw=raw, salts=salts).set_path(qb.PATH_INTERP)
     assert_parity(interp.render(T + 999, group=G)[:, 0, :], ref, "float", "interp")
+
+
+def test_fused_kernels_hand_over_to_the_interpreters_when_they_do_not_serve_a_call():
+    """K2 has no group mix; K1f needs an lfo segment of at least one 32-sample window (sample rate >= ~23 kHz): both banks
+    still render, through the interpreters, and match the oracle"""
+    V, T = 64, 3000
+    wl = workloads.c2_lowpass_bank(V=V, T=T)
+    bank = make_bank(wl)
+    assert bank.kernel() == "k_noise_svf_scan"
+    assert_parity(bank.render(T, group=2)[:, 0, :], oracle_voices(wl, range(V), T, group=2), "float", "K2 bank, group mix")
+    # poly-synth voices at 8 kHz: the envelope's control points are 9-15 samples apart
+    f = np.linspace(60, 900, V).astype(np.float32)
+
+    def voice(fv):
+        osc = {"op": ">>", "n": 0.0, "inputs": [{"op": f"sine({fv!r})"}, {"op": "lowpass(700.0,1.5)"}]}
+        return {"op": "sr()", "n": 8000.0, "net": {"op": "*", "n": 0.0, "inputs": [osc, {"op": "ar(0.01,1.0,0.2,4.0)"}]}}
+
+    tmpl = build(voice(220.0), Net)
+    raw = np.stack([f, np.full(V, 700, np.float32), np.full(V, 1.5, np.float32), np.full(V, 0.01, np.float32), np.ones(V, np.float32),
+                    np.full(V, 0.2, np.float32), np.full(V, 4, np.float32)], 1)
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    b2 = Bank(tmpl, V, raw=raw, salts=salts)
+    assert b2.kernel() == "k_polysynth"
+    ref = render_bank([build(voice(float(x)), ONet).set_salt(int(s)) for x, s in zip(f, salts)], T, group=32, threads=4)
+    assert_parity(b2.render(T, group=32)[:, 0, :], ref, "float", "poly-synth bank at 8 kHz")
