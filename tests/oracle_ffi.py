@@ -198,10 +198,12 @@ class ONet:
         return out[:, :self.outputs()]
 
 
-def render_bank(nets, n_samples, group=1, threads=1):
-    """voice-major [V/group, T]"""
+def render_bank(nets, n_samples, group=1, threads=1, out=None):
+    """voice-major [V/group, T]; `out` lets a timing caller pass a buffer whose pages are already resident"""
     arr = (C.c_void_p * len(nets))(*[n.h for n in nets])
-    out = np.zeros((len(nets) // group, n_samples), dtype=np.float32)
+    if out is None:
+        out = np.zeros((len(nets) // group, n_samples), dtype=np.float32)
+    assert out.shape == (len(nets) // group, n_samples) and out.dtype == np.float32 and out.flags.c_contiguous
     lib().qo_render_bank(arr, len(nets), n_samples, group, threads, _fptr(out))
     return out
 
