@@ -101,14 +101,51 @@ struct TvSample {
   __device__ __forceinline__ uint32_t count() const { return 1u; }
 };
 
+// Operand cursor of one instruction.  The generic form resolves an operand index at every access (Lane, TvSample and any
+// access outside a per-sample loop).
+template <class LaneT>
+struct Operands {
+  LaneT& L; const Instr& I; int k;
+  __device__ __forceinline__ Operands(LaneT& l, const Instr& i, bool start) : L(l), I(i), k(0) { if (start) k = L.first(); }
+  __device__ __forceinline__ bool more() const { return L.more(k); }
+  __device__ __forceinline__ void next() { k = L.next(k); }
+  __device__ __forceinline__ float& out(int q) const { return L.out((int)I.out, q); }
+  __device__ __forceinline__ float& in(int q) const { return L.in((int)I.in[q]); }
+};
+// Block lanes walk their BT samples with one pointer per operand: the index arithmetic (is the operand a temporary or a
+// scalar, times the lane stride) is done once per instruction instead of once per access (it was 7 of every ~25 issued
+// instructions of an `add`), and pointers of operands a case does not touch are dead code.
+template <int BT>
+struct BlockOperands {
+  BlockLane<BT>& L; const Instr& I;
+  float* po; float* pi[5]; int si[5]; int k;
+  __device__ __forceinline__ BlockOperands(BlockLane<BT>& l, const Instr& i, bool) : L(l), I(i), k(0) {
+    L.j = 0;
+    po = L.x + (int)I.out * L.nt;
+#pragma unroll
+    for (int q = 0; q < 5; q++) { const int f = (int)I.in[q]; pi[q] = L.x + f * L.nt; si[q] = f >= L.PS ? L.nt : 0; }
+  }
+  __device__ __forceinline__ bool more() const { return k < L.n; }
+  __device__ __forceinline__ void next() {
+    k++; L.j = k; po += L.nt;
+#pragma unroll
+    for (int q = 0; q < 5; q++) pi[q] += si[q];
+  }
+  __device__ __forceinline__ float& out(int q) const { return po[q * BT * L.nt]; }
+  __device__ __forceinline__ float& in(int q) const { return *pi[q]; }
+};
+template <class LaneT> struct OperandsOf { typedef Operands<LaneT> type; };
+template <int BT> struct OperandsOf<BlockLane<BT>> { typedef BlockOperands<BT> type; };
+
 #define X(i) L.at((int)(i))
-// applies a case body to every sample of the lane's block (exactly once for Lane / TvSample)
-#define QG_EACH for (int k_ = L.first(); L.more(k_); k_ = L.next(k_))
+// applies a case body to every sample of the lane's block (exactly once for Lane / TvSample); inside it `q_` is the
+// per-sample cursor, outside it the function-scope `q_` of exec() resolves operands by index
+#define QG_EACH for (typename OperandsOf<LaneT>::type q_(L, I, true); q_.more(); q_.next())
 #define XU(i) __float_as_uint(X(i))
 #define SETU(i, u) X(i) = __uint_as_float(u)
 // operand access by role inside exec(): k-th output, k-th input operand, parameter/state scalar
-#define XO(k) L.out((int)I.out, (int)(k))
-#define XI(k) L.in((int)I.in[k])
+#define XO(k) q_.out((int)(k))
+#define XI(k) q_.in(k)
 #define XS(i) L.sc((int)(i))
 #define XSU(i) __float_as_uint(XS(i))
 #define SETSU(i, u) XS(i) = __uint_as_float(u)
@@ -167,6 +204,7 @@ __device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim,
 // Execute one instruction for this lane.  `pc` is only touched by control-flow ops.
 template <class LaneT>
 __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
+  Operands<LaneT> q_(L, I, false);   // operand access outside a per-sample loop
   switch (I.op) {
     case OP_NOP: break;
     case OP_MOV: QG_EACH { XO(0) = XI(0); } break;
@@ -740,15 +778,21 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
       const Instr I = code[i];
       if (I.op == OP_DELAY) {
         // whole-block delay line access: all reads first (independent loads), then the writes
-        const uint32_t len = ring_len(L, I.aux), idx = __float_as_uint(L.x[I.s * nt]);
+        const Ring rg = L.ring_tab[I.aux];
+        const uint32_t len = rg.length, idx = __float_as_uint(L.x[I.s * nt]);
         if (len >= (uint32_t)BT) {
+          float* const rb = L.rings + (size_t)rg.offset * (size_t)L.Vp + (size_t)v;   // this voice's column of the ring
+          const uint32_t Vp = (uint32_t)L.Vp;
           float o[BT];
 #pragma unroll
-          for (int j = 0; j < BT; j++) if (j < n) o[j] = ring_at(L, I.aux, ring_wrap(idx + (uint32_t)j, len));
+          for (int j = 0; j < BT; j++) if (j < n) o[j] = rb[(size_t)ring_wrap(idx + (uint32_t)j, len) * Vp];
+          const float* src = L.x + (int)I.in[0] * nt;
+          const int sstep = (int)I.in[0] >= PS ? nt : 0;
 #pragma unroll
-          for (int j = 0; j < BT; j++) if (j < n) ring_at(L, I.aux, ring_wrap(idx + (uint32_t)j, len)) = L.tr(I.in[0], j);
+          for (int j = 0; j < BT; j++) if (j < n) rb[(size_t)ring_wrap(idx + (uint32_t)j, len) * Vp] = src[j * sstep];
+          float* dst = L.x + (int)I.out * nt;
 #pragma unroll
-          for (int j = 0; j < BT; j++) if (j < n) L.tr(I.out, j) = o[j];
+          for (int j = 0; j < BT; j++) if (j < n) dst[j * nt] = o[j];
           L.x[I.s * nt] = __uint_as_float(ring_wrap(idx + (uint32_t)n, len));
           continue;
         }
@@ -765,7 +809,9 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
       for (int c = 0; c < a.n_out; c++) {
         const int ox = blk_index<BT>(a.out_x[c], PS);
         float* trow = tiles + (((size_t)c * nwarps + warp) * 32 + lane) * TW;
-        for (int j = 0; j < n; j++) trow[j] = L.tr(ox, j);
+        const float* src = L.x + ox * nt;
+        const int sstep = ox >= PS ? nt : 0;
+        for (int j = 0; j < n; j++) trow[j] = src[j * sstep];
       }
       __syncwarp();
       for (int c = 0; c < a.n_out; c++) {
