@@ -347,6 +347,7 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   b->block_ok = !(t.h.flags & TAPE_DIVERGENT);
   for (const Instr& i : t.code) {
     if ((i.op == OP_FB_READ || i.op == OP_FB_WRITE) && t.rings[i.aux].length < (uint32_t)interp_block_len()) b->block_ok = false;
+    if (i.op == OP_FB1_READ || i.op == OP_FB1_WRITE) b->block_ok = false;
     // reset()/trig_reset()/reset_v() rewind OTHER ops' state in the middle of a block: sample-by-sample only
     if (i.op >= OP_KR_BEGIN && i.op <= OP_SEQ_END) b->block_ok = false;
   }

@@ -329,6 +329,14 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
     case OP_POL: QG_EACH { float a = XI(0), b = XI(1); XO(0) = hypotf(a, b); XO(1) = atan2f(b, a); } break;
     case OP_CAR: QG_EACH { float a = XI(0), b = XI(1); XO(0) = a * cosf(b); XO(1) = a * sinf(b); } break;
     case OP_DIVN: QG_EACH { XO(0) = XI(0) / (float)I.n; } break;
+    case OP_JOIN: QG_EACH {   // left-to-right sum of n <= 5 operands, divided by aux when aux != 0 (join(n): mean of n)
+      float s = XI(0);
+      if (I.n > 1) s += XI(1);
+      if (I.n > 2) s += XI(2);
+      if (I.n > 3) s += XI(3);
+      if (I.n > 4) s += XI(4);
+      XO(0) = I.aux ? s / (float)I.aux : s;
+    } break;
     case OP_PAN: QG_EACH { float x = XI(0); XO(0) = XS(I.p) * x; XO(1) = XS(I.p + 1) * x; } break;
     case OP_PAN_VAR: QG_EACH {
       float x = XI(0), pan = XI(1);
@@ -528,16 +536,31 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       if (XI(1) != 0.0f) XS(I.s) = XI(0);
       XO(0) = XS(I.s);
     } break;
-    case OP_QUANTIZE: QG_EACH {   // nodes.rs:213-228
-      float n = XI(0), range = XS(I.p);
-      float wrapped = n - range * floorf(n / range);
-      float nearest = 0.0f, dist = FLT_MAX;
-      for (uint32_t k = 0; k < I.aux2; k++) {
-        float v = L.tables[I.aux + k];
-        float d = fabsf(wrapped - v);
-        if (d < dist) { nearest = v; dist = d; }
+    case OP_QUANTIZE: {   // nodes.rs:213-228
+      // short step tables (the scenes use 8 entries) are read once per instruction; a NaN pad never wins `d < dist`
+      float tb[8];
+      const bool small = I.aux2 <= 8u;
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) tb[k] = (small && k < I.aux2) ? L.tables[I.aux + k] : __int_as_float(0x7fc00000);
+      QG_EACH {
+        float n = XI(0), range = XS(I.p);
+        float wrapped = n - range * floorf(n / range);
+        float nearest = 0.0f, dist = FLT_MAX;
+        if (small) {
+#pragma unroll
+          for (uint32_t k = 0; k < 8; k++) {
+            float d = fabsf(wrapped - tb[k]);
+            if (d < dist) { nearest = tb[k]; dist = d; }
+          }
+        } else {
+          for (uint32_t k = 0; k < I.aux2; k++) {
+            float v = L.tables[I.aux + k];
+            float d = fabsf(wrapped - v);
+            if (d < dist) { nearest = v; dist = d; }
+          }
+        }
+        XO(0) = n + nearest - wrapped;
       }
-      XO(0) = n + nearest - wrapped;
     } break;
     case OP_ARR_GET: QG_EACH {   // nodes.rs:143-149
       uint64_t k = d_as_usize(XI(0));
@@ -628,6 +651,8 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       if (I.n) SETSU(I.s, ring_wrap(i + L.count(), len));
       break;
     }
+    case OP_FB1_READ: QG_EACH { XO(0) = XI(0) + XS(I.s); } break;
+    case OP_FB1_WRITE: QG_EACH { XS(I.s) = XI(0); } break;
     // ---------------------------------------------------------------- spectral nodes (per-lane path)
     case OP_RFFT: QG_EACH {   // nodes.rs:625-642
       uint32_t N = 1u << I.n, i = XSU(I.s), nx = i + 1 == N ? 0 : i + 1;
@@ -778,7 +803,8 @@ __global__ void __launch_bounds__(128) k_interp_blk(InterpArgs a) {
       const Instr I = code[i];
       if (I.op == OP_DELAY) {
         // whole-block delay line access: all reads first (independent loads), then the writes
-        const Ring rg = L.ring_tab[I.aux];
+        const uint2 rg2 = __ldg(reinterpret_cast<const uint2*>(L.ring_tab + I.aux));   // {offset, length} in one load
+        Ring rg; rg.offset = rg2.x; rg.length = rg2.y;
         const uint32_t len = rg.length, idx = __float_as_uint(L.x[I.s * nt]);
         if (len >= (uint32_t)BT) {
           float* const rb = L.rings + (size_t)rg.offset * (size_t)L.Vp + (size_t)v;   // this voice's column of the ring

@@ -205,15 +205,22 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
     case NK_REVERSE: for (int i = 0; i < n.n_out; i++) out.push_back(in[n.n_in - 1 - i]); break;
     case NK_ZERO_SRC: for (int i = 0; i < n.n_out; i++) out.push_back(zero()); break;
     case NK_JOIN: {
-      uint16_t acc = in[0];
-      for (int i = 1; i < n.n_in; i++) {
-        Instr& a = emit(OP_ADD);
-        a.in[0] = acc; a.in[1] = in[i]; a.out = temp();
-        acc = a.out;
-      }
-      Instr& d = emit(OP_DIVN);
-      d.in[0] = acc; d.n = (uint16_t)n.n_in; d.out = temp();
-      out.push_back(d.out);
+      // left-to-right sum, five operands per instruction; the last instruction divides by n
+      uint16_t acc = NONE;
+      int i = 0;
+      do {
+        uint16_t ops[5];
+        int k = 0;
+        if (acc != NONE) ops[k++] = acc;
+        while (k < 5 && i < n.n_in) ops[k++] = in[i++];
+        uint16_t o = temp();
+        Instr& a = emit(OP_JOIN);
+        for (int q = 0; q < k; q++) a.in[q] = ops[q];
+        a.n = (uint16_t)k; a.out = o;
+        a.aux = i >= n.n_in ? (uint32_t)n.n_in : 0u;
+        acc = o;
+      } while (i < n.n_in);
+      out.push_back(acc);
       break;
     }
     case NK_PAN: {
@@ -566,6 +573,23 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
       double len = std::round((double)n.raw[0] * n.sr);
       uint32_t L = len < 1.0 ? 1u : (len > 4.0e8 ? 400000000u : (uint32_t)len);
       int ch = n.n_in;
+      if (L == 1) {   // one value per channel: state, not a ring (a dependent HBM round trip per sample otherwise)
+        std::vector<uint16_t> held, mixed1;
+        for (int c = 0; c < ch; c++) {
+          held.push_back(state(1));
+          Instr& r = emit(OP_FB1_READ);
+          r.in[0] = in[c]; r.s = held[c]; r.out = temp();
+          mixed1.push_back(r.out);
+        }
+        std::vector<uint16_t> o1 = graph(n.kids[0], mixed1);
+        if (!err.empty()) return {};
+        for (int c = 0; c < ch; c++) {
+          Instr& w = emit(OP_FB1_WRITE);
+          w.in[0] = o1[c]; w.s = held[c];
+        }
+        out = o1;
+        break;
+      }
       uint16_t idx = state(1);
       std::vector<uint32_t> rg;
       std::vector<uint16_t> mixed;

@@ -43,7 +43,7 @@ enum Op : uint16_t {
   OP_WRAP1,      // P[p]=x                 (functions.rs:1156-1160)
   OP_MIRROR,     // P[p]=p0, p1, r         (functions.rs:1163-1181)
   OP_POL, OP_CAR,   // 2 -> 2 (out, out+1)
-  OP_JOIN,       // mean of n contiguous-by-list operands: uses in[0..n) (n <= 5) else chained by lowering
+  OP_JOIN,       // T[out] = X[in0] + ... + X[in(n-1)] left to right (n <= 5), divided by aux when aux != 0 (join(n): mean)
   OP_DIVN,       // T[out] = X[a] / n
   OP_PAN,        // fixed pan: P[p]=l, P[p+1]=r ; 1 -> 2
   OP_PAN_VAR,    // (x, pan) -> 2 ; S[s]=cached pan, S[s+1]=l, S[s+2]=r
@@ -93,6 +93,10 @@ enum Op : uint16_t {
   // ---- feedback (FunDSP FeedbackUnit): ring aux, S[s]=u32 index
   OP_FB_READ,    // T[out] = X[a] + ring[idx]
   OP_FB_WRITE,   // ring[idx] = X[a] ; n = 1 on the last channel -> advance idx
+  // one-sample feedback (the default `feedback()` of process.rs:1500-1507): the delay line is ONE value, kept in the
+  // state region (shared memory during a launch) instead of an HBM ring.  Sample-by-sample kernels only.
+  OP_FB1_READ,   // T[out] = X[a] + S[s]
+  OP_FB1_WRITE,  // S[s] = X[a]
   // ---- spectral nodes, per-lane path (nodes.rs:601-700): rings aux.. hold the node's buffers, aux2 = twiddle
   //      table offset, n = log2(N), S[s] = u32 count.  RFFT rings: in[N], re[N], im[N]; IFFT: in_re in_im out_re out_im
   OP_RFFT, OP_IFFT,

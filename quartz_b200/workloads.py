@@ -186,7 +186,7 @@ def c5_mixed(V=1048576, T=96000, G=32, v0=0):
     def c_expr(gg):
         return _sr(_pipe("white()", {"op": "feedback()", "net": _L(f"mul({gg!r})"), "delay": None}))
     out.append(Workload("c5c_feedback", c_expr(0.9), np.stack([np.zeros(n, np.float32), g], axis=1), salts_for(vc), T, G,
-                        lambda v: c_expr(float(g[v])), 8.0 + 4.0 / G, "hbm", "1-sample feedback line in HBM: 8 B state traffic per voice-sample"))
+                        lambda v: c_expr(float(g[v])), 4.0 / G, "fp32", "1-sample feedback: the held sample lives in the state region (shared memory during a launch)"))
     # D: delay(1024 samples) + lowpole
     vd = np.arange(v0 + 3 * n, v0 + 4 * n)
     hz = _loguniform(uniform01(vd, 15), 100.0, 8000.0).astype(np.float32)
