@@ -56,25 +56,49 @@ struct qg_bank {
 };
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static thread_local int g_code = QG_OK;   // status of the last failure on this thread (entry points that return a handle)
+static int fail(int code, const std::string& msg) { g_err = msg; g_code = code; return code; }
 #define CU(call)                                                                                         \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
     if (e_ != cudaSuccess) {                                                                             \
       g_err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;                       \
+      g_code = QG_ERR_CUDA;                                                                              \
       return QG_ERR_CUDA;                                                                                \
     }                                                                                                    \
   } while (0)
+// nothing may unwind across the C boundary (the reference builds with panic = 'abort', Cargo.toml:57): entry points that
+// run host code which can allocate wrap their body in guard_int
+template <typename F>
+static int guard_int(F f) {
+  try {
+    return f();
+  } catch (const std::exception& e) {
+    return fail(QG_ERR_ARG, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return fail(QG_ERR_ARG, "internal error");
+  }
+}
+// a device allocation that lives for one call
+template <typename T>
+struct DevTmp {
+  T* p = nullptr;
+  ~DevTmp() { if (p) cudaFree(p); }
+};
 
 template <typename F>
 static qg_net* guard_net(F f) {
   try {
     return new qg_net{f()};
   } catch (const std::exception& e) {
-    g_err = std::string("internal error: ") + e.what();
+    fail(QG_ERR_ARG, std::string("internal error: ") + e.what());
+    return nullptr;
+  } catch (...) {
+    fail(QG_ERR_ARG, "internal error");
     return nullptr;
   }
 }
+static std::vector<float> fv(const float* arr, int n) { return (arr && n > 0) ? std::vector<float>(arr, arr + n) : std::vector<float>(); }
 static std::vector<const Graph*> gv(const qg_net* const* nets, int n) {
   std::vector<const Graph*> v;
   for (int i = 0; i < n; i++) v.push_back(nets && nets[i] ? &nets[i]->g : nullptr);
@@ -151,19 +175,18 @@ int qg_net_outputs(const qg_net* n) { return n ? n->g.outputs() : 0; }
 int qg_net_size(const qg_net* n) { return n ? n->g.size() : 0; }
 int qg_net_set_sample_rate(qg_net* n, double sr) {
   if (!n) return fail(QG_ERR_ARG, "null net");
-  n->g.set_sample_rate(sr);
-  return QG_OK;
+  return guard_int([&] { n->g.set_sample_rate(sr); return (int)QG_OK; });
 }
 const char* qg_net_unsupported(const qg_net* n) { return (n && !n->g.unsupported.empty()) ? n->g.unsupported.c_str() : nullptr; }
 qg_net* qg_connect(const char* op, const qg_net* const* nets, int n, double number, int node_limit) {
   return guard_net([&] { return connect(op ? op : "", gv(nets, n), number, node_limit); });
 }
 qg_net* qg_array_op(const char* kind, const char* op_str, const float* arr, int n) {
-  return guard_net([&] { return array_op(kind ? kind : "", op_str ? op_str : "", std::vector<float>(arr, arr + n)); });
+  return guard_net([&] { return array_op(kind ? kind : "", op_str ? op_str : "", fv(arr, n)); });
 }
-qg_net* qg_get(const float* arr, int n) { return guard_net([&] { return make_get(std::vector<float>(arr, arr + n)); }); }
-qg_net* qg_quantize(const float* arr, int n) { return guard_net([&] { return make_quantize(std::vector<float>(arr, arr + n)); }); }
-qg_net* qg_wave(const float* arr, int n) { return guard_net([&] { return make_wave(std::vector<float>(arr, arr + n)); }); }
+qg_net* qg_get(const float* arr, int n) { return guard_net([&] { return make_get(fv(arr, n)); }); }
+qg_net* qg_quantize(const float* arr, int n) { return guard_net([&] { return make_quantize(fv(arr, n)); }); }
+qg_net* qg_wave(const float* arr, int n) { return guard_net([&] { return make_wave(fv(arr, n)); }); }
 qg_net* qg_feedback(const qg_net* net, int has_delay, double delay) {
   return guard_net([&] { return net ? make_feedback(net->g, has_delay != 0, delay) : Graph(0, 0); });
 }
@@ -182,29 +205,41 @@ qg_net* qg_var(float value) { return guard_net([&] { return make_var(value); });
 
 int qg_net_raw_count(const qg_net* n) {
   if (!n) return 0;
-  std::vector<float> r;
-  collect_raw(n->g, &r);
-  return (int)r.size();
+  int count = 0;
+  guard_int([&] { std::vector<float> r; collect_raw(n->g, &r); count = (int)r.size(); return (int)QG_OK; });
+  return count;
 }
 int qg_net_raw_params(const qg_net* n, float* out, int cap) {
   if (!n) return 0;
-  std::vector<float> r;
-  collect_raw(n->g, &r);
-  for (int i = 0; i < (int)r.size() && i < cap; i++) out[i] = r[i];
-  return (int)r.size();
+  int count = 0;
+  guard_int([&] {
+    std::vector<float> r;
+    collect_raw(n->g, &r);
+    for (int i = 0; out && i < (int)r.size() && i < cap; i++) out[i] = r[i];
+    count = (int)r.size();
+    return (int)QG_OK;
+  });
+  return count;
 }
-uint64_t qg_net_signature(const qg_net* n) { return n ? structure_signature(n->g) : 0; }
+uint64_t qg_net_signature(const qg_net* n) {
+  if (!n) return 0;
+  uint64_t sig = 0;
+  guard_int([&] { sig = structure_signature(n->g); return (int)QG_OK; });
+  return sig;
+}
 int qg_net_tape_info(const qg_net* n, int* n_instr, int* n_params, int* n_state, int* n_temps, int* divergent) {
   if (!n) return fail(QG_ERR_ARG, "null net");
-  Tape t;
-  std::string err;
-  if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
-  if (n_instr) *n_instr = (int)t.h.n_instr;
-  if (n_params) *n_params = (int)t.h.n_params;
-  if (n_state) *n_state = (int)t.h.n_state;
-  if (n_temps) *n_temps = (int)t.h.n_temps;
-  if (divergent) *divergent = (t.h.flags & TAPE_DIVERGENT) ? 1 : 0;
-  return QG_OK;
+  return guard_int([&] {
+    Tape t;
+    std::string err;
+    if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
+    if (n_instr) *n_instr = (int)t.h.n_instr;
+    if (n_params) *n_params = (int)t.h.n_params;
+    if (n_state) *n_state = (int)t.h.n_state;
+    if (n_temps) *n_temps = (int)t.h.n_temps;
+    if (divergent) *divergent = (t.h.flags & TAPE_DIVERGENT) ? 1 : 0;
+    return (int)QG_OK;
+  });
 }
 
 // ------------------------------------------------------------------------------------ device
@@ -269,26 +304,25 @@ static int bank_init_state(qg_bank* b, const uint64_t* salts) {
   qg_ctx* c = b->ctx;
   const Tape& t = b->tape;
   int NS = (int)t.h.n_state;
-  uint32_t* d_def = nullptr;
-  HashInit* d_hi = nullptr;
-  uint64_t* d_salts = nullptr;
-  int rc = upload(&d_def, t.state_init, c->stream);
+  DevTmp<uint32_t> d_def;
+  DevTmp<HashInit> d_hi;
+  DevTmp<uint64_t> d_salts;
+  int rc = upload(&d_def.p, t.state_init, c->stream);
   if (rc) return rc;
-  rc = upload(&d_hi, t.hash_init, c->stream);
+  rc = upload(&d_hi.p, t.hash_init, c->stream);
   if (rc) return rc;
   if (salts) {
     std::vector<uint64_t> s((size_t)b->Vp, 0);
     for (long v = 0; v < b->V; v++) s[v] = salts[v];
-    rc = upload(&d_salts, s, c->stream);
+    rc = upload(&d_salts.p, s, c->stream);
     if (rc) return rc;
     CU(cudaStreamSynchronize(c->stream));   // `s` is about to go out of scope
   }
   if (NS > 0) {
-    CU(launch_init_state(b->d_state_init, d_def, NS, b->Vp, d_hi, (int)t.hash_init.size(), d_salts, c->stream));
+    CU(launch_init_state(b->d_state_init, d_def.p, NS, b->Vp, d_hi.p, (int)t.hash_init.size(), d_salts.p, c->stream));
     c->launches++;
   }
   CU(cudaStreamSynchronize(c->stream));
-  cudaFree(d_def); cudaFree(d_hi); cudaFree(d_salts);
   return QG_OK;
 }
 
@@ -329,12 +363,11 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
     CU(cudaStreamSynchronize(c->stream));
     b->biquad_scan_ok = biquads_well_conditioned(t, [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V);
   } else if (P > 0) {
-    float* d_tmpl = nullptr;
-    if ((rc = upload(&d_tmpl, t.params, c->stream))) return rc;
-    CU(launch_broadcast_params(b->d_params, d_tmpl, P, b->Vp, c->stream));
+    DevTmp<float> d_tmpl;
+    if ((rc = upload(&d_tmpl.p, t.params, c->stream))) return rc;
+    CU(launch_broadcast_params(b->d_params, d_tmpl.p, P, b->Vp, c->stream));
     c->launches++;
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d_tmpl);
   }
   if ((rc = bank_init_state(b, salts))) return rc;
   if (!(raw_matrix && R > 0 && P > 0)) b->biquad_scan_ok = biquads_well_conditioned(t, [&](int p, long) { return t.params[p]; }, 1);
@@ -355,16 +388,20 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
 }
 
 qg_bank* qg_bank_create(qg_ctx* ctx, const qg_net* tmpl, long n_voices, const float* raw, const uint64_t* salts) {
-  if (!ctx || !tmpl || n_voices <= 0) { g_err = "qg_bank_create: bad arguments"; return nullptr; }
+  if (!ctx || !tmpl || n_voices <= 0) { fail(QG_ERR_ARG, "qg_bank_create: bad arguments"); return nullptr; }
   qg_bank* b = new (std::nothrow) qg_bank();
   if (!b) return nullptr;
   b->ctx = ctx; b->V = n_voices; b->path = QG_PATH_AUTO;
   std::string err;
   try {
-    if (!lower(tmpl->g, &b->tape, &err)) { g_err = err; delete b; return nullptr; }
+    if (!lower(tmpl->g, &b->tape, &err)) { fail(QG_ERR_UNSUPPORTED, err); delete b; return nullptr; }
     if (bank_build(b, raw, salts) != QG_OK) { bank_release(b); return nullptr; }
   } catch (const std::exception& e) {
-    g_err = std::string("internal error: ") + e.what();
+    fail(QG_ERR_ARG, std::string("internal error: ") + e.what());
+    bank_release(b);
+    return nullptr;
+  } catch (...) {
+    fail(QG_ERR_ARG, "internal error");
     bank_release(b);
     return nullptr;
   }
@@ -372,7 +409,7 @@ qg_bank* qg_bank_create(qg_ctx* ctx, const qg_net* tmpl, long n_voices, const fl
 }
 
 qg_bank* qg_bank_from_nets(qg_ctx* ctx, const qg_net* const* nets, long n, const uint64_t* salts) {
-  if (!ctx || !nets || n <= 0 || !nets[0]) { g_err = "qg_bank_from_nets: bad arguments"; return nullptr; }
+  if (!ctx || !nets || n <= 0 || !nets[0]) { fail(QG_ERR_ARG, "qg_bank_from_nets: bad arguments"); return nullptr; }
   try {
     uint64_t sig = structure_signature(nets[0]->g);
     std::vector<float> r0;
@@ -381,17 +418,20 @@ qg_bank* qg_bank_from_nets(qg_ctx* ctx, const qg_net* const* nets, long n, const
     std::vector<float> raw((size_t)n * std::max<size_t>(R, 1));
     for (long v = 0; v < n; v++) {
       if (!nets[v] || structure_signature(nets[v]->g) != sig) {
-        g_err = "qg_bank_from_nets: net " + std::to_string(v) + " does not have the structure of net 0";
+        fail(QG_ERR_MISMATCH, "qg_bank_from_nets: net " + std::to_string(v) + " does not have the structure of net 0");
         return nullptr;
       }
       std::vector<float> r;
       collect_raw(nets[v]->g, &r);
-      if (r.size() != R) { g_err = "qg_bank_from_nets: parameter count mismatch"; return nullptr; }
+      if (r.size() != R) { fail(QG_ERR_MISMATCH, "qg_bank_from_nets: parameter count mismatch"); return nullptr; }
       for (size_t k = 0; k < R; k++) raw[(size_t)v * R + k] = r[k];
     }
     return qg_bank_create(ctx, nets[0], n, R ? raw.data() : nullptr, salts);
   } catch (const std::exception& e) {
-    g_err = std::string("internal error: ") + e.what();
+    fail(QG_ERR_ARG, std::string("internal error: ") + e.what());
+    return nullptr;
+  } catch (...) {
+    fail(QG_ERR_ARG, "internal error");
     return nullptr;
   }
 }
@@ -447,8 +487,18 @@ long qg_bank_out_rows(const qg_bank* b, int group) {
 
 // var() semantics (process.rs:1382-1385): the control plane rewrites one op-string parameter while the graph runs.
 // The new value applies to every voice from the next render call on; state is untouched.
+static int bank_set_raw(qg_bank* b, int raw_index, float value);
 int qg_bank_set_raw(qg_bank* b, int raw_index, float value) {
   if (!b) return fail(QG_ERR_ARG, "null bank");
+  return guard_int([&] { return bank_set_raw(b, raw_index, value); });
+}
+// a parameter update can move a direct-form biquad next to z = 1: from then on the bank keeps the reference's operation
+// order for its biquads (no scans), exactly like a bank built with those coefficients
+static void bank_biquads_now_ill_conditioned(qg_bank* b) {
+  b->biquad_scan_ok = false;
+  if (b->fused.id == FUSED_NOISE_SVF && b->fused.p[1] == 2) b->fused.id = FUSED_NONE;
+}
+static int bank_set_raw(qg_bank* b, int raw_index, float value) {
   Tape& t = b->tape;
   const int R = (int)t.h.n_raw, P = (int)t.h.n_params;
   if (raw_index < 0 || raw_index >= R) return fail(QG_ERR_ARG, "raw parameter index out of range");
@@ -461,19 +511,20 @@ int qg_bank_set_raw(qg_bank* b, int raw_index, float value) {
     std::vector<float> pv(t.params);
     t.derive(t.raw.data(), pv.data());
     t.params = pv;
-    float* d_tmpl = nullptr;
-    int rc = upload(&d_tmpl, t.params, c->stream);
+    DevTmp<float> d_tmpl;
+    int rc = upload(&d_tmpl.p, t.params, c->stream);
     if (rc) return rc;
-    CU(launch_broadcast_params(b->d_params, d_tmpl, P, b->Vp, c->stream));
+    CU(launch_broadcast_params(b->d_params, d_tmpl.p, P, b->Vp, c->stream));
     c->launches++;
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d_tmpl);
+    if (!biquads_well_conditioned(t, [&](int p, long) { return t.params[p]; }, 1)) bank_biquads_now_ill_conditioned(b);
   } else {
     std::vector<float> host;
     for (long v = 0; v < b->V; v++) b->raw[(size_t)v * R + raw_index] = value;
     derive_table(t, b->raw.data(), R, b->V, b->Vp, &host);
     CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (!biquads_well_conditioned(t, [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V)) bank_biquads_now_ill_conditioned(b);
   }
   return QG_OK;
 }
@@ -561,6 +612,7 @@ static int ensure(float** p, size_t* have, size_t need) {
 int qg_bank_render(qg_bank* b, long T, int layout, int group, float* h_out) {
   if (!b || !h_out) return fail(QG_ERR_ARG, "qg_bank_render: bad arguments");
   if (b->tape.h.n_inputs != 0) return fail(QG_ERR_ARITY, "render needs a net with 0 inputs (process.rs:1345)");
+  if (T <= 0) return QG_OK;
   if (group < 1) group = 1;
   const size_t rows = (size_t)(b->V / group) * b->tape.h.n_outputs;
   const size_t bytes = rows * (size_t)T * sizeof(float);
@@ -577,29 +629,35 @@ int qg_bank_render(qg_bank* b, long T, int layout, int group, float* h_out) {
       const size_t cb = rows * (size_t)Tc * sizeof(float);
       int rc = ensure(&b->d_scratch, &b->scratch_bytes, 2 * cb);
       if (rc) return rc;
-      cudaStream_t copy_stream;
-      CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-      cudaEvent_t rendered[2], copied[2];
-      for (int i = 0; i < 2; i++) { CU(cudaEventCreateWithFlags(&rendered[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)); }
+      cudaStream_t copy_stream = nullptr;
+      cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+      cudaError_t ce = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+      for (int i = 0; i < 2 && ce == cudaSuccess; i++) {
+        ce = cudaEventCreateWithFlags(&rendered[i], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+      }
       int k = 0;
       rc = QG_OK;
-      for (long t0 = 0; t0 < T && rc == QG_OK; t0 += Tc, k ^= 1) {
+      // no early return inside the loop: the copy stream and the events are released below on every path
+      for (long t0 = 0; t0 < T && rc == QG_OK && ce == cudaSuccess; t0 += Tc, k ^= 1) {
         long n = T - t0 < Tc ? T - t0 : Tc;
         float* d = b->d_scratch + (size_t)k * rows * Tc;
-        if (t0 >= 2 * Tc) CU(cudaStreamWaitEvent(c->stream, copied[k], 0));      // staging buffer k is free again
+        if (t0 >= 2 * Tc) ce = cudaStreamWaitEvent(c->stream, copied[k], 0);      // staging buffer k is free again
+        if (ce != cudaSuccess) break;
         rc = render_impl(b, n, layout, group, nullptr, d);                        // rows of n samples, pitch n
         if (rc) break;
-        CU(cudaEventRecord(rendered[k], c->stream));
-        CU(cudaStreamWaitEvent(copy_stream, rendered[k], 0));
-        CU(cudaMemcpy2DAsync(h_out + t0, (size_t)T * sizeof(float), d, (size_t)n * sizeof(float), (size_t)n * sizeof(float), rows,
-                             cudaMemcpyDeviceToHost, copy_stream));
-        CU(cudaEventRecord(copied[k], copy_stream));
+        ce = cudaEventRecord(rendered[k], c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(copy_stream, rendered[k], 0);
+        if (ce == cudaSuccess)
+          ce = cudaMemcpy2DAsync(h_out + t0, (size_t)T * sizeof(float), d, (size_t)n * sizeof(float), (size_t)n * sizeof(float), rows,
+                                 cudaMemcpyDeviceToHost, copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(copied[k], copy_stream);
       }
-      cudaError_t e1 = cudaStreamSynchronize(copy_stream), e2 = cudaStreamSynchronize(c->stream);
-      for (int i = 0; i < 2; i++) { cudaEventDestroy(rendered[i]); cudaEventDestroy(copied[i]); }
-      cudaStreamDestroy(copy_stream);
+      cudaError_t e1 = copy_stream ? cudaStreamSynchronize(copy_stream) : cudaSuccess, e2 = cudaStreamSynchronize(c->stream);
+      for (int i = 0; i < 2; i++) { if (rendered[i]) cudaEventDestroy(rendered[i]); if (copied[i]) cudaEventDestroy(copied[i]); }
+      if (copy_stream) cudaStreamDestroy(copy_stream);
       if (rc) return rc;
-      CU(e1); CU(e2);
+      CU(ce); CU(e1); CU(e2);
       return QG_OK;
     }
   }
@@ -615,6 +673,7 @@ int qg_bank_render(qg_bank* b, long T, int layout, int group, float* h_out) {
 int qg_bank_process(qg_bank* b, long T, int layout, const float* h_in, float* h_out) {
   if (!b) return fail(QG_ERR_ARG, "null bank");
   const Tape& t = b->tape;
+  if (T <= 0) return QG_OK;
   size_t ib = (size_t)b->V * t.h.n_inputs * (size_t)T * sizeof(float);
   size_t ob = (size_t)b->V * t.h.n_outputs * (size_t)T * sizeof(float);
   if ((ib && !h_in) || (ob && !h_out)) return fail(QG_ERR_ARG, "qg_bank_process: null buffer");
@@ -694,7 +753,7 @@ int qg_net_render(qg_ctx* ctx, const qg_net* net, long n, float* h_out) {
   if (!ctx || !net || !h_out) return fail(QG_ERR_ARG, "qg_net_render: bad arguments");
   if (net->g.inputs() != 0) return fail(QG_ERR_ARITY, "render needs a net with 0 inputs (process.rs:1345)");
   qg_bank* b = qg_bank_create(ctx, net, 1, nullptr, nullptr);
-  if (!b) return QG_ERR_UNSUPPORTED;
+  if (!b) return g_code != QG_OK ? g_code : QG_ERR_UNSUPPORTED;
   int rc = qg_bank_render(b, n, QG_LAYOUT_FRAME_MAJOR, 1, h_out);
   qg_bank_free(b);
   return rc;
@@ -703,7 +762,7 @@ int qg_net_tick(qg_ctx* ctx, const qg_net* net, const float* in, int n_in, float
   if (!ctx || !net) return fail(QG_ERR_ARG, "qg_net_tick: bad arguments");
   if (net->g.inputs() != n_in || net->g.outputs() != n_out) return fail(QG_ERR_ARITY, "tick: arity mismatch (process.rs:1322)");
   qg_bank* b = qg_bank_create(ctx, net, 1, nullptr, nullptr);
-  if (!b) return QG_ERR_UNSUPPORTED;
+  if (!b) return g_code != QG_OK ? g_code : QG_ERR_UNSUPPORTED;
   int rc = qg_bank_process(b, 1, QG_LAYOUT_FRAME_MAJOR, in, out);
   qg_bank_free(b);
   return rc;

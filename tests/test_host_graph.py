@@ -178,3 +178,24 @@ def test_rust_binding_declares_only_exported_entry_points():
     for n in names:
         assert re.search(r"\b%s\(" % n, header), n
         assert hasattr(lib, n), n
+
+
+def test_c_abi_tolerates_null_and_negative_arguments():
+    """the reference never fails on this path (failures degrade to silence, functions.rs:1225): the C ABI answers bad
+    pointers / sizes with a status or an empty result, never with a crash or an exception across the boundary"""
+    lib = _ffi.lib()   # status codes: include/quartz_gpu.h (QG_OK 0, QG_ERR_ARG 1, QG_ERR_UNSUPPORTED 2)
+    for fn in (lib.qg_quantize, lib.qg_get, lib.qg_wave):
+        for arr, n in ((None, 5), (None, 0), (None, -3)):
+            h = fn(arr, n)
+            assert h, fn
+            assert lib.qg_net_inputs(h) >= 0 and lib.qg_net_outputs(h) >= 0
+            lib.qg_net_free(h)
+    n = Net.str_to_net("lowpass(800,2)")
+    assert lib.qg_net_raw_params(n.h, None, 8) == 2          # count only
+    assert lib.qg_net_raw_count(None) == 0 and lib.qg_net_signature(None) == 0
+    assert lib.qg_net_tape_info(None, None, None, None, None, None) == 1
+    assert lib.qg_net_tape_info(n.h, None, None, None, None, None) == 0      # every out-pointer is optional
+    assert lib.qg_net_tape_info(Net.str_to_net("moog(1000,0.5)").h, None, None, None, None, None) == 2
+    assert b"moog" in lib.qg_last_error()
+    assert lib.qg_bank_reset(None) == 1 and lib.qg_bank_set_raw(None, 0, 1.0) == 1
+    assert not lib.qg_bank_create(None, n.h, 4, None, None)
