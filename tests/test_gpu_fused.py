@@ -245,3 +245,30 @@ def test_fused_kernels_hand_over_to_the_interpreters_when_they_do_not_serve_a_ca
     assert b2.kernel() == "k_polysynth"
     ref = render_bank([build(voice(float(x)), ONet).set_salt(int(s)) for x, s in zip(f, salts)], T, group=32, threads=4)
     assert_parity(b2.render(T, group=32)[:, 0, :], ref, "float", "poly-synth bank at 8 kHz")
+
+
+def test_parameter_update_that_ruins_the_conditioning_leaves_the_scan_kernel():
+    """var() semantics (process.rs:1382-1385): a parameter rewritten while the bank runs.  Sweeping a resonator next to
+    z = 1 makes its direct form ill-conditioned; from that update on the bank must evaluate it in the reference's operation
+    order (same rule as at construction), with its filter state carried over"""
+    V, T = 4096, 4096
+    sr = lambda g: {"op": "sr()", "n": 48000.0, "net": g}
+    tmpl = build(sr({"op": ">>", "n": 0, "inputs": [{"op": "white()"}, {"op": "resonator(1000,50)"}]}), Net)
+    salts = np.arange(1, V + 1, dtype=np.uint64)
+    raw = np.tile(np.array([[1000.0, 50.0]], dtype=np.float32), (V, 1))
+    bank = Bank(tmpl, V, raw=raw, salts=salts)
+    twin = Bank(tmpl, V, raw=raw, salts=salts).set_path(qb.PATH_INTERP)      # operation-order path from the start
+    assert bank.kernel() == "k_noise_svf_scan"
+    a0, b0 = bank.render(T)[:, 0, :], twin.render(T)[:, 0, :]
+    assert_parity(a0[:64], b0[:64], "float", "before the update")
+    for bk in (bank, twin):
+        bk.set_raw(0, 30.0)
+        bk.set_raw(1, 10.0)
+    assert bank.kernel() != "k_noise_svf_scan", bank.kernel()
+    a1, b1 = bank.render(T)[:, 0, :], twin.render(T)[:, 0, :]
+    assert np.isfinite(a1).all() and np.abs(a1).max() > 1e-3
+    # The two banks reach the update with filter states that differ by f32 rounding (scan vs operation order), and the new
+    # filter amplifies exactly such differences (its round-off gain is what took it off the scan path), so the segments
+    # agree to ~6e-4 of full scale, not to the 1e-4 parity bound; a lost or re-initialised state would differ by O(scale).
+    scale = float(np.abs(b1[:64]).max())
+    assert float(np.abs(a1[:64] - b1[:64]).max()) <= 1e-2 * scale
