@@ -37,10 +37,12 @@ typedef struct qg_bank qg_bank;  /* V voices that share one op tape, resident on
 
 enum { QG_OK = 0, QG_ERR_ARG = 1, QG_ERR_UNSUPPORTED = 2, QG_ERR_CUDA = 3, QG_ERR_ARITY = 4, QG_ERR_MISMATCH = 5 };
 enum { QG_LAYOUT_VOICE_MAJOR = 0, QG_LAYOUT_FRAME_MAJOR = 1 };
-enum { QG_PATH_AUTO = 0, QG_PATH_INTERP = 1, QG_PATH_TV = 2, QG_PATH_INTERP_SAMPLE = 3 };   /* kernel selection: AUTO picks a
-   fused kernel when the tape matches, the time-vector interpreter (one CTA per voice) for spectral / small feed-forward
-   banks, else the lane interpreter (block mode for feed-forward tapes); INTERP forces the lane interpreter,
-   INTERP_SAMPLE its sample-by-sample kernel */
+enum { QG_PATH_AUTO = 0, QG_PATH_INTERP = 1, QG_PATH_TV = 2, QG_PATH_INTERP_SAMPLE = 3, QG_PATH_SPECIALISED = 4 };   /* kernel
+   selection: AUTO picks a fused kernel when the tape matches, the time-vector interpreter (one CTA per voice) for spectral /
+   small feed-forward banks, else the lane interpreter (block mode for feed-forward tapes); INTERP forces the lane
+   interpreter, INTERP_SAMPLE its sample-by-sample kernel; SPECIALISED compiles a lane kernel for this bank's tape with
+   NVRTC (seconds, once per bank; uniform tapes only; fails with QG_ERR_UNSUPPORTED when NVRTC or the tape does not allow
+   it) — opt-in, never chosen by AUTO */
 
 const char* qg_last_error(void);
 const char* qg_version(void);
@@ -72,6 +74,9 @@ int qg_net_raw_count(const qg_net* net);                       /* number of op-s
 int qg_net_raw_params(const qg_net* net, float* out, int cap);
 uint64_t qg_net_signature(const qg_net* net);                  /* equal <=> same tape modulo parameter values */
 int qg_net_tape_info(const qg_net* net, int* n_instr, int* n_params, int* n_state, int* n_temps, int* divergent);
+/* the CUDA translation unit the tape specialiser compiles for this graph (NVRTC; see quartz_b200/csrc/spec_kernel.cuh):
+   returns its length (copies at most cap - 1 characters into buf, which may be NULL) or a negated QG_ERR_* status */
+long qg_net_spec_source(const qg_net* net, char* buf, long cap);
 
 /* ---- device ---- */
 qg_ctx* qg_ctx_create(int device, void* cuda_stream /* cudaStream_t, or NULL for a private stream */);

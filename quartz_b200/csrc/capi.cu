@@ -14,6 +14,7 @@
 #include "graph.h"
 #include "kernels.h"
 #include "lower.h"
+#include "spec.h"
 
 using namespace qg;
 
@@ -53,6 +54,7 @@ struct qg_bank {
   bool biquad_scan_ok = true;   // every direct-form biquad of every voice may be re-associated (scans) within the tolerance
   bool block_ok = false;   // the tape may run on the block-mode lane interpreter (k_interp_blk)
   int ring_mode = 0;   // 0: rings laid out [pos][voice] (lane kernels); 1: [voice][pos] (time-vector kernel)
+  SpecKernel spec;     // K1s: lane kernel compiled for this tape (only after qg_bank_set_path(QG_PATH_SPECIALISED))
 };
 
 static thread_local std::string g_err;
@@ -242,6 +244,28 @@ int qg_net_tape_info(const qg_net* n, int* n_instr, int* n_params, int* n_state,
   });
 }
 
+// The translation unit the tape specialiser hands to NVRTC for this graph (spec.cpp); returns the length needed
+// (excluding the terminator) or a negative status.  Copies at most cap - 1 characters.
+long qg_net_spec_source(const qg_net* n, char* buf, long cap) {
+  if (!n) return -(long)fail(QG_ERR_ARG, "null net");
+  long need = 0;
+  int rc = guard_int([&] {
+    Tape t;
+    std::string err;
+    if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
+    if (!spec_supported(t, &err)) return fail(QG_ERR_UNSUPPORTED, "tape cannot be specialised: " + err);
+    std::string src = spec_source(t);
+    need = (long)src.size();
+    if (buf && cap > 0) {
+      long k = std::min<long>(need, cap - 1);
+      memcpy(buf, src.data(), (size_t)k);
+      buf[k] = 0;
+    }
+    return (int)QG_OK;
+  });
+  return rc == QG_OK ? need : -(long)rc;
+}
+
 // ------------------------------------------------------------------------------------ device
 qg_ctx* qg_ctx_create(int device, void* stream) {
   int n = 0;
@@ -297,6 +321,7 @@ static void bank_release(qg_bank* b) {
   cudaFree(b->d_code); cudaFree(b->d_out_x); cudaFree(b->d_params); cudaFree(b->d_state); cudaFree(b->d_state_init); cudaFree(b->d_state_keep);
   cudaFree(b->d_rings); cudaFree(b->d_ring_tab); cudaFree(b->d_resets); cudaFree(b->d_tables); cudaFree(b->d_scratch);
   cudaFree(b->d_in); cudaFree(b->d_fused_scratch);
+  spec_release(&b->spec);
   delete b;
 }
 
@@ -458,6 +483,7 @@ int qg_bank_reset(qg_bank* b) {
 }
 // which kernel family serves voice-major, group-1 renders: 0 lane interpreter, 1 fused, 2 time-vector interpreter
 static int bank_family(const qg_bank* b) {
+  if (b->path == QG_PATH_SPECIALISED) return b->spec.fn ? 3 : 0;
   if (b->path == QG_PATH_INTERP || b->path == QG_PATH_INTERP_SAMPLE) return 0;
   if (b->path == QG_PATH_TV) return b->tv.ok ? 2 : 0;
   if (b->fused.id != FUSED_NONE) return 1;
@@ -467,6 +493,14 @@ static int bank_family(const qg_bank* b) {
 int qg_bank_set_path(qg_bank* b, int path) {
   if (!b) return fail(QG_ERR_ARG, "null bank");
   int before = bank_family(b) == 2;
+  if (path == QG_PATH_SPECIALISED && !b->spec.fn) {
+    CU(cudaSetDevice(b->ctx->device));
+    std::string err;
+    bool ok = false;
+    int rc = guard_int([&] { ok = spec_compile(b->tape, &b->spec, &err); return (int)QG_OK; });
+    if (rc != QG_OK) return rc;
+    if (!ok) return fail(QG_ERR_UNSUPPORTED, err);
+  }
   b->path = path;
   if ((bank_family(b) == 2) != before) return qg_bank_reset(b);   // the two interpreters lay delay lines out differently
   return QG_OK;
@@ -476,6 +510,7 @@ const char* qg_bank_kernel(const qg_bank* b) {
   int f = bank_family(b);
   if (f == 1) return fused_name(b->fused.id);
   if (f == 2) return "k_interp_tv";
+  if (f == 3) return "k_spec";
   if (b->tape.h.flags & TAPE_DIVERGENT) return "k_interp<divergent>";
   return (b->block_ok && b->path != QG_PATH_INTERP_SAMPLE) ? "k_interp_blk" : "k_interp<uniform>";
 }
@@ -587,6 +622,12 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   a.in_frame_major = layout == QG_LAYOUT_FRAME_MAJOR; a.out_frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
   a.group = group;
   int l = 0;
+  if (family == 3) {
+    cudaError_t se = spec_launch(b->spec, a, c->stream, &l);
+    c->launches += l;
+    CU(se);
+    return QG_OK;
+  }
   cudaError_t e = launch_interp(a, (t.h.flags & TAPE_DIVERGENT) != 0, b->block_ok && b->path != QG_PATH_INTERP_SAMPLE, c->stream, &l);
   c->launches += l;
   if (e == cudaErrorInvalidConfiguration) return fail(QG_ERR_UNSUPPORTED, "tape needs more shared memory per voice than one SM offers");

@@ -3,7 +3,9 @@
 // FunDSP 0.18.2 algorithms restated from the published designs (Simper SVF, RBJ/Butterworth biquads, one-pole
 // filters); the crate source is not vendored in /root/reference — see DESIGN.md "parity tiers".
 #pragma once
+#if !defined(__CUDACC_RTC__)
 #include <math.h>
+#endif
 
 #if defined(__CUDACC__)
 #define QG_HD __host__ __device__ __forceinline__

@@ -3,8 +3,12 @@
 // default IEEE div/sqrt and no FTZ so that trigger/threshold paths (`!= 0.`, `>=`, quantize, ramp wrap) decide
 // exactly like the CPU; transcendental functions come from libdevice and agree to ~2 ulp (DESIGN.md tolerance).
 #pragma once
+#if defined(__CUDACC_RTC__)
+#include "rtc_compat.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "coefs.h"
 

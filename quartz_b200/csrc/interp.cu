@@ -12,9 +12,13 @@
 // one 128-byte line; per-lane working values X live in shared memory as X[index][thread] (bank = thread, so
 // every access is conflict-free); outputs are staged through per-warp shared tiles and written as full sectors
 // (voice-major) or, for group mixes, summed left-to-right over the voices of a group (K6).
+#if defined(__CUDACC_RTC__)
+#include "rtc_compat.h"
+#else
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
+#endif
 
 #include "dev_math.cuh"
 #include "kernels.h"
@@ -679,6 +683,8 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
   }
 }
 
+// spec.cpp compiles this file up to here (QG_SPEC_ONLY) together with a kernel specialised for one tape
+#if !defined(QG_SPEC_ONLY)
 // ------------------------------------------------------------------------------------------------ kernels
 template <bool DIVERGENT>
 __global__ void __launch_bounds__(128) k_interp(InterpArgs a) {
@@ -1575,5 +1581,7 @@ cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float
   k_mix_rows<<<(unsigned)((T + 255) / 256), 256, 0, stream>>>(rows, R, T, scale, out);
   return cudaGetLastError();
 }
+
+#endif  // !QG_SPEC_ONLY
 
 }  // namespace qg

@@ -1,7 +1,11 @@
 // Kernel argument blocks and launchers (device code lives in interp.cu / fused.cu / fft.cu).
 #pragma once
+#if defined(__CUDACC_RTC__)
+#include "rtc_compat.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 #include "tape.h"
 
@@ -56,6 +60,7 @@ struct TvArgs {
   // the consuming instructions, whereas values derived in the kernel were being re-materialised at every use
   int PS, ps_off, tmp_off, oldv_off, fr_off, fi_off, lti_off, scan_off, segi_off, segt_off;
 };
+#if !defined(__CUDACC_RTC__)   // launchers: host side only
 size_t tv_smem_bytes(const TvArgs& a);
 cudaError_t launch_interp_tv(const TvArgs& a, cudaStream_t stream, int* launches);
 
@@ -71,5 +76,6 @@ cudaError_t launch_reset_state(float* state, const float* state_init, const uint
 cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream);
 cudaError_t launch_stereo_frames(const float* src, int n_ch, long n, float* frames, cudaStream_t stream);
 cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream);
+#endif
 
 }  // namespace qg

@@ -1,0 +1,37 @@
+// Tape specialisation (K1s): a lane kernel compiled for ONE tape with NVRTC, see spec_kernel.cuh.
+#pragma once
+#include <string>
+
+#include "lower.h"
+
+namespace qg {
+
+// Uniform tapes without per-lane FFT nodes can be specialised; `why` names the first obstacle otherwise.
+bool spec_supported(const Tape& t, std::string* why);
+// The translation unit NVRTC compiles for this tape (includes interp.cu and spec_kernel.cuh by name: the include path is
+// the csrc/ directory next to the library).
+std::string spec_source(const Tape& t);
+
+}  // namespace qg
+
+#if !defined(QG_SPEC_HOST_ONLY)
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace qg {
+
+struct SpecKernel {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t fn = nullptr;
+  double compile_seconds = 0.0;
+};
+// Compiles spec_source(t) for sm_100a with the NVRTC found at run time (dlopen: the library has no link-time dependency on
+// it) and loads the cubin.  Returns false with `err` set when NVRTC is missing, the sources next to the library are not
+// found, or compilation fails — the caller keeps the interpreter.
+bool spec_compile(const Tape& t, SpecKernel* out, std::string* err);
+cudaError_t spec_launch(const SpecKernel& k, const InterpArgs& a, cudaStream_t stream, int* launches);
+void spec_release(SpecKernel* k);
+
+}  // namespace qg
+#endif

@@ -9,7 +9,11 @@
 //   X[P+NS, P+NS+T)    temporaries — edge values of the current sample (net inputs first)
 // Long delay lines live in HBM rings laid out [pos][voice] so a warp touches one 128-byte line per access.
 #pragma once
+#if defined(__CUDACC_RTC__)
+#include "rtc_compat.h"
+#else
 #include <stdint.h>
+#endif
 
 namespace qg {
 

@@ -12,7 +12,7 @@ from . import _ffi
 from ._ffi import QuartzGpuError, check, lib
 
 LAYOUT_VOICE_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
-PATH_AUTO, PATH_INTERP, PATH_TV, PATH_INTERP_SAMPLE = 0, 1, 2, 3
+PATH_AUTO, PATH_INTERP, PATH_TV, PATH_INTERP_SAMPLE, PATH_SPECIALISED = 0, 1, 2, 3, 4
 NODE_LIMIT_DEFAULT = 500   # src/main.rs:72
 
 _CTX = {}
@@ -201,6 +201,15 @@ class Net:
 
     def signature(self):
         return lib().qg_net_signature(self.h)
+
+    def spec_source(self):
+        """the CUDA translation unit the tape specialiser would compile for this graph (uniform tapes only)"""
+        n = lib().qg_net_spec_source(self.h, None, 0)
+        if n < 0:
+            check(int(-n))
+        buf = C.create_string_buffer(int(n) + 1)
+        lib().qg_net_spec_source(self.h, buf, int(n) + 1)
+        return buf.value.decode()
 
     def tape_info(self):
         v = [C.c_int(0) for _ in range(5)]
