@@ -1,6 +1,6 @@
 """K1s — the tape-specialised lane kernel (qg_bank_set_path(QG_PATH_SPECIALISED), csrc/spec.cpp + spec_kernel.cuh): the tape
 is compiled into the kernel with NVRTC, exec() is the same code as in every interpreter, so results must be BIT-IDENTICAL to
-the sample-by-sample interpreter.  Opt-in in round 1 (AUTO never selects it); this file sorts last on purpose."""
+the sample-by-sample interpreter.  Opt-in in round 1 (AUTO never selects it); this file sorts after every other test file on purpose."""
 import numpy as np
 import pytest
 
