@@ -52,6 +52,72 @@ __device__ __forceinline__ void spec_run(RegLane& L, int& pc) {
   }
 }
 
+#if defined(QG_SPEC_PREFETCH)
+// EXPERIMENTAL (QG_SPEC_PREFETCH=1 in the environment at qg_bank_set_path time; not yet run on hardware): delay lines
+// without a dependent HBM load per sample.  A delay op's ring position is a counter, and the reads of 8 consecutive samples
+// do not depend on the writes of those samples when the ring is at least 8 long (the rule of K1b's whole-block access):
+// per block of 8 samples the kernel issues all ring reads of every such delay op up front (independent loads), runs the 8
+// samples out of registers, then stores the 8 writes.
+constexpr int SPEC_BT = 8;
+__host__ __device__ constexpr bool spec_is_pref(int i) { return kTape[i].op == OP_DELAY && kRingLen[kTape[i].aux] >= (uint32_t)SPEC_BT; }
+__host__ __device__ constexpr int spec_pref_before(int upto) { int c = 0; for (int k = 0; k < upto; k++) c += spec_is_pref(k) ? 1 : 0; return c; }
+constexpr int SPEC_ND = spec_pref_before(SPEC_N);
+
+struct DelayBlock {
+  float rd[SPEC_ND > 0 ? SPEC_ND : 1][SPEC_BT];
+  float wr[SPEC_ND > 0 ? SPEC_ND : 1][SPEC_BT];
+};
+
+// j is a template parameter so that every rd / wr subscript is a literal (registers)
+template <int i, int j>
+__device__ __forceinline__ void spec_run_blk(RegLane& L, DelayBlock& D, int& pc) {
+  if constexpr (i < SPEC_N) {
+    constexpr Instr I = kTape[i];
+    if constexpr (spec_is_pref(i)) {
+      constexpr int d = spec_pref_before(i);
+      D.wr[d][j] = L.x[I.in[0]];
+      L.x[I.out] = D.rd[d][j];
+    } else {
+      exec(I, L, pc);
+    }
+    spec_run_blk<i + 1, j>(L, D, pc);
+  }
+}
+template <int i>
+__device__ __forceinline__ void spec_ring_reads(RegLane& L, DelayBlock& D, int n) {
+  if constexpr (i < SPEC_N) {
+    if constexpr (spec_is_pref(i)) {
+      constexpr Instr I = kTape[i];
+      constexpr int d = spec_pref_before(i);
+      constexpr uint32_t len = kRingLen[I.aux];
+      const uint32_t idx = __float_as_uint(L.x[I.s]);
+      float* const rb = L.rings + (size_t)L.ring_tab[I.aux].offset * (size_t)L.Vp + (size_t)L.v;
+#pragma unroll
+      for (int j = 0; j < SPEC_BT; j++)
+        if (j < n) D.rd[d][j] = rb[(size_t)ring_wrap(idx + (uint32_t)j, len) * (size_t)L.Vp];
+    }
+    spec_ring_reads<i + 1>(L, D, n);
+  }
+}
+template <int i>
+__device__ __forceinline__ void spec_ring_writes(RegLane& L, DelayBlock& D, int n) {
+  if constexpr (i < SPEC_N) {
+    if constexpr (spec_is_pref(i)) {
+      constexpr Instr I = kTape[i];
+      constexpr int d = spec_pref_before(i);
+      constexpr uint32_t len = kRingLen[I.aux];
+      const uint32_t idx = __float_as_uint(L.x[I.s]);
+      float* const rb = L.rings + (size_t)L.ring_tab[I.aux].offset * (size_t)L.Vp + (size_t)L.v;
+#pragma unroll
+      for (int j = 0; j < SPEC_BT; j++)
+        if (j < n) rb[(size_t)ring_wrap(idx + (uint32_t)j, len) * (size_t)L.Vp] = D.wr[d][j];
+      L.x[I.s] = __uint_as_float(ring_wrap(idx + (uint32_t)n, len));
+    }
+    spec_ring_writes<i + 1>(L, D, n);
+  }
+}
+#endif
+
 extern "C" __global__ void __launch_bounds__(128) k_spec(InterpArgs a) {
   const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   float* tiles = QG_SMEM_F;                                  // [n_out][nwarps][32][33]
@@ -66,6 +132,9 @@ extern "C" __global__ void __launch_bounds__(128) k_spec(InterpArgs a) {
   for (int k = 0; k < SPEC_NT; k++) L.x[SPEC_P + SPEC_NS + k] = 0.0f;
 
   const int warp_v0 = blockIdx.x * nt + warp * 32;
+#if defined(QG_SPEC_PREFETCH)
+  DelayBlock D;
+#endif
   for (long t = 0; t < a.T; t++) {
 #pragma unroll
     for (int c = 0; c < SPEC_NIN; c++) {
@@ -73,7 +142,26 @@ extern "C" __global__ void __launch_bounds__(128) k_spec(InterpArgs a) {
       L.x[SPEC_P + SPEC_NS + c] = v < a.V ? a.in[idx] : 0.0f;
     }
     int pc = 0;
+#if defined(QG_SPEC_PREFETCH)
+    {
+      const int j = (int)(t & (SPEC_BT - 1));
+      const int n = (a.T - (t - j)) < SPEC_BT ? (int)(a.T - (t - j)) : SPEC_BT;      // samples in this block
+      if (j == 0) spec_ring_reads<0>(L, D, n);
+      switch (j) {
+        case 0: spec_run_blk<0, 0>(L, D, pc); break;
+        case 1: spec_run_blk<0, 1>(L, D, pc); break;
+        case 2: spec_run_blk<0, 2>(L, D, pc); break;
+        case 3: spec_run_blk<0, 3>(L, D, pc); break;
+        case 4: spec_run_blk<0, 4>(L, D, pc); break;
+        case 5: spec_run_blk<0, 5>(L, D, pc); break;
+        case 6: spec_run_blk<0, 6>(L, D, pc); break;
+        default: spec_run_blk<0, 7>(L, D, pc); break;
+      }
+      if (j == n - 1) spec_ring_writes<0>(L, D, n);
+    }
+#else
     spec_run<0>(L, pc);
+#endif
     // ---- outputs: same staging and the same left-to-right group mix as k_interp
     if (a.out_frame_major) {
       if (v < a.V) {
