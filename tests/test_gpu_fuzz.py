@@ -184,6 +184,18 @@ def float_graph(rng):
 
 
 PATHS = [("auto", qb.PATH_AUTO), ("lane_block", qb.PATH_INTERP), ("lane_sample", qb.PATH_INTERP_SAMPLE), ("time_vector", qb.PATH_TV)]
+if os.environ.get("QG_FUZZ_SPEC") == "1":   # also through K1s, the tape-specialised kernel (opt-in: ~0.5 s of NVRTC per graph)
+    PATHS.append(("specialised", qb.PATH_SPECIALISED))
+
+
+def _bank_on(net, V, salts, path):
+    bank = Bank(net, V, salts=salts)
+    try:
+        return bank.set_path(path)
+    except qb.QuartzGpuError as e:
+        if path == qb.PATH_SPECIALISED and "cannot be specialised" in str(e):
+            return None      # nested-net control flow / spectral nodes stay on the interpreters
+        raise
 
 
 def _check(expr, tol, n, seed, n_out=1):
@@ -194,7 +206,9 @@ def _check(expr, tol, n, seed, n_out=1):
     ref = np.stack([build(expr, ONet).set_salt(int(s)).render(n).T for s in salts])     # [V, outputs, n]
     seen = set()
     for pname, path in PATHS:
-        bank = Bank(net, V, salts=salts).set_path(path)
+        bank = _bank_on(net, V, salts, path)
+        if bank is None:
+            continue
         if (pname == "time_vector" and bank.kernel() != "k_interp_tv") or bank.kernel() in seen and pname != "auto":
             continue
         seen.add(bank.kernel())
@@ -290,7 +304,9 @@ def test_random_process_chains(seed):
     salts = np.arange(1, V + 1, dtype=np.uint64)
     seen = set()
     for pname, path in PATHS:
-        bank = Bank(net, V, salts=salts).set_path(path)
+        bank = _bank_on(net, V, salts, path)
+        if bank is None:
+            continue
         if (pname == "time_vector" and bank.kernel() != "k_interp_tv") or bank.kernel() in seen and pname != "auto":
             continue
         seen.add(bank.kernel())
