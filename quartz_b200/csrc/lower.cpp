@@ -823,6 +823,53 @@ TvPlan plan_tv(const Tape& t, size_t smem_limit) {
   return pl;
 }
 
+// Structural self-check of a finished tape: every index an interpreter will dereference without looking is in range.  The
+// kernels trust the tape (no bounds checks in the sample loop), so a lowering bug must stop here, by name, on the host.
+static bool validate_tape(const Tape& t, std::string* err) {
+  const uint32_t P = t.h.n_params, NS = t.h.n_state, NT = t.h.n_temps, NX = P + NS + NT, N = t.h.n_instr;
+  auto bad = [&](size_t k, const char* what) {
+    if (err) *err = "internal error: invalid tape (instruction " + std::to_string(k) + ": " + what + ")";
+    return false;
+  };
+  if (t.code.size() != N || t.params.size() != P || t.state_init.size() != NS || t.state_keep.size() != NS ||
+      t.rings.size() != t.h.n_rings || t.out_x.size() != t.h.n_outputs)
+    return bad(0, "header does not match the tables");
+  for (size_t k = 0; k < t.code.size(); k++) {
+    const Instr& i = t.code[k];
+    if (i.op >= OP_COUNT_) return bad(k, "opcode");
+    if (i.out >= std::max(NX, 1u) || i.p >= std::max(NX, 1u) || i.s >= std::max(NX, 1u)) return bad(k, "operand index");
+    for (uint16_t x : i.in) if (x >= std::max(NX, 1u)) return bad(k, "input index");
+    switch (i.op) {
+      case OP_DELAY: case OP_TAP: case OP_SAMP_DELAY: case OP_FB_READ: case OP_FB_WRITE:
+        if (i.aux >= t.rings.size() || t.rings[i.aux].length == 0) return bad(k, "ring id");
+        break;
+      case OP_RFFT: if (i.aux + 2 >= t.rings.size()) return bad(k, "ring id"); break;
+      case OP_IFFT: if (i.aux + 3 >= t.rings.size()) return bad(k, "ring id"); break;
+      case OP_KR_BEGIN: case OP_JNE_IDX: case OP_SEQ_GATE:
+        if (i.aux > N) return bad(k, "jump target");
+        break;
+      case OP_QUANTIZE: case OP_ARR_GET: case OP_WAVE:
+        if ((uint64_t)i.aux + i.aux2 > t.tables.size()) return bad(k, "table range");
+        break;
+      case OP_SVF: case OP_BIQUAD: case OP_ONEPOLE:
+        if (i.aux >= t.h.n_lti) return bad(k, "filter index");
+        break;
+      default: break;
+    }
+  }
+  for (uint16_t o : t.out_x) if (o >= std::max(NX, 1u)) return bad(0, "output index");
+  uint64_t ring_floats = 0;
+  for (const Ring& r : t.rings) {
+    if (r.offset != ring_floats) return bad(0, "ring offsets are not contiguous");
+    ring_floats += r.length;
+  }
+  if (ring_floats != t.h.ring_floats) return bad(0, "ring_floats");
+  for (const ResetRange& r : t.resets)
+    if (r.s_lo > r.s_hi || r.s_hi > P + NS || r.s_lo < P || r.ring_lo > r.ring_hi || r.ring_hi > t.rings.size()) return bad(0, "reset range");
+  for (const HashInit& h : t.hash_init) if (h.state >= NS) return bad(0, "hash-initialised state index");
+  return true;
+}
+
 bool lower(const Graph& g, Tape* out, std::string* err) {
   Tape& t = *out;
   t = Tape();
@@ -919,7 +966,7 @@ bool lower(const Graph& g, Tape* out, std::string* err) {
   for (size_t i = 0; i < P; i++) p[i] = t.params[i];
   t.derive(t.raw.data(), p.data());
   t.params = p;
-  return true;
+  return validate_tape(t, err);
 }
 
 }  // namespace qg
