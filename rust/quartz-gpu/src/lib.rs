@@ -11,6 +11,7 @@ use std::ffi::{c_char, c_double, c_float, c_int, c_long, c_void, CStr, CString};
 #[repr(C)] pub struct qg_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct qg_bank { _p: [u8; 0] }
 
+#[allow(dead_code)]   // the whole C surface is declared; the safe wrappers below use what quartz needs
 extern "C" {
     fn qg_last_error() -> *const c_char;
     fn qg_str_to_net(op: *const c_char) -> *mut qg_net;
@@ -43,7 +44,35 @@ extern "C" {
     fn qg_bank_free(b: *mut qg_bank);
     fn qg_bank_reset(b: *mut qg_bank) -> c_int;
     fn qg_bank_render(b: *mut qg_bank, n: c_long, layout: c_int, group: c_int, out: *mut c_float) -> c_int;
+    // the rest of include/quartz_gpu.h: introspection, device buffers, kernel selection, block path with inputs
+    fn qg_version() -> *const c_char;
+    fn qg_net_new(n_in: c_int, n_out: c_int) -> *mut qg_net;
+    fn qg_net_render(c: *mut qg_ctx, n: *const qg_net, len: c_long, out: *mut c_float) -> c_int;
+    fn qg_net_raw_count(n: *const qg_net) -> c_int;
+    fn qg_net_raw_params(n: *const qg_net, out: *mut c_float, cap: c_int) -> c_int;
+    fn qg_net_signature(n: *const qg_net) -> u64;
+    fn qg_net_tape_info(n: *const qg_net, n_instr: *mut c_int, n_params: *mut c_int, n_state: *mut c_int, n_temps: *mut c_int,
+                        divergent: *mut c_int) -> c_int;
+    fn qg_net_spec_source(n: *const qg_net, buf: *mut c_char, cap: c_long) -> c_long;
+    fn qg_ctx_synchronize(c: *mut qg_ctx) -> c_int;
+    fn qg_ctx_launch_count(c: *const qg_ctx) -> c_long;
+    fn qg_ctx_measure_fp32_tflops(c: *mut qg_ctx) -> c_double;
+    fn qg_device_alloc(c: *mut qg_ctx, bytes: usize) -> *mut c_void;
+    fn qg_device_free(c: *mut qg_ctx, p: *mut c_void);
+    fn qg_host_alloc_pinned(bytes: usize) -> *mut c_void;
+    fn qg_host_free_pinned(p: *mut c_void);
+    fn qg_bank_set_path(b: *mut qg_bank, path: c_int) -> c_int;
+    fn qg_bank_kernel(b: *const qg_bank) -> *const c_char;
+    fn qg_bank_out_rows(b: *const qg_bank, group: c_int) -> c_long;
+    fn qg_bank_render_device(b: *mut qg_bank, n: c_long, layout: c_int, group: c_int, d_out: *mut c_float) -> c_int;
+    fn qg_bank_process(b: *mut qg_bank, n: c_long, layout: c_int, input: *const c_float, out: *mut c_float) -> c_int;
+    fn qg_mix_rows_device(c: *mut qg_ctx, d_rows: *const c_float, rows: c_long, n: c_long, scale: c_float, d_out: *mut c_float) -> c_int;
 }
+
+/// kernel selection of a bank (QG_PATH_* in include/quartz_gpu.h)
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+#[repr(i32)]
+pub enum Path { Auto = 0, Interp = 1, TimeVector = 2, InterpSample = 3, Specialised = 4 }
 
 pub fn last_error() -> String {
     unsafe { CStr::from_ptr(qg_last_error()).to_string_lossy().into_owned() }
@@ -164,6 +193,46 @@ pub fn render_many(ctx: &GpuContext, nets: &[&GpuNet], salts: Option<&[u64]>, le
     let rc = unsafe { qg_bank_render(bank, len as c_long, 0, 1, out.as_mut_ptr()) };
     unsafe { qg_bank_free(bank) };
     if rc != 0 { Err(last_error()) } else { Ok(out) }
+}
+
+/// V voices that share one graph structure, resident on one GPU: the unit of throughput work (BASELINE configs[1..4]).
+/// `raw` is the per-voice op-string parameter table [V][raw_count] (None: every voice = the template), `salts` re-seed the
+/// hash-derived state per voice.
+pub struct GpuBank { bank: *mut qg_bank, voices: usize, outputs: usize }
+unsafe impl Send for GpuBank {}
+impl GpuBank {
+    pub fn new(ctx: &GpuContext, template: &GpuNet, voices: usize, raw: Option<&[f32]>, salts: Option<&[u64]>) -> Result<GpuBank, String> {
+        let raw_count = unsafe { qg_net_raw_count(template.0) } as usize;
+        if let Some(r) = raw { if r.len() != voices * raw_count { return Err("raw table must be [voices][raw_count]".into()); } }
+        if let Some(s) = salts { if s.len() != voices { return Err("one salt per voice".into()); } }
+        let bank = unsafe { qg_bank_create(ctx.0, template.0, voices as c_long, raw.map_or(std::ptr::null(), |r| r.as_ptr()),
+                                           salts.map_or(std::ptr::null(), |s| s.as_ptr())) };
+        if bank.is_null() { return Err(last_error()); }
+        Ok(GpuBank { bank, voices, outputs: template.outputs() })
+    }
+    /// name of the kernel family the next render uses ("k_noise_svf_scan", "k_interp_blk", "k_interp_tv", "k_spec", ...)
+    pub fn kernel(&self) -> String { unsafe { CStr::from_ptr(qg_bank_kernel(self.bank)).to_string_lossy().into_owned() } }
+    /// `Path::Specialised` compiles a kernel for this bank's tape with NVRTC (once; fails if NVRTC or the tape do not allow it)
+    pub fn set_path(&mut self, path: Path) -> Result<(), String> {
+        if unsafe { qg_bank_set_path(self.bank, path as c_int) } != 0 { Err(last_error()) } else { Ok(()) }
+    }
+    pub fn reset(&mut self) { unsafe { qg_bank_reset(self.bank); } }
+    /// voice-major rows [voices / group][outputs][len]; `group` > 1 mixes consecutive voices (sum left to right, scaled by 1/group)
+    pub fn render(&mut self, len: usize, group: usize) -> Result<Vec<f32>, String> {
+        let rows = unsafe { qg_bank_out_rows(self.bank, group as c_int) } as usize;
+        let mut out = vec![0f32; rows * len];
+        let rc = unsafe { qg_bank_render(self.bank, len as c_long, 0, group as c_int, out.as_mut_ptr()) };
+        if rc != 0 { Err(last_error()) } else { Ok(out) }
+    }
+    /// block path with external inputs (AudioUnit::process): `input` voice-major [voices][inputs][len]
+    pub fn process(&mut self, len: usize, input: &[f32]) -> Result<Vec<f32>, String> {
+        let mut out = vec![0f32; self.voices * self.outputs * len];
+        let rc = unsafe { qg_bank_process(self.bank, len as c_long, 0, input.as_ptr(), out.as_mut_ptr()) };
+        if rc != 0 { Err(last_error()) } else { Ok(out) }
+    }
+}
+impl Drop for GpuBank {
+    fn drop(&mut self) { unsafe { qg_bank_free(self.bank) } }
 }
 
 /// AudioUnit served from GPU-rendered blocks (0 inputs, C outputs); what `slot.set(.., Box::new(..))`

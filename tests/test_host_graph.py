@@ -178,6 +178,8 @@ def test_rust_binding_declares_only_exported_entry_points():
     for n in names:
         assert re.search(r"\b%s\(" % n, header), n
         assert hasattr(lib, n), n
+    declared = set(re.findall(r"\b(qg_[a-z_0-9]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S)))
+    assert declared == set(names), declared ^ set(names)      # the binding covers the whole header
 
 
 def test_c_abi_tolerates_null_and_negative_arguments():
