@@ -68,3 +68,17 @@ def test_oracle_in_tree_nodes_known_answers():
     bins = np.array([f.tick([0.0]) for _ in range(8)])
     ref = np.fft.fft(x.astype(np.float64))
     assert np.abs(bins[:, 0] + 1j * bins[:, 1] - ref).max() < 1e-4
+
+
+DIGEST = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_exact_digest.json")))
+
+
+@pytest.mark.parametrize("name", sorted(DIGEST))
+def test_oracle_behaviour_is_frozen_on_the_exact_cases(name):
+    """the oracle IS the parity reference of the GPU path: its output on every bit-exact case is pinned by digest
+    (tests/golden/make_oracle_digest.py), so an edit of oracle/ that changes behaviour shows up here, on the CPU"""
+    from tests import cases
+    from tests.golden.make_oracle_digest import digest
+    expr, n = next((c[1], c[2]) for c in cases.RENDER if c[0] == name)
+    h, shape = digest(expr, n)
+    assert shape == DIGEST[name]["shape"] and h == DIGEST[name]["sha1"], name
