@@ -244,3 +244,42 @@ def test_seq_nodes_rs_74_106():
     seq = {"op": "seq()", "inputs": [pipe("dc(300)", "ramp()"), pipe("dc(1100)", "ramp()"), pipe("dc(50)", "ramp()")]}
     x = np.stack([trig, idx, delay, dur], axis=1)
     assert _bits_equal(build(seq, ONet).process(x)[:, 0], exp)
+
+
+# ---------------------------------------------------------------- spectral nodes: the in-tree buffering around the FFTs
+@pytest.mark.parametrize("n,start", [(64, 0), (64, 16), (256, 192), (8, 5)])
+def test_rfft_node_buffering_nodes_rs_625_642(n, start):
+    """count starts at `start`; the transform of the buffer runs when the counter is 0, BEFORE the current sample is stored;
+    bin i for i <= n/2, conj(bin n-i) above.  The FFT itself is external (microfft): numpy f64 within tolerance."""
+    rng = np.random.default_rng(20 + n + start)
+    T = 5 * n + 7
+    x = rng.uniform(-1, 1, T).astype(np.float32)
+    buf, spec, count, exp = np.zeros(n, np.float32), np.zeros(n // 2 + 1, np.complex128), start, []
+    for t in range(T):
+        i = count
+        count = 0 if count + 1 == n else count + 1
+        if i == 0:
+            spec = np.fft.rfft(buf.astype(np.float64))
+        buf[i] = x[t]
+        z = spec[i] if i <= n // 2 else np.conj(spec[n - i])
+        exp.append([z.real, z.imag])
+    got = build({"op": f"rfft({n},{start})"}, ONet).process(x[:, None])
+    assert np.abs(got - np.array(exp)).max() <= 2e-6 * np.sqrt(n) * max(1.0, np.abs(np.array(exp)).max())
+
+
+@pytest.mark.parametrize("n,start", [(64, 0), (64, 48), (8, 3)])
+def test_ifft_node_buffering_nodes_rs_681_692(n, start):
+    """full complex n-point inverse of the buffered frame, unity-gain round-trip convention (1/n)"""
+    rng = np.random.default_rng(40 + n + start)
+    T = 4 * n + 5
+    x = rng.uniform(-1, 1, (T, 2)).astype(np.float32)
+    buf, out, count, exp = np.zeros(n, np.complex128), np.zeros(n, np.complex128), start, []
+    for t in range(T):
+        i = count
+        count = 0 if count + 1 == n else count + 1
+        if i == 0:
+            out = np.fft.ifft(buf)
+        buf[i] = complex(x[t, 0], x[t, 1])
+        exp.append([out[i].real, out[i].imag])
+    got = build({"op": f"ifft({n},{start})"}, ONet).process(x)
+    assert np.abs(got - np.array(exp)).max() <= 1e-6
