@@ -3,6 +3,7 @@
 Rust semantics define: saturating `as usize` casts (negative, NaN, huge), strict `<` tie-breaking, out-of-range indices,
 zero / negative-zero triggers.  CPU only — this hardens the pinned tier of oracle/ beyond the eight scene vectors."""
 import math
+import zlib
 
 import numpy as np
 import pytest
@@ -283,3 +284,114 @@ def test_ifft_node_buffering_nodes_rs_681_692(n, start):
         exp.append([out[i].real, out[i].imag])
     got = build({"op": f"ifft({n},{start})"}, ONet).process(x)
     assert np.abs(got - np.array(exp)).max() <= 1e-6
+
+
+# ---------------------------------------------------------------- in-tree closures (functions.rs) with Rust scalar semantics
+def as_i32(x):
+    x = float(x)
+    if math.isnan(x):
+        return 0
+    return max(-2**31, min(2**31 - 1, int(x))) if math.isfinite(x) else (2**31 - 1 if x > 0 else -2**31)
+
+
+def wrap_i32(v):
+    v &= 0xFFFFFFFF
+    return v - 2**32 if v >= 2**31 else v
+
+
+def rust_min(a, b):
+    return b if math.isnan(a) else (a if math.isnan(b) else (a if a < b else b))
+
+
+def rust_max(a, b):
+    return b if math.isnan(a) else (a if math.isnan(b) else (a if a > b else b))
+
+
+def fmod32(a, b):
+    with np.errstate(all="ignore"):
+        return f32(np.fmod(f32(a), f32(b)))
+
+
+def rem_euclid(a, b):
+    r = fmod32(a, b)
+    with np.errstate(all="ignore"):
+        return f32(r + f32(abs(f32(b)))) if r < 0.0 else r
+
+
+def mirror(x, p0, p1):
+    p0, p1 = f32(min(p0, p1)), f32(max(p0, p1))
+    r = f32(p1 - p0)
+    n = f32(x) if (np.isfinite(x) and abs(float(x)) >= float(np.finfo(np.float32).tiny)) else f32(0.0)    # is_normal()
+    if p0 <= n <= p1:
+        return n
+    distance = f32(min(f32(n - p1), f32(p0 - n)))
+    folds = f32(np.floor(f32(distance / r)))
+    rest = f32(distance - f32(folds * r))
+    if (n > p1 and fmod32(folds, 2.0) == 0.0) or (n < p0 and fmod32(folds, 2.0) != 0.0):
+        return f32(p0 + rest)
+    return f32(p1 - rest)
+
+
+def pdhalf_bi(a, b):
+    mid = f32(max(-1.0, min(1.0, float(b)))) if not math.isnan(float(b)) else f32(b)
+    if a < mid:
+        slope = f32(f32(1.0) / f32(mid + f32(1.0))) if mid != -1.0 else f32(0.0)
+        return f32(slope * a)
+    slope = f32(f32(1.0) / f32(f32(1.0) - mid)) if mid != 1.0 else f32(0.0)
+    return f32(f32(slope * f32(a - mid)) + f32(0.5))
+
+
+def pdhalf_uni(a, b):
+    mid = f32(1.0) if b >= 1.0 else (f32(0.0) if b <= -1.0 else f32(f32(b + f32(1.0)) / f32(2.0)))
+    if a < mid:
+        slope = f32(f32(0.5) / mid) if mid != 0.0 else f32(0.0)
+        return f32(slope * a)
+    slope = f32(f32(0.5) / f32(f32(1.0) - mid)) if mid != 1.0 else f32(0.0)
+    return f32(f32(slope * f32(a - mid)) + f32(0.5))
+
+
+def shift_amount(x):
+    return as_usize(x) & 31          # Wrapping<i32> << usize masks the amount (functions.rs:966-990)
+
+
+BINARY = {   # op string -> scalar model of the 2-input closure (functions.rs:824-1000, 677-706)
+    ">()": lambda a, b: f32(a > b), "<()": lambda a, b: f32(a < b), "==()": lambda a, b: f32(a == b),
+    "!=()": lambda a, b: f32(a != b), ">=()": lambda a, b: f32(a >= b), "<=()": lambda a, b: f32(a <= b),
+    "min()": lambda a, b: f32(rust_min(float(a), float(b))), "max()": lambda a, b: f32(rust_max(float(a), float(b))),
+    "rem()": rem_euclid,
+    "bitand()": lambda a, b: f32(as_i32(a) & as_i32(b)), "bitor()": lambda a, b: f32(as_i32(a) | as_i32(b)),
+    "bitxor()": lambda a, b: f32(as_i32(a) ^ as_i32(b)),
+    "shl()": lambda a, b: f32(wrap_i32(as_i32(a) << shift_amount(b))), "shr()": lambda a, b: f32(as_i32(a) >> shift_amount(b)),
+    "pdhalf_bi()": pdhalf_bi, "pdhalf_uni()": pdhalf_uni,
+}
+
+
+@pytest.mark.parametrize("op", sorted(BINARY))
+def test_binary_closures_functions_rs(op):
+    rng = np.random.default_rng(zlib.crc32(op.encode()))
+    x = rng.uniform(-40, 40, (1500, 2)).astype(np.float32)
+    if "pdhalf" in op:
+        x = (x / f32(30.0)).astype(np.float32)
+    x[:10] = [[1, 1], [0, 1], [1, 0], [3e9, 2], [-3e9, 2], [5, 33], [5, -1], [np.nan, 1], [2, np.nan], [np.inf, 3]]
+    if op in ("min()", "max()", "==()", "!=()", ">=()", "<=()"):
+        x[1:3] = [[0.5, 1], [1, 0.5]]        # keep +0 / -0 ordering out of min / max
+    with np.errstate(all="ignore"):
+        exp = np.array([BINARY[op](f32(a), f32(b)) for a, b in x], np.float32)
+    got = build({"op": op}, ONet).process(x)[:, 0]
+    same = (got.view(np.uint32) == exp.view(np.uint32)) | (np.isnan(got) & np.isnan(exp))
+    assert same.all(), (op, x[~same][:4], got[~same][:4], exp[~same][:4])
+
+
+def test_wrap_and_mirror_functions_rs_1149_1181():
+    rng = np.random.default_rng(77)
+    x = rng.uniform(-300, 300, 3000).astype(np.float32)
+    x[:8] = [0.0, -12.0, 36.0, 36.5, -12.5, np.inf, np.nan, 1e-40]
+    with np.errstate(all="ignore"):
+        p0, r = f32(-12.0), f32(48.0)
+        w2 = np.array([f32(fmod32(f32(fmod32(f32(v - p0), r) + r), r) + p0) for v in x], np.float32)
+        w1 = np.array([f32(v - f32(f32(7.0) * f32(np.floor(f32(v / f32(7.0)))))) for v in x], np.float32)
+        mi = np.array([mirror(v, -1.0, 2.0) for v in (x / f32(10.0)).astype(np.float32)], np.float32)
+    for op, inp, exp in (("wrap(-12,36)", x, w2), ("wrap(7)", x, w1), ("mirror(-1,2)", (x / f32(10.0)).astype(np.float32), mi)):
+        got = build({"op": op}, ONet).process(inp[:, None])[:, 0]
+        same = (got.view(np.uint32) == exp.view(np.uint32)) | (np.isnan(got) & np.isnan(exp))
+        assert same.all(), (op, inp[~same][:4], got[~same][:4], exp[~same][:4])
