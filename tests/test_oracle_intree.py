@@ -208,7 +208,7 @@ def rround(x):
     x = float(x)
     if math.isnan(x) or math.isinf(x):
         return x
-    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
+    return math.copysign(math.floor(abs(x) + 0.5), x)      # the sign survives: round(-0.3) = -0.0
 
 
 def test_seq_nodes_rs_74_106():
@@ -395,3 +395,27 @@ def test_wrap_and_mirror_functions_rs_1149_1181():
         got = build({"op": op}, ONet).process(inp[:, None])[:, 0]
         same = (got.view(np.uint32) == exp.view(np.uint32)) | (np.isnan(got) & np.isnan(exp))
         assert same.all(), (op, inp[~same][:4], got[~same][:4], exp[~same][:4])
+
+
+UNARY = {   # Rust std f32 methods reached by functions.rs:1066-1075, 1183-1185
+    "abs()": lambda v: f32(abs(v)),
+    "signum()": lambda v: v if math.isnan(float(v)) else f32(math.copysign(1.0, float(v))),          # signum(±0) = ±1
+    "floor()": lambda v: f32(np.floor(v)), "ceil()": lambda v: f32(np.ceil(v)),
+    "fract()": lambda v: f32(v - f32(np.trunc(v))),
+    "round()": lambda v: f32(rround(v)),                                                            # half away from zero
+    "sqrt()": lambda v: f32(np.sqrt(v)), "recip()": lambda v: f32(f32(1.0) / v),
+    "deg()": lambda v: f32(v * f32(57.2957795130823208767981548141051703)),                          # f32::to_degrees constant
+    "rad()": lambda v: f32(v * f32(f32(np.pi) / f32(180.0))),
+}
+
+
+@pytest.mark.parametrize("op", sorted(UNARY))
+def test_unary_std_closures_functions_rs(op):
+    rng = np.random.default_rng(zlib.crc32(op.encode()))
+    x = rng.uniform(-50, 50, 2000).astype(np.float32)
+    x[:12] = [0.0, -0.0, 0.5, -0.5, 1.5, 2.5, -2.5, 1e-40, 3e9, np.inf, -np.inf, np.nan]
+    with np.errstate(all="ignore"):
+        exp = np.array([UNARY[op](f32(v)) for v in x], np.float32)
+    got = build({"op": op}, ONet).process(x[:, None])[:, 0]
+    same = (got.view(np.uint32) == exp.view(np.uint32)) | (np.isnan(got) & np.isnan(exp))
+    assert same.all(), (op, x[~same][:4], got[~same][:4], exp[~same][:4])
