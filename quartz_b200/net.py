@@ -247,6 +247,34 @@ class Net:
         return out.reshape(n, self.outputs())
 
 
+RENDER_LEN_CAP = 10_000_000   # process.rs:1342
+
+
+def render_op(net, number, arr=None, ctx=None):
+    """The `render` circle (process.rs:1339-1353) with its guards: `len = min(number as usize, 10^7)`; a net that is not
+    0-in / 1-out leaves the circle's array untouched (returns `arr`); otherwise the array is cleared and filled with `len`
+    ticks (state advances, as `net.tick` does on the circle's own Net)."""
+    x = float(number)
+    n = 0 if (x != x or x <= 0.0) else int(min(x, float(RENDER_LEN_CAP)))      # saturating `as usize`, NaN -> 0
+    n = min(n, RENDER_LEN_CAP)
+    if net.inputs() != 0 or net.outputs() != 1:
+        return arr
+    if n == 0:
+        return np.zeros(0, dtype=np.float32)
+    return net.render(n, ctx=ctx)[:, 0]
+
+
+def apply_op(net, input_arr, arr=None, ctx=None):
+    """The `apply` circle (process.rs:1318-1326): one frame through the graph when the input array has exactly
+    `net.inputs()` entries (output resized to `net.outputs()`), else the circle's array stays as it was."""
+    a = _f32(input_arr).reshape(-1)
+    if net.inputs() != len(a):
+        return arr
+    if net.outputs() == 0:
+        return np.zeros(0, dtype=np.float32)
+    return net.tick(a, ctx=ctx)
+
+
 def str_to_net(op):
     return Net.str_to_net(op)
 

@@ -201,3 +201,18 @@ def test_c_abi_tolerates_null_and_negative_arguments():
     assert b"moog" in lib.qg_last_error()
     assert lib.qg_bank_reset(None) == 1 and lib.qg_bank_set_raw(None, 0, 1.0) == 1
     assert not lib.qg_bank_create(None, n.h, 4, None, None)
+
+
+def test_render_and_apply_circles_keep_the_reference_guards():
+    """process.rs:1339-1353 / 1318-1326: guard paths never touch the device, so they are checked here"""
+    keep = np.array([1.0, 2.0], dtype=np.float32)
+    two_out, one_in = Net.str_to_net("dc(1,2)"), Net.str_to_net("lowpass(800,2)")
+    assert qb.render_op(two_out, 100, arr=keep) is keep            # not 0-in / 1-out: the array is left alone
+    assert qb.render_op(one_in, 100, arr=keep) is keep
+    osc = Net.str_to_net("sine(440)")
+    for number in (0, -5, float("nan"), 0.9):                      # `as usize` saturates: len 0 -> cleared array
+        out = qb.render_op(osc, number, arr=keep)
+        assert out is not keep and out.shape == (0,)
+    assert qb.net.RENDER_LEN_CAP == 10_000_000
+    assert qb.apply_op(one_in, [0.1, 0.2], arr=keep) is keep       # input length != net.inputs()
+    assert qb.apply_op(Net.str_to_net("sink()"), [0.5], arr=keep).shape == (0,)
