@@ -225,7 +225,7 @@ struct Feedback : Unit {   // FunDSP FeedbackUnit [U]: out = x(in + out delayed 
   Feedback(const Feedback& o) : x(new Net(*o.x)), delay(o.delay), ch(o.ch), samples(o.samples), idx(o.idx), buf(o.buf), tb(o.tb) {}
   void set_len(double sr) {
     double s = std::round(delay * sr);
-    samples = s < 1.0 ? 1 : (size_t)s;
+    samples = !(s >= 1.0) ? 1 : (s > 4.0e8 ? (size_t)400000000 : (size_t)s);   // NaN / negative / zero: one sample
     buf.assign(ch, std::vector<float>(samples, 0.0f));
     idx = 0;
   }

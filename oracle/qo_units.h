@@ -454,7 +454,7 @@ struct Delay : Unit {   // fixed delay of max(1, round(t·sr)) samples [U]
   explicit Delay(float t_) : t(t_) { set_sr(DEFAULT_SR); }
   static size_t length(float t, double sr) {
     double n = std::round((double)t * sr);
-    return n < 1.0 ? 1 : (size_t)n;
+    return !(n >= 1.0) ? 1 : (n > 4.0e8 ? (size_t)400000000 : (size_t)n);   // NaN / negative / zero: one sample
   }
   int ins() const override { return 1; }
   int outs() const override { return 1; }

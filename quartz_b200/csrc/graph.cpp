@@ -282,23 +282,28 @@ Graph connect(const std::string& op, const std::vector<const Graph*>& nets, doub
   for (const Graph* np : nets) if (np && !np->unsupported.empty() && unsup.empty()) unsup = np->unsupported;
   int reps = as_i32(std::fmax((float)number, 1.0f));   // `.max(1.) as i32` (process.rs:1744, 1825)
   for (int r = 0; r < reps; r++) {
+    // a pass that combines nothing (arity guards, node limit) leaves `graph` as it was, so every later pass would do the
+    // same: stop instead of spinning through up to 2^31 repetitions (the result is the reference's, without its wait)
+    bool changed = false;
     for (const Graph* np : nets) {
       if (!np) continue;
-      if (empty) { graph = *np; empty = false; continue; }
+      if (empty) { graph = *np; empty = false; changed = true; continue; }
       int gi = graph.inputs(), go = graph.outputs(), ni = np->inputs(), no = np->outputs();
       if (op == "+" || op == "*") {   // process.rs:1751-1759
         if (go == no) {
           if (graph.size() >= node_limit) continue;
           graph = Graph::combine(op[0], std::move(graph), *np);
+          changed = true;
         }
       } else {   // process.rs:1833-1844
         if (graph.size() >= node_limit) continue;
-        if (op == ">>") { if (go == ni) graph = Graph::combine('>', std::move(graph), *np); }
-        else if (op == "|") graph = Graph::combine('|', std::move(graph), *np);
-        else if (op == "&") { if (gi == ni && go == no) graph = Graph::combine('&', std::move(graph), *np); }
-        else if (op == "^") { if (gi == ni) graph = Graph::combine('^', std::move(graph), *np); }
+        if (op == ">>") { if (go == ni) { graph = Graph::combine('>', std::move(graph), *np); changed = true; } }
+        else if (op == "|") { graph = Graph::combine('|', std::move(graph), *np); changed = true; }
+        else if (op == "&") { if (gi == ni && go == no) { graph = Graph::combine('&', std::move(graph), *np); changed = true; } }
+        else if (op == "^") { if (gi == ni) { graph = Graph::combine('^', std::move(graph), *np); changed = true; } }
       }
     }
+    if (!changed) break;
   }
   if (graph.unsupported.empty()) graph.unsupported = unsup;
   return graph;

@@ -468,7 +468,7 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
     case NK_DELAY: {
       raw(n, true);
       double len = std::round((double)n.raw[0] * n.sr);
-      uint32_t L = len < 1.0 ? 1u : (len > 4.0e8 ? 400000000u : (uint32_t)len);
+      uint32_t L = !(len >= 1.0) ? 1u : (len > 4.0e8 ? 400000000u : (uint32_t)len);   // NaN / negative / zero: one sample
       Instr& i = emit(OP_DELAY);
       i.in[0] = in[0]; i.aux = ring(L); i.s = state(1); i.out = temp();
       out.push_back(i.out);
@@ -571,7 +571,7 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
     case NK_FEEDBACK: {   // FeedbackUnit: out = x(in + out delayed by max(1, round(delay*sr)) samples)
       raw(n, true);
       double len = std::round((double)n.raw[0] * n.sr);
-      uint32_t L = len < 1.0 ? 1u : (len > 4.0e8 ? 400000000u : (uint32_t)len);
+      uint32_t L = !(len >= 1.0) ? 1u : (len > 4.0e8 ? 400000000u : (uint32_t)len);   // NaN / negative / zero: one sample
       int ch = n.n_in;
       if (L == 1) {   // one value per channel: state, not a ring (a dependent HBM round trip per sample otherwise)
         std::vector<uint16_t> held, mixed1;

@@ -216,3 +216,22 @@ def test_render_and_apply_circles_keep_the_reference_guards():
     assert qb.net.RENDER_LEN_CAP == 10_000_000
     assert qb.apply_op(one_in, [0.1, 0.2], arr=keep) is keep       # input length != net.inputs()
     assert qb.apply_op(Net.str_to_net("sink()"), [0.5], arr=keep).shape == (0,)
+
+
+def test_pathological_numbers_neither_hang_nor_corrupt_the_tape():
+    """found by fuzzing the C ABI on the CPU: a NaN delay time used to lower to a zero-length ring (now: one sample, like the
+    oracle), and a repeat count of 1e30 used to spin through 2^31 no-op passes"""
+    import time
+    for op in ("delay(NaN)", "delay(-1)", "delay(0)"):
+        a, b = Net.str_to_net(op), ONet.str_to_net(op)
+        assert (a.inputs(), a.outputs()) == (b.inputs(), b.outputs()) == (1, 1)
+        assert a.tape_info()["n_instr"] == 1
+        assert b.process(np.arange(1, 6, dtype=np.float32)[:, None])[:, 0].tolist() == [0.0, 1.0, 2.0, 3.0, 4.0]   # one-sample delay
+    assert Net.feedback(Net.str_to_net("mul(0.5)"), delay=float("nan")).tape_info()["n_instr"] > 0
+    t0 = time.perf_counter()
+    s, lp = Net.str_to_net("sine(440)"), Net.str_to_net("lowpass()")
+    g = Net.connect(">>", [s, lp], number=1e30)              # arity guard skips `lowpass()`: every pass is a no-op
+    assert (g.inputs(), g.outputs(), g.size()) == (0, 1, 1)
+    g = Net.connect("|", [s], number=float("inf"), node_limit=10)
+    assert g.size() == 10
+    assert time.perf_counter() - t0 < 2.0
