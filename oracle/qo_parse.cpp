@@ -171,7 +171,7 @@ static UnitP map3(std::function<float(float, float, float)> f) {
   return U(new Map(3, 1, [f](const float* i, float* o) { o[0] = f(i[0], i[1], i[2]); }));
 }
 static UnitP pipe(UnitP a, UnitP b) { return U(new Comp(0, std::move(a), std::move(b))); }
-static UnitP stack(UnitP a, UnitP b) { return U(new Comp(1, std::move(a), std::move(b))); }
+[[maybe_unused]] static UnitP stack(UnitP a, UnitP b) { return U(new Comp(1, std::move(a), std::move(b))); }
 static UnitP branch(UnitP a, UnitP b) { return U(new Comp(2, std::move(a), std::move(b))); }
 static UnitP constant(std::vector<float> v) { return U(new Constant(std::move(v))); }
 static NetP W(UnitP u) { return Net::wrap(std::move(u)); }
