@@ -147,7 +147,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--path", default="auto", choices=["auto", "interp"])
+    ap.add_argument("--path", default="auto", choices=["auto", "interp", "specialised"],
+                    help="specialised: K1s (NVRTC, opt-in) for every bank whose tape allows it and has no delay line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -190,6 +191,17 @@ def main():
     bank = banks[0]
     if args.path == "interp":
         [b.set_path(qb.PATH_INTERP) for b in banks]
+
+    def specialise(b, w):
+        """K1s where it pays today: uniform tapes without a delay line (a ring load per sample is still dependent there)"""
+        if "delay" in w.name or b.kernel() not in ("k_interp_blk", "k_interp<uniform>"):
+            return                                 # fused / time-vector banks keep their kernel
+        try:
+            b.set_path(qb.PATH_SPECIALISED)
+        except qb.QuartzGpuError:
+            pass                                   # tape not specialisable / NVRTC missing: the bank keeps its AUTO kernel
+    if args.path == "specialised":
+        [specialise(b, w) for b, w in zip(banks, wls)]
     rows_l = [(w.V // w.group) * t.outputs() for t, w in zip(tmpls, wls)]
     rows = sum(rows_l)
     T = wl.T
@@ -271,6 +283,8 @@ def main():
                 b2 = qb.Bank(t, w.V, raw=w.raw, salts=w.salts, ctx=ctx)
                 if args.path == "interp":
                     b2.set_path(qb.PATH_INTERP)
+                if args.path == "specialised":
+                    specialise(b2, w)              # the NVRTC compile is inside the end-to-end time
                 for t0 in range(0, w.T, T_host):
                     n = min(T_host, w.T - t0)
                     b2.render(n, group=w.group, out=host_view(k, n))
