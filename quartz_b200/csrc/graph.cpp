@@ -281,6 +281,9 @@ Graph connect(const std::string& op, const std::vector<const Graph*>& nets, doub
   std::string unsup;
   for (const Graph* np : nets) if (np && !np->unsupported.empty() && unsup.empty()) unsup = np->unsupported;
   int reps = as_i32(std::fmax((float)number, 1.0f));   // `.max(1.) as i32` (process.rs:1744, 1825)
+  // a tape addresses at most 2^16 words, so a graph beyond 2^16 vertices can never be lowered: a caller-supplied limit above
+  // that only decides how much memory the composition burns before lowering refuses it
+  node_limit = std::min(node_limit, 1 << 16);
   for (int r = 0; r < reps; r++) {
     // a pass that combines nothing (arity guards, node limit) leaves `graph` as it was, so every later pass would do the
     // same: stop instead of spinning through up to 2^31 repetitions (the result is the reference's, without its wait)
