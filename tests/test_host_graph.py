@@ -234,4 +234,4 @@ def test_pathological_numbers_neither_hang_nor_corrupt_the_tape():
     assert (g.inputs(), g.outputs(), g.size()) == (0, 1, 1)
     g = Net.connect("|", [s], number=float("inf"), node_limit=10)
     assert g.size() == 10
-    assert time.perf_counter() - t0 < 2.0
+    assert time.perf_counter() - t0 < 20.0      # was minutes; generous for a loaded CI host
