@@ -733,10 +733,12 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     if (look_tiles == 0) return cudaErrorNotSupported;
 #define QG_PS(LPV, OSCV) k_polysynth<LPV, OSCV><<<a.Vp / PS_THREADS, PS_THREADS, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, a.group, look_tiles, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], pl.p[7], a.tables ? a.tables + pl.p[6] : nullptr, a.out)
     if (pl.p[5] && !a.tables) return cudaErrorNotSupported;
-    if (pl.p[4]) { if (pl.p[5]) QG_PS(true, 1); else QG_PS(true, 0); }
-    else { if (pl.p[5]) QG_PS(false, 1); else QG_PS(false, 0); }
-#undef QG_PS
     if (launches) *launches += 1;
+    // sine voices: two voices per lane in packed f32x2 arithmetic (fused_poly.cu); the wavetable oscillators (a 4-point
+    // interpolated table read per sample) keep one voice per lane
+    if (!pl.p[5]) return launch_polysynth_x2(pl, a, look_tiles * 32, stream);
+    if (pl.p[4]) QG_PS(true, 1); else QG_PS(false, 1);
+#undef QG_PS
     return cudaGetLastError();
   }
   return cudaErrorNotSupported;

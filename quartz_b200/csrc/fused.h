@@ -31,5 +31,7 @@ struct FusedArgs {
 FusedPlan plan_fused(const Tape& t);
 const char* fused_name(int id);
 cudaError_t launch_fused(const FusedPlan& plan, const FusedArgs& a, cudaStream_t stream, int* launches);
+// FUSED_SINE_SVF_ENV with the sine oscillator: packed two-voices-per-lane kernel (fused_poly.cu); win = envelope window (32 / 64)
+cudaError_t launch_polysynth_x2(const FusedPlan& plan, const FusedArgs& a, int win, cudaStream_t stream);
 
 }  // namespace qg

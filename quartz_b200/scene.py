@@ -1,4 +1,4 @@
-"""Scene (RON) importer: turns a saved quartz patch into graph expressions that `tests.graphs.build` / `Net` evaluate.
+"""Scene (RON) importer: turns a saved quartz patch into graph expressions that `quartz_b200.graphs.build` / `Net` evaluate.
 
 A scene is the Bevy RON dump written by `save_scene` (/root/reference/src/main.rs:324-370): per circle the components
 `Op`, `Number`, `Arr`, `Order`, `Holes`; per hole a `WhiteHole{bh_parent, link_types, open}` or `BlackHole`

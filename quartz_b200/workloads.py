@@ -169,7 +169,9 @@ def c5_mixed(V=1048576, T=96000, G=32, v0=0):
         return _sr(_pipe(pitch, "ramp()", "mul(TAU)", "sin()"))
     out.append(Workload("c5a_quantised_osc", a_expr(2.0, 110.0), np.stack([rate, np.full(n, 24, np.float32), np.full(n, 12, np.float32),
                         base, np.full(n, 6.2831855, np.float32)], axis=1), salts_for(va), T, G,
-                        lambda v: a_expr(float(rate[v]), float(base[v])), 4.0 / G, "fp32", "ramp osc + quantize + semitone_ratio"))
+                        lambda v: a_expr(float(rate[v]), float(base[v])), 4.0 / G, "fp32",
+                        "ramp osc + quantize + semitone_ratio; ~56 flop per voice-sample (2 ramps 6, quantize: floor/div/8-entry scan 22, "
+                        "exp2 12, sin 12, 4 muls)", flops_per_unit=56.0))
     # B: noise into a shift register clocked by ramp() >> <(0.5) >> rise(), 8 taps averaged
     vb = np.arange(v0 + n, v0 + 2 * n)
     clk = _loguniform(uniform01(vb, 13), 20.0, 2000.0).astype(np.float32)
@@ -178,7 +180,9 @@ def c5_mixed(V=1048576, T=96000, G=32, v0=0):
         return _sr(_pipe({"op": "|", "n": 0.0, "inputs": [_L("white()"), _pipe(f"dc({c!r})", "ramp()", "<(0.5)", "rise()")]},
                          "shift_reg()", "join(8)"))
     out.append(Workload("c5b_shift_reg", b_expr(100.0), np.stack([clk, np.full(n, 0.5, np.float32)], axis=1), salts_for(vb), T, G,
-                        lambda v: b_expr(float(clk[v])), 4.0 / G, "fp32", "white -> shift_reg clocked by a ramp edge detector"))
+                        lambda v: b_expr(float(clk[v])), 4.0 / G, "fp32",
+                        "white -> shift_reg clocked by a ramp edge detector; ~30 op per voice-sample (hash 9, ramp 3, compare + rise 3, "
+                        "8-tap shift 8, mean 8)", flops_per_unit=30.0))
     # C: one-pole feedback  y = g (x + y[n-1])
     vc = np.arange(v0 + 2 * n, v0 + 3 * n)
     g = (0.5 + uniform01(vc, 14) * 0.49).astype(np.float32)
@@ -186,7 +190,9 @@ def c5_mixed(V=1048576, T=96000, G=32, v0=0):
     def c_expr(gg):
         return _sr(_pipe("white()", {"op": "feedback()", "net": _L(f"mul({gg!r})"), "delay": None}))
     out.append(Workload("c5c_feedback", c_expr(0.9), np.stack([np.zeros(n, np.float32), g], axis=1), salts_for(vc), T, G,
-                        lambda v: c_expr(float(g[v])), 4.0 / G, "fp32", "1-sample feedback: the held sample lives in the state region (shared memory during a launch)"))
+                        lambda v: c_expr(float(g[v])), 4.0 / G, "fp32",
+                        "1-sample feedback: the held sample lives in the state region; ~11 op per voice-sample (hash 9, add, mul)",
+                        flops_per_unit=11.0))
     # D: delay(1024 samples) + lowpole
     vd = np.arange(v0 + 3 * n, v0 + 4 * n)
     hz = _loguniform(uniform01(vd, 15), 100.0, 8000.0).astype(np.float32)
@@ -195,7 +201,8 @@ def c5_mixed(V=1048576, T=96000, G=32, v0=0):
     def d_expr(h):
         return _sr(_pipe("white()", f"delay({dt!r})", f"lowpole({h!r})"))
     out.append(Workload("c5d_delay_lowpole", d_expr(1000.0), np.stack([np.full(n, dt, np.float32), hz], axis=1), salts_for(vd), T, G,
-                        lambda v: d_expr(float(hz[v])), 8.0 + 4.0 / G, "hbm", "1024-sample delay ring in HBM: 8 B state traffic per voice-sample"))
+                        lambda v: d_expr(float(hz[v])), 8.0 + 4.0 / G, "hbm", "1024-sample delay ring in HBM: 8 B state traffic per voice-sample; "
+                        "~12 op (hash 9, lowpole 3)", flops_per_unit=12.0))
     return out
 
 

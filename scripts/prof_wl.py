@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import quartz_b200 as qb
 from quartz_b200 import workloads
-from tests.graphs import build
+from quartz_b200.graphs import build
 name, T = sys.argv[1], int(sys.argv[2])
 kw = {"T": T}
 if len(sys.argv) > 3: kw["V"] = int(sys.argv[3])

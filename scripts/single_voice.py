@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import quartz_b200 as qb
-from tests.graphs import build, pipe, stack, L
+from quartz_b200.graphs import build, pipe, stack, L
 T = 480000
 def sr(g): return {"op": "sr()", "net": g, "n": 48000.0}
 GRAPHS = {

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import quartz_b200 as qb
 from quartz_b200 import workloads
-from tests.graphs import build
+from quartz_b200.graphs import build
 
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 9600
