@@ -48,20 +48,18 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// x^k for x >= 0 through ex2(k lg2 x): relative error ~ |k log2 x| * 2e-7 — the control-point values this feeds are in
-// [0, 1] and the audio tolerance is 1e-4.  k == 1 (the `ar` attack of configs[2]) stays exact.
-__device__ __forceinline__ float pow_fast(float x, float k) {
-  if (k == 1.0f) return x;
-  if (k == 0.0f) return 1.0f;
-  return exp2f(k * __log2f(x));
-}
-// lfo control functions with constant parameters: xd, xD, ar (functions.rs:505-507, 517-540, 547-555)
+// lfo control functions with constant parameters: xd, xD, ar (functions.rs:505-507, 517-540, 547-555).  Every shape ends
+// in one ex2(k lg2 x): relative error ~ |k log2 x| * 2e-7 — the control-point values are in [0, 1] and the audio tolerance
+// is 1e-4.  k == 1 (the `ar` attack of configs[2]) stays exact.  Selects only: `shape` is warp-uniform.
 __device__ __forceinline__ float env_point(int shape, float tt, float c0, float c1, float c2, float c3) {
-  if (shape == 0) return __expf(-tt * c0);
-  if (shape == 1) return tt < c0 ? pow_fast((c0 - tt) * rcp_approx(c0), c1) : 0.0f;
-  if (tt < c0) return pow_fast(tt * rcp_approx(c0), c1);
-  if (tt < c0 + c2) return pow_fast((c2 - (tt - c0)) * rcp_approx(c2), c3);
-  return 0.0f;
+  const bool s0 = shape == 0, s1 = shape == 1, att = tt < c0;
+  const float x = s1 ? (c0 - tt) * rcp_approx(c0) : (att ? tt * rcp_approx(c0) : (c2 - (tt - c0)) * rcp_approx(c2));
+  const float k = (s1 || att) ? c1 : c3;
+  const bool live = s0 || (s1 ? att : tt < c0 + c2);
+  float r = exp2f(s0 ? -tt * c0 * 1.4426950408889634f : k * __log2f(x));
+  r = (!s0 && k == 1.0f) ? x : r;
+  r = (!s0 && k == 0.0f) ? 1.0f : r;
+  return live ? r : 0.0f;
 }
 // FunDSP rnd1: (hash >> 11) as f64 / 2^53, rounded to f32 — one RN rounding of the 53-bit integer, then an exact scaling
 __device__ __forceinline__ float rnd1_f32(uint64_t x) { return __ull2float_rn(d_hash64a(x) >> 11) * (1.0f / 9007199254740992.0f); }
@@ -96,7 +94,7 @@ __global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ p
   uint32_t first[2] = {__float_as_uint(firstw.x), __float_as_uint(firstw.y)};
   float2 nt1 = f2(0.0f, 0.0f), nv1 = nt1, invC, invN = nt1;
   uint32_t ncross[2] = {0u, 0u};
-  bool crossed[2] = {false, false}, have_next[2] = {false, false};
+  bool crossed[2] = {false, false};
   // prologue: bring each envelope "inside a segment" exactly like the per-sample code would on its first tick
 #pragma unroll
   for (int j = 0; j < 2; j++) {
@@ -145,65 +143,72 @@ __global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ p
   const int chunks = win >> 2;             // 16-byte chunks per tile row
   const int chunk_shift = win == 64 ? 4 : 3;
   const float gscale = 1.0f / (float)G;
-  for (long tb = 0; tb < T; tb += win) {
-    const int n = (T - tb) < (long)win ? (int)(T - tb) : win;
-    // ---- window boundary (warp-uniform point): consume a crossed control point, look one ahead, anchor both lines at the
-    // window's first sample, advance the exact time recurrence over the window
+
+  // ---- window boundary (warp-uniform point), for the window of n samples that starts at the current time: consume a
+  // crossed control point, look one ahead, anchor both lines at the window's first sample, advance the exact time
+  // recurrence over the window.  Straight-line code (selects, no branches) so that the two voices' chains — 64-bit hash,
+  // MUFU sequences — interleave with each other and with the group sums of the window that just ended; n == 0 is harmless.
+  auto boundary = [&](int n) {
+    bool slow_any = false;
+    float e_first[2], dt_j[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-      if (crossed[j]) {
-        comp(t0, j) = comp(t1, j); comp(ev0, j) = comp(ev1, j); comp(t1, j) = comp(nt1, j); comp(ev1, j) = comp(nv1, j);
-        comp(invC, j) = comp(invN, j);
-        ncross[j] += 1u;
-        have_next[j] = false;
-      }
+      const bool cr = crossed[j];
+      comp(t0, j) = cr ? comp(t1, j) : comp(t0, j);
+      comp(ev0, j) = cr ? comp(ev1, j) : comp(ev0, j);
+      comp(t1, j) = cr ? comp(nt1, j) : comp(t1, j);
+      comp(ev1, j) = cr ? comp(nv1, j) : comp(ev1, j);
+      comp(invC, j) = cr ? comp(invN, j) : comp(invC, j);
+      ncross[j] += cr ? 1u : 0u;
+      // the control point after t1 (recomputed every window: the same value for as long as the segment stands)
+      const float nt = comp(t1, j) + d_lerp(0.75f, 1.25f, rnd1_f32(th[j] + (uint64_t)ncross[j])) * 0.002f;
+      comp(nt1, j) = nt;
+      comp(nv1, j) = env_point(env_shape, nt, compc(ec0, j), compc(ec1, j), compc(ec2, j), compc(ec3, j));
+      comp(invN, j) = rcp_approx(nt - comp(t1, j));
+      // exact t += sd, n times: inside one binade the rounded step is a constant (two equal steps imply it stays constant:
+      // a tie can only alternate on the first step), so the window's times are e + i * d in closed form
+      const float e = comp(et, j), sd = compc(esd, j);
+      const float e1 = e + sd, e2 = e1 + sd, d = e1 - e;
+      const float e_end = __fmaf_rn((float)n, d, e), e_last = __fmaf_rn((float)(n - 1), d, e);
+      const bool fast = (e2 - e1) == d && (__float_as_uint(e) >> 23) == (__float_as_uint(e_end) >> 23) && e > 0.0f;
+      slow_any = slow_any || !fast;
+      e_first[j] = e;
+      dt_j[j] = d;
+      comp(et, j) = e_end;
+      crossed[j] = n > 0 && e_last >= comp(t1, j);
     }
-    if (__any_sync(0xffffffffu, !have_next[0] || !have_next[1])) {
+    if (__any_sync(0xffffffffu, slow_any)) {     // start of a render, binade crossings (a handful of windows per render): step
 #pragma unroll
       for (int j = 0; j < 2; j++) {
-        if (!have_next[j]) {
-          const float nt = comp(t1, j) + d_lerp(0.75f, 1.25f, rnd1_f32(th[j] + (uint64_t)ncross[j])) * 0.002f;
-          comp(nt1, j) = nt;
-          comp(nv1, j) = env_point(env_shape, nt, compc(ec0, j), compc(ec1, j), compc(ec2, j), compc(ec3, j));
-          comp(invN, j) = rcp_approx(nt - comp(t1, j));
-          have_next[j] = true;
-        }
+        const float e = e_first[j], sd = compc(esd, j);
+        float w = e, e_last = e;
+        for (int i = 0; i < n; i++) { e_last = w; w += sd; }
+        comp(et, j) = w;
+        dt_j[j] = n > 0 ? (w - e) * rcp_approx((float)n) : sd;
+        crossed[j] = n > 0 && e_last >= comp(t1, j);
       }
     }
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-      const float e = comp(et, j), sd = compc(esd, j);
-      // exact t += sd, n times: inside one binade the rounded step is a constant (two equal steps imply it stays constant:
-      // a tie can only alternate on the first step), so the window's times are e + i * d in closed form; otherwise step
-      const float e1 = e + sd, e2 = e1 + sd, d = e1 - e;
-      const float e_end = __fmaf_rn((float)n, d, e);
-      float e_last, dt;
-      if ((e2 - e1) == d && (__float_as_uint(e) >> 23) == (__float_as_uint(e_end) >> 23) && e > 0.0f) {
-        e_last = __fmaf_rn((float)(n - 1), d, e);
-        comp(et, j) = e_end;
-        dt = d;
-      } else {
-        float w = e;
-        e_last = e;
-        for (int i = 0; i < n; i++) { e_last = w; w += sd; }
-        comp(et, j) = w;
-        dt = (w - e) * rcp_approx((float)n);
-      }
-      crossed[j] = e_last >= comp(t1, j);
+      const float e = e_first[j];
       // lines through (t0, v0)-(t1, v1) and (t1, v1)-(nt1, nv1), evaluated at the window's first sample, stepped by dt
       const float gC = (comp(ev1, j) - comp(ev0, j)) * comp(invC, j), gN = (comp(nv1, j) - comp(ev1, j)) * comp(invN, j);
       const float lc = __fmaf_rn(gC, e - comp(t0, j), comp(ev0, j)), ln = __fmaf_rn(gN, e - comp(t1, j), comp(ev1, j));
       // concave kink (slope decreases): min of the two lines; convex: max = -min of the negated lines
       const float s = gN <= gC ? 1.0f : -1.0f;
-      if (s != comp(sgn, j)) {
-        comp(sgn, j) = s;
-        comp(stau, j) = -comp(stau, j);
-        comp(ic1, j) = -comp(ic1, j);
-        comp(ic2, j) = -comp(ic2, j);
-      }
+      const float flip = s * comp(sgn, j);       // -1: the voice changes sign for this window
+      comp(sgn, j) = s;
+      comp(stau, j) *= flip;
+      comp(ic1, j) *= flip;
+      comp(ic2, j) *= flip;
       comp(sC, j) = s * lc; comp(sN, j) = s * ln;
-      comp(dC, j) = s * gC * dt; comp(dN, j) = s * gN * dt;
+      comp(dC, j) = s * gC * dt_j[j]; comp(dN, j) = s * gN * dt_j[j];
     }
+  };
+
+  boundary(T < (long)win ? (int)T : win);
+  for (long tb = 0; tb < T; tb += win) {
+    const int n = (T - tb) < (long)win ? (int)(T - tb) : win;
     // ---- the window's samples
     auto full_window = [&](auto small_t) {
 #pragma unroll 2
@@ -231,16 +236,26 @@ __global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ p
       }
     }
     __syncwarp();
-    // ---- group sums (tile rows of a group top to bottom = voices left to right, pairs first) and 16-byte stores
+    // ---- the next window's boundary work shares a basic block with this window's group sums
+    {
+      const long left = T - tb - n;
+      boundary(left < (long)win ? (int)left : win);
+    }
+    // ---- group sums (pairwise tree over the group's tile rows) and 16-byte stores
     for (int it = lane; it < NOUT * chunks; it += 32) {
       const int orow = it >> chunk_shift, ch = it & (chunks - 1);
-      float4 acc = tile4[(orow * RPO) * (PX_PITCH / 4) + ch];
+      float2 lo[RPO], hi[RPO];
 #pragma unroll
-      for (int k = 1; k < RPO; k++) {
+      for (int k = 0; k < RPO; k++) {
         const float4 r = tile4[(orow * RPO + k) * (PX_PITCH / 4) + ch];
-        const float2 lo = __fadd2_rn(f2(acc.x, acc.y), f2(r.x, r.y)), hi = __fadd2_rn(f2(acc.z, acc.w), f2(r.z, r.w));
-        acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+        lo[k] = f2(r.x, r.y); hi[k] = f2(r.z, r.w);
       }
+#pragma unroll
+      for (int w = 1; w < RPO; w *= 2) {
+#pragma unroll
+        for (int k = 0; k + w < RPO; k += 2 * w) { lo[k] = __fadd2_rn(lo[k], lo[k + w]); hi[k] = __fadd2_rn(hi[k], hi[k + w]); }
+      }
+      float4 acc = make_float4(lo[0].x, lo[0].y, hi[0].x, hi[0].y);
       long orow_g;       // output row
       bool valid;
       if (G == 1) {      // tile row r < 32: voice 2r of the warp; r >= 32: voice 2(r - 32) + 1
