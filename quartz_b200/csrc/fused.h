@@ -26,6 +26,7 @@ struct FusedArgs {
   size_t* scratch_bytes;
   float sample_rate;
   const float* tables;    // the bank's table region (wavetable sets)
+  int settle = 0;         // FUSED_SINE_SVF_ENV: samples after which every voice's SVF has forgotten its state to 1e-9 (0: unknown)
 };
 
 FusedPlan plan_fused(const Tape& t);

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "dev_math.cuh"
@@ -67,15 +69,22 @@ __device__ __forceinline__ float rnd1_f32(uint64_t x) { return __ull2float_rn(d_
 constexpr int PX_PITCH = 68;   // floats per tile row: 64 samples + 4 (rows stay 16-byte aligned, STS.128 / LDS.128 conflict-free)
 
 template <bool LP, int G>
-__global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ params, float* __restrict__ state, int Vp, int V,
+__global__ void __launch_bounds__(32, 16) k_polysynth_x2(const float* __restrict__ params, float* __restrict__ state, int Vp, int V,
                                                     long T, int win, int vec_ok, int p_f, int p_sd, int p_svf, int p_env, int s_ph,
-                                                    int s_svf, int s_env, int env_shape, float* __restrict__ out) {
+                                                    int s_svf, int s_env, int env_shape, float* __restrict__ out, int S, long T1,
+                                                    int W, float* __restrict__ state_out) {
   constexpr int ROWS = G == 1 ? 64 : 32;   // tile rows: one per voice, or one per lane (the pair is summed in the lane)
   constexpr int RPO = G == 1 ? 1 : G / 2;  // tile rows per output row
   constexpr int NOUT = ROWS / RPO;         // output rows of one warp
   __shared__ __align__(16) float tile[ROWS * PX_PITCH];
   const int lane = threadIdx.x;
-  const int v0 = blockIdx.x * 64;          // first voice of the warp (Vp is a multiple of 128: padded voices copy the last one)
+  // S == 2: two warps per block of 64 voices split the render in time.  Role 0 renders [0, T1).  Role 1 walks the exact
+  // recurrences (phase, envelope time, control points) over [0, T1 - W) without rendering, lets the SVF settle from zero
+  // state over the W samples before T1 (W >= the filter's decay to 1e-9, fused_settle()), then renders [T1, T) and owns
+  // the final state.  More warps per scheduler hide the latency that 2 voices per lane concentrate in one warp.
+  const int NB = gridDim.x / S;
+  const int role = blockIdx.x / NB;
+  const int v0 = (blockIdx.x - role * NB) * 64;   // first voice of the warp (Vp is a multiple of 128: padded voices copy the last one)
   const int va = v0 + 2 * lane;
 #define PRM2(i) (*reinterpret_cast<const float2*>(&params[(size_t)(i) * Vp + va]))
 #define ST2(i) (*reinterpret_cast<float2*>(&state[(size_t)(i) * Vp + va]))
@@ -206,9 +215,72 @@ __global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ p
     }
   };
 
-  boundary(T < (long)win ? (int)T : win);
-  for (long tb = 0; tb < T; tb += win) {
-    const int n = (T - tb) < (long)win ? (int)(T - tb) : win;
+  const long t_begin = role == 0 ? 0 : T1 - W;              // multiples of win
+  const long t_end = (S == 2 && role == 0) ? T1 : T;
+  const long t_emit = role == 0 ? 0 : T1;
+  if (role == 1 && t_begin > 0) {
+    // ---- pre-pass over [0, t_begin): state only.  Phase: the reference's f32 recurrence, sample by sample (it has no
+    // closed form: the rounding depends on the binade the running sum is in).
+    if (small_inc) {
+#pragma unroll 8
+      for (long i = 0; i < t_begin; i++) {
+        ph = __fadd2_rn(ph, inc);
+        ph = __fadd2_rn(ph, f2(-ge_one(ph.x), -ge_one(ph.y)));
+      }
+    } else {
+      for (long i = 0; i < t_begin; i++) {
+        ph = __fadd2_rn(ph, inc);
+        ph = f2(ph.x - floorf(ph.x), ph.y - floorf(ph.y));
+      }
+    }
+    // Envelope time: exact closed form inside a binade (as in boundary()), in strides that grow while it holds.  Control
+    // points: the reference consumes one at the first sample whose time reaches it, so after the pre-pass every control
+    // point <= the time of the last pre-pass sample is gone.
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const float sd = compc(esd, j);
+      float e = comp(et, j), e_last = e;
+      long left = t_begin;
+      long stride = 64;
+      while (left > 0) {
+        const long k = left < stride ? left : stride;
+        const float e1 = e + sd, e2 = e1 + sd, d = e1 - e;
+        const float e_end = __fmaf_rn((float)k, d, e);
+        if ((e2 - e1) == d && (__float_as_uint(e) >> 23) == (__float_as_uint(e_end) >> 23) && e > 0.0f) {
+          e_last = __fmaf_rn((float)(k - 1), d, e);
+          e = e_end;
+          left -= k;
+          if (stride < 65536) stride *= 2;
+        } else if (k <= 8) {
+          for (long i = 0; i < k; i++) { e_last = e; e += sd; }
+          left -= k;
+        } else {
+          stride = k / 8;
+        }
+      }
+      comp(et, j) = e;
+      bool moved = false;
+      while (e_last >= comp(t1, j)) {
+        comp(t0, j) = comp(t1, j);
+        comp(t1, j) = comp(t0, j) + d_lerp(0.75f, 1.25f, rnd1_f32(th[j] + (uint64_t)ncross[j])) * 0.002f;
+        ncross[j] += 1u;
+        moved = true;
+      }
+      if (moved) {
+        comp(ev0, j) = env_point(env_shape, comp(t0, j), compc(ec0, j), compc(ec1, j), compc(ec2, j), compc(ec3, j));
+        comp(ev1, j) = env_point(env_shape, comp(t1, j), compc(ec0, j), compc(ec1, j), compc(ec2, j), compc(ec3, j));
+        comp(invC, j) = rcp_approx(comp(t1, j) - comp(t0, j));
+      }
+    }
+  }
+  if (role == 1) { ic1 = f2(0.0f, 0.0f); ic2 = ic1; }      // the SVF settles over [T1 - W, T1)
+  {
+    const long left = t_end - t_begin;
+    boundary(left < (long)win ? (int)left : win);
+  }
+  for (long tb = t_begin; tb < t_end; tb += win) {
+    const int n = (t_end - tb) < (long)win ? (int)(t_end - tb) : win;
+    const bool emit = tb >= t_emit;
     // ---- the window's samples
     auto full_window = [&](auto small_t) {
 #pragma unroll 2
@@ -238,11 +310,11 @@ __global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ p
     __syncwarp();
     // ---- the next window's boundary work shares a basic block with this window's group sums
     {
-      const long left = T - tb - n;
+      const long left = t_end - tb - n;
       boundary(left < (long)win ? (int)left : win);
     }
     // ---- group sums (pairwise tree over the group's tile rows) and 16-byte stores
-    for (int it = lane; it < NOUT * chunks; it += 32) {
+    for (int it = lane; emit && it < NOUT * chunks; it += 32) {
       const int orow = it >> chunk_shift, ch = it & (chunks - 1);
       float2 lo[RPO], hi[RPO];
 #pragma unroll
@@ -290,7 +362,9 @@ __global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ p
     th[j] += (uint64_t)ncross[j];
     if (comp(sgn, j) < 0.0f) { comp(ic1, j) = -comp(ic1, j); comp(ic2, j) = -comp(ic2, j); }
   }
-  if (va < V) {     // va + 1 may be the first padded voice: its words are padding too (Vp > V), writing them is harmless
+#undef ST2
+#define ST2(i) (*reinterpret_cast<float2*>(&state_out[(size_t)(i) * Vp + va]))
+  if (va < V && role == S - 1) {     // va + 1 may be the first padded voice: its words are padding too (Vp > V), writing them is harmless
     ST2(s_ph) = ph; ST2(s_svf) = ic1; ST2(s_svf + 1) = ic2;
     ST2(s_env) = et; ST2(s_env + 1) = t0; ST2(s_env + 2) = t1; ST2(s_env + 3) = ev0; ST2(s_env + 4) = ev1;
     ST2(s_env + 5) = f2(__uint_as_float((uint32_t)th[0]), __uint_as_float((uint32_t)th[1]));
@@ -307,8 +381,37 @@ __global__ void __launch_bounds__(32) k_polysynth_x2(const float* __restrict__ p
 // the one-voice-per-lane kernel in fused.cu)
 cudaError_t launch_polysynth_x2(const FusedPlan& pl, const FusedArgs& a, int win, cudaStream_t stream) {
   const int vec_ok = ((((size_t)(uintptr_t)a.out) & 15) == 0 && (a.T & 3) == 0) ? 1 : 0;
-  const unsigned blocks = (unsigned)(a.Vp / 64);
-#define QG_PX(LPV, GV) k_polysynth_x2<LPV, GV><<<blocks, 32, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, win, vec_ok, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], pl.p[7], a.out)
+  const int NB = a.Vp / 64;
+  // time segments (see the kernel): worthwhile while the bank leaves schedulers short of warps, possible when the filters
+  // forget their state within a small part of the render
+  int S = 1, W = 0;
+  long T1 = a.T;
+  const char* force = getenv("QG_POLY_SEGMENTS");
+  const bool allow = !(force && force[0] == '1');
+  if (allow && NB <= 148 * 12 && a.settle > 0) {
+    W = (a.settle + win - 1) / win * win;
+    if (a.T >= 16L * W && a.T >= 32768) {
+      S = 2;
+      // role 1 spends ~0.12 of a rendered sample's cost on a pre-pass sample: T1 = (T1 - W) * 0.12 + (T - T1 + W)
+      T1 = (long)(((double)a.T + 0.88 * (double)W) / 1.88) / win * win;
+      if (T1 <= W || T1 >= a.T) { S = 1; T1 = a.T; W = 0; }
+    }
+  }
+  float* state_out = a.state;
+  const int rows = std::max(pl.s[0] + 1, std::max(pl.s[1] + 2, pl.s[2] + 8));
+  if (S == 2) {   // role 1 finishes while role 0 warps of other blocks may not have read their start state yet
+    const size_t need = (size_t)rows * a.Vp * sizeof(float);
+    if (need > *a.scratch_bytes) {
+      if (*a.scratch) cudaFree(*a.scratch);
+      *a.scratch = nullptr; *a.scratch_bytes = 0;
+      cudaError_t e = cudaMalloc((void**)a.scratch, need);
+      if (e != cudaSuccess) return e;
+      *a.scratch_bytes = need;
+    }
+    state_out = *a.scratch;
+  }
+  const unsigned blocks = (unsigned)(NB * S);
+#define QG_PX(LPV, GV) k_polysynth_x2<LPV, GV><<<blocks, 32, 0, stream>>>(a.params, a.state, a.Vp, a.V, a.T, win, vec_ok, pl.p[0], pl.p[1], pl.p[2], pl.p[3], pl.s[0], pl.s[1], pl.s[2], pl.p[7], a.out, S, T1, W, state_out)
 #define QG_PX_G(LPV)                                     \
   switch (a.group) {                                     \
     case 1: QG_PX(LPV, 1); break;                        \
@@ -322,7 +425,14 @@ cudaError_t launch_polysynth_x2(const FusedPlan& pl, const FusedArgs& a, int win
   if (pl.p[4]) { QG_PX_G(true) } else { QG_PX_G(false) }
 #undef QG_PX_G
 #undef QG_PX
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || S == 1) return e;
+  // the final state (phase; SVF ic1, ic2; the envelope's 8 words) moves from the scratch table into the bank's
+  const size_t row = (size_t)a.Vp * sizeof(float);
+  e = cudaMemcpyAsync(a.state + (size_t)pl.s[0] * a.Vp, state_out + (size_t)pl.s[0] * a.Vp, row, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(a.state + (size_t)pl.s[1] * a.Vp, state_out + (size_t)pl.s[1] * a.Vp, 2 * row, cudaMemcpyDeviceToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(a.state + (size_t)pl.s[2] * a.Vp, state_out + (size_t)pl.s[2] * a.Vp, 8 * row, cudaMemcpyDeviceToDevice, stream);
+  return e;
 }
 
 }  // namespace qg
