@@ -39,11 +39,14 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 __device__ __forceinline__ float& comp(float2& v, int j) { return j ? v.y : v.x; }
 __device__ __forceinline__ float compc(const float2& v, int j) { return j ? v.y : v.x; }
-// 1.0f when x >= 1 else 0.0f (FSET.BF): the wrap of a phase in [0, 2) is then one packed subtract
-__device__ __forceinline__ float ge_one(float x) {
-  float r;
-  asm("set.ge.f32.f32 %0, %1, 0f3F800000;" : "=f"(r) : "f"(x));
-  return r;
+// FunDSP Sine: phase -= floor(phase).  For a phase in [0, 2) (0 <= increment < 1) that is a conditional -1: w = p - 1 is
+// exact when p >= 1 and negative otherwise, and as UNSIGNED integers bits(w) < bits(p) exactly when w >= 0 — one packed add
+// and an integer min per voice (ALU pipe).  (FSET.BF, the float-valued compare, measured at ~4 cycles per warp instruction
+// on B200: it made the wrap the most expensive part of the recurrence.)
+__device__ __forceinline__ float2 wrap01(float2 p) {
+  const float2 w = __fadd2_rn(p, make_float2(-1.0f, -1.0f));
+  return make_float2(__uint_as_float(min(__float_as_uint(p.x), __float_as_uint(w.x))),
+                     __uint_as_float(min(__float_as_uint(p.y), __float_as_uint(w.y))));
 }
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
@@ -125,8 +128,7 @@ __global__ void __launch_bounds__(32, 16) k_polysynth_x2(const float* __restrict
   auto sample = [&](float2& ys, float2& m, auto small_t) {
     const float2 p = ph;
     ph = __fadd2_rn(p, inc);
-    // FunDSP Sine: phase -= floor(phase).  For 0 <= inc < 1 the sum is in [0, 2): exactly a conditional -1
-    if (decltype(small_t)::value) ph = __fadd2_rn(ph, f2(-ge_one(ph.x), -ge_one(ph.y)));
+    if (decltype(small_t)::value) ph = wrap01(ph);
     else ph = f2(ph.x - floorf(ph.x), ph.y - floorf(ph.y));
     // sine reads the phase BEFORE the step; MUFU.SIN works on the fractional revolution, so p in [0, 1) needs no folding
     const float2 arg = __fmul2_rn(p, stau);
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(32, 16) k_polysynth_x2(const float* __restrict
 #pragma unroll 8
       for (long i = 0; i < t_begin; i++) {
         ph = __fadd2_rn(ph, inc);
-        ph = __fadd2_rn(ph, f2(-ge_one(ph.x), -ge_one(ph.y)));
+        ph = wrap01(ph);
       }
     } else {
       for (long i = 0; i < t_begin; i++) {
