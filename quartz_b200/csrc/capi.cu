@@ -51,7 +51,6 @@ struct qg_bank {
   size_t fused_scratch_bytes = 0;
   std::vector<float> raw;      // host copy of the per-voice raw parameters [V][R] (empty: every voice = template)
   FusedPlan fused;
-  int fused_settle = 0;   // poly-synth banks: svf_settle_samples() of the current parameters
   TvPlan tv;
   bool biquad_scan_ok = true;   // every direct-form biquad of every voice may be re-associated (scans) within the tolerance
   bool block_ok = false;   // the tape may run on the block-mode lane interpreter (k_interp_blk)
@@ -162,23 +161,6 @@ static bool biquads_well_conditioned(const Tape& t, ParamAt param, long V) {
     }
   }
   return true;
-}
-
-// Samples after which a fixed Simper SVF has forgotten its state to 1e-9: spectral radius of the tick's state matrix
-// A = [[2 a1 - 1, -2 a2], [2 a2, 1 - 2 a3]], maximum over the bank's voices (0: some voice never does).  The poly-synth
-// kernel may split a render in time only when this is a small part of it (fused_poly.cu).
-template <typename ParamAt>
-static int svf_settle_samples(int p_svf, ParamAt param, long V) {
-  double worst = 0.0;
-  for (long v = 0; v < V; v++) {
-    const double a1 = param(p_svf, v), a2 = param(p_svf + 1, v), a3 = param(p_svf + 2, v);
-    const double tr = 2.0 * a1 - 2.0 * a3, det = (2.0 * a1 - 1.0) * (1.0 - 2.0 * a3) + 4.0 * a2 * a2;
-    const double disc = 0.25 * tr * tr - det;
-    const double rho = disc < 0.0 ? std::sqrt(det) : std::fabs(0.5 * tr) + std::sqrt(disc);
-    if (!(rho < 1.0)) return 0;
-    if (rho > 0.0) worst = std::max(worst, std::log(1e-9) / std::log(rho));
-  }
-  return worst < 1.0e8 ? (int)std::ceil(worst) + 1 : 0;
 }
 
 extern "C" {
@@ -407,8 +389,6 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
     CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     b->biquad_scan_ok = biquads_well_conditioned(t, [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V);
-    if (b->fused.id == FUSED_SINE_SVF_ENV)
-      b->fused_settle = svf_settle_samples(b->fused.p[2], [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V);
   } else if (P > 0) {
     DevTmp<float> d_tmpl;
     if ((rc = upload(&d_tmpl.p, t.params, c->stream))) return rc;
@@ -419,7 +399,6 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   if ((rc = bank_init_state(b, salts))) return rc;
   if (!(raw_matrix && R > 0 && P > 0)) {
     b->biquad_scan_ok = biquads_well_conditioned(t, [&](int p, long) { return t.params[p]; }, 1);
-    if (b->fused.id == FUSED_SINE_SVF_ENV) b->fused_settle = svf_settle_samples(b->fused.p[2], [&](int p, long) { return t.params[p]; }, 1);
   }
   if (b->fused.id == FUSED_NOISE_SVF && b->fused.p[1] == 2 && !b->biquad_scan_ok) b->fused.id = FUSED_NONE;
   b->tv = plan_tv(t, (size_t)180 * 1024);
@@ -577,7 +556,6 @@ static int bank_set_raw(qg_bank* b, int raw_index, float value) {
     c->launches++;
     CU(cudaStreamSynchronize(c->stream));
     if (!biquads_well_conditioned(t, [&](int p, long) { return t.params[p]; }, 1)) bank_biquads_now_ill_conditioned(b);
-    if (b->fused.id == FUSED_SINE_SVF_ENV) b->fused_settle = svf_settle_samples(b->fused.p[2], [&](int p, long) { return t.params[p]; }, 1);
   } else {
     std::vector<float> host;
     for (long v = 0; v < b->V; v++) b->raw[(size_t)v * R + raw_index] = value;
@@ -585,8 +563,6 @@ static int bank_set_raw(qg_bank* b, int raw_index, float value) {
     CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (!biquads_well_conditioned(t, [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V)) bank_biquads_now_ill_conditioned(b);
-    if (b->fused.id == FUSED_SINE_SVF_ENV)
-      b->fused_settle = svf_settle_samples(b->fused.p[2], [&](int p, long v) { return host[(size_t)p * b->Vp + v]; }, b->V);
   }
   return QG_OK;
 }
@@ -630,7 +606,6 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     fa.params = b->d_params; fa.state = b->d_state; fa.V = (int)b->V; fa.Vp = b->Vp; fa.T = T; fa.group = group; fa.out = d_out;
     fa.scratch = &b->d_fused_scratch; fa.scratch_bytes = &b->fused_scratch_bytes; fa.sample_rate = t.h.sample_rate;
     fa.tables = b->d_tables;
-    fa.settle = b->fused_settle;
     int l = 0;
     cudaError_t fe = launch_fused(b->fused, fa, c->stream, &l);
     c->launches += l;

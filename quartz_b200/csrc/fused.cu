@@ -736,8 +736,9 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     if (launches) *launches += 1;
     // sine voices: two voices per lane in packed f32x2 arithmetic (fused_poly.cu); the wavetable oscillators (a 4-point
     // interpolated table read per sample) keep one voice per lane
-    if (!pl.p[5]) return launch_polysynth_x2(pl, a, look_tiles * 32, stream);
-    if (pl.p[4]) QG_PS(true, 1); else QG_PS(false, 1);
+    if (!pl.p[5] && look_tiles == 2) return launch_polysynth_x2(pl, a, stream);
+    if (pl.p[5]) { if (pl.p[4]) QG_PS(true, 1); else QG_PS(false, 1); }
+    else { if (pl.p[4]) QG_PS(true, 0); else QG_PS(false, 0); }   // sine below 44.1 kHz: 32-sample envelope windows
 #undef QG_PS
     return cudaGetLastError();
   }

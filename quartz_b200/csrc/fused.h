@@ -26,13 +26,12 @@ struct FusedArgs {
   size_t* scratch_bytes;
   float sample_rate;
   const float* tables;    // the bank's table region (wavetable sets)
-  int settle = 0;         // FUSED_SINE_SVF_ENV: samples after which every voice's SVF has forgotten its state to 1e-9 (0: unknown)
 };
 
 FusedPlan plan_fused(const Tape& t);
 const char* fused_name(int id);
 cudaError_t launch_fused(const FusedPlan& plan, const FusedArgs& a, cudaStream_t stream, int* launches);
-// FUSED_SINE_SVF_ENV with the sine oscillator: packed two-voices-per-lane kernel (fused_poly.cu); win = envelope window (32 / 64)
-cudaError_t launch_polysynth_x2(const FusedPlan& plan, const FusedArgs& a, int win, cudaStream_t stream);
+// FUSED_SINE_SVF_ENV with the sine oscillator: packed two-voices-per-lane kernel (fused_poly.cu), 64-sample envelope windows
+cudaError_t launch_polysynth_x2(const FusedPlan& plan, const FusedArgs& a, cudaStream_t stream);
 
 }  // namespace qg

@@ -94,28 +94,6 @@ def test_polysynth_full_length_subset():
     assert_parity(got, ref, "float", "c3 full length")
 
 
-def test_polysynth_time_segments_equal_the_one_pass_render():
-    """small poly-synth banks split a long render between two warps per voice block (fused_poly.cu): the second half
-    starts from recurrences walked exactly (phase, envelope time, control points) and an SVF settled over the filter's
-    decay time.  Same samples as the one-pass render to ~1e-7, same persisted state (the continuation agrees)"""
-    import os
-    wl = workloads.c3_polysynth(V=128, T=120000)
-    G = 32
-    two = make_bank(wl)
-    a = np.concatenate([two.render(wl.T, group=G)[:, 0, :], two.render(5000, group=G)[:, 0, :]], axis=1)
-    os.environ["QG_POLY_SEGMENTS"] = "1"
-    try:
-        one = make_bank(wl)
-        b = np.concatenate([one.render(wl.T, group=G)[:, 0, :], one.render(5000, group=G)[:, 0, :]], axis=1)
-    finally:
-        del os.environ["QG_POLY_SEGMENTS"]
-    assert float(np.abs(a - b).max()) < 2e-6, float(np.abs(a - b).max())
-    assert float(np.abs(a).max()) > 1e-3
-    ref = oracle_voices(wl, range(128), wl.T + 5000, group=G)
-    assert_parity(a, ref, "float", "two time segments vs oracle")
-    assert_parity(b, ref, "float", "one pass vs oracle")
-
-
 def test_hello_440_full_length():
     """BASELINE configs[0]: sine(440), 10 s at 48 kHz through the render path."""
     wl = workloads.c1_hello()
