@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -55,7 +56,9 @@ struct qg_bank {
   bool biquad_scan_ok = true;   // every direct-form biquad of every voice may be re-associated (scans) within the tolerance
   bool block_ok = false;   // the tape may run on the block-mode lane interpreter (k_interp_blk)
   int ring_mode = 0;   // 0: rings laid out [pos][voice] (lane kernels); 1: [voice][pos] (time-vector kernel)
-  SpecKernel spec;     // K1s: lane kernel compiled for this tape (only after qg_bank_set_path(QG_PATH_SPECIALISED))
+  SpecKernel spec;     // K1s: lane kernel compiled for this tape (qg_bank_set_path(QG_PATH_SPECIALISED), or AUTO once it pays)
+  bool spec_auto_ok = false, spec_auto_tried = false;
+  double lane_work = 0.0;   // voice-samples this bank has rendered on a lane interpreter (AUTO specialises past a threshold)
 };
 
 static thread_local std::string g_err;
@@ -405,6 +408,7 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   if (!b->biquad_scan_ok) b->tv.sequential = true;   // those biquads are stepped by one thread in the reference's operation order
   // block mode evaluates an instruction for a whole block of samples before the next one: valid for feed-forward tapes,
   // and for feedback loops whose delay line is at least one block long
+  b->spec_auto_ok = spec_auto_ok(t);
   b->block_ok = !(t.h.flags & TAPE_DIVERGENT);
   for (const Instr& i : t.code) {
     if ((i.op == OP_FB_READ || i.op == OP_FB_WRITE) && t.rings[i.aux].length < (uint32_t)interp_block_len()) b->block_ok = false;
@@ -487,6 +491,8 @@ int qg_bank_reset(qg_bank* b) {
 // which kernel family serves voice-major, group-1 renders: 0 lane interpreter, 1 fused, 2 time-vector interpreter
 static int bank_family(const qg_bank* b) {
   if (b->path == QG_PATH_SPECIALISED) return b->spec.fn ? 3 : 0;
+  if (b->path == QG_PATH_AUTO && b->spec.fn && b->fused.id == FUSED_NONE && !(b->tv.ok && (b->tv.has_fft || b->V <= (b->tv.sequential ? 256 : 2048))))
+    return 3;   // AUTO specialised this lane-interpreter bank (bank_auto_specialise)
   if (b->path == QG_PATH_INTERP || b->path == QG_PATH_INTERP_SAMPLE) return 0;
   if (b->path == QG_PATH_TV) return b->tv.ok ? 2 : 0;
   if (b->fused.id != FUSED_NONE) return 1;
@@ -577,6 +583,25 @@ static int check_group(const qg_bank* b, int layout, int group) {
   return QG_OK;
 }
 
+// AUTO: a bank that runs on a lane interpreter gets its tape compiled into the kernel (K1s) as soon as a kernel for this tape
+// is in the process-wide cache, or once the bank has enough work behind and ahead of it to pay for ~1 s of NVRTC
+// (QG_SPEC_MIN_WORK voice-samples, default 1e10; QG_SPEC_AUTO=0 switches the policy off).  A failed compile leaves the bank
+// where it was.
+static void bank_auto_specialise(qg_bank* b, long T) {
+  if (b->path != QG_PATH_AUTO || b->spec.fn || b->spec_auto_tried || !b->spec_auto_ok) return;
+  const char* ea = getenv("QG_SPEC_AUTO");
+  const bool enabled = !(ea && ea[0] == '0');
+  const char* ew = getenv("QG_SPEC_MIN_WORK");
+  const double wv = ew ? atof(ew) : 0.0, min_work = wv > 0.0 ? wv : 1.0e10;
+  if (!enabled) return;
+  if (spec_cached(b->tape, &b->spec)) return;
+  b->lane_work += (double)b->V * (double)T;
+  if (b->lane_work < min_work) return;
+  b->spec_auto_tried = true;
+  std::string err;
+  try { spec_compile(b->tape, &b->spec, &err); } catch (...) {}
+}
+
 static int render_impl(qg_bank* b, long T, int layout, int group, const float* d_in, float* d_out) {
   qg_ctx* c = b->ctx;
   const Tape& t = b->tape;
@@ -584,6 +609,7 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   if (T <= 0) return QG_OK;
   int rc = check_group(b, layout, group);
   if (rc) return rc;
+  if (bank_family(b) == 0) bank_auto_specialise(b, T);
   const int family = bank_family(b);
   if (family == 2 && group == 1) {
     TvArgs ta;

@@ -25,11 +25,16 @@ struct SpecKernel {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t fn = nullptr;
   double compile_seconds = 0.0;
+  bool shared = false;   // owned by the process-wide cache (spec.cpp): never unloaded by a bank
 };
 // Compiles spec_source(t) for sm_100a with the NVRTC found at run time (dlopen: the library has no link-time dependency on
 // it) and loads the cubin.  Returns false with `err` set when NVRTC is missing, the sources next to the library are not
 // found, or compilation fails — the caller keeps the interpreter.
 bool spec_compile(const Tape& t, SpecKernel* out, std::string* err);
+// AUTO policy helpers: the tape's specialised kernel would not pay a dependent HBM load per sample; the kernel is already in
+// the process-wide cache (no compile needed)
+bool spec_auto_ok(const Tape& t);
+bool spec_cached(const Tape& t, SpecKernel* out);
 cudaError_t spec_launch(const SpecKernel& k, const InterpArgs& a, cudaStream_t stream, int* launches);
 void spec_release(SpecKernel* k);
 

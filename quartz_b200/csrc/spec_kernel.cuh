@@ -43,25 +43,17 @@ __device__ __forceinline__ uint32_t ring_len(const RegLane& L, uint32_t r) { ret
 __device__ __forceinline__ void reset_range(const RegLane&, uint32_t) {}
 __device__ __forceinline__ void lane_fft(const RegLane&, uint32_t, uint32_t, int, const float*, bool) {}
 
-template <int i>
-__device__ __forceinline__ void spec_run(RegLane& L, int& pc) {
-  if constexpr (i < SPEC_N) {
-    constexpr Instr I = kTape[i];
-    exec(I, L, pc);
-    spec_run<i + 1>(L, pc);
-  }
-}
-
-#if defined(QG_SPEC_PREFETCH)
-// EXPERIMENTAL (QG_SPEC_PREFETCH=1 in the environment at qg_bank_set_path time; not yet run on hardware): delay lines
-// without a dependent HBM load per sample.  A delay op's ring position is a counter, and the reads of 8 consecutive samples
-// do not depend on the writes of those samples when the ring is at least 8 long (the rule of K1b's whole-block access):
-// per block of 8 samples the kernel issues all ring reads of every such delay op up front (independent loads), runs the 8
-// samples out of registers, then stores the 8 writes.
-constexpr int SPEC_BT = 8;
-__host__ __device__ constexpr bool spec_is_pref(int i) { return kTape[i].op == OP_DELAY && kRingLen[kTape[i].aux] >= (uint32_t)SPEC_BT; }
+// Delay lines without a dependent HBM load per sample.  A delay op's ring position is a counter, and the reads of 8
+// consecutive samples do not depend on the writes of those samples when the ring is at least 8 long (the rule of K1b's
+// whole-block access): per block of 8 samples the kernel issues all ring reads of every such delay op up front (8
+// independent 128-byte lines per warp and op), runs the 8 samples out of registers, then stores the 8 writes.
+// Measured without it (round 1): one dependent load per sample made configs[4]'s delay archetype 6x SLOWER than K1b.
+__host__ __device__ constexpr bool spec_is_pref(int i) { return kTape[i].op == OP_DELAY && kRingLen[kTape[i].aux] >= 8u; }
 __host__ __device__ constexpr int spec_pref_before(int upto) { int c = 0; for (int k = 0; k < upto; k++) c += spec_is_pref(k) ? 1 : 0; return c; }
 constexpr int SPEC_ND = spec_pref_before(SPEC_N);
+// samples per block: 8 when a delay line is prefetched, else 1 (the tape is instantiated once per sample of a block, and
+// NVRTC's compile time grows with it)
+constexpr int SPEC_BT = SPEC_ND > 0 ? 8 : 1;
 
 struct DelayBlock {
   float rd[SPEC_ND > 0 ? SPEC_ND : 1][SPEC_BT];
@@ -116,11 +108,76 @@ __device__ __forceinline__ void spec_ring_writes(RegLane& L, DelayBlock& D, int 
     spec_ring_writes<i + 1>(L, D, n);
   }
 }
-#endif
+
+struct SpecOut {
+  float* tiles;
+  int lane, warp, nwarps, warp_v0;
+};
+
+// one sample (index j of its block): inputs, the tape, outputs parked in the warp's 32 x 33 tile (or stored, frame-major)
+template <int j>
+__device__ __forceinline__ void spec_sample(const InterpArgs& a, RegLane& L, DelayBlock& D, const SpecOut& o, long t) {
+  const int v = L.v;
+#pragma unroll
+  for (int c = 0; c < SPEC_NIN; c++) {
+    size_t idx = a.in_frame_major ? ((size_t)t * a.V + v) * SPEC_NIN + c : ((size_t)v * SPEC_NIN + c) * a.T + t;
+    L.x[SPEC_P + SPEC_NS + c] = v < a.V ? a.in[idx] : 0.0f;
+  }
+  int pc = 0;
+  spec_run_blk<0, j>(L, D, pc);
+  if (a.out_frame_major) {
+    if (v < a.V) {
+#pragma unroll
+      for (int c = 0; c < SPEC_NOUT; c++) a.out[((size_t)t * a.V + v) * SPEC_NOUT + c] = L.x[kOutX[c]];
+    }
+  } else {
+    const int tt = (int)(t & 31);
+#pragma unroll
+    for (int c = 0; c < SPEC_NOUT; c++) o.tiles[(((size_t)c * o.nwarps + o.warp) * 32 + o.lane) * 33 + tt] = L.x[kOutX[c]];
+  }
+}
+// voice-major outputs: the tile holds samples t - (t & 31) .. t; same staging and the same left-to-right group mix as k_interp
+__device__ __noinline__ void spec_flush(const InterpArgs& a, const SpecOut& o, long t) {
+  const int tt = (int)(t & 31);
+  __syncwarp();
+  const long t_base = t - tt;
+  const int ncols = tt + 1;
+  for (int c = 0; c < SPEC_NOUT; c++) {
+    const float* tile = o.tiles + ((size_t)c * o.nwarps + o.warp) * 32 * 33;
+    if (a.group <= 1) {
+      for (int r = 0; r < 32; r++) {
+        int vv = o.warp_v0 + r;
+        if (vv < a.V && o.lane < ncols) a.out[((size_t)vv * SPEC_NOUT + c) * a.T + t_base + o.lane] = tile[r * 33 + o.lane];
+      }
+    } else {
+      const int G = a.group;
+      const float inv = 1.0f / (float)G;
+      for (int g0 = 0; g0 < 32; g0 += G) {
+        int gi = (o.warp_v0 + g0) / G;
+        if (o.warp_v0 + g0 + G <= a.V && o.lane < ncols) {
+          float acc = tile[g0 * 33 + o.lane];
+          for (int r = 1; r < G; r++) acc += tile[(g0 + r) * 33 + o.lane];
+          a.out[((size_t)gi * SPEC_NOUT + c) * a.T + t_base + o.lane] = acc * inv;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+template <int j>
+__device__ __forceinline__ void spec_block(const InterpArgs& a, RegLane& L, DelayBlock& D, const SpecOut& o, long t0, int n) {
+  if constexpr (j < SPEC_BT) {
+    if (j < n) spec_sample<j>(a, L, D, o, t0 + j);
+    spec_block<j + 1>(a, L, D, o, t0, n);
+  }
+}
 
 extern "C" __global__ void __launch_bounds__(128) k_spec(InterpArgs a) {
-  const int nt = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  float* tiles = QG_SMEM_F;                                  // [n_out][nwarps][32][33]
+  const int nt = blockDim.x, tid = threadIdx.x;
+  SpecOut o;
+  o.tiles = QG_SMEM_F;                                       // [n_out][nwarps][32][33]
+  o.lane = tid & 31; o.warp = tid >> 5; o.nwarps = nt >> 5;
+  o.warp_v0 = blockIdx.x * nt + o.warp * 32;
   const int v = blockIdx.x * nt + tid;                       // padded voice index, always < Vp
   RegLane L;
   L.v = v; L.Vp = a.Vp; L.rings = a.rings; L.ring_tab = a.ring_tab; L.tables = a.tables;
@@ -130,75 +187,14 @@ extern "C" __global__ void __launch_bounds__(128) k_spec(InterpArgs a) {
   for (int s = 0; s < SPEC_NS; s++) L.x[SPEC_P + s] = a.state[(size_t)s * a.Vp + v];
 #pragma unroll
   for (int k = 0; k < SPEC_NT; k++) L.x[SPEC_P + SPEC_NS + k] = 0.0f;
-
-  const int warp_v0 = blockIdx.x * nt + warp * 32;
-#if defined(QG_SPEC_PREFETCH)
   DelayBlock D;
-#endif
-  for (long t = 0; t < a.T; t++) {
-#pragma unroll
-    for (int c = 0; c < SPEC_NIN; c++) {
-      size_t idx = a.in_frame_major ? ((size_t)t * a.V + v) * SPEC_NIN + c : ((size_t)v * SPEC_NIN + c) * a.T + t;
-      L.x[SPEC_P + SPEC_NS + c] = v < a.V ? a.in[idx] : 0.0f;
-    }
-    int pc = 0;
-#if defined(QG_SPEC_PREFETCH)
-    {
-      const int j = (int)(t & (SPEC_BT - 1));
-      const int n = (a.T - (t - j)) < SPEC_BT ? (int)(a.T - (t - j)) : SPEC_BT;      // samples in this block
-      if (j == 0) spec_ring_reads<0>(L, D, n);
-      switch (j) {
-        case 0: spec_run_blk<0, 0>(L, D, pc); break;
-        case 1: spec_run_blk<0, 1>(L, D, pc); break;
-        case 2: spec_run_blk<0, 2>(L, D, pc); break;
-        case 3: spec_run_blk<0, 3>(L, D, pc); break;
-        case 4: spec_run_blk<0, 4>(L, D, pc); break;
-        case 5: spec_run_blk<0, 5>(L, D, pc); break;
-        case 6: spec_run_blk<0, 6>(L, D, pc); break;
-        default: spec_run_blk<0, 7>(L, D, pc); break;
-      }
-      if (j == n - 1) spec_ring_writes<0>(L, D, n);
-    }
-#else
-    spec_run<0>(L, pc);
-#endif
-    // ---- outputs: same staging and the same left-to-right group mix as k_interp
-    if (a.out_frame_major) {
-      if (v < a.V) {
-#pragma unroll
-        for (int c = 0; c < SPEC_NOUT; c++) a.out[((size_t)t * a.V + v) * SPEC_NOUT + c] = L.x[kOutX[c]];
-      }
-    } else {
-      const int tt = (int)(t & 31);
-#pragma unroll
-      for (int c = 0; c < SPEC_NOUT; c++) tiles[(((size_t)c * nwarps + warp) * 32 + lane) * 33 + tt] = L.x[kOutX[c]];
-      if (tt == 31 || t == a.T - 1) {
-        __syncwarp();
-        const long t_base = t - tt;
-        const int ncols = tt + 1;
-        for (int c = 0; c < SPEC_NOUT; c++) {
-          const float* tile = tiles + ((size_t)c * nwarps + warp) * 32 * 33;
-          if (a.group <= 1) {
-            for (int r = 0; r < 32; r++) {
-              int vv = warp_v0 + r;
-              if (vv < a.V && lane < ncols) a.out[((size_t)vv * SPEC_NOUT + c) * a.T + t_base + lane] = tile[r * 33 + lane];
-            }
-          } else {
-            const int G = a.group;
-            const float inv = 1.0f / (float)G;
-            for (int g0 = 0; g0 < 32; g0 += G) {
-              int gi = (warp_v0 + g0) / G;
-              if (warp_v0 + g0 + G <= a.V && lane < ncols) {
-                float acc = tile[g0 * 33 + lane];
-                for (int r = 1; r < G; r++) acc += tile[(g0 + r) * 33 + lane];
-                a.out[((size_t)gi * SPEC_NOUT + c) * a.T + t_base + lane] = acc * inv;
-              }
-            }
-          }
-        }
-        __syncwarp();
-      }
-    }
+  for (long t0 = 0; t0 < a.T; t0 += SPEC_BT) {
+    const int n = (a.T - t0) < SPEC_BT ? (int)(a.T - t0) : SPEC_BT;      // samples in this block
+    spec_ring_reads<0>(L, D, n);
+    spec_block<0>(a, L, D, o, t0, n);
+    spec_ring_writes<0>(L, D, n);
+    // blocks start on multiples of SPEC_BT (a divisor of 32): a tile fills exactly at a block's end
+    if (!a.out_frame_major && (((t0 + n) & 31) == 0 || t0 + n == a.T)) spec_flush(a, o, t0 + n - 1);
   }
 #pragma unroll
   for (int s = 0; s < SPEC_NS; s++) a.state[(size_t)s * a.Vp + v] = L.x[SPEC_P + s];

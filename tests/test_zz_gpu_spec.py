@@ -1,6 +1,8 @@
 """K1s — the tape-specialised lane kernel (qg_bank_set_path(QG_PATH_SPECIALISED), csrc/spec.cpp + spec_kernel.cuh): the tape
 is compiled into the kernel with NVRTC, exec() is the same code as in every interpreter, so results must be BIT-IDENTICAL to
-the sample-by-sample interpreter.  Opt-in in round 1 (AUTO never selects it); this file sorts after every other test file on purpose."""
+the sample-by-sample interpreter.  AUTO selects it for lane-interpreter banks once the bank's work pays for the compile, or at
+once when the tape's kernel is already in the process-wide cache."""
+import os
 import numpy as np
 import pytest
 
@@ -47,7 +49,6 @@ def test_tapes_that_cannot_be_specialised_are_refused_by_name():
 UNIFORM = [c for c in cases.RENDER if not any(k in repr(c[1]) for k in ("kr()", "s()", "reset", "select()", "seq()", "rfft", "ifft"))]
 
 
-@pytest.mark.xfail(strict=False, reason="broad sweep of K1s written after the round's GPU minutes were spent: first run is the round-end one")
 @pytest.mark.parametrize("name,expr,n,tol", UNIFORM, ids=[c[0] for c in UNIFORM])
 def test_specialised_kernel_matches_the_interpreter_on_every_uniform_case(name, expr, n, tol):
     net = build(expr, Net)
@@ -59,3 +60,39 @@ def test_specialised_kernel_matches_the_interpreter_on_every_uniform_case(name, 
     spec = specialised(Bank(net, V, salts=salts))
     a, b = ref.render(min(n, 2048)), spec.render(min(n, 2048))
     assert (a.view(np.uint32) == b.view(np.uint32)).all(), f"{name}: max diff {np.nanmax(np.abs(a - b)):.3e}"
+
+
+def test_auto_specialises_a_lane_bank_once_its_work_pays_for_the_compile_and_reuses_cached_kernels():
+    """AUTO policy (capi.cu: bank_auto_specialise): below QG_SPEC_MIN_WORK voice-samples a bank stays on its interpreter; past
+    it the tape is compiled into the kernel, the state carries over bit for bit, and a later bank of the same tape gets
+    the cached kernel on its first render.  Taps / feedback rings keep the block-mode interpreter (dependent ring loads)."""
+    wl = workloads.c5_mixed(V=4 * 2048, T=4096)[3]          # delay(1024 samples) + lowpole: the prefetched delay line
+    net = build(wl.expr, Net)
+    ref = Bank(net, wl.V, raw=wl.raw, salts=wl.salts).set_path(qb.PATH_INTERP_SAMPLE)
+    os.environ["QG_SPEC_MIN_WORK"] = str(float(wl.V * 3000))
+    try:
+        bank = Bank(net, wl.V, raw=wl.raw, salts=wl.salts)
+        assert bank.kernel() == "k_interp_blk"
+        a0, b0 = ref.render(2000, group=32), bank.render(2000, group=32)      # 2000 < 3000: still the interpreter
+        assert bank.kernel() == "k_interp_blk"
+        a1, b1 = ref.render(2096, group=32), bank.render(2096, group=32)      # cumulative work passes the threshold
+        if bank.kernel() != "k_spec":
+            pytest.skip("NVRTC not available on this box: AUTO keeps the interpreter")
+        a2, b2 = ref.render(1000, group=32), bank.render(1000, group=32)
+        for x, y in ((a0, b0), (a1, b1), (a2, b2)):
+            assert (x.view(np.uint32) == y.view(np.uint32)).all()
+    finally:
+        del os.environ["QG_SPEC_MIN_WORK"]
+    again = Bank(net, wl.V, raw=wl.raw, salts=wl.salts)                        # default threshold (1e10): cache hit
+    ref.reset()
+    x, y = ref.render(500), again.render(500)
+    assert again.kernel() == "k_spec"
+    assert (x.view(np.uint32) == y.view(np.uint32)).all()
+    tap = build({"op": ">>", "n": 0.0, "inputs": [{"op": "|", "n": 0.0, "inputs": [{"op": "white()"}, {"op": "dc(0.01)"}]}, {"op": "tap(0.001,0.05)"}]}, Net)
+    os.environ["QG_SPEC_MIN_WORK"] = "1"
+    try:
+        tb = Bank(tap, 4096)
+        tb.render(256)
+        assert tb.kernel() != "k_spec", tb.kernel()
+    finally:
+        del os.environ["QG_SPEC_MIN_WORK"]
