@@ -1,6 +1,5 @@
 """The in-tree nodes driven through qg_bank_process with the edge-case inputs of tests/test_oracle_intree.py (NaN / inf /
-huge / negative indices and triggers, -0.0 triggers, zero durations) on every lane kernel, bit for bit against the oracle.
-Written after the round's GPU minutes were spent: non-strict xfail until its first hardware run (file sorts last)."""
+huge / negative indices and triggers, -0.0 triggers, zero durations) on every lane kernel, bit for bit against the oracle."""
 import numpy as np
 import pytest
 
@@ -10,7 +9,7 @@ from tests.graphs import build, pipe
 from tests.oracle_ffi import ONet
 from tests.test_oracle_intree import inputs
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run is the round-end one")]
+pytestmark = pytest.mark.gpu
 
 RAMPS = [pipe("dc(300)", "ramp()"), pipe("dc(1100)", "ramp()"), pipe("dc(50)", "ramp()")]
 
