@@ -42,7 +42,8 @@ enum { QG_PATH_AUTO = 0, QG_PATH_INTERP = 1, QG_PATH_TV = 2, QG_PATH_INTERP_SAMP
    small feed-forward banks, else the lane interpreter (block mode for feed-forward tapes); INTERP forces the lane
    interpreter, INTERP_SAMPLE its sample-by-sample kernel; SPECIALISED compiles a lane kernel for this bank's tape with
    NVRTC (seconds, once per bank; uniform tapes only; fails with QG_ERR_UNSUPPORTED when NVRTC or the tape does not allow
-   it) — opt-in, never chosen by AUTO */
+   it); AUTO chooses it by itself for lane banks whose work pays for the compile */
+enum { QG_SAMPLE_F32 = 0, QG_SAMPLE_I16 = 1, QG_SAMPLE_U16 = 2 };   /* cpal::SampleFormat as src/audio.rs:56-59 dispatches it */
 
 const char* qg_last_error(void);
 const char* qg_version(void);
@@ -112,6 +113,12 @@ int qg_bank_set_raw(qg_bank* bank, int raw_index, float value);
 /* Stream path (src/audio.rs:85-118) for a one-voice bank: n frames, non-normal -> 0, clamp to [-1,1], interleaved L R;
  * mono graphs get a silent right channel, other arities play silence (src/process.rs:1896-1905). */
 int qg_bank_render_stereo(qg_bank* bank, long n_frames, float* h_frames);
+/* The same frames in the device's sample type (`T::from_sample`, src/audio.rs:47-59, 115-116): h_frames holds
+ * 2 * n_frames samples of f32, i16 ((s * 32768) as i16, saturating) or u16 (offset binary). */
+int qg_bank_render_stereo_as(qg_bank* bank, long n_frames, int sample_format /* QG_SAMPLE_* */, void* h_frames);
+/* Value copy of a bank WITH its state (the reference deep-clones a Net, state included, on every hop: src/process.rs:1316,
+ * 1336, 1499, 1558, 1895; AudioUnit is DynClone): both banks continue independently and identically. */
+qg_bank* qg_bank_clone(const qg_bank* bank);
 /* Sum the rows of a device buffer [rows][n] into d_out[n] (rows added in index order), scaled. */
 int qg_mix_rows_device(qg_ctx* ctx, const float* d_rows, long rows, long n, float scale, float* d_out);
 

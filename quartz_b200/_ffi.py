@@ -61,6 +61,8 @@ SIGNATURES = {
     "qg_bank_process": (ci, [vp, cl, ci, vp, vp]),
     "qg_bank_set_raw": (ci, [vp, ci, cf]),
     "qg_bank_render_stereo": (ci, [vp, cl, vp]),
+    "qg_bank_render_stereo_as": (ci, [vp, cl, ci, vp]),
+    "qg_bank_clone": (vp, [vp]),
     "qg_mix_rows_device": (ci, [vp, vp, cl, cl, cf, vp]),
     "qg_net_render": (ci, [vp, vp, cl, vp]),
     "qg_net_tick": (ci, [vp, vp, fp, ci, fp, ci]),

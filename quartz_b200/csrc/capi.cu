@@ -380,13 +380,15 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   b->fused = plan_fused(t);
   // ---- parameters: derive per voice on the host (same libm as the reference would use), or broadcast the template
   if (raw_matrix && R > 0) b->raw.assign(raw_matrix, raw_matrix + (size_t)b->V * R);
-  if (raw_matrix && R > 0 && P > 0) {
+  if (raw_matrix && R > 0) {   // also for tapes without device parameters (pass() >> delay(x)): the delay still shapes the tape
     for (int r = 0; r < R; r++) {
       if (!t.raw_structural[r]) continue;
       for (long v = 0; v < b->V; v++)
         if (memcmp(&raw_matrix[(size_t)v * R + r], &t.raw[r], 4) != 0)
           return fail(QG_ERR_MISMATCH, "raw parameter " + std::to_string(r) + " shapes the tape (delay length / reset period) and must be equal for every voice");
     }
+  }
+  if (raw_matrix && R > 0 && P > 0) {
     std::vector<float> host;
     derive_table(t, raw_matrix, R, b->V, b->Vp, &host);
     CU(cudaMemcpyAsync(b->d_params, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -759,9 +761,12 @@ int qg_bank_process(qg_bank* b, long T, int layout, const float* h_in, float* h_
   return QG_OK;
 }
 
-// Stream path: n sanitised, clamped, interleaved stereo frames of a one-voice bank (src/audio.rs:85-118)
-int qg_bank_render_stereo(qg_bank* b, long n, float* h_frames) {
+// Stream path: n sanitised, clamped, interleaved stereo frames of a one-voice bank (src/audio.rs:85-118) in the device
+// sample type: f32, i16 or u16 (`T::from_sample`, audio.rs:115-116)
+int qg_bank_render_stereo_as(qg_bank* b, long n, int sample_format, void* h_frames) {
   if (!b || !h_frames) return fail(QG_ERR_ARG, "qg_bank_render_stereo: bad arguments");
+  if (sample_format != QG_SAMPLE_F32 && sample_format != QG_SAMPLE_I16 && sample_format != QG_SAMPLE_U16)
+    return fail(QG_ERR_ARG, "unsupported sample format (cpal offers f32, i16, u16: audio.rs:47-59)");
   if (b->V != 1 || b->tape.h.n_inputs != 0) return fail(QG_ERR_ARITY, "stream path needs one 0-input graph (process.rs:1896)");
   if (n <= 0) return QG_OK;
   qg_ctx* c = b->ctx;
@@ -770,16 +775,67 @@ int qg_bank_render_stereo(qg_bank* b, long n, float* h_frames) {
   const size_t sb = (size_t)std::max(no, 1) * n * sizeof(float), fb = (size_t)2 * n * sizeof(float);
   int rc = ensure(&b->d_scratch, &b->scratch_bytes, sb + fb);
   if (rc) return rc;
-  float* d_frames = b->d_scratch + (size_t)std::max(no, 1) * n;
+  // frames first: k_stereo_frames stores float2, which needs 8-byte alignment whatever n and the channel count are
+  float* d_frames = b->d_scratch;
+  float* d_src = b->d_scratch + (size_t)2 * n;
   if (no == 1 || no == 2) {
-    rc = render_impl(b, n, QG_LAYOUT_VOICE_MAJOR, 1, nullptr, b->d_scratch);
+    rc = render_impl(b, n, QG_LAYOUT_VOICE_MAJOR, 1, nullptr, d_src);
     if (rc) return rc;
   }
-  CU(launch_stereo_frames(b->d_scratch, (no == 1 || no == 2) ? no : 0, n, d_frames, c->stream));
+  const int n_ch = (no == 1 || no == 2) ? no : 0;
+  size_t out_bytes = fb;
+  if (sample_format == QG_SAMPLE_F32) CU(launch_stereo_frames(d_src, n_ch, n, d_frames, c->stream));
+  else {
+    CU(launch_stereo_frames_i16(d_src, n_ch, n, sample_format == QG_SAMPLE_U16 ? 1 : 0, d_frames, c->stream));
+    out_bytes = (size_t)2 * n * sizeof(int16_t);
+  }
   c->launches++;
-  CU(cudaMemcpyAsync(h_frames, d_frames, fb, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(h_frames, d_frames, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return QG_OK;
+}
+int qg_bank_render_stereo(qg_bank* b, long n, float* h_frames) { return qg_bank_render_stereo_as(b, n, QG_SAMPLE_F32, h_frames); }
+
+// Value copy of a bank WITH its state (the reference deep-clones a Net, state included, on every hop: process.rs:1316, 1336,
+// 1499, 1558, 1895; FunDSP's AudioUnit is DynClone): parameters, state, delay lines and the kernel choice are copied device
+// to device; both banks continue independently and identically.
+qg_bank* qg_bank_clone(const qg_bank* src) {
+  if (!src) { fail(QG_ERR_ARG, "qg_bank_clone: null bank"); return nullptr; }
+  qg_bank* b = nullptr;
+  try {
+    b = new qg_bank();
+    b->ctx = src->ctx; b->tape = src->tape; b->V = src->V; b->Vp = src->Vp; b->path = src->path;
+    b->raw = src->raw; b->fused = src->fused; b->tv = src->tv; b->biquad_scan_ok = src->biquad_scan_ok;
+    b->block_ok = src->block_ok; b->ring_mode = src->ring_mode; b->state_ready = src->state_ready;
+    b->spec_auto_ok = src->spec_auto_ok; b->spec_auto_tried = src->spec_auto_tried; b->lane_work = src->lane_work;
+    if (src->spec.fn && src->spec.shared) b->spec = src->spec;     // kernels live in the process-wide cache
+  } catch (...) {
+    delete b;
+    fail(QG_ERR_ARG, "qg_bank_clone: out of memory");
+    return nullptr;
+  }
+  qg_ctx* c = b->ctx;
+  const Tape& t = b->tape;
+  const size_t P = t.h.n_params, NS = t.h.n_state;
+  auto dup = [&](auto** dst, const auto* from, size_t bytes) -> bool {
+    bytes = std::max<size_t>(bytes, 4);
+    if (cudaMalloc((void**)dst, bytes) != cudaSuccess) return false;
+    return !from || cudaMemcpyAsync(*dst, from, bytes, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+  };
+  bool ok = cudaSetDevice(c->device) == cudaSuccess;
+  ok = ok && dup(&b->d_code, src->d_code, t.code.size() * sizeof(Instr)) && dup(&b->d_out_x, src->d_out_x, t.out_x.size() * sizeof(uint16_t)) &&
+       dup(&b->d_ring_tab, src->d_ring_tab, t.rings.size() * sizeof(Ring)) && dup(&b->d_resets, src->d_resets, t.resets.size() * sizeof(ResetRange)) &&
+       dup(&b->d_tables, src->d_tables, t.tables.size() * sizeof(float)) && dup(&b->d_state_keep, src->d_state_keep, t.state_keep.size()) &&
+       dup(&b->d_params, src->d_params, P * b->Vp * sizeof(float)) && dup(&b->d_state, src->d_state, NS * b->Vp * sizeof(float)) &&
+       dup(&b->d_state_init, src->d_state_init, NS * b->Vp * sizeof(float)) &&
+       dup(&b->d_rings, src->d_rings, (size_t)t.h.ring_floats * b->Vp * sizeof(float));
+  ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+  if (!ok) {
+    fail(QG_ERR_CUDA, std::string("qg_bank_clone: ") + cudaGetErrorString(cudaGetLastError()));
+    bank_release(b);
+    return nullptr;
+  }
+  return b;
 }
 
 int qg_mix_rows_device(qg_ctx* c, const float* d_rows, long rows, long n, float scale, float* d_out) {

@@ -288,6 +288,10 @@ Graph connect(const std::string& op, const std::vector<const Graph*>& nets, doub
     // a pass that combines nothing (arity guards, node limit) leaves `graph` as it was, so every later pass would do the
     // same: stop instead of spinning through up to 2^31 repetitions (the result is the reference's, without its wait)
     bool changed = false;
+    // ... and so does a pass over operands of size 0 without ports (a failed str_to_net, an empty connective): combining
+    // them succeeds without growing anything, the node limit is never reached
+    const int size0 = graph.size(), in0 = graph.inputs(), out0 = graph.outputs();
+    const bool was_empty = empty;
     for (const Graph* np : nets) {
       if (!np) continue;
       if (empty) { graph = *np; empty = false; changed = true; continue; }
@@ -307,6 +311,7 @@ Graph connect(const std::string& op, const std::vector<const Graph*>& nets, doub
       }
     }
     if (!changed) break;
+    if (!was_empty && graph.size() == size0 && graph.inputs() == in0 && graph.outputs() == out0) break;
   }
   if (graph.unsupported.empty()) graph.unsupported = unsup;
   return graph;
@@ -315,6 +320,8 @@ Graph connect(const std::string& op, const std::vector<const Graph*>& nets, doub
 // Rust `format!("{}", f32)`: shortest decimal that round-trips, never an exponent.
 static std::string fmt_f32(float v) {
   char buf[512];
+  if (v != v) return "NaN";                       // Rust's Display for f32
+  if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
   for (int prec = 1; prec < 12; prec++) {
     snprintf(buf, sizeof buf, "%.*g", prec, (double)v);
     if (strtof(buf, nullptr) == v) break;

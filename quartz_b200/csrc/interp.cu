@@ -921,6 +921,21 @@ __global__ void k_stereo_frames(const float* __restrict__ src, int n_ch, long n,
   r = d_is_normal(r) ? d_clamp(r, -1.0f, 1.0f) : 0.0f;
   reinterpret_cast<float2*>(frames)[t] = make_float2(l, r);
 }
+// the same frames in the device sample types cpal offers besides f32 (audio.rs:115-116 `T::from_sample`, dasp_sample's
+// conversions [external, restated]): i16 = (s * 32768) as i16 (Rust's float -> int cast truncates and saturates),
+// u16 = that value in offset binary
+__global__ void k_stereo_frames_i16(const float* __restrict__ src, int n_ch, long n, int offset_binary, uint32_t* __restrict__ frames) {
+  long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  float l = 0.0f, r = 0.0f;
+  if (n_ch == 1) l = src[t];
+  else if (n_ch == 2) { l = src[t]; r = src[n + t]; }
+  l = d_is_normal(l) ? d_clamp(l, -1.0f, 1.0f) : 0.0f;
+  r = d_is_normal(r) ? d_clamp(r, -1.0f, 1.0f) : 0.0f;
+  int li = max(-32768, min(32767, d_as_i32(l * 32768.0f))), ri = max(-32768, min(32767, d_as_i32(r * 32768.0f)));
+  if (offset_binary) { li += 32768; ri += 32768; }
+  frames[t] = ((uint32_t)li & 0xffffu) | ((uint32_t)ri << 16);          // little-endian L then R
+}
 
 // full mix of the rows of a [R][T] buffer into one [T] row: rows are added in index order (per output sample)
 __global__ void k_mix_rows(const float* rows, int R, long T, float scale, float* out) {
@@ -1575,6 +1590,10 @@ cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int
 }
 cudaError_t launch_stereo_frames(const float* src, int n_ch, long n, float* frames, cudaStream_t stream) {
   k_stereo_frames<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, n_ch, n, frames);
+  return cudaGetLastError();
+}
+cudaError_t launch_stereo_frames_i16(const float* src, int n_ch, long n, int offset_binary, void* frames, cudaStream_t stream) {
+  k_stereo_frames_i16<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, n_ch, n, offset_binary, (uint32_t*)frames);
   return cudaGetLastError();
 }
 cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream) {

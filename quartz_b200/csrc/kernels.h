@@ -75,6 +75,8 @@ cudaError_t launch_init_state(float* state_init, const uint32_t* defaults, int N
 cudaError_t launch_reset_state(float* state, const float* state_init, const uint8_t* keep, int NS, int Vp, cudaStream_t stream);
 cudaError_t launch_broadcast_params(float* params, const float* tmpl, int P, int Vp, cudaStream_t stream);
 cudaError_t launch_stereo_frames(const float* src, int n_ch, long n, float* frames, cudaStream_t stream);
+// i16 (offset_binary = 0) or u16 (1) frames, interleaved L R
+cudaError_t launch_stereo_frames_i16(const float* src, int n_ch, long n, int offset_binary, void* frames, cudaStream_t stream);
 cudaError_t launch_mix_rows(const float* rows, int R, long T, float scale, float* out, cudaStream_t stream);
 #endif
 

@@ -114,10 +114,21 @@ struct Lower {
   int wt_offset[4] = {-1, -1, -1, -1};   // wavetable sets already placed in the tables region
   explicit Lower(Tape& t_) : t(t_) {}
 
-  uint16_t temp(int n = 1) { int i = n_temps; n_temps += n; return (uint16_t)(R_TEMP | i); }
-  uint16_t param(float v) { t.params.push_back(v); return (uint16_t)(t.params.size() - 1); }
-  uint16_t params(int n, float v = 0.0f) { uint16_t b = (uint16_t)t.params.size(); t.params.resize(t.params.size() + n, v); return b; }
+  // 16-bit operand indices: 15 bits of temporaries, 14 of parameters and of state.  Checked at allocation — an index that
+  // wrapped would alias an earlier word and the tape would render wrong audio instead of being refused (the temporary-reuse
+  // pass compacts indices later, from whatever they already are).
+  void too_large() { if (err.empty()) err = "graph too large for one tape (parameter/state/temporary index overflow)"; }
+  uint16_t temp(int n = 1) {
+    if (n_temps + n > 0x7fff) { too_large(); return (uint16_t)R_TEMP; }
+    int i = n_temps; n_temps += n; return (uint16_t)(R_TEMP | i);
+  }
+  uint16_t param(float v) { return params(1, v); }
+  uint16_t params(int n, float v = 0.0f) {
+    if (t.params.size() + (size_t)n > 0x3fff) { too_large(); return 0; }
+    uint16_t b = (uint16_t)t.params.size(); t.params.resize(t.params.size() + n, v); return b;
+  }
   uint16_t state(int n = 1, uint32_t init = 0) {
+    if (t.state_init.size() + (size_t)n > 0x3fff) { too_large(); return (uint16_t)R_STATE; }
     uint16_t b = (uint16_t)t.state_init.size();
     t.state_init.resize(t.state_init.size() + n, init);
     t.state_keep.resize(t.state_init.size(), 0);
@@ -125,6 +136,7 @@ struct Lower {
   }
   uint16_t zero() { if (zero_p < 0) zero_p = param(0.0f); return (uint16_t)zero_p; }
   uint32_t ring(uint32_t len) {
+    if (t.rings.size() >= 0xffff) { too_large(); return 0; }     // reset ranges address rings with 16 bits
     Ring r;
     r.offset = t.h.ring_floats;
     r.length = len;

@@ -13,6 +13,7 @@ from ._ffi import QuartzGpuError, check, lib
 
 LAYOUT_VOICE_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
 PATH_AUTO, PATH_INTERP, PATH_TV, PATH_INTERP_SAMPLE, PATH_SPECIALISED = 0, 1, 2, 3, 4
+SAMPLE_F32, SAMPLE_I16, SAMPLE_U16 = 0, 1, 2      # cpal::SampleFormat as audio.rs:56-59 dispatches it
 NODE_LIMIT_DEFAULT = 500   # src/main.rs:72
 
 _CTX = {}
@@ -340,11 +341,21 @@ class Bank:
         """var(): rewrite one op-string parameter for every voice (process.rs:1382-1385)"""
         check(lib().qg_bank_set_raw(self.h, int(raw_index), float(value)))
 
-    def render_stereo(self, n):
-        """stream path (audio.rs:85-118): [n, 2] sanitised, clamped, interleaved frames of a one-voice bank"""
-        out = np.zeros((n, 2), dtype=np.float32)
-        check(lib().qg_bank_render_stereo(self.h, int(n), out.ctypes.data_as(C.c_void_p)))
+    def render_stereo(self, n, sample_format=SAMPLE_F32):
+        """stream path (audio.rs:85-118): [n, 2] sanitised, clamped, interleaved frames of a one-voice bank, in the device's
+        sample type (`T::from_sample`, audio.rs:56-59, 115-116): f32, i16 or u16"""
+        out = np.zeros((n, 2), dtype={SAMPLE_F32: np.float32, SAMPLE_I16: np.int16, SAMPLE_U16: np.uint16}[sample_format])
+        check(lib().qg_bank_render_stereo_as(self.h, int(n), int(sample_format), out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def clone(self):
+        """value copy WITH state, like `Net::clone` (process.rs:1316, 1336, 1499, 1558, 1895): both continue identically"""
+        h = lib().qg_bank_clone(self.h)
+        if not h:
+            raise QuartzGpuError(_ffi.last_error())
+        b = Bank.__new__(Bank)
+        b.ctx, b.h, b.n_voices, b.n_in, b.n_out = self.ctx, h, self.n_voices, self.n_in, self.n_out
+        return b
 
     def render_device(self, n, d_out, layout=LAYOUT_VOICE_MAJOR, group=1):
         check(lib().qg_bank_render_device(self.h, int(n), layout, group, C.c_void_p(d_out)))

@@ -66,6 +66,8 @@ extern "C" {
     fn qg_bank_out_rows(b: *const qg_bank, group: c_int) -> c_long;
     fn qg_bank_render_device(b: *mut qg_bank, n: c_long, layout: c_int, group: c_int, d_out: *mut c_float) -> c_int;
     fn qg_bank_process(b: *mut qg_bank, n: c_long, layout: c_int, input: *const c_float, out: *mut c_float) -> c_int;
+    fn qg_bank_render_stereo_as(b: *mut qg_bank, n_frames: c_long, sample_format: c_int, frames: *mut c_void) -> c_int;
+    fn qg_bank_clone(b: *const qg_bank) -> *mut qg_bank;
     fn qg_mix_rows_device(c: *mut qg_ctx, d_rows: *const c_float, rows: c_long, n: c_long, scale: c_float, d_out: *mut c_float) -> c_int;
 }
 
@@ -198,7 +200,7 @@ pub fn render_many(ctx: &GpuContext, nets: &[&GpuNet], salts: Option<&[u64]>, le
 /// V voices that share one graph structure, resident on one GPU: the unit of throughput work (BASELINE configs[1..4]).
 /// `raw` is the per-voice op-string parameter table [V][raw_count] (None: every voice = the template), `salts` re-seed the
 /// hash-derived state per voice.
-pub struct GpuBank { bank: *mut qg_bank, voices: usize, outputs: usize }
+pub struct GpuBank { bank: *mut qg_bank, voices: usize, inputs: usize, outputs: usize }
 unsafe impl Send for GpuBank {}
 impl GpuBank {
     pub fn new(ctx: &GpuContext, template: &GpuNet, voices: usize, raw: Option<&[f32]>, salts: Option<&[u64]>) -> Result<GpuBank, String> {
@@ -208,7 +210,7 @@ impl GpuBank {
         let bank = unsafe { qg_bank_create(ctx.0, template.0, voices as c_long, raw.map_or(std::ptr::null(), |r| r.as_ptr()),
                                            salts.map_or(std::ptr::null(), |s| s.as_ptr())) };
         if bank.is_null() { return Err(last_error()); }
-        Ok(GpuBank { bank, voices, outputs: template.outputs() })
+        Ok(GpuBank { bank, voices, inputs: template.inputs(), outputs: template.outputs() })
     }
     /// name of the kernel family the next render uses ("k_noise_svf_scan", "k_interp_blk", "k_interp_tv", "k_spec", ...)
     pub fn kernel(&self) -> String { unsafe { CStr::from_ptr(qg_bank_kernel(self.bank)).to_string_lossy().into_owned() } }
@@ -226,9 +228,17 @@ impl GpuBank {
     }
     /// block path with external inputs (AudioUnit::process): `input` voice-major [voices][inputs][len]
     pub fn process(&mut self, len: usize, input: &[f32]) -> Result<Vec<f32>, String> {
+        if input.len() != self.voices * self.inputs * len { return Err("input must be [voices][inputs][len]".into()); }
         let mut out = vec![0f32; self.voices * self.outputs * len];
         let rc = unsafe { qg_bank_process(self.bank, len as c_long, 0, input.as_ptr(), out.as_mut_ptr()) };
         if rc != 0 { Err(last_error()) } else { Ok(out) }
+    }
+}
+/// value copy WITH state (parameters, filter state, delay lines), like `Net::clone`
+impl GpuBank {
+    pub fn try_clone(&self) -> Result<GpuBank, String> {
+        let bank = unsafe { qg_bank_clone(self.bank) };
+        if bank.is_null() { Err(last_error()) } else { Ok(GpuBank { bank, voices: self.voices, inputs: self.inputs, outputs: self.outputs }) }
     }
 }
 impl Drop for GpuBank {
@@ -236,23 +246,32 @@ impl Drop for GpuBank {
 }
 
 /// AudioUnit served from GPU-rendered blocks (0 inputs, C outputs); what `slot.set(.., Box::new(..))`
-/// (src/process.rs:1897) receives instead of the CPU Net.
+/// (src/process.rs:1897) receives instead of the CPU Net.  A failed device call latches `error` and the unit plays
+/// silence from then on (nothing may unwind: the reference builds with panic='abort', Cargo.toml:57).
 pub struct GpuRender {
+    ctx: *mut qg_ctx,    // borrowed: the GpuContext must outlive every unit made from it
+    net: GpuNet,         // the graph this unit renders (set_sample_rate rebuilds the bank from it)
     bank: *mut qg_bank,
     outputs: usize,
     block: Vec<f32>,     // voice-major [outputs][BLOCK]
     pos: usize,
+    pub error: Option<String>,
 }
 unsafe impl Send for GpuRender {}
 unsafe impl Sync for GpuRender {}
 const BLOCK: usize = 4096;
+
+/// sample types of the cpal stream (src/audio.rs:56-59); QG_SAMPLE_* in include/quartz_gpu.h
+#[derive(Clone, Copy, Debug, PartialEq, Eq)]
+#[repr(i32)]
+pub enum SampleFormat { F32 = 0, I16 = 1, U16 = 2 }
 
 impl GpuRender {
     pub fn new(ctx: &GpuContext, net: &GpuNet) -> Result<GpuRender, String> {
         let bank = unsafe { qg_bank_create(ctx.0, net.0, 1, std::ptr::null(), std::ptr::null()) };
         if bank.is_null() { return Err(last_error()); }
         let outputs = net.outputs();
-        Ok(GpuRender { bank, outputs, block: vec![0.0; outputs * BLOCK], pos: BLOCK })
+        Ok(GpuRender { ctx: ctx.0, net: net.clone(), bank, outputs, block: vec![0.0; outputs * BLOCK], pos: BLOCK, error: None })
     }
     /// var() update from the control plane (src/process.rs:1382-1385): takes effect at the next block
     pub fn set_var(&mut self, raw_index: usize, value: f32) -> Result<(), String> {
@@ -263,21 +282,56 @@ impl GpuRender {
         let mut frames = vec![0f32; 2 * n];
         if unsafe { qg_bank_render_stereo(self.bank, n as c_long, frames.as_mut_ptr()) } != 0 { Err(last_error()) } else { Ok(frames) }
     }
+    /// the same frames as the stream's own sample type (`T::from_sample`, src/audio.rs:115-116)
+    pub fn stereo_frames_i16(&mut self, n: usize) -> Result<Vec<i16>, String> {
+        let mut frames = vec![0i16; 2 * n];
+        let rc = unsafe { qg_bank_render_stereo_as(self.bank, n as c_long, SampleFormat::I16 as c_int, frames.as_mut_ptr() as *mut c_void) };
+        if rc != 0 { Err(last_error()) } else { Ok(frames) }
+    }
+    pub fn stereo_frames_u16(&mut self, n: usize) -> Result<Vec<u16>, String> {
+        let mut frames = vec![0u16; 2 * n];
+        let rc = unsafe { qg_bank_render_stereo_as(self.bank, n as c_long, SampleFormat::U16 as c_int, frames.as_mut_ptr() as *mut c_void) };
+        if rc != 0 { Err(last_error()) } else { Ok(frames) }
+    }
     fn refill(&mut self) {
-        unsafe { qg_bank_render(self.bank, BLOCK as c_long, 0, 1, self.block.as_mut_ptr()); }
+        if self.error.is_none() && unsafe { qg_bank_render(self.bank, BLOCK as c_long, 0, 1, self.block.as_mut_ptr()) } != 0 {
+            self.error = Some(last_error());
+        }
+        if self.error.is_some() { self.block.iter_mut().for_each(|s| *s = 0.0); }   // never replay a stale block
         self.pos = 0;
     }
 }
 impl Drop for GpuRender {
     fn drop(&mut self) { unsafe { qg_bank_free(self.bank) } }
 }
+/// FunDSP's AudioUnit is DynClone and quartz deep-clones a Net, state included, on every hop (src/process.rs:1316, 1336,
+/// 1499, 1558, 1895): the clone owns a device-to-device copy of parameters, state and delay lines and resumes at the same
+/// position of the same look-ahead block.  If the device copy fails the clone plays silence with `error` set.
 impl Clone for GpuRender {
-    fn clone(&self) -> Self { unimplemented!("clone the GpuNet and build a new GpuRender: device state is not shared") }
+    fn clone(&self) -> Self {
+        let mut bank = unsafe { qg_bank_clone(self.bank) };
+        let mut error = self.error.clone();
+        if bank.is_null() {
+            error = Some(last_error());
+            bank = std::ptr::null_mut();   // qg_bank_free(NULL) and every render on NULL are harmless (QG_ERR_ARG)
+        }
+        GpuRender { ctx: self.ctx, net: self.net.clone(), bank, outputs: self.outputs, block: self.block.clone(), pos: self.pos, error }
+    }
 }
 
 impl fundsp::audiounit::AudioUnit for GpuRender {
     fn reset(&mut self) { unsafe { qg_bank_reset(self.bank); } self.pos = BLOCK; }
-    fn set_sample_rate(&mut self, _sample_rate: f64) { /* baked into the tape: rebuild from a GpuNet after sr() */ }
+    /// `sr()` reaches every unit of the graph (src/process.rs:1571-1573).  Coefficients and delay lengths are derived from
+    /// the sample rate when the tape is lowered, so the bank is rebuilt from the stored graph; like FunDSP's own
+    /// `set_sample_rate` on delay lines, that restarts the state.
+    fn set_sample_rate(&mut self, sample_rate: f64) {
+        self.net.set_sample_rate(sample_rate);
+        let bank = unsafe { qg_bank_create(self.ctx, self.net.0, 1, std::ptr::null(), std::ptr::null()) };
+        if bank.is_null() { self.error = Some(last_error()); return; }
+        unsafe { qg_bank_free(self.bank) };
+        self.bank = bank;
+        self.pos = BLOCK;
+    }
     fn tick(&mut self, _input: &[f32], output: &mut [f32]) {
         if self.pos == BLOCK { self.refill(); }
         for c in 0..self.outputs { output[c] = self.block[c * BLOCK + self.pos]; }

@@ -235,3 +235,28 @@ def test_pathological_numbers_neither_hang_nor_corrupt_the_tape():
     g = Net.connect("|", [s], number=float("inf"), node_limit=10)
     assert g.size() == 10
     assert time.perf_counter() - t0 < 20.0      # was minutes; generous for a loaded CI host
+
+
+def test_empty_operands_do_not_spin_the_repeat_count():
+    """combining size-0, port-less operands (a failed str_to_net, an empty connective) succeeds without growing anything, so
+    the node limit never stops the repeat loop: a circle Number of 1e30 used to run 2^31 passes on the caller's thread"""
+    import time
+    t0 = time.perf_counter()
+    e = Net.str_to_net("no_such_op(1)")
+    assert (e.inputs(), e.outputs(), e.size()) == (0, 0, 0)
+    for op in ("|", ">>", "&", "^", "+", "*"):
+        g = Net.connect(op, [e, e], number=1e30)
+        assert (g.inputs(), g.outputs(), g.size()) == (0, 0, 0), op
+    assert time.perf_counter() - t0 < 10.0
+
+
+def test_a_tape_that_overflows_its_index_space_is_refused_not_aliased():
+    """16-bit operand indices: a sum of 20,000 sines needs more temporaries than 15 bits address before the reuse pass runs;
+    the lowering has to stop at the allocation, with QG_ERR_UNSUPPORTED, instead of wrapping onto earlier words"""
+    s = Net.str_to_net("sine(440)")
+    big = Net.connect("+", [s], number=20000, node_limit=1 << 16)
+    assert big.size() == 39999          # 20,000 sines + 19,999 adders
+    with pytest.raises(qb.QuartzGpuError, match="too large"):
+        big.tape_info()
+    ok = Net.connect("+", [s], number=300)
+    assert ok.tape_info()["n_instr"] >= 300
