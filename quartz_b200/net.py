@@ -344,7 +344,7 @@ class Bank:
     def render_stereo(self, n, sample_format=SAMPLE_F32):
         """stream path (audio.rs:85-118): [n, 2] sanitised, clamped, interleaved frames of a one-voice bank, in the device's
         sample type (`T::from_sample`, audio.rs:56-59, 115-116): f32, i16 or u16"""
-        out = np.zeros((n, 2), dtype={SAMPLE_F32: np.float32, SAMPLE_I16: np.int16, SAMPLE_U16: np.uint16}[sample_format])
+        out = np.zeros((n, 2), dtype={SAMPLE_I16: np.int16, SAMPLE_U16: np.uint16}.get(sample_format, np.float32))
         check(lib().qg_bank_render_stereo_as(self.h, int(n), int(sample_format), out.ctypes.data_as(C.c_void_p)))
         return out
 
