@@ -37,12 +37,13 @@ typedef struct qg_bank qg_bank;  /* V voices that share one op tape, resident on
 
 enum { QG_OK = 0, QG_ERR_ARG = 1, QG_ERR_UNSUPPORTED = 2, QG_ERR_CUDA = 3, QG_ERR_ARITY = 4, QG_ERR_MISMATCH = 5 };
 enum { QG_LAYOUT_VOICE_MAJOR = 0, QG_LAYOUT_FRAME_MAJOR = 1 };
-enum { QG_PATH_AUTO = 0, QG_PATH_INTERP = 1, QG_PATH_TV = 2, QG_PATH_INTERP_SAMPLE = 3, QG_PATH_SPECIALISED = 4 };   /* kernel
+enum { QG_PATH_AUTO = 0, QG_PATH_INTERP = 1, QG_PATH_TV = 2, QG_PATH_INTERP_SAMPLE = 3, QG_PATH_SPECIALISED = 4, QG_PATH_SPECTRAL = 5 };   /* kernel
    selection: AUTO picks a fused kernel when the tape matches, the time-vector interpreter (one CTA per voice) for spectral /
    small feed-forward banks, else the lane interpreter (block mode for feed-forward tapes); INTERP forces the lane
    interpreter, INTERP_SAMPLE its sample-by-sample kernel; SPECIALISED compiles a lane kernel for this bank's tape with
    NVRTC (seconds, once per bank; uniform tapes only; fails with QG_ERR_UNSUPPORTED when NVRTC or the tape does not allow
-   it); AUTO chooses it by itself for lane banks whose work pays for the compile */
+   it); AUTO chooses it by itself for lane banks whose work pays for the compile; SPECTRAL forces the frame-parallel path
+   for rfft -> bin chain -> ifft patches (src/nodes.rs:601-700), which AUTO takes for bulk renders of such patches */
 enum { QG_SAMPLE_F32 = 0, QG_SAMPLE_I16 = 1, QG_SAMPLE_U16 = 2 };   /* cpal::SampleFormat as src/audio.rs:56-59 dispatches it */
 
 const char* qg_last_error(void);
@@ -78,6 +79,9 @@ int qg_net_tape_info(const qg_net* net, int* n_instr, int* n_params, int* n_stat
 /* the CUDA translation unit the tape specialiser compiles for this graph (NVRTC; see quartz_b200/csrc/spec_kernel.cuh):
    returns its length (copies at most cap - 1 characters into buf, which may be NULL) or a negated QG_ERR_* status */
 long qg_net_spec_source(const qg_net* net, char* buf, long cap);
+/* 1 when the graph qualifies for the frame-parallel spectral path (QG_PATH_SPECTRAL): rfft -> stateless bin chain -> ifft
+   segments (src/nodes.rs:601-700) fed by pure functions of time; fills the plan's shape.  0 when it does not, < 0: -QG_ERR_* */
+int qg_net_spectral_info(const qg_net* net, int* n_segments, int* n_streams, int* n_instr, int* round_len);
 
 /* ---- device ---- */
 qg_ctx* qg_ctx_create(int device, void* cuda_stream /* cudaStream_t, or NULL for a private stream */);

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/csrc"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall -Xptxas -v"
 OUT=../libquartz_gpu.so
-SRCS="graph.cpp parse.cpp lower.cpp spec.cpp capi.cu interp.cu fused.cu fused_poly.cu"
+SRCS="graph.cpp parse.cpp lower.cpp spec.cpp capi.cu interp.cu fused.cu fused_poly.cu spectral.cu"
 newest=$(ls -t $SRCS *.h *.cuh ../build.sh | head -1)
 if [ -f "$OUT" ] && [ "$OUT" -nt "$newest" ]; then exit 0; fi
 mkdir -p ../_obj

@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include "lower.h"
 #include "spec.h"
+#include "spectral.h"
 
 using namespace qg;
 
@@ -59,6 +60,17 @@ struct qg_bank {
   SpecKernel spec;     // K1s: lane kernel compiled for this tape (qg_bank_set_path(QG_PATH_SPECIALISED), or AUTO once it pays)
   bool spec_auto_ok = false, spec_auto_tried = false;
   double lane_work = 0.0;   // voice-samples this bank has rendered on a lane interpreter (AUTO specialises past a threshold)
+  // K5, the frame-parallel spectral path: evaluates from the state at reset plus an absolute sample time (it neither reads
+  // nor writes d_state / d_rings), so a bank renders EITHER on K5 or on the other kernels between two resets
+  SpPlan sp;
+  Instr* d_sp_code = nullptr;
+  SpSegment* d_sp_segs = nullptr;
+  SpItem* d_sp_items = nullptr;
+  uint16_t* d_sp_out_x = nullptr;
+  long sp_time = 0;             // samples K5 has rendered since the last reset
+  bool sp_started = false;      // K5 has rendered since the last reset
+  bool other_started = false;   // another kernel has
+  bool last_k5 = false;         // the previous render ran on K5 (survives a reset: qg_bank_kernel names what a repeat would use)
 };
 
 static thread_local std::string g_err;
@@ -248,6 +260,25 @@ int qg_net_tape_info(const qg_net* n, int* n_instr, int* n_params, int* n_state,
   });
 }
 
+// Frame-parallel spectral plan of a graph (spectral.h): 1 and the plan's shape when the tape qualifies, else 0
+int qg_net_spectral_info(const qg_net* n, int* n_segments, int* n_streams, int* n_instr, int* round_len) {
+  if (!n) return -fail(QG_ERR_ARG, "null net");
+  int ok = 0;
+  int rc = guard_int([&] {
+    Tape t;
+    std::string err;
+    if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
+    SpPlan p = plan_spectral(t);
+    ok = p.ok ? 1 : 0;
+    if (n_segments) *n_segments = (int)p.segs.size();
+    if (n_streams) *n_streams = p.n_streams;
+    if (n_instr) *n_instr = (int)p.code.size();
+    if (round_len) *round_len = p.C;
+    return (int)QG_OK;
+  });
+  return rc == QG_OK ? ok : -rc;
+}
+
 // The translation unit the tape specialiser hands to NVRTC for this graph (spec.cpp); returns the length needed
 // (excluding the terminator) or a negative status.  Copies at most cap - 1 characters.
 long qg_net_spec_source(const qg_net* n, char* buf, long cap) {
@@ -325,6 +356,7 @@ static void bank_release(qg_bank* b) {
   cudaFree(b->d_code); cudaFree(b->d_out_x); cudaFree(b->d_params); cudaFree(b->d_state); cudaFree(b->d_state_init); cudaFree(b->d_state_keep);
   cudaFree(b->d_rings); cudaFree(b->d_ring_tab); cudaFree(b->d_resets); cudaFree(b->d_tables); cudaFree(b->d_scratch);
   cudaFree(b->d_in); cudaFree(b->d_fused_scratch);
+  cudaFree(b->d_sp_code); cudaFree(b->d_sp_segs); cudaFree(b->d_sp_items); cudaFree(b->d_sp_out_x);
   spec_release(&b->spec);
   delete b;
 }
@@ -407,6 +439,13 @@ static int bank_build(qg_bank* b, const float* raw_matrix /* [V][R] or null */, 
   }
   if (b->fused.id == FUSED_NOISE_SVF && b->fused.p[1] == 2 && !b->biquad_scan_ok) b->fused.id = FUSED_NONE;
   b->tv = plan_tv(t, (size_t)180 * 1024);
+  b->sp = plan_spectral(t);
+  if (b->sp.ok) {
+    if ((rc = upload(&b->d_sp_code, b->sp.code, c->stream))) return rc;
+    if ((rc = upload(&b->d_sp_segs, b->sp.segs, c->stream))) return rc;
+    if ((rc = upload(&b->d_sp_items, b->sp.items, c->stream))) return rc;
+    if ((rc = upload(&b->d_sp_out_x, b->sp.out_x, c->stream))) return rc;
+  }
   if (!b->biquad_scan_ok) b->tv.sequential = true;   // those biquads are stepped by one thread in the reference's operation order
   // block mode evaluates an instruction for a whole block of samples before the next one: valid for feed-forward tapes,
   // and for feedback loops whose delay line is at least one block long
@@ -486,12 +525,22 @@ int qg_bank_reset(qg_bank* b) {
     CU(cudaMemcpyAsync(b->d_state, b->d_state_init, ns, cudaMemcpyDeviceToDevice, c->stream));
   }
   b->state_ready = true;
+  b->sp_time = 0; b->sp_started = false; b->other_started = false;
   size_t rb = (size_t)b->tape.h.ring_floats * b->Vp * sizeof(float);
   if (rb) CU(cudaMemsetAsync(b->d_rings, 0, rb, c->stream));
   return QG_OK;
 }
+// K5 serves a bank from its reset on (see qg_bank): forced with QG_PATH_SPECTRAL, or chosen by AUTO when the first render after
+// a reset is a bulk one (a block-wise stream of short calls stays on the time-vector kernel, where var() updates apply)
+static const double kSpectralAutoWork = 262144.0;   // voice-samples
+static bool bank_spectral(const qg_bank* b, long T) {
+  if (!b->sp.ok || b->other_started) return false;
+  if (b->path == QG_PATH_SPECTRAL || b->sp_started) return true;
+  return b->path == QG_PATH_AUTO && (T <= 0 || ((double)b->V * (double)T >= kSpectralAutoWork && T >= 4L * b->sp.C));
+}
 // which kernel family serves voice-major, group-1 renders: 0 lane interpreter, 1 fused, 2 time-vector interpreter
 static int bank_family(const qg_bank* b) {
+  if (b->path == QG_PATH_SPECTRAL) return 2;   // (render_impl asks bank_spectral() first)
   if (b->path == QG_PATH_SPECIALISED) return b->spec.fn ? 3 : 0;
   if (b->path == QG_PATH_AUTO && b->spec.fn && b->fused.id == FUSED_NONE && !(b->tv.ok && (b->tv.has_fft || b->V <= (b->tv.sequential ? 256 : 2048))))
     return 3;   // AUTO specialised this lane-interpreter bank (bank_auto_specialise)
@@ -504,6 +553,11 @@ static int bank_family(const qg_bank* b) {
 int qg_bank_set_path(qg_bank* b, int path) {
   if (!b) return fail(QG_ERR_ARG, "null bank");
   int before = bank_family(b) == 2;
+  if (path < QG_PATH_AUTO || path > QG_PATH_SPECTRAL) return fail(QG_ERR_ARG, "unknown path");
+  if (path == QG_PATH_SPECTRAL && !b->sp.ok)
+    return fail(QG_ERR_UNSUPPORTED, "the frame-parallel spectral path needs rfft -> stateless bin chain -> ifft segments fed by "
+                                    "signals that are pure functions of time (noise, wave tables, delays of those)");
+  const bool was_k5 = b->sp_started;
   if (path == QG_PATH_SPECIALISED && !b->spec.fn) {
     CU(cudaSetDevice(b->ctx->device));
     std::string err;
@@ -513,11 +567,15 @@ int qg_bank_set_path(qg_bank* b, int path) {
     if (!ok) return fail(QG_ERR_UNSUPPORTED, err);
   }
   b->path = path;
+  if ((was_k5 && path != QG_PATH_SPECTRAL && path != QG_PATH_AUTO) || (path == QG_PATH_SPECTRAL && b->other_started))
+    return qg_bank_reset(b);                   // K5 keeps its state as a sample time, the other kernels as state words
   if ((bank_family(b) == 2) != before) return qg_bank_reset(b);   // the two interpreters lay delay lines out differently
   return QG_OK;
 }
 const char* qg_bank_kernel(const qg_bank* b) {
   if (!b) return "";
+  if (b->sp.ok && !b->other_started && (b->path == QG_PATH_SPECTRAL || b->sp_started || (b->path == QG_PATH_AUTO && b->last_k5)))
+    return "k_spectral_frames";
   int f = bank_family(b);
   if (f == 1) return fused_name(b->fused.id);
   if (f == 2) return "k_interp_tv";
@@ -549,6 +607,9 @@ static int bank_set_raw(qg_bank* b, int raw_index, float value) {
   const int R = (int)t.h.n_raw, P = (int)t.h.n_params;
   if (raw_index < 0 || raw_index >= R) return fail(QG_ERR_ARG, "raw parameter index out of range");
   if (t.raw_structural[raw_index]) return fail(QG_ERR_MISMATCH, "this parameter shapes the tape (delay length / reset period): rebuild the bank");
+  if (b->sp_started)
+    return fail(QG_ERR_MISMATCH, "this bank is rendering on the frame-parallel spectral path, which evaluates from the state at reset: "
+                                 "reset it first, or select QG_PATH_TV before the first render to stream with var() updates");
   qg_ctx* c = b->ctx;
   CU(cudaSetDevice(c->device));
   t.raw[raw_index] = value;
@@ -604,6 +665,7 @@ static void bank_auto_specialise(qg_bank* b, long T) {
   try { spec_compile(b->tape, &b->spec, &err); } catch (...) {}
 }
 
+static int ensure(float** p, size_t* have, size_t need);
 static int render_impl(qg_bank* b, long T, int layout, int group, const float* d_in, float* d_out) {
   qg_ctx* c = b->ctx;
   const Tape& t = b->tape;
@@ -611,6 +673,34 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   if (T <= 0) return QG_OK;
   int rc = check_group(b, layout, group);
   if (rc) return rc;
+  if (!d_in && group == 1 && bank_spectral(b, T)) {
+    SpArgs sa;
+    memset(&sa, 0, sizeof sa);
+    int ring = 0;
+    const size_t yb = spectral_y_bytes(b->sp, b->V, &ring);
+    rc = ensure(&b->d_fused_scratch, &b->fused_scratch_bytes, yb);
+    if (rc) return rc;
+    sa.code = b->d_sp_code; sa.n_code = (int)b->sp.code.size(); sa.segs = b->d_sp_segs; sa.n_segs = (int)b->sp.segs.size();
+    sa.items = b->d_sp_items; sa.n_items = (int)b->sp.items.size(); sa.out_x = b->d_sp_out_x; sa.n_out = (int)t.h.n_outputs;
+    sa.params = b->d_params; sa.state_init = b->d_state_init; sa.tables = b->d_tables;
+    sa.P = (int)t.h.n_params; sa.NS = (int)t.h.n_state; sa.V = (int)b->V; sa.Vp = b->Vp;
+    sa.y = b->d_fused_scratch; sa.ring = ring; sa.n_streams = b->sp.n_streams; sa.out = d_out; sa.T = T; sa.t0 = b->sp_time;
+    sa.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
+    sa.C = b->sp.C; sa.post_lo = b->sp.post_lo; sa.post_hi = b->sp.post_hi;
+    sa.n_slots_frame = b->sp.n_slots_frame; sa.n_slots_post = b->sp.n_slots_post;
+    int l = 0;
+    cudaError_t se = launch_spectral(sa, b->sp, c->stream, &l);
+    c->launches += l;
+    if (se != cudaErrorNotSupported) {
+      CU(se);
+      b->sp_started = true; b->sp_time += T; b->last_k5 = true;
+      return QG_OK;
+    }
+    if (b->sp_started || b->path == QG_PATH_SPECTRAL) return fail(QG_ERR_UNSUPPORTED, "the spectral path needs more shared memory than one SM offers");
+  }
+  if (b->sp_started) return fail(QG_ERR_MISMATCH, "this bank is rendering on the frame-parallel spectral path (no group mix, no inputs): reset it first");
+  if (b->path == QG_PATH_SPECTRAL) return fail(QG_ERR_ARG, "QG_PATH_SPECTRAL renders group-1 banks without inputs");
+  b->other_started = true; b->last_k5 = false;
   if (bank_family(b) == 0) bank_auto_specialise(b, T);
   const int family = bank_family(b);
   if (family == 2 && group == 1) {
@@ -809,6 +899,7 @@ qg_bank* qg_bank_clone(const qg_bank* src) {
     b->block_ok = src->block_ok; b->ring_mode = src->ring_mode; b->state_ready = src->state_ready;
     b->spec_auto_ok = src->spec_auto_ok; b->spec_auto_tried = src->spec_auto_tried; b->lane_work = src->lane_work;
     if (src->spec.fn && src->spec.shared) b->spec = src->spec;     // kernels live in the process-wide cache
+    b->sp = src->sp; b->sp_time = src->sp_time; b->sp_started = src->sp_started; b->other_started = src->other_started; b->last_k5 = src->last_k5;
   } catch (...) {
     delete b;
     fail(QG_ERR_ARG, "qg_bank_clone: out of memory");
@@ -829,6 +920,9 @@ qg_bank* qg_bank_clone(const qg_bank* src) {
        dup(&b->d_params, src->d_params, P * b->Vp * sizeof(float)) && dup(&b->d_state, src->d_state, NS * b->Vp * sizeof(float)) &&
        dup(&b->d_state_init, src->d_state_init, NS * b->Vp * sizeof(float)) &&
        dup(&b->d_rings, src->d_rings, (size_t)t.h.ring_floats * b->Vp * sizeof(float));
+  if (ok && b->sp.ok)
+    ok = dup(&b->d_sp_code, src->d_sp_code, b->sp.code.size() * sizeof(Instr)) && dup(&b->d_sp_segs, src->d_sp_segs, b->sp.segs.size() * sizeof(SpSegment)) &&
+         dup(&b->d_sp_items, src->d_sp_items, b->sp.items.size() * sizeof(SpItem)) && dup(&b->d_sp_out_x, src->d_sp_out_x, b->sp.out_x.size() * sizeof(uint16_t));
   ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
   if (!ok) {
     fail(QG_ERR_CUDA, std::string("qg_bank_clone: ") + cudaGetErrorString(cudaGetLastError()));

@@ -160,8 +160,8 @@ __device__ __forceinline__ uint32_t ring_len(const Lane& L, uint32_t r) { return
 __device__ __forceinline__ uint32_t ring_wrap(uint32_t pos, uint32_t len) { return pos >= len ? pos - len : pos; }
 __device__ __forceinline__ uint32_t ring_len(const TvSample&, uint32_t) { return 1u; }
 
-__device__ __noinline__ void reset_range(const TvSample&, uint32_t) {}
-__device__ __noinline__ void reset_range(const Lane& L, uint32_t id) {
+static __device__ __noinline__ void reset_range(const TvSample&, uint32_t) {}
+static __device__ __noinline__ void reset_range(const Lane& L, uint32_t id) {
   ResetRange r = L.resets[id];
   for (int s = r.s_lo; s < r.s_hi; s++)
     if (!L.state_keep[s - L.P]) X(s) = L.state_init[(size_t)(s - L.P) * L.Vp + L.v];   // a nested seq() keeps its event list
@@ -172,8 +172,8 @@ __device__ __noinline__ void reset_range(const Lane& L, uint32_t id) {
 }
 
 // in-place radix-2 FFT over two of the lane's HBM rings (re, im); inverse scales by 1/N
-__device__ __noinline__ void lane_fft(const TvSample&, uint32_t, uint32_t, int, const float*, bool) {}
-__device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim, int lg, const float* tw, bool inverse) {
+static __device__ __noinline__ void lane_fft(const TvSample&, uint32_t, uint32_t, int, const float*, bool) {}
+static __device__ __noinline__ void lane_fft(const Lane& L, uint32_t rre, uint32_t rim, int lg, const float* tw, bool inverse) {
   uint32_t N = 1u << lg;
   for (uint32_t i = 1, j = 0; i < N; i++) {
     uint32_t bit = N >> 1;

@@ -112,7 +112,8 @@ struct Lower {
   int n_temps = 0;
   int zero_p = -1;
   int wt_offset[4] = {-1, -1, -1, -1};   // wavetable sets already placed in the tables region
-  explicit Lower(Tape& t_) : t(t_) {}
+  long tw_offset[32];                    // twiddle tables already placed, by log2 of the transform size
+  explicit Lower(Tape& t_) : t(t_) { for (long& o : tw_offset) o = -1; }
 
   // 16-bit operand indices: 15 bits of temporaries, 14 of parameters and of state.  Checked at allocation — an index that
   // wrapped would alias an earlier word and the tape would render wrong audio instead of being refused (the temporary-reuse
@@ -673,17 +674,22 @@ std::vector<uint16_t> Lower::node(const Node& n, const std::vector<uint16_t>& in
       ring(N); ring(N);
       if (!r) ring(N);
       // twiddle table: w_k = exp(-2*pi*i*k/N), k < N/2, rounded from f64 like a precomputed f32 table
-      std::vector<float> tw(N);
-      for (uint32_t k = 0; k < N / 2; k++) {
-        double a = -2.0 * 3.14159265358979323846 * (double)k / (double)N;
-        tw[2 * k] = (float)std::cos(a);
-        tw[2 * k + 1] = (float)std::sin(a);
+      // (one table per transform size and tape, at an even offset: the frame kernels read a twiddle as one float2)
+      if (lg < 32 && tw_offset[lg] < 0) {
+        std::vector<float> tw(N);
+        for (uint32_t k = 0; k < N / 2; k++) {
+          double a = -2.0 * 3.14159265358979323846 * (double)k / (double)N;
+          tw[2 * k] = (float)std::cos(a);
+          tw[2 * k + 1] = (float)std::sin(a);
+        }
+        if (t.tables.size() & 1) t.tables.push_back(0.0f);
+        tw_offset[lg] = (long)table(tw);
       }
       uint16_t s = state(1, (uint32_t)n.mode);   // count starts at `start`
       Instr& i = emit(r ? OP_RFFT : OP_IFFT);
       i.in[0] = in[0];
       if (!r) i.in[1] = in[1];
-      i.n = (uint16_t)lg; i.aux = first; i.aux2 = table(tw); i.s = s; i.out = temp(2);
+      i.n = (uint16_t)lg; i.aux = first; i.aux2 = (uint32_t)tw_offset[lg]; i.s = s; i.out = temp(2);
       out = {i.out, (uint16_t)(i.out + 1)};
       break;
     }

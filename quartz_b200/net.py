@@ -12,7 +12,7 @@ from . import _ffi
 from ._ffi import QuartzGpuError, check, lib
 
 LAYOUT_VOICE_MAJOR, LAYOUT_FRAME_MAJOR = 0, 1
-PATH_AUTO, PATH_INTERP, PATH_TV, PATH_INTERP_SAMPLE, PATH_SPECIALISED = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_INTERP, PATH_TV, PATH_INTERP_SAMPLE, PATH_SPECIALISED, PATH_SPECTRAL = 0, 1, 2, 3, 4, 5
 SAMPLE_F32, SAMPLE_I16, SAMPLE_U16 = 0, 1, 2      # cpal::SampleFormat as audio.rs:56-59 dispatches it
 NODE_LIMIT_DEFAULT = 500   # src/main.rs:72
 
@@ -216,6 +216,14 @@ class Net:
         v = [C.c_int(0) for _ in range(5)]
         check(lib().qg_net_tape_info(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("n_instr", "n_params", "n_state", "n_temps", "divergent"), [x.value for x in v]))
+
+    def spectral_info(self):
+        """shape of the frame-parallel spectral plan (QG_PATH_SPECTRAL), or None when the graph does not qualify"""
+        v = [C.c_int(0) for _ in range(4)]
+        rc = lib().qg_net_spectral_info(self.h, *[C.byref(x) for x in v])
+        if rc < 0:
+            raise QuartzGpuError(_ffi.last_error())
+        return dict(zip(("n_segments", "n_streams", "n_instr", "round_len"), [x.value for x in v])) if rc else None
 
     def _voice(self, ctx=None):
         if self._bank is None:

@@ -91,3 +91,81 @@ def test_round_trip_property_full_frame_size():
     lat = 2 * N
     err = np.abs(y[:, lat + N:] - 0.375 * x[:, 0, N:T - lat]).max()
     assert err < 2e-4, err
+
+
+# ---------------------------------------------------------------------------------------------- K5: frame-parallel path
+def _gate(N, J, V, T, thr=None):
+    return workloads.c4_spectral(V=V, T=T, N=N, J=J, thr=0.25 * np.sqrt(N) if thr is None else thr)
+
+
+@pytest.mark.parametrize("N,J,V,T", [(64, 4, 5, 1000), (256, 4, 3, 3000), (2048, 4, 2, 14000), (128, 2, 4, 900), (8, 1, 2, 100)])
+def test_frame_parallel_spectral_path_matches_oracle_and_time_vector_kernel(N, J, V, T):
+    """K5 evaluates whole frames from the state at reset + absolute sample time; same transform arithmetic and the same
+    op code as the time-vector kernel, so the two agree BIT FOR BIT, and with the oracle within the float tolerance"""
+    wl = _gate(N, J, V, T)
+    k5 = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_SPECTRAL)
+    assert k5.kernel() == "k_spectral_frames"
+    got = k5.render(T)[:, 0, :]
+    tv = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_TV).render(T)[:, 0, :]
+    assert np.array_equal(got, tv)
+    assert_parity(got, oracle(wl, V, T), "float", f"K5 N={N}")
+    # frame-major output
+    fm = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_SPECTRAL).render(T, layout=qb.LAYOUT_FRAME_MAJOR)
+    assert np.array_equal(fm[:, :, 0].T, got)
+
+
+def test_frame_parallel_path_continues_across_uneven_calls_and_resets():
+    N, J, V = 256, 4, 6
+    chunks = (1, 7, 255, 257, 2, 1024, 700, 3000)
+    T = sum(chunks)
+    wl = _gate(N, J, V, T)
+    ref = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_TV).render(T)
+    b = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_SPECTRAL)
+    assert np.array_equal(np.concatenate([b.render(k) for k in chunks], axis=2), ref)
+    b.reset()
+    assert np.array_equal(b.render(1000), ref[:, :, :1000])
+    c = b.clone()                                   # the clone carries the sample time
+    assert np.array_equal(c.render(500), ref[:, :, 1000:1500]) and np.array_equal(b.render(500), ref[:, :, 1000:1500])
+    # var() updates need real state: refused by name on a bank that is mid-render on K5, fine after a reset + PATH_TV
+    with pytest.raises(qb.QuartzGpuError, match="reset"):
+        b.set_raw(0, 1.0)
+    # leaving K5 resets the bank (its state is a sample time, not state words)
+    b.set_path(qb.PATH_TV)
+    assert b.kernel() == "k_interp_tv" and np.array_equal(b.render(T), ref)
+
+
+def test_auto_takes_the_frame_parallel_path_for_bulk_renders_only():
+    N, J = 64, 4
+    wl = _gate(N, J, 64, 8192)
+    b = Bank(build(wl.expr, Net), 64, salts=wl.salts)
+    assert b.kernel() == "k_interp_tv"
+    small = b.render(1000)                          # a short first call: block-wise streaming stays on the time-vector kernel
+    assert b.kernel() == "k_interp_tv"
+    b.reset()
+    bulk = b.render(8192)                           # 64 x 8192 voice-samples: bulk
+    assert b.kernel() == "k_spectral_frames"
+    assert np.array_equal(bulk[:, :, :1000], small)
+    ref = Bank(build(wl.expr, Net), 64, salts=wl.salts).set_path(qb.PATH_TV).render(8192)
+    assert np.array_equal(bulk, ref)
+    with pytest.raises(qb.QuartzGpuError, match="spectral"):
+        Bank(build(pipe("white()", "lowpass(500,1)"), Net), 4).set_path(qb.PATH_SPECTRAL)
+
+
+@pytest.mark.parametrize("chain", [
+    [],                                                            # rfft straight into ifft: a 2N delay
+    ["pol()", "car()"],
+    [stack("mul(0.5)", "add(0.25)")],                              # chain(0) != 0: zero-initialised positions must stay zero
+    [stack(pipe("abs()", "sqrt()"), "mul(-1)")],
+], ids=["identity", "pol_car", "affine", "nonlinear"])
+@pytest.mark.parametrize("start", [0, 5, 32])
+def test_frame_parallel_path_on_other_bin_chains(chain, start):
+    N = 64
+    expr = pipe(stack("white()"), f"rfft({N},{start})", *chain, f"ifft({N},{start})", stack(pipe("mul(0.7)", "tanh()"), "pass()"))
+    V, T = 3, 700
+    salts = np.arange(3, 3 + V, dtype=np.uint64)
+    b = Bank(build(expr, Net), V, salts=salts).set_path(qb.PATH_SPECTRAL)
+    got = np.concatenate([b.render(123), b.render(T - 123)], axis=2)
+    tv = Bank(build(expr, Net), V, salts=salts).set_path(qb.PATH_TV).render(T)
+    assert np.array_equal(got, tv)
+    ref = np.stack([build(expr, ONet).set_salt(int(s)).render(T).T for s in salts])
+    assert_parity(got, ref, "float", "chain")
