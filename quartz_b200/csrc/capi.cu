@@ -909,9 +909,8 @@ qg_bank* qg_bank_clone(const qg_bank* src) {
   const Tape& t = b->tape;
   const size_t P = t.h.n_params, NS = t.h.n_state;
   auto dup = [&](auto** dst, const auto* from, size_t bytes) -> bool {
-    bytes = std::max<size_t>(bytes, 4);
-    if (cudaMalloc((void**)dst, bytes) != cudaSuccess) return false;
-    return !from || cudaMemcpyAsync(*dst, from, bytes, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+    if (cudaMalloc((void**)dst, std::max<size_t>(bytes, 8)) != cudaSuccess) return false;   // never copy past a small source
+    return !from || bytes == 0 || cudaMemcpyAsync(*dst, from, bytes, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
   };
   bool ok = cudaSetDevice(c->device) == cudaSuccess;
   ok = ok && dup(&b->d_code, src->d_code, t.code.size() * sizeof(Instr)) && dup(&b->d_out_x, src->d_out_x, t.out_x.size() * sizeof(uint16_t)) &&

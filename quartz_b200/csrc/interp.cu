@@ -331,7 +331,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       XO(0) = res;
     } break;
     case OP_POL: QG_EACH { float a = XI(0), b = XI(1); XO(0) = hypotf(a, b); XO(1) = atan2f(b, a); } break;
-    case OP_CAR: QG_EACH { float a = XI(0), b = XI(1); XO(0) = a * cosf(b); XO(1) = a * sinf(b); } break;
+    case OP_CAR: QG_EACH { float a = XI(0), b = XI(1), sn, cs; sincosf(b, &sn, &cs); XO(0) = a * cs; XO(1) = a * sn; } break;
     case OP_DIVN: QG_EACH { XO(0) = XI(0) / (float)I.n; } break;
     case OP_JOIN: QG_EACH {   // left-to-right sum of n <= 5 operands, divided by aux when aux != 0 (join(n): mean of n)
       float s = XI(0);

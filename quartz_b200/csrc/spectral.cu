@@ -17,6 +17,8 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -206,6 +208,40 @@ struct Planner {
   }
   void begin() { mt.clear(); slots = 0; memo.clear(); }
 
+  // How the chain's two results behave when the input bin is conjugated: +1 unchanged, -1 negated, 0 unknown.  The streamed
+  // bins above N/2 are conjugates of those below (nodes.rs:640-641); when both results have a known type the frame kernel
+  // evaluates the chain on bins 0 .. N/2 only and mirrors the rest.  Only identities that hold BIT FOR BIT are used: any
+  // function of unchanged values is unchanged; x+y, x-y keep a common type; products multiply types; |x|, x^2, hypotf, cosf
+  // are even and sinf, atan2f(y, .) odd in the device library's implementations (sign handled by copysign / odd polynomials).
+  void conj_types(const std::vector<Instr>& code, int xr, int xi, int* t_re, int* t_im) {
+    std::map<int, int> ty;
+    ty[PS] = +1; ty[PS + 1] = -1;
+    auto T = [&](int x) { if (x < PS) return +1; auto it = ty.find(x); return it == ty.end() ? 0 : it->second; };
+    for (const Instr& I : code) {
+      const int ni = n_in_of(I);
+      bool all_even = true;
+      for (int q = 0; q < ni; q++) all_even = all_even && T(I.in[q]) == +1;
+      const int a = ni > 0 ? T(I.in[0]) : +1, b = ni > 1 ? T(I.in[1]) : +1;
+      int o0 = 0, o1 = 0;
+      if (all_even) o0 = o1 = +1;
+      else switch (I.op) {
+        case OP_MOV: case OP_CUBED: case OP_SIN: o0 = a; break;
+        case OP_ADD: case OP_SUB: o0 = a == b ? a : 0; break;
+        case OP_MUL: o0 = a * b; break;
+        case OP_ABS: case OP_SQUARED: case OP_COS: o0 = a != 0 ? +1 : 0; break;
+        case OP_HYPOT: o0 = (a != 0 && b != 0) ? +1 : 0; break;
+        case OP_ATAN2: o0 = b == +1 ? a : 0; break;                  // atan2f(in0 = y, in1 = x)
+        case OP_POL: o0 = (a != 0 && b != 0) ? +1 : 0; o1 = a == +1 ? b : 0; break;   // hypotf(a, b), atan2f(b, a)
+        case OP_CAR: o0 = a * (b != 0 ? +1 : 0); o1 = a * b; break;                   // a cosf(b), a sinf(b)
+        default: break;
+      }
+      ty[I.out] = o0;
+      if (n_out_of(I) > 1) ty[I.out + 1] = o1;
+    }
+    *t_re = T(xr); *t_im = T(xi);
+    if (*t_re == 0 || *t_im == 0) *t_re = *t_im = 0;
+  }
+
   bool build() {
     if (!classify()) return false;
     const int S = (int)rfft_instr.size();
@@ -256,6 +292,7 @@ struct Planner {
       pl.code.insert(pl.code.end(), mt.begin(), mt.end());
       sg.ch_hi = (int)pl.code.size();
       sg.rf_x = PS; sg.in_re_x = xr; sg.in_im_x = xi;
+      conj_types(mt, xr, xi, &sg.sym_re, &sg.sym_im);
     }
     // chain instructions after their ifft would have been classified BIN only if they read BIN values, which the closed
     // segment check rejects; instructions of class BIN that no ifft consumes are dead code
@@ -311,57 +348,84 @@ SpPlan plan_spectral(const Tape& t) {
   Planner P(t, pl);
   pl.ok = P.build();
   if (!pl.ok) { SpPlan none; return none; }
+  if (getenv("QG_DEBUG_PLAN"))
+    fprintf(stderr, "spectral plan: %zu segments, %zu instr, %d frame slots, %d post slots, %d streams, sym %d %d\n", pl.segs.size(),
+            pl.code.size(), pl.n_slots_frame, pl.n_slots_post, pl.n_streams, pl.segs[0].sym_re, pl.segs[0].sym_im);
   return pl;
 }
 
 // ------------------------------------------------------------------------------------------------ device
-#define FPAD(i) ((i) + ((i) >> 5))
+// Transform buffers hold interleaved complex values (one LDS.64 / STS.64 per point), padded by one element per 16.
+#define CPAD(i) ((i) + ((i) >> 4))
 
-// radix-2 DIT butterflies, 2^R points per thread carried through R consecutive stages in registers (the schedule of
-// k_interp_tv's transforms: bit-identical to the plain radix-2 loop of the oracle)
-template <int R>
-__device__ __forceinline__ void sp_fft_pass(float* fr, float* fi, int lg, int s, const float* __restrict__ tw, bool inverse, int tid, int nth) {
-  const uint32_t N = 1u << lg, h = 1u << s;
+// Radix-2 DIT butterflies, 2^R points per thread carried through R consecutive stages in registers (the schedule of
+// k_interp_tv's transforms: bit-identical to the plain radix-2 loop of the oracle).  sgn = +1 forward, -1 inverse: the
+// inverse conjugates the twiddle, and -(w.y) == w.y * -1 exactly.  LG and S are compile-time: every index below is an
+// immediate offset from one per-thread base.
+template <int LG, int S, int R>
+__device__ __forceinline__ void sp_fft_pass(float2* f, const float2* __restrict__ tw, float sgn, int tid, int nth) {
+  constexpr uint32_t N = 1u << LG, h = 1u << S;
   for (uint32_t g = tid; g < (N >> R); g += nth) {
-    const uint32_t k = g & (h - 1), base = ((g >> s) << (s + R)) | k;
-    float xr[1 << R], xi[1 << R];
+    const uint32_t k = g & (h - 1), base = ((g >> S) << (S + R)) | k;
+    float2 x[1 << R];
 #pragma unroll
-    for (int m = 0; m < (1 << R); m++) { const uint32_t idx = base + (uint32_t)m * h; xr[m] = fr[FPAD(idx)]; xi[m] = fi[FPAD(idx)]; }
+    for (int m = 0; m < (1 << R); m++) x[m] = f[CPAD(base + (uint32_t)m * h)];
 #pragma unroll
     for (int q = 0; q < R; q++) {
+      constexpr int dummy = 0; (void)dummy;
       const int hq = 1 << q;
+      float2 w[1 << (R - 1)];                      // the 2^q distinct twiddles of stage S + q
+#pragma unroll
+      for (int e = 0; e < hq; e++) {
+        const uint32_t ti = (k + (uint32_t)e * h) << (LG - 1 - (S + q));
+        w[e] = __ldg(tw + ti);
+        w[e].y *= sgn;
+      }
 #pragma unroll
       for (int m = 0; m < (1 << R); m++) {
         if (m & hq) continue;
-        const uint32_t kq = k + (uint32_t)(m & (hq - 1)) * h;
-        const uint32_t ti = kq << (lg - 1 - (s + q));
-        const float2 w = __ldg(reinterpret_cast<const float2*>(tw) + ti);
-        const float wr = w.x, wi = inverse ? -w.y : w.y;
-        const float ur = xr[m], ui = xi[m], vr = xr[m + hq], vi = xi[m + hq];
-        const float tr = vr * wr - vi * wi, tim = vr * wi + vi * wr;
-        xr[m] = ur + tr; xi[m] = ui + tim;
-        xr[m + hq] = ur - tr; xi[m + hq] = ui - tim;
+        const float wr = w[m & (hq - 1)].x, wi = w[m & (hq - 1)].y;
+        const float2 u = x[m], v = x[m + hq];
+        const float tr = v.x * wr - v.y * wi, tim = v.x * wi + v.y * wr;
+        x[m] = make_float2(u.x + tr, u.y + tim);
+        x[m + hq] = make_float2(u.x - tr, u.y - tim);
       }
     }
 #pragma unroll
-    for (int m = 0; m < (1 << R); m++) { const uint32_t idx = base + (uint32_t)m * h; fr[FPAD(idx)] = xr[m]; fi[FPAD(idx)] = xi[m]; }
+    for (int m = 0; m < (1 << R); m++) f[CPAD(base + (uint32_t)m * h)] = x[m];
   }
 }
-__device__ __forceinline__ void sp_fft(float* fr, float* fi, int lg, const float* tw, bool inverse, int tid, int nth) {
-  for (int s = 0; s < lg;) {
-    const int r = lg - s >= 3 ? 3 : lg - s;
-    if (r == 3) sp_fft_pass<3>(fr, fi, lg, s, tw, inverse, tid, nth);
-    else if (r == 2) sp_fft_pass<2>(fr, fi, lg, s, tw, inverse, tid, nth);
-    else sp_fft_pass<1>(fr, fi, lg, s, tw, inverse, tid, nth);
-    s += r;
+template <int LG, int S>
+__device__ __forceinline__ void sp_fft_from(float2* f, const float2* tw, float sgn, int tid, int nth) {
+  if constexpr (S < LG) {
+    constexpr int R = LG - S >= 3 ? 3 : LG - S;
+    sp_fft_pass<LG, S, R>(f, tw, sgn, tid, nth);
     __syncthreads();
+    sp_fft_from<LG, S + R>(f, tw, sgn, tid, nth);
+  }
+}
+template <int LG>
+__device__ __noinline__ void sp_fft_n(float2* f, const float2* tw, float sgn, int tid, int nth) { sp_fft_from<LG, 0>(f, tw, sgn, tid, nth); }
+__device__ __forceinline__ void sp_fft(float2* f, int lg, const float2* tw, float sgn, int tid, int nth) {
+  switch (lg) {
+    case 3: sp_fft_n<3>(f, tw, sgn, tid, nth); break;
+    case 4: sp_fft_n<4>(f, tw, sgn, tid, nth); break;
+    case 5: sp_fft_n<5>(f, tw, sgn, tid, nth); break;
+    case 6: sp_fft_n<6>(f, tw, sgn, tid, nth); break;
+    case 7: sp_fft_n<7>(f, tw, sgn, tid, nth); break;
+    case 8: sp_fft_n<8>(f, tw, sgn, tid, nth); break;
+    case 9: sp_fft_n<9>(f, tw, sgn, tid, nth); break;
+    case 10: sp_fft_n<10>(f, tw, sgn, tid, nth); break;
+    case 11: sp_fft_n<11>(f, tw, sgn, tid, nth); break;
+    default: sp_fft_n<12>(f, tw, sgn, tid, nth); break;
   }
 }
 
 struct SpSmem { int ps_off, tmp_off, f_off; };   // float offsets: [code] [P + NS scalars] [slots x HB] [transform buffers]
 
 // Evaluates mini-tape [lo, hi) for the n consecutive sample times tbase .. tbase + n - 1 (thread tid owns columns tid,
-// tid + nth, ...: a thread only ever reads columns it wrote, so no barrier is needed between instructions).
+// tid + nth, ...: a thread only ever reads columns it wrote, so no barrier is needed between instructions).  Times are
+// 64-bit only here, at the block level: per sample everything is a 32-bit offset from the block's base.
 __device__ __forceinline__ void sp_eval(const Instr* code, int lo, int hi, long tbase, int n, int HB, int PS, const SpSmem& sm,
                                         const SpArgs& a, int v, int tid, int nth) {
   float* ps = QG_SMEM_F + sm.ps_off;
@@ -369,35 +433,40 @@ __device__ __forceinline__ void sp_eval(const Instr* code, int lo, int hi, long 
   for (int pc = lo; pc < hi; pc++) {
     const Instr I = code[pc];
     float* o = tmp + ((int)I.out - PS) * HB;
-    const long d = (long)(int32_t)I.pad;
+    const long tb = tbase + (long)(int32_t)I.pad;           // time of column 0 for this instruction
     switch (I.op) {
       case OP_NOISE: {
-        const uint32_t c0 = __float_as_uint(ps[I.s]);
-        for (int j = tid; j < n; j += nth) o[j] = d_noise(c0 + (uint32_t)(tbase + j + d) + 1u);
+        const uint32_t c0 = __float_as_uint(ps[I.s]) + (uint32_t)tb + 1u;
+        for (int j = tid; j < n; j += nth) o[j] = d_noise(c0 + (uint32_t)j);
         break;
       }
       case OP_WAVE: {
         const long len = (long)I.aux2;
-        long m = ((long)__float_as_uint(ps[I.s]) + tbase + d + tid) % len;
-        if (m < 0) m += len;
-        const long step = nth % len;
-        for (int j = tid; j < n; j += nth) { o[j] = a.tables[I.aux + (uint32_t)m]; m += step; if (m >= len) m -= len; }
+        long m0 = ((long)__float_as_uint(ps[I.s]) + tb + tid) % len;
+        if (m0 < 0) m0 += len;
+        const uint32_t ulen = (uint32_t)len, step = (uint32_t)(nth % len);
+        uint32_t m = (uint32_t)m0;
+        const float* tab = a.tables + I.aux;
+        for (int j = tid; j < n; j += nth) { o[j] = __ldg(tab + m); m += step; if (m >= ulen) m -= ulen; }
         break;
       }
       case OP_IMPULSE: {
         const bool armed = __float_as_uint(ps[I.s]) == 0u;
-        for (int j = tid; j < n; j += nth) o[j] = (armed && tbase + j + d == 0) ? 1.0f : 0.0f;
+        const int jz = (tb <= 0 && -tb < (long)n) ? (int)-tb : -1;
+        for (int j = tid; j < n; j += nth) o[j] = (armed && j == jz) ? 1.0f : 0.0f;
         break;
       }
       case OP_DELAY: case OP_TICK: {   // the shifted input, silent while the line is still filling
         const int x = I.in[0];
-        if (x < PS) { const float c = ps[x]; for (int j = tid; j < n; j += nth) o[j] = tbase + j + d >= 0 ? c : 0.0f; }
-        else { const float* src = tmp + (x - PS) * HB; for (int j = tid; j < n; j += nth) o[j] = tbase + j + d >= 0 ? src[j] : 0.0f; }
+        const int jz = tb >= 0 ? 0 : (-tb > (long)n ? n : (int)-tb);     // columns below jz lie before the stream's start
+        if (x < PS) { const float c = ps[x]; for (int j = tid; j < n; j += nth) o[j] = j >= jz ? c : 0.0f; }
+        else { const float* src = tmp + (x - PS) * HB; for (int j = tid; j < n; j += nth) o[j] = j >= jz ? src[j] : 0.0f; }
         break;
       }
       case OP_STREAM_IN: {
         const float* y = a.y + ((size_t)I.aux * a.V + v) * (size_t)a.ring;
-        for (int j = tid; j < n; j += nth) o[j] = y[(tbase + j) & (long)(a.ring - 1)];
+        const uint32_t r0 = (uint32_t)tbase, mask = (uint32_t)a.ring - 1u;
+        for (int j = tid; j < n; j += nth) o[j] = y[(r0 + (uint32_t)j) & mask];
         break;
       }
       default: {
@@ -421,11 +490,12 @@ __device__ __forceinline__ void sp_stage(const SpArgs& a, const SpSmem& sm, int 
   for (int s = tid; s < a.NS; s += nth) ps[a.P + s] = a.state_init[(size_t)s * a.Vp + v];
 }
 
-// One CTA = one frame: (voice, work item of a round, round).  c0 = first round of this launch.
-__global__ void __launch_bounds__(256) k_spectral_frames(SpArgs a, long c0, int n_rounds, int HB, SpSmem sm) {
+// One CTA = one frame: (voice, work item of a round, round).  c0 = first round of this launch.  HB = columns per
+// mini-tape block = N_max / 2 + 1 (the non-redundant bins of the largest transform in one block).
+__global__ void __launch_bounds__(256, 3) k_spectral_frames(SpArgs a, long c0, int n_rounds, int HB, SpSmem sm) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const int per_voice = a.n_items * n_rounds;
-  const int v = blockIdx.x / per_voice, w = blockIdx.x % per_voice;
+  const int v = (int)(blockIdx.x / (unsigned)per_voice), w = (int)(blockIdx.x % (unsigned)per_voice);
   const SpItem it = a.items[w % a.n_items];
   const long c = c0 + w / a.n_items;
   const SpSegment sg = a.segs[it.seg];
@@ -434,14 +504,15 @@ __global__ void __launch_bounds__(256) k_spectral_frames(SpArgs a, long c0, int 
   const long tau = tb - N;                                                            // its bins were streamed from tau on
   float* yre = sg.y_re >= 0 ? a.y + ((size_t)sg.y_re * a.V + v) * (size_t)a.ring : nullptr;
   float* yim = sg.y_im >= 0 ? a.y + ((size_t)sg.y_im * a.V + v) * (size_t)a.ring : nullptr;
-  const long lo = a.t0, hi = a.t0 + a.T;         // only these sample times are read by this call's post pass
-  if (tb >= hi || tb + N <= lo) return;
+  // only sample times of this call are read by its post pass: columns [i_lo, i_hi) of the frame
+  const long lo = a.t0 - tb, hi = a.t0 + a.T - tb;
+  if (hi <= 0 || lo >= N) return;
+  const int i_lo = lo > 0 ? (int)lo : 0, i_hi = hi < N ? (int)hi : N;
+  const uint32_t ymask = (uint32_t)a.ring - 1u, y0 = (uint32_t)tb;
   if (tau + N <= 0) {                            // every position of B predates the stream: the inverse transform of zeros
-    for (int i = tid; i < N; i += nth) {
-      const long t = tb + i;
-      if (t < lo || t >= hi) continue;
-      if (yre) yre[t & (long)(a.ring - 1)] = 0.0f;
-      if (yim) yim[t & (long)(a.ring - 1)] = 0.0f;
+    for (int i = i_lo + tid; i < i_hi; i += nth) {
+      if (yre) yre[(y0 + (uint32_t)i) & ymask] = 0.0f;
+      if (yim) yim[(y0 + (uint32_t)i) & ymask] = 0.0f;
     }
     return;
   }
@@ -449,57 +520,71 @@ __global__ void __launch_bounds__(256) k_spectral_frames(SpArgs a, long c0, int 
   sp_stage(a, sm, v, tid, nth);
   float* ps = QG_SMEM_F + sm.ps_off;
   float* tmp = QG_SMEM_F + sm.tmp_off;
-  float* fr = QG_SMEM_F + sm.f_off;
-  float* fi = fr + FPAD(N);
-  float* gr = fi + FPAD(N);
-  float* gi = gr + FPAD(N);
+  float2* f = reinterpret_cast<float2*>(QG_SMEM_F + sm.f_off);
+  float2* g = f + CPAD(N) + 1;
   __syncthreads();
-  const float* tw = a.tables + sg.tw;
-  const int hb = HB < N ? HB : N;
+  const float2* tw = reinterpret_cast<const float2*>(a.tables + sg.tw);
+  const int sh = 32 - lg;
   // ---- the frame's N input samples x[tau - N + m], bit-reversed into the transform buffer
-  for (int m0 = 0; m0 < N; m0 += hb) {
-    const long t0 = tau - N + m0;
-    if (t0 + hb > 0) sp_eval(code, sg.pre_lo, sg.pre_hi, t0, hb, HB, PS, sm, a, v, tid, nth);
+  {
+    const int hb = N < HB - 1 ? N : HB - 1;                  // HB - 1 = N_max / 2: a power of two
     const bool scalar = sg.pre_x < PS;
     const float cs = scalar ? ps[sg.pre_x] : 0.0f;
     const float* src = tmp + (sg.pre_x - PS) * HB;
-    for (int j = tid; j < hb; j += nth) {
-      const uint32_t rv = __brev((uint32_t)(m0 + j)) >> (32 - lg);
-      fr[FPAD(rv)] = t0 + j >= 0 ? (scalar ? cs : src[j]) : 0.0f;
-      fi[FPAD(rv)] = 0.0f;
+    for (int m0 = 0; m0 < N; m0 += hb) {
+      const long t0 = tau - N + m0;
+      if (t0 + hb > 0) sp_eval(code, sg.pre_lo, sg.pre_hi, t0, hb, HB, PS, sm, a, v, tid, nth);
+      const int jz = t0 >= 0 ? 0 : (-t0 > (long)hb ? hb : (int)-t0);
+      for (int j = tid; j < hb; j += nth) {
+        const uint32_t rv = __brev((uint32_t)(m0 + j)) >> sh;
+        f[CPAD(rv)] = make_float2(j >= jz ? (scalar ? cs : src[j]) : 0.0f, 0.0f);
+      }
     }
   }
   __syncthreads();
-  sp_fft(fr, fi, lg, tw, false, tid, nth);
-  // ---- the bin chain on all N streamed bins (conjugate mirror above N/2, nodes.rs:637-642), into the inverse transform's
-  // input; positions whose sample time was negative keep the buffer's initial zero
-  for (int i0 = 0; i0 < N; i0 += hb) {
+  sp_fft(f, lg, tw, 1.0f, tid, nth);
+  // ---- the bin chain on the streamed bins (conjugate mirror above N/2, nodes.rs:637-642), into the inverse transform's
+  // input; positions whose sample time was negative keep the buffer's initial zero.  A chain whose results have a known
+  // behaviour under conjugation (plan: sym_re / sym_im) runs on bins 0 .. N/2 only.
+  {
+    const bool sym = sg.sym_re != 0;
+    const int half = N >> 1, nb = half + 1 <= HB ? half + 1 : HB;      // bins per block
+    const int i_end = sym ? half + 1 : N;
+    const int iz = tau >= 0 ? 0 : (-tau > (long)N ? N : (int)-tau);     // bins below iz predate the stream
     float* c_re = tmp;            // slots 0, 1 = the rfft's two outputs
     float* c_im = tmp + HB;
-    for (int j = tid; j < hb; j += nth) {
-      const int i = i0 + j;
-      if (i <= N / 2) { c_re[j] = fr[FPAD(i)]; c_im[j] = fi[FPAD(i)]; }
-      else { c_re[j] = fr[FPAD(N - i)]; c_im[j] = -fi[FPAD(N - i)]; }
-    }
-    sp_eval(code, sg.ch_lo, sg.ch_hi, tau + i0, hb, HB, PS, sm, a, v, tid, nth);
     const float* o_re = sg.in_re_x < PS ? nullptr : tmp + (sg.in_re_x - PS) * HB;
     const float* o_im = sg.in_im_x < PS ? nullptr : tmp + (sg.in_im_x - PS) * HB;
-    for (int j = tid; j < hb; j += nth) {
-      const int i = i0 + j;
-      const bool live = tau + i >= 0;
-      const uint32_t rv = __brev((uint32_t)i) >> (32 - lg);
-      gr[FPAD(rv)] = live ? (o_re ? o_re[j] : ps[sg.in_re_x]) : 0.0f;
-      gi[FPAD(rv)] = live ? (o_im ? o_im[j] : ps[sg.in_im_x]) : 0.0f;
+    const float k_re = o_re ? 0.0f : ps[sg.in_re_x], k_im = o_im ? 0.0f : ps[sg.in_im_x];
+    const float s_re = (float)sg.sym_re, s_im = (float)sg.sym_im;
+    for (int i0 = 0; i0 < i_end; i0 += nb) {
+      const int n = i_end - i0 < nb ? i_end - i0 : nb;
+      for (int j = tid; j < n; j += nth) {
+        const int i = i0 + j;
+        float2 z;
+        if (i <= half) z = f[CPAD(i)];
+        else { z = f[CPAD(N - i)]; z.y = -z.y; }
+        c_re[j] = z.x; c_im[j] = z.y;
+      }
+      sp_eval(code, sg.ch_lo, sg.ch_hi, tau + i0, n, HB, PS, sm, a, v, tid, nth);
+      for (int j = tid; j < n; j += nth) {
+        const int i = i0 + j;
+        const float2 z = make_float2(o_re ? o_re[j] : k_re, o_im ? o_im[j] : k_im);
+        g[CPAD(__brev((uint32_t)i) >> sh)] = i >= iz ? z : make_float2(0.0f, 0.0f);
+        if (sym && i > 0 && i < half) {
+          const int im = N - i;
+          g[CPAD(__brev((uint32_t)im) >> sh)] = im >= iz ? make_float2(z.x * s_re, z.y * s_im) : make_float2(0.0f, 0.0f);
+        }
+      }
     }
   }
   __syncthreads();
-  sp_fft(gr, gi, lg, tw, true, tid, nth);
+  sp_fft(g, lg, tw, -1.0f, tid, nth);
   const float sc = 1.0f / (float)N;
-  for (int i = tid; i < N; i += nth) {
-    const long t = tb + i;
-    if (t < lo || t >= hi) continue;
-    if (yre) yre[t & (long)(a.ring - 1)] = gr[FPAD(i)] * sc;
-    if (yim) yim[t & (long)(a.ring - 1)] = gi[FPAD(i)] * sc;
+  for (int i = i_lo + tid; i < i_hi; i += nth) {
+    const float2 z = g[CPAD(i)];
+    if (yre) yre[(y0 + (uint32_t)i) & ymask] = z.x * sc;
+    if (yim) yim[(y0 + (uint32_t)i) & ymask] = z.y * sc;
   }
 }
 
@@ -507,7 +592,7 @@ __global__ void __launch_bounds__(256) k_spectral_frames(SpArgs a, long c0, int 
 __global__ void __launch_bounds__(256) k_spectral_post(SpArgs a, long t_lo, long t_hi, int HB, SpSmem sm) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const int nblk = (int)((t_hi - t_lo + HB - 1) / HB);
-  const int v = blockIdx.x / nblk, b = blockIdx.x % nblk;
+  const int v = (int)(blockIdx.x / (unsigned)nblk), b = (int)(blockIdx.x % (unsigned)nblk);
   const long tbase = t_lo + (long)b * HB;
   const int n = (int)(t_hi - tbase < HB ? t_hi - tbase : HB), PS = a.P + a.NS;
   const Instr* code = reinterpret_cast<const Instr*>(qg_smem);
@@ -516,13 +601,13 @@ __global__ void __launch_bounds__(256) k_spectral_post(SpArgs a, long t_lo, long
   sp_eval(code, a.post_lo, a.post_hi, tbase, n, HB, PS, sm, a, v, tid, nth);
   const float* ps = QG_SMEM_F + sm.ps_off;
   const float* tmp = QG_SMEM_F + sm.tmp_off;
+  const size_t t = (size_t)(tbase - a.t0);
   for (int c = 0; c < a.n_out; c++) {
     const int ox = a.out_x[c];
-    for (int j = tid; j < n; j += nth) {
-      const long t = tbase + j - a.t0;
-      const size_t o = a.frame_major ? ((size_t)t * a.V + v) * a.n_out + c : ((size_t)v * a.n_out + c) * a.T + t;
-      a.out[o] = ox < PS ? ps[ox] : tmp[(ox - PS) * HB + j];
-    }
+    float* o = a.frame_major ? a.out + (t * a.V + v) * a.n_out + c : a.out + ((size_t)v * a.n_out + c) * a.T + t;
+    const size_t stride = a.frame_major ? (size_t)a.V * a.n_out : 1;
+    if (ox < PS) { const float k = ps[ox]; for (int j = tid; j < n; j += nth) o[j * stride] = k; }
+    else { const float* src = tmp + (ox - PS) * HB; for (int j = tid; j < n; j += nth) o[j * stride] = src[j]; }
   }
 }
 
@@ -542,13 +627,13 @@ cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t strea
   const int C = p.C, PS = a.P + a.NS;
   int max_n = 0;
   for (const SpSegment& s : p.segs) max_n = std::max(max_n, 1 << s.lg);
-  const int HB = std::min(512, max_n);
+  const int HBf = max_n / 2 + 1, HBp = 512;
   SpSmem sf, sp;
   sf.ps_off = sp.ps_off = a.n_code * (int)(sizeof(Instr) / 4);
   sf.tmp_off = sp.tmp_off = sf.ps_off + ((PS + 3) & ~3);
-  sf.f_off = sf.tmp_off + std::max(2, p.n_slots_frame) * HB;
+  sf.f_off = (sf.tmp_off + std::max(2, p.n_slots_frame) * HBf + 3) & ~3;
   sp.f_off = 0;
-  const size_t smem_f = (size_t)(sf.f_off + 4 * FPAD(max_n)) * 4, smem_p = (size_t)(sp.tmp_off + std::max(1, p.n_slots_post) * HB) * 4;
+  const size_t smem_f = (size_t)sf.f_off * 4 + 2 * (size_t)(CPAD(max_n) + 1) * 8, smem_p = (size_t)(sp.tmp_off + std::max(1, p.n_slots_post) * HBp) * 4;
   if (smem_f > 200 * 1024 || smem_p > 200 * 1024) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(k_spectral_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e != cudaSuccess) return e;
@@ -559,7 +644,7 @@ cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t strea
   const int R = a.ring / C - 1;     // rounds per launch
   auto frames = [&](long c, int n) {
     const long blocks = (long)a.V * a.n_items * n;
-    k_spectral_frames<<<(unsigned)blocks, 256, smem_f, stream>>>(a, c, n, HB, sf);
+    k_spectral_frames<<<(unsigned)blocks, 256, smem_f, stream>>>(a, c, n, HBf, sf);
     if (launches) *launches += 1;
   };
   frames(c_first, 1);
@@ -568,8 +653,8 @@ cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t strea
     frames(c, n);
     const long t_lo = std::max(A, c * (long)C), t_hi = std::min(E, (c + n) * (long)C);
     if (t_hi > t_lo) {
-      const long nblk = (t_hi - t_lo + HB - 1) / HB;
-      k_spectral_post<<<(unsigned)(a.V * nblk), 256, smem_p, stream>>>(a, t_lo, t_hi, HB, sp);
+      const long nblk = (t_hi - t_lo + HBp - 1) / HBp;
+      k_spectral_post<<<(unsigned)(a.V * nblk), 256, smem_p, stream>>>(a, t_lo, t_hi, HBp, sp);
       if (launches) *launches += 1;
     }
   }

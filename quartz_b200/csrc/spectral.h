@@ -26,6 +26,7 @@ struct SpSegment {      // one `rfft(N, start) -> chain -> ifft(N, start)` insta
   int in_re_x, in_im_x; // X indices of the ifft's two inputs (chain outputs, scalars or the rfft outputs themselves)
   int tw;               // twiddle table offset in the bank's table region
   int y_re, y_im;       // stream index of the ifft's outputs in the Y ring, -1 when the post-graph never reads it
+  int sym_re, sym_im;   // the chain's results under conjugation of the input bin: +1 unchanged, -1 negated; 0 0 = unknown
 };
 struct SpItem { int seg, frame; };   // work item of one round: frame `frame` (0 .. C/N - 1) of segment `seg`
 
