@@ -79,6 +79,9 @@ int qg_net_tape_info(const qg_net* net, int* n_instr, int* n_params, int* n_stat
 /* the CUDA translation unit the tape specialiser compiles for this graph (NVRTC; see quartz_b200/csrc/spec_kernel.cuh):
    returns its length (copies at most cap - 1 characters into buf, which may be NULL) or a negated QG_ERR_* status */
 long qg_net_spec_source(const qg_net* net, char* buf, long cap);
+/* the template voice's DEVICE parameters (filter coefficients, pan weights, 1/sr ... as the lowering derives them from the
+   op-string parameters): returns their count, copies at most cap values; < 0: -QG_ERR_* */
+int qg_net_device_params(const qg_net* net, float* out, int cap);
 /* 1 when the graph qualifies for the frame-parallel spectral path (QG_PATH_SPECTRAL): rfft -> stateless bin chain -> ifft
    segments (src/nodes.rs:601-700) fed by pure functions of time; fills the plan's shape.  0 when it does not, < 0: -QG_ERR_* */
 int qg_net_spectral_info(const qg_net* net, int* n_segments, int* n_streams, int* n_instr, int* round_len);

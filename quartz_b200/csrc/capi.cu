@@ -260,6 +260,22 @@ int qg_net_tape_info(const qg_net* n, int* n_instr, int* n_params, int* n_state,
   });
 }
 
+// Device parameters of the template voice, as the lowering derives them (filter coefficients, pan weights, 1/sr ...): what
+// every kernel reads as X[0, P).  Returns P (copies at most cap values) or a negated status.
+int qg_net_device_params(const qg_net* n, float* out, int cap) {
+  if (!n) return -fail(QG_ERR_ARG, "null net");
+  int count = 0;
+  int rc = guard_int([&] {
+    Tape t;
+    std::string err;
+    if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
+    count = (int)t.params.size();
+    for (int i = 0; i < count && i < cap && out; i++) out[i] = t.params[i];
+    return (int)QG_OK;
+  });
+  return rc == QG_OK ? count : -rc;
+}
+
 // Frame-parallel spectral plan of a graph (spectral.h): 1 and the plan's shape when the tape qualifies, else 0
 int qg_net_spectral_info(const qg_net* n, int* n_segments, int* n_streams, int* n_instr, int* round_len) {
   if (!n) return -fail(QG_ERR_ARG, "null net");

@@ -217,6 +217,15 @@ class Net:
         check(lib().qg_net_tape_info(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("n_instr", "n_params", "n_state", "n_temps", "divergent"), [x.value for x in v]))
 
+    def device_params(self):
+        """the template voice's device parameters as the lowering derives them (filter coefficients, pan weights ...)"""
+        n = lib().qg_net_device_params(self.h, None, 0)
+        if n < 0:
+            raise QuartzGpuError(_ffi.last_error())
+        out = np.zeros(max(n, 1), np.float32)
+        lib().qg_net_device_params(self.h, _fptr(out), n)
+        return out[:n]
+
     def spectral_info(self):
         """shape of the frame-parallel spectral plan (QG_PATH_SPECTRAL), or None when the graph does not qualify"""
         v = [C.c_int(0) for _ in range(4)]

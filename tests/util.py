@@ -1,4 +1,10 @@
+import json
+import os
+
 import numpy as np
+
+# QG_PARITY_LOG=<file>: every float comparison appends {what, peak, max_abs_err, residual_db} — the evidence behind RELATIVE_OK
+_LOG = os.environ.get("QG_PARITY_LOG")
 
 
 def assert_parity(got, ref, tol, what=""):
@@ -27,4 +33,8 @@ def assert_parity(got, ref, tol, what=""):
     assert err.max() <= 1e-4 * scale, f"{what}: max abs err {err.max():.3e} (scale {scale:.3g})"
     rms = float(np.sqrt(np.mean((g - r) ** 2))) / scale
     db = 20 * np.log10(max(rms, 1e-30))
+    if _LOG:
+        with open(_LOG, "a") as f:
+            f.write(json.dumps({"what": what, "peak": float(np.abs(r).max()), "max_abs_err": float(err.max()),
+                                "residual_db_abs": float(20 * np.log10(max(rms * scale, 1e-30)))}) + "\n")
     assert db <= -90.0, f"{what}: residual {db:.1f} dBFS"
