@@ -93,7 +93,7 @@ def cpu_baseline(wls, seconds_target=12.0, threads=None):
     units / total extrapolated time."""
     from quartz_b200.graphs import build
     from tests.oracle_ffi import ONet, render_bank
-    threads = threads or os.cpu_count() or 1
+    threads = threads or len(os.sched_getaffinity(0)) or 1    # the cores this rank may use (a multi-rank run binds ranks to NUMA nodes)
     per_bank = []
     for wl in wls:
         per_bank.append(_cpu_sample(wl, seconds_target / len(wls), threads, build, ONet, render_bank))
@@ -183,6 +183,34 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs of the GPU's NUMA node: with 8 ranks per box the
+    device->host ingest is the end-to-end limiter, and a buffer on the far socket halves what a rank gets.  Returns a note."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bdf = out[-12:] if len(out) >= 12 else None          # 00000000:1B:00.0 -> 0000:1b:00.0
+        if not bdf:
+            return "numa: bus id unknown"
+        node = int(open(f"/sys/bus/pci/devices/{bdf.lower()}/numa_node").read())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa: node {node} has no usable cpu"
+        os.sched_setaffinity(0, cpus)
+        return f"numa: bound to node {node} ({len(cpus)} cpus)"
+    except Exception as e:   # the binding is an optimisation, never a requirement
+        return f"numa: not bound ({type(e).__name__})"
+
+
 class Runner:
     """one GPU context + the timing protocol shared by the headline and the sub-configs"""
 
@@ -194,6 +222,7 @@ class Runner:
         self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
         # the library launches on the stream it is given; use a real (non-legacy) torch stream so that torch CUDA
         # events bracket exactly those launches
+        self.numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "numa: one rank, not bound"
         self.stream = torch.cuda.Stream()
         torch.cuda.set_stream(self.stream)
         self.ctx = qb.Context(local_rank, stream=self.stream.cuda_stream)
@@ -430,6 +459,7 @@ class Runner:
                 "d2h_gbs": out_bytes / dt / 1e9, "d2h_link_gbs": d2h_peak_min,
                 "d2h_link_note": f"one {nb >> 20} MiB pinned copy per rank, all {world} rank(s) copying at the same time, slowest rank",
                 "host_buffer": ("pinned" if pinned else "pageable") + ("" if T_host == T else f", streamed in blocks of {T_host} samples"),
+                "host_placement": self.numa,
                 "note": "bank build from host tables + render + device->host copy of every output sample (pinned host buffer)",
                 "checksum": checksum}
 

@@ -184,7 +184,8 @@ def test_a_cloned_bank_carries_its_state_and_both_continue_like_the_oracle(path)
     rb2 = b.render(300)
     whole = qb.Bank(build(expr, Net), V, salts=salts).set_path(path).render(777 + 500 + 300)
     assert np.array_equal(ra1, rb1)
-    assert np.array_equal(np.concatenate([first, rb1, rb2], axis=2), whole)
+    # (block-level scans re-associate per hop, and hops follow the call boundaries: chunked vs whole is a float comparison)
+    assert_parity(np.concatenate([first, rb1, rb2], axis=2), whole, "float", "clone, chunked")
     ref = np.stack([build(expr, ONet).set_salt(int(s)).render(1577).T for s in salts])
     assert_parity(whole, ref, "float", "clone")
     b.reset()                               # reset of the clone restores ITS initial state (same init table)

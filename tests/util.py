@@ -7,9 +7,18 @@ import numpy as np
 _LOG = os.environ.get("QG_PARITY_LOG")
 
 
-def assert_parity(got, ref, tol, what=""):
+# The north star states the f32 tolerances as ABSOLUTE numbers (max abs error <= 1e-4, residual <= -90 dBFS re full scale 1.0).
+# That cannot hold for a signal far above full scale (one ulp of 1,500 is 1.2e-4), so the cases below — and only they — are
+# compared relative to the reference's peak.  The list is measured, not guessed: a full `-m gpu` run with QG_PARITY_LOG
+# (1,376 float comparisons, 676 of them on signals peaking above 1.0) found exactly one that needs it.
+RELATIVE_OK = {
+    "lowpass(1.2)": "process case driven with inputs in [200, 2000]: output peak 1,494, error 2.4e-4 = 1.3 ulp of the signal",
+}
+
+
+def assert_parity(got, ref, tol, what="", relative=False):
     """Parity bar from BASELINE.md section 5: bit-exact for integer/trigger state; for f32 audio max abs error
-    <= 1e-4 and residual <= -90 dBFS, both relative to max(1, peak of the reference)."""
+    <= 1e-4 and residual <= -90 dBFS, absolute (full scale = 1.0) except for the listed RELATIVE_OK cases."""
     got = np.asarray(got, dtype=np.float32)
     ref = np.asarray(ref, dtype=np.float32)
     assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
@@ -28,9 +37,10 @@ def assert_parity(got, ref, tol, what=""):
     if not fin.any():
         return
     g, r = got[fin].astype(np.float64), ref[fin].astype(np.float64)
-    scale = max(1.0, float(np.abs(r).max()))
+    peak = float(np.abs(r).max())
+    scale = max(1.0, peak) if (relative or what in RELATIVE_OK) else 1.0
     err = np.abs(g - r)
-    assert err.max() <= 1e-4 * scale, f"{what}: max abs err {err.max():.3e} (scale {scale:.3g})"
+    assert err.max() <= 1e-4 * scale, f"{what}: max abs err {err.max():.3e} (scale {scale:.3g}, reference peak {peak:.3g})"
     rms = float(np.sqrt(np.mean((g - r) ** 2))) / scale
     db = 20 * np.log10(max(rms, 1e-30))
     if _LOG:
