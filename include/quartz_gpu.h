@@ -85,6 +85,8 @@ int qg_net_device_params(const qg_net* net, float* out, int cap);
 /* 1 when the graph qualifies for the frame-parallel spectral path (QG_PATH_SPECTRAL): rfft -> stateless bin chain -> ifft
    segments (src/nodes.rs:601-700) fed by pure functions of time; fills the plan's shape.  0 when it does not, < 0: -QG_ERR_* */
 int qg_net_spectral_info(const qg_net* net, int* n_segments, int* n_streams, int* n_instr, int* round_len);
+/* the translation unit NVRTC compiles for that plan (quartz_b200/csrc/spectral_kernel.cuh); contract of qg_net_spec_source */
+long qg_net_spectral_spec_source(const qg_net* net, char* buf, long cap);
 
 /* ---- device ---- */
 qg_ctx* qg_ctx_create(int device, void* cuda_stream /* cudaStream_t, or NULL for a private stream */);

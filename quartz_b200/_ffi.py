@@ -41,6 +41,7 @@ SIGNATURES = {
     "qg_net_tape_info": (ci, [vp, ip, ip, ip, ip, ip]),
     "qg_net_spec_source": (cl, [vp, C.c_char_p, cl]),
     "qg_net_spectral_info": (ci, [vp, ip, ip, ip, ip]),
+    "qg_net_spectral_spec_source": (cl, [vp, C.c_char_p, cl]),
     "qg_net_device_params": (ci, [vp, fp, ci]),
     "qg_ctx_create": (vp, [ci, vp]),
     "qg_ctx_destroy": (None, [vp]),

@@ -71,6 +71,8 @@ struct qg_bank {
   bool sp_started = false;      // K5 has rendered since the last reset
   bool other_started = false;   // another kernel has
   bool last_k5 = false;         // the previous render ran on K5 (survives a reset: qg_bank_kernel names what a repeat would use)
+  SpectralKernels sp_spec;      // K5s: the plan compiled into the kernels (NVRTC, cached process-wide by plan)
+  bool sp_spec_tried = false;
 };
 
 static thread_local std::string g_err;
@@ -306,6 +308,28 @@ long qg_net_spec_source(const qg_net* n, char* buf, long cap) {
     if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
     if (!spec_supported(t, &err)) return fail(QG_ERR_UNSUPPORTED, "tape cannot be specialised: " + err);
     std::string src = spec_source(t);
+    need = (long)src.size();
+    if (buf && cap > 0) {
+      long k = std::min<long>(need, cap - 1);
+      memcpy(buf, src.data(), (size_t)k);
+      buf[k] = 0;
+    }
+    return (int)QG_OK;
+  });
+  return rc == QG_OK ? need : -(long)rc;
+}
+
+// The translation unit compiled for the graph's frame-parallel spectral plan (K5s, spectral_kernel.cuh); same contract
+long qg_net_spectral_spec_source(const qg_net* n, char* buf, long cap) {
+  if (!n) return -(long)fail(QG_ERR_ARG, "null net");
+  long need = 0;
+  int rc = guard_int([&] {
+    Tape t;
+    std::string err;
+    if (!lower(n->g, &t, &err)) return fail(QG_ERR_UNSUPPORTED, err);
+    SpPlan p = plan_spectral(t);
+    if (!p.ok) return fail(QG_ERR_UNSUPPORTED, "the graph has no frame-parallel spectral plan");
+    std::string src = spectral_spec_source(p, t);
     need = (long)src.size();
     if (buf && cap > 0) {
       long k = std::min<long>(need, cap - 1);
@@ -591,7 +615,7 @@ int qg_bank_set_path(qg_bank* b, int path) {
 const char* qg_bank_kernel(const qg_bank* b) {
   if (!b) return "";
   if (b->sp.ok && !b->other_started && (b->path == QG_PATH_SPECTRAL || b->sp_started || (b->path == QG_PATH_AUTO && b->last_k5)))
-    return "k_spectral_frames";
+    return b->sp_spec.frames ? "k_sp_frames" : "k_spectral_frames";
   int f = bank_family(b);
   if (f == 1) return fused_name(b->fused.id);
   if (f == 2) return "k_interp_tv";
@@ -704,8 +728,20 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     sa.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
     sa.C = b->sp.C; sa.post_lo = b->sp.post_lo; sa.post_hi = b->sp.post_hi;
     sa.n_slots_frame = b->sp.n_slots_frame; sa.n_slots_post = b->sp.n_slots_post;
+    // K5s: a bulk render pays for compiling the plan into the kernels (about 2 s once per plan and process, then cached).
+    // QG_SPECTRAL_SPEC=1 specialises every K5 bank, =0 none; a failed compile keeps the generic kernels.
+    if (!b->sp_spec.frames && !b->sp_spec_tried) {
+      const char* es = getenv("QG_SPECTRAL_SPEC");
+      const bool force = es && es[0] == '1', never = es && es[0] == '0';
+      if (!never && (force || (double)b->V * (double)T >= 1.0e8)) {
+        b->sp_spec_tried = true;
+        std::string err;
+        try { spectral_spec_compile(b->sp, t, &b->sp_spec, &err); } catch (...) {}
+        if (!b->sp_spec.frames && force) return fail(QG_ERR_UNSUPPORTED, "QG_SPECTRAL_SPEC=1: " + err);
+      }
+    }
     int l = 0;
-    cudaError_t se = launch_spectral(sa, b->sp, c->stream, &l);
+    cudaError_t se = launch_spectral(sa, b->sp, c->stream, &l, b->sp_spec.frames, b->sp_spec.post);
     c->launches += l;
     if (se != cudaErrorNotSupported) {
       CU(se);
@@ -915,7 +951,7 @@ qg_bank* qg_bank_clone(const qg_bank* src) {
     b->block_ok = src->block_ok; b->ring_mode = src->ring_mode; b->state_ready = src->state_ready;
     b->spec_auto_ok = src->spec_auto_ok; b->spec_auto_tried = src->spec_auto_tried; b->lane_work = src->lane_work;
     if (src->spec.fn && src->spec.shared) b->spec = src->spec;     // kernels live in the process-wide cache
-    b->sp = src->sp; b->sp_time = src->sp_time; b->sp_started = src->sp_started; b->other_started = src->other_started; b->last_k5 = src->last_k5;
+    b->sp = src->sp; b->sp_time = src->sp_time; b->sp_started = src->sp_started; b->other_started = src->other_started; b->last_k5 = src->last_k5; b->sp_spec = src->sp_spec; b->sp_spec_tried = src->sp_spec_tried;
   } catch (...) {
     delete b;
     fail(QG_ERR_ARG, "qg_bank_clone: out of memory");

@@ -191,7 +191,7 @@ template <int K, int STORE>
 struct __align__(1024) WarpSmem {
   float4 tile[K / 4 * 32];
   float4 mp[5];          // A^(K*2^i) as (a, b, c, d)
-  float4 rc[K / 2];      // homogeneous response rows C*A^i, two samples per entry: (r1_i, r1_{i+1}, r2_i, r2_{i+1})
+  float4 rc[K / 2];      // homogeneous response rows C*A^i: (r1_i, r2_i, r1_{i+1}, r2_{i+1})
   float lin[STORE == 1 ? 32 * K : 4];
 };
 
@@ -221,9 +221,9 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
   if (lane == 0) {
     double m11 = 1, m12 = 0, m21 = 0, m22 = 1;
     float* rcf = reinterpret_cast<float*>(W.rc);
-    for (int i = 0; i < K; i++) {   // pairs of samples: (r1_i, r1_{i+1}, r2_i, r2_{i+1}), the operand layout of the packed correction
-      rcf[4 * (i >> 1) + (i & 1)] = (float)(c1 * m11 + c2 * m21);
-      rcf[4 * (i >> 1) + 2 + (i & 1)] = (float)(c1 * m12 + c2 * m22);
+    for (int i = 0; i < K; i++) {
+      rcf[2 * i] = (float)(c1 * m11 + c2 * m21);
+      rcf[2 * i + 1] = (float)(c1 * m12 + c2 * m22);
       double n11 = A11 * m11 + A12 * m21, n12 = A11 * m12 + A12 * m22, n21 = A21 * m11 + A22 * m21, n22 = A21 * m12 + A22 * m22;
       m11 = n11; m12 = n12; m21 = n21; m22 = n22;
     }
@@ -331,15 +331,14 @@ __global__ void __launch_bounds__(128, 7) k_noise_svf_scan(const float* __restri
         if (lane == 0) bulk_wait_read_0();          // the previous block's copy has finished reading W.lin
         __syncwarp();
       }
-      const float2 hh1 = make_float2(h1, h1), hh2 = make_float2(h2, h2);
 #pragma unroll
       for (int i4 = 0; i4 < K / 4; i4++) {
         float4 y = W.tile[slot(i4)];
         const float4 ra = W.rc[2 * i4], rb = W.rc[2 * i4 + 1];
-        // two samples per packed FMA (FFMA2): y_i += r1_i h1 + r2_i h2, the same two roundings per sample as before
-        const float2 ya = __ffma2_rn(make_float2(ra.x, ra.y), hh1, __ffma2_rn(make_float2(ra.z, ra.w), hh2, make_float2(y.x, y.y)));
-        const float2 yb = __ffma2_rn(make_float2(rb.x, rb.y), hh1, __ffma2_rn(make_float2(rb.z, rb.w), hh2, make_float2(y.z, y.w)));
-        y = make_float4(ya.x, ya.y, yb.x, yb.y);
+        y.x = __fmaf_rn(ra.x, h1, __fmaf_rn(ra.y, h2, y.x));
+        y.y = __fmaf_rn(ra.z, h1, __fmaf_rn(ra.w, h2, y.y));
+        y.z = __fmaf_rn(rb.x, h1, __fmaf_rn(rb.y, h2, y.z));
+        y.w = __fmaf_rn(rb.z, h1, __fmaf_rn(rb.w, h2, y.w));
         if (swz) W.tile[slot(i4)] = y;
         else if (STORE == 1) reinterpret_cast<float4*>(&W.lin[lane * K])[i4] = y;
         else { float* g = orow + t + lane * K + 4 * i4; g[0] = y.x; g[1] = y.y; g[2] = y.z; g[3] = y.w; }

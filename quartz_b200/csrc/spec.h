@@ -18,6 +18,7 @@ std::string spec_source(const Tape& t);
 #include <cuda_runtime.h>
 
 #include "kernels.h"
+#include "spectral.h"
 
 namespace qg {
 
@@ -37,6 +38,16 @@ bool spec_auto_ok(const Tape& t);
 bool spec_cached(const Tape& t, SpecKernel* out);
 cudaError_t spec_launch(const SpecKernel& k, const InterpArgs& a, cudaStream_t stream, int* launches);
 void spec_release(SpecKernel* k);
+
+// K5s: the frame-parallel spectral kernels compiled for one plan (spectral_kernel.cuh); cached process-wide by source, never
+// unloaded.  Same failure modes as spec_compile: the caller keeps the generic kernels of spectral.cu.
+struct SpectralKernels {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t frames = nullptr, post = nullptr;
+  double compile_seconds = 0.0;
+};
+std::string spectral_spec_source(const SpPlan& p, const Tape& t);
+bool spectral_spec_compile(const SpPlan& p, const Tape& t, SpectralKernels* out, std::string* err);
 
 }  // namespace qg
 #endif

@@ -355,71 +355,7 @@ SpPlan plan_spectral(const Tape& t) {
 }
 
 // ------------------------------------------------------------------------------------------------ device
-// Transform buffers hold interleaved complex values (one LDS.64 / STS.64 per point), padded by one element per 16.
-#define CPAD(i) ((i) + ((i) >> 4))
-
-// Radix-2 DIT butterflies, 2^R points per thread carried through R consecutive stages in registers (the schedule of
-// k_interp_tv's transforms: bit-identical to the plain radix-2 loop of the oracle).  sgn = +1 forward, -1 inverse: the
-// inverse conjugates the twiddle, and -(w.y) == w.y * -1 exactly.  LG and S are compile-time: every index below is an
-// immediate offset from one per-thread base.
-template <int LG, int S, int R>
-__device__ __forceinline__ void sp_fft_pass(float2* f, const float2* __restrict__ tw, float sgn, int tid, int nth) {
-  constexpr uint32_t N = 1u << LG, h = 1u << S;
-  for (uint32_t g = tid; g < (N >> R); g += nth) {
-    const uint32_t k = g & (h - 1), base = ((g >> S) << (S + R)) | k;
-    float2 x[1 << R];
-#pragma unroll
-    for (int m = 0; m < (1 << R); m++) x[m] = f[CPAD(base + (uint32_t)m * h)];
-#pragma unroll
-    for (int q = 0; q < R; q++) {
-      constexpr int dummy = 0; (void)dummy;
-      const int hq = 1 << q;
-      float2 w[1 << (R - 1)];                      // the 2^q distinct twiddles of stage S + q
-#pragma unroll
-      for (int e = 0; e < hq; e++) {
-        const uint32_t ti = (k + (uint32_t)e * h) << (LG - 1 - (S + q));
-        w[e] = __ldg(tw + ti);
-        w[e].y *= sgn;
-      }
-#pragma unroll
-      for (int m = 0; m < (1 << R); m++) {
-        if (m & hq) continue;
-        const float wr = w[m & (hq - 1)].x, wi = w[m & (hq - 1)].y;
-        const float2 u = x[m], v = x[m + hq];
-        const float tr = v.x * wr - v.y * wi, tim = v.x * wi + v.y * wr;
-        x[m] = make_float2(u.x + tr, u.y + tim);
-        x[m + hq] = make_float2(u.x - tr, u.y - tim);
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < (1 << R); m++) f[CPAD(base + (uint32_t)m * h)] = x[m];
-  }
-}
-template <int LG, int S>
-__device__ __forceinline__ void sp_fft_from(float2* f, const float2* tw, float sgn, int tid, int nth) {
-  if constexpr (S < LG) {
-    constexpr int R = LG - S >= 3 ? 3 : LG - S;
-    sp_fft_pass<LG, S, R>(f, tw, sgn, tid, nth);
-    __syncthreads();
-    sp_fft_from<LG, S + R>(f, tw, sgn, tid, nth);
-  }
-}
-template <int LG>
-__device__ __noinline__ void sp_fft_n(float2* f, const float2* tw, float sgn, int tid, int nth) { sp_fft_from<LG, 0>(f, tw, sgn, tid, nth); }
-__device__ __forceinline__ void sp_fft(float2* f, int lg, const float2* tw, float sgn, int tid, int nth) {
-  switch (lg) {
-    case 3: sp_fft_n<3>(f, tw, sgn, tid, nth); break;
-    case 4: sp_fft_n<4>(f, tw, sgn, tid, nth); break;
-    case 5: sp_fft_n<5>(f, tw, sgn, tid, nth); break;
-    case 6: sp_fft_n<6>(f, tw, sgn, tid, nth); break;
-    case 7: sp_fft_n<7>(f, tw, sgn, tid, nth); break;
-    case 8: sp_fft_n<8>(f, tw, sgn, tid, nth); break;
-    case 9: sp_fft_n<9>(f, tw, sgn, tid, nth); break;
-    case 10: sp_fft_n<10>(f, tw, sgn, tid, nth); break;
-    case 11: sp_fft_n<11>(f, tw, sgn, tid, nth); break;
-    default: sp_fft_n<12>(f, tw, sgn, tid, nth); break;
-  }
-}
+#include "spectral_fft.cuh"
 
 struct SpSmem { int ps_off, tmp_off, f_off; };   // float offsets: [code] [P + NS scalars] [slots x HB] [transform buffers]
 
@@ -623,7 +559,8 @@ size_t spectral_y_bytes(const SpPlan& p, long V, int* ring) {
 
 static long floor_div(long a, long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
 
-cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t stream, int* launches) {
+cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t stream, int* launches, cudaKernel_t spec_frames,
+                            cudaKernel_t spec_post) {
   const int C = p.C, PS = a.P + a.NS;
   int max_n = 0;
   for (const SpSegment& s : p.segs) max_n = std::max(max_n, 1 << s.lg);
@@ -634,17 +571,36 @@ cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t strea
   sf.f_off = (sf.tmp_off + std::max(2, p.n_slots_frame) * HBf + 3) & ~3;
   sp.f_off = 0;
   const size_t smem_f = (size_t)sf.f_off * 4 + 2 * (size_t)(CPAD(max_n) + 1) * 8, smem_p = (size_t)(sp.tmp_off + std::max(1, p.n_slots_post) * HBp) * 4;
-  if (smem_f > 200 * 1024 || smem_p > 200 * 1024) return cudaErrorNotSupported;
-  cudaError_t e = cudaFuncSetAttribute(k_spectral_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_spectral_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
-  if (e != cudaSuccess) return e;
+  const bool spec = spec_frames && spec_post;                 // K5s: kernels compiled for this plan (spectral_kernel.cuh)
+  const size_t smem_s = 2 * (size_t)(CPAD(max_n) + 1) * 8;    // their only shared memory: the two transform buffers
+  const int HBs = 1024;                                       // SP_POST_BLOCK
+  cudaError_t e;
+  if (spec) {
+    if (smem_s > 48 * 1024) {
+      e = cudaFuncSetAttribute((const void*)spec_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+      if (e != cudaSuccess) return e;
+    }
+  } else {
+    if (smem_f > 200 * 1024 || smem_p > 200 * 1024) return cudaErrorNotSupported;
+    e = cudaFuncSetAttribute(k_spectral_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_spectral_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p);
+    if (e != cudaSuccess) return e;
+  }
   const long A = a.t0, E = a.t0 + a.T;
   const long c_first = floor_div(A, C) - 1, c_last = floor_div(E - 1, C);
   const int R = a.ring / C - 1;     // rounds per launch
+  cudaError_t le = cudaSuccess;
   auto frames = [&](long c, int n) {
     const long blocks = (long)a.V * a.n_items * n;
-    k_spectral_frames<<<(unsigned)blocks, 256, smem_f, stream>>>(a, c, n, HBf, sf);
+    if (spec) {
+      SpArgs aa = a;
+      void* args[] = {&aa, &c, &n};
+      cudaError_t r = cudaLaunchKernel((const void*)spec_frames, dim3((unsigned)blocks), dim3(256), args, smem_s, stream);
+      if (r != cudaSuccess) le = r;
+    } else {
+      k_spectral_frames<<<(unsigned)blocks, 256, smem_f, stream>>>(a, c, n, HBf, sf);
+    }
     if (launches) *launches += 1;
   };
   frames(c_first, 1);
@@ -653,11 +609,21 @@ cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t strea
     frames(c, n);
     const long t_lo = std::max(A, c * (long)C), t_hi = std::min(E, (c + n) * (long)C);
     if (t_hi > t_lo) {
-      const long nblk = (t_hi - t_lo + HBp - 1) / HBp;
-      k_spectral_post<<<(unsigned)(a.V * nblk), 256, smem_p, stream>>>(a, t_lo, t_hi, HBp, sp);
+      if (spec) {
+        const long nblk = (t_hi - t_lo + HBs - 1) / HBs;
+        SpArgs aa = a;
+        long lo_ = t_lo, hi_ = t_hi;
+        void* args[] = {&aa, &lo_, &hi_};
+        cudaError_t r = cudaLaunchKernel((const void*)spec_post, dim3((unsigned)(a.V * nblk)), dim3(256), args, 0, stream);
+        if (r != cudaSuccess) le = r;
+      } else {
+        const long nblk = (t_hi - t_lo + HBp - 1) / HBp;
+        k_spectral_post<<<(unsigned)(a.V * nblk), 256, smem_p, stream>>>(a, t_lo, t_hi, HBp, sp);
+      }
       if (launches) *launches += 1;
     }
   }
+  if (le != cudaSuccess) return le;
   return cudaGetLastError();
 }
 

@@ -212,6 +212,15 @@ class Net:
         lib().qg_net_spec_source(self.h, buf, int(n) + 1)
         return buf.value.decode()
 
+    def spectral_spec_source(self):
+        """the CUDA translation unit compiled for this graph's frame-parallel spectral plan (K5s)"""
+        n = lib().qg_net_spectral_spec_source(self.h, None, 0)
+        if n < 0:
+            check(int(-n))
+        buf = C.create_string_buffer(int(n) + 1)
+        lib().qg_net_spectral_spec_source(self.h, buf, int(n) + 1)
+        return buf.value.decode()
+
     def tape_info(self):
         v = [C.c_int(0) for _ in range(5)]
         check(lib().qg_net_tape_info(self.h, *[C.byref(x) for x in v]))

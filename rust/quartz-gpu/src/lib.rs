@@ -55,6 +55,7 @@ extern "C" {
                         divergent: *mut c_int) -> c_int;
     fn qg_net_spec_source(n: *const qg_net, buf: *mut c_char, cap: c_long) -> c_long;
     fn qg_net_device_params(n: *const qg_net, out: *mut c_float, cap: c_int) -> c_int;
+    fn qg_net_spectral_spec_source(n: *const qg_net, buf: *mut c_char, cap: c_long) -> c_long;
     fn qg_net_spectral_info(n: *const qg_net, n_segments: *mut c_int, n_streams: *mut c_int, n_instr: *mut c_int, round_len: *mut c_int) -> c_int;
     fn qg_ctx_synchronize(c: *mut qg_ctx) -> c_int;
     fn qg_ctx_launch_count(c: *const qg_ctx) -> c_long;

@@ -169,3 +169,42 @@ def test_frame_parallel_path_on_other_bin_chains(chain, start):
     assert np.array_equal(got, tv)
     ref = np.stack([build(expr, ONet).set_salt(int(s)).render(T).T for s in salts])
     assert_parity(got, ref, "float", "chain")
+
+
+@pytest.mark.parametrize("N,J,V,T", [(64, 4, 5, 1000), (2048, 4, 2, 14000), (128, 2, 4, 900)])
+def test_specialised_spectral_kernels_are_bit_identical_to_the_generic_ones(N, J, V, T, monkeypatch):
+    """K5s (the plan compiled into the kernels by NVRTC): same arithmetic in the same order as the generic K5 kernels"""
+    wl = _gate(N, J, V, T)
+    monkeypatch.setenv("QG_SPECTRAL_SPEC", "0")
+    gen = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_SPECTRAL)
+    want = gen.render(T)
+    assert gen.kernel() == "k_spectral_frames"
+    monkeypatch.setenv("QG_SPECTRAL_SPEC", "1")
+    sp = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_SPECTRAL)
+    try:
+        got = np.concatenate([sp.render(T // 3), sp.render(T - T // 3)], axis=2)
+    except qb.QuartzGpuError as e:
+        if "NVRTC" in str(e):
+            pytest.skip("NVRTC not available on this box")
+        raise
+    assert sp.kernel() == "k_sp_frames"
+    assert np.array_equal(got, want)
+    fm = Bank(build(wl.expr, Net), V, salts=wl.salts).set_path(qb.PATH_SPECTRAL).render(T, layout=qb.LAYOUT_FRAME_MAJOR)
+    assert np.array_equal(fm[:, :, 0].T, want[:, 0, :])
+
+
+@pytest.mark.parametrize("chain", [[], ["pol()", "car()"], [stack("mul(0.5)", "add(0.25)")]], ids=["identity", "pol_car", "affine"])
+def test_specialised_spectral_kernels_on_other_bin_chains(chain, monkeypatch):
+    N, start, V, T = 64, 5, 3, 700
+    expr = pipe(stack("white()"), f"rfft({N},{start})", *chain, f"ifft({N},{start})", stack(pipe("mul(0.7)", "tanh()"), "pass()"))
+    salts = np.arange(3, 3 + V, dtype=np.uint64)
+    tv = Bank(build(expr, Net), V, salts=salts).set_path(qb.PATH_TV).render(T)
+    monkeypatch.setenv("QG_SPECTRAL_SPEC", "1")
+    b = Bank(build(expr, Net), V, salts=salts).set_path(qb.PATH_SPECTRAL)
+    try:
+        got = b.render(T)
+    except qb.QuartzGpuError as e:
+        if "NVRTC" in str(e):
+            pytest.skip("NVRTC not available on this box")
+        raise
+    assert b.kernel() == "k_sp_frames" and np.array_equal(got, tv)

@@ -59,3 +59,19 @@ def test_specialised_units_of_diverse_render_cases_compile_without_spills(name):
     expr = next(c[1] for c in cases.RENDER if c[0] == name)
     size, log = nvrtc_compile(build(expr, Net).spec_source())
     assert size > 0 and "0 bytes spill stores" in log, log[-600:]
+
+
+@pytest.mark.parametrize("N,J", [(2048, 4), (64, 2)])
+def test_spectral_plan_units_compile_for_sm100a(N, J):
+    """K5s: the frame-parallel spectral plan of configs[3] compiled into its kernels (spectral_kernel.cuh)"""
+    wl = workloads.c4_spectral(V=4, T=1000, N=N, J=J)
+    net = build(wl.expr, Net)
+    info = net.spectral_info()
+    assert info == {"n_segments": J, "n_streams": J, "n_instr": info["n_instr"], "round_len": N}
+    src = net.spectral_spec_source()
+    assert f"#define SP_NSEG {J}" in src and f"#define SP_C {N}" in src and '#include "spectral_kernel.cuh"' in src
+    size, log = nvrtc_compile(src)
+    assert size > 0 and "k_sp_frames" in log and "k_sp_post" in log
+    assert "0 bytes spill stores" in log.split("Function properties for k_sp_frames")[1][:200], log[-1200:]   # X in registers
+    with pytest.raises(qb.QuartzGpuError, match="spectral plan"):
+        build(pipe("white()", "lowpole(100)"), Net).spectral_spec_source()

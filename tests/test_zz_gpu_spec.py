@@ -66,8 +66,11 @@ def test_auto_specialises_a_lane_bank_once_its_work_pays_for_the_compile_and_reu
     """AUTO policy (capi.cu: bank_auto_specialise): below QG_SPEC_MIN_WORK voice-samples a bank stays on its interpreter; past
     it the tape is compiled into the kernel, the state carries over bit for bit, and a later bank of the same tape gets
     the cached kernel on its first render.  Taps / feedback rings keep the block-mode interpreter (dependent ring loads)."""
-    wl = workloads.c5_mixed(V=4 * 4096, T=4096)[3]          # delay(1024 samples) + lowpole: the prefetched delay line
-    net = build(wl.expr, Net)
+    wl = workloads.c5_mixed(V=4 * 4096, T=4096)[3]          # delay + lowpole: the prefetched delay line
+    # a delay length no other test uses: kernels are cached process-wide BY TAPE, and in a whole-suite run an earlier test
+    # has already compiled configs[4]'s own archetype — this bank would then start out specialised
+    net = build({"op": "sr()", "n": 48000.0, "net": {"op": ">>", "n": 0.0, "inputs": [{"op": "white()"}, {"op": "delay(0.0201875)"}, {"op": "lowpole(1000)"}]}}, Net)
+    wl.raw = np.stack([np.full(wl.V, np.float32(0.0201875)), wl.raw[:, 1]], axis=1)
     ref = Bank(net, wl.V, raw=wl.raw, salts=wl.salts).set_path(qb.PATH_INTERP_SAMPLE)
     os.environ["QG_SPEC_MIN_WORK"] = str(float(wl.V * 3000))
     try:
