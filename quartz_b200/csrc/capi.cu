@@ -72,7 +72,8 @@ struct qg_bank {
   bool other_started = false;   // another kernel has
   bool last_k5 = false;         // the previous render ran on K5 (survives a reset: qg_bank_kernel names what a repeat would use)
   SpectralKernels sp_spec;      // K5s: the plan compiled into the kernels (NVRTC, cached process-wide by plan)
-  bool sp_spec_tried = false;
+  bool sp_spec_tried = false, sp_cache_checked = false;
+  double sp_work = 0.0;         // voice-samples this bank has rendered on K5 (AUTO compiles K5s past a threshold)
 };
 
 static thread_local std::string g_err;
@@ -728,12 +729,18 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
     sa.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
     sa.C = b->sp.C; sa.post_lo = b->sp.post_lo; sa.post_hi = b->sp.post_hi;
     sa.n_slots_frame = b->sp.n_slots_frame; sa.n_slots_post = b->sp.n_slots_post;
-    // K5s: a bulk render pays for compiling the plan into the kernels (about 2 s once per plan and process, then cached).
-    // QG_SPECTRAL_SPEC=1 specialises every K5 bank, =0 none; a failed compile keeps the generic kernels.
-    if (!b->sp_spec.frames && !b->sp_spec_tried) {
+    // K5s: compiling the plan into the kernels costs ~2 s of NVRTC once per plan and process (cached after that) and makes a
+    // render 2.2x faster: AUTO compiles once the bank has QG_SPECTRAL_MIN_WORK voice-samples (default 2e9) behind and ahead of
+    // it, or at once when the plan's kernels are already in the cache.  QG_SPECTRAL_SPEC=1 specialises every K5 bank, =0 none;
+    // a failed compile keeps the generic kernels.
+    if (!b->sp_spec.frames) {
       const char* es = getenv("QG_SPECTRAL_SPEC");
       const bool force = es && es[0] == '1', never = es && es[0] == '0';
-      if (!never && (force || (double)b->V * (double)T >= 1.0e8)) {
+      if (!never && !b->sp_cache_checked) { b->sp_cache_checked = true; spectral_spec_cached(b->sp, t, &b->sp_spec); }
+      b->sp_work += (double)b->V * (double)T;
+      const char* ew = getenv("QG_SPECTRAL_MIN_WORK");
+      const double wv = ew ? atof(ew) : 0.0, min_work = wv > 0.0 ? wv : 2.0e9;
+      if (!never && !b->sp_spec.frames && !b->sp_spec_tried && (force || b->sp_work >= min_work)) {
         b->sp_spec_tried = true;
         std::string err;
         try { spectral_spec_compile(b->sp, t, &b->sp_spec, &err); } catch (...) {}
@@ -951,7 +958,7 @@ qg_bank* qg_bank_clone(const qg_bank* src) {
     b->block_ok = src->block_ok; b->ring_mode = src->ring_mode; b->state_ready = src->state_ready;
     b->spec_auto_ok = src->spec_auto_ok; b->spec_auto_tried = src->spec_auto_tried; b->lane_work = src->lane_work;
     if (src->spec.fn && src->spec.shared) b->spec = src->spec;     // kernels live in the process-wide cache
-    b->sp = src->sp; b->sp_time = src->sp_time; b->sp_started = src->sp_started; b->other_started = src->other_started; b->last_k5 = src->last_k5; b->sp_spec = src->sp_spec; b->sp_spec_tried = src->sp_spec_tried;
+    b->sp = src->sp; b->sp_time = src->sp_time; b->sp_started = src->sp_started; b->other_started = src->other_started; b->last_k5 = src->last_k5; b->sp_spec = src->sp_spec; b->sp_spec_tried = src->sp_spec_tried; b->sp_cache_checked = src->sp_cache_checked; b->sp_work = src->sp_work;
   } catch (...) {
     delete b;
     fail(QG_ERR_ARG, "qg_bank_clone: out of memory");

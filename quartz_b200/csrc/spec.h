@@ -48,6 +48,7 @@ struct SpectralKernels {
 };
 std::string spectral_spec_source(const SpPlan& p, const Tape& t);
 bool spectral_spec_compile(const SpPlan& p, const Tape& t, SpectralKernels* out, std::string* err);
+bool spectral_spec_cached(const SpPlan& p, const Tape& t, SpectralKernels* out);   // already compiled in this process
 
 }  // namespace qg
 #endif
