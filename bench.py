@@ -420,14 +420,22 @@ class Runner:
 
         h2d = sum((0 if w.raw is None else w.raw.nbytes) + w.salts.nbytes for w in wls)
 
+        dbg = bool(os.environ.get("QG_BENCH_DEBUG"))
+
         def e2e_step():
             for k, (t, w) in enumerate(zip(tmpls, wls)):
+                ta = time.perf_counter()
                 b2 = qb.Bank(t, w.V, raw=w.raw, salts=w.salts, ctx=ctx)
                 self.set_paths([b2], [w])          # --path specialised: the NVRTC compile is inside the end-to-end time
+                tb = time.perf_counter()
                 for t0 in range(0, w.T, T_host):
                     n = min(T_host, w.T - t0)
                     b2.render(n, group=w.group, out=host_view(k, n))
+                tc = time.perf_counter()
+                kern = b2.kernel()
                 del b2
+                if dbg:
+                    print(f"  e2e {w.name}: build {tb - ta:.4f} s, render+copy {tc - tb:.4f} s ({kern}), free {time.perf_counter() - tc:.4f} s", file=sys.stderr)
 
         e2e_step()
         self.barrier()

@@ -690,9 +690,9 @@ cudaError_t launch_fused(const FusedPlan& pl, const FusedArgs& a, cudaStream_t s
     if (S > 1) {
       size_t need = (size_t)a.V * (S + 1) * 2 * sizeof(float);
       if (need > *a.scratch_bytes) {
-        if (*a.scratch) cudaFree(*a.scratch);
+        if (*a.scratch) cudaFreeAsync(*a.scratch, stream);   // bank buffers live in the stream-ordered pool (capi.cu: dev_malloc)
         *a.scratch = nullptr; *a.scratch_bytes = 0;
-        cudaError_t e = cudaMalloc((void**)a.scratch, need);
+        cudaError_t e = cudaMallocAsync((void**)a.scratch, need, stream);
         if (e != cudaSuccess) return e;
         *a.scratch_bytes = need;
       }
