@@ -81,6 +81,42 @@ def test_c4_full_size_round_trip():
     assert err < 2e-4, err
 
 
+def test_c4_full_size_gate_rows_do_not_depend_on_the_bank_or_the_kernel():
+    """configs[3] as benchmarked: 1,024 channels x 1,440,000 samples of the spectral gate on the frame-parallel path (K5s when
+    NVRTC is there).  A channel rendered inside the full bank equals — bit for bit, the transforms share their arithmetic —
+    the same channel rendered alone on the time-vector kernel, and the oracle within the float tolerance (first 60,000
+    samples: the scalar oracle needs ~1 s per 10,000 channel-samples)."""
+    wl = workloads.c4_spectral()
+    full = Bank(build(wl.expr, Net), wl.V, salts=wl.salts)
+    d = _render_device(full, wl.V, wl.T)
+    assert full.kernel() in ("k_spectral_frames", "k_sp_frames")
+    chans = [0, 511, 1023]
+    got = d[torch.as_tensor(chans, device="cuda")].cpu().numpy()
+    tail = d[:, -4096:].abs().max().item()
+    del d
+    assert 0.0 < tail < 4.0                                   # the last frames were rendered, and are audio
+    small = _sub_bank(wl, np.asarray(chans)).set_path(qb.PATH_TV)
+    assert small.kernel() == "k_interp_tv"
+    assert np.array_equal(got, small.render(wl.T)[:, 0, :])
+    n = 60000
+    ref = render_bank([build(wl.expr, ONet).set_salt(int(wl.salts[v])) for v in chans[:2]], n, threads=8)
+    assert_parity(got[:2, :n], ref, "float", "c4 full size vs oracle")
+
+
+def test_c4_round_trip_on_the_frame_parallel_path():
+    """every bin passing (thr < 0), a wave-table source: the patch is a pure 2N delay x 0.375 of its input — through K5"""
+    N, J, V, T = 2048, 4, 64, 40000
+    rng = np.random.default_rng(11)
+    src = rng.uniform(-1, 1, 4096).astype(np.float32)
+    expr = workloads.spectral_graph(N, J, -1.0, workloads.hann(N), source={"op": "wave()", "arr": [float(v) for v in src]})
+    bank = Bank(build(expr, Net), V).set_path(qb.PATH_SPECTRAL)
+    y = bank.render(T)[:, 0, :]
+    x = np.tile(src, T // 4096 + 1)[:T]
+    lat = 2 * N
+    err = np.abs(y[:, lat + N:] - 0.375 * x[None, N:T - lat]).max()
+    assert err < 2e-4, err
+
+
 def test_c5_full_size_group_rows_do_not_depend_on_the_bank():
     """configs[4]: 1,048,576 voices (4 archetypes x 262,144), group-mixed by 32; 0.25 s per voice here (the property does
     not depend on the length; the 2 s render is the bench's)"""
