@@ -188,11 +188,14 @@ def bind_to_gpu_numa_node(index):
     device->host ingest is the end-to-end limiter, and a buffer on the far socket halves what a rank gets.  Returns a note."""
     try:
         import torch
-        bdf = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
-        if bdf is None:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = None
+        if all(hasattr(pr, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{int(pr.pci_domain_id):04x}:{int(pr.pci_bus_id):02x}:{int(pr.pci_device_id):02x}.0"
+        if bdf is None or not os.path.exists(f"/sys/bus/pci/devices/{bdf}"):
             out = subprocess.run(["nvidia-smi", f"--id={index}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
                                  capture_output=True, text=True, timeout=20).stdout.strip()
-            bdf = out[-12:] if len(out) >= 12 else None          # 00000000:1B:00.0 -> 0000:1b:00.0
+            bdf = out[-12:].lower() if len(out) >= 12 else None          # 00000000:1B:00.0 -> 0000:1b:00.0
         if not bdf:
             return "numa: bus id unknown"
         node = int(open(f"/sys/bus/pci/devices/{bdf.lower()}/numa_node").read())
@@ -203,8 +206,8 @@ def bind_to_gpu_numa_node(index):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return f"numa: node {node} has no usable cpu"
+        if len(cpus) < 8:        # a container that exposes only a few of the node's cores: leave the rank where it is
+            return f"numa: node {node} offers {len(cpus)} usable cpus, not bound"
         os.sched_setaffinity(0, cpus)
         return f"numa: bound to node {node} ({len(cpus)} cpus)"
     except Exception as e:   # the binding is an optimisation, never a requirement
