@@ -351,3 +351,112 @@ def test_random_graphs_in_ragged_banks(seed):
             bank = Bank(net, V, salts=salts).set_path(path)
             got = np.concatenate([bank.render(401, group=G)[:, 0, :], bank.render(n - 401, group=G)[:, 0, :]], axis=1)
             assert_parity(got, ref, "exact" if exact else "float", f"seed {seed} G={G} [{pname}: {bank.kernel()}] {g}")
+
+
+# ---------------------------------------------------------------- spectral family (the frame-parallel path, K5 / K5s)
+def _ra_source(rng):
+    """a pure function of time: counter noise, a wave table, an impulse, constants, delays / ticks and stateless maps of those"""
+    k = rng.integers(0, 5)
+    if k == 0:
+        g = L("white()")
+    elif k == 1:
+        g = {"op": "wave()", "arr": [round(float(x), 3) for x in rng.uniform(-1, 1, int(rng.choice([7, 16, 33, 64])))]}
+    elif k == 2:
+        g = pipe("impulse()", f"mul({_c(rng, 0.5, 3)})")
+    elif k == 3:
+        g = mul("white()", {"op": "wave()", "arr": [round(float(x), 3) for x in rng.uniform(0, 1, int(rng.choice([16, 32])))]})
+    else:
+        g = add("white()", L(f"dc({_c(rng, -0.5, 0.5)})"))
+    for _ in range(int(rng.integers(0, 3))):
+        j = rng.integers(0, 5)
+        if j == 0:
+            g = pipe(g, f"delay({_c(rng, 0.0001, 0.004, 5)})")
+        elif j == 1:
+            g = pipe(g, "tick()")
+        elif j == 2:
+            g = pipe(g, f"mul({_c(rng, -2, 2)})")
+        elif j == 3:
+            g = pipe(g, "tanh()")
+        else:
+            g = add(g, pipe("white()", f"delay({_c(rng, 0.0002, 0.002, 5)})", "mul(0.25)"))
+    return g
+
+
+def _bin_chain(rng):
+    """stateless (re, im) -> (re, im) maps: conjugation-equivariant ones (the mirrored half is derived) and others (every bin
+    is evaluated), including chains with chain(0) != 0"""
+    k = rng.integers(0, 8)
+    thr = _c(rng, 0.1, 3)
+    if k == 0:
+        return []
+    if k == 1:   # the gate of assets/spectral-gate
+        return ["pol()", stack(pipe(branch(f">({thr})", "pass()"), mul("pass()", "pass()")), "pass()"), "car()"]
+    if k == 2:
+        return [stack(f"mul({_c(rng, -2, 2)})", f"mul({_c(rng, -2, 2)})")]
+    if k == 3:   # not equivariant: a constant lands in the imaginary part
+        return [stack(f"add({_c(rng, -0.3, 0.3)})", f"add({_c(rng, -0.3, 0.3)})")]
+    if k == 4:
+        return ["pol()", stack("sqrt()", f"mul({_c(rng, 0.5, 2)})"), "car()"]
+    if k == 5:   # swaps the parts
+        return ["reverse()"] if rng.uniform() < 0.5 else [f"rotate({_c(rng, -3, 3)},{_c(rng, 0.5, 1.5)})"]
+    if k == 6:
+        return [stack("abs()", "pass()")]
+    return [stack(pipe("squared()", f"min({thr})"), "cubed()")]
+
+
+def spectral_graph(rng):
+    n = int(rng.choice([8, 16, 64, 128, 256]))
+    J = int(rng.choice([1, 2, 4]))
+    insts = []
+    for j in range(J):
+        st = int(rng.integers(0, n)) if rng.uniform() < 0.5 else (j * n // J) % n
+        src = _ra_source(rng) if (j == 0 or rng.uniform() < 0.4) else insts[0][0]
+        insts.append((src, pipe(src, f"rfft({n},{st})", *_bin_chain(rng), f"ifft({n},{st})")))
+    outs = []
+    for src, seg in insts:
+        k = rng.integers(0, 3)
+        if k == 0:
+            outs.append(pipe(seg, "chan(1,0)"))
+        elif k == 1:
+            outs.append(pipe(seg, "join(2)"))                       # real and imaginary parts both read
+        else:
+            outs.append(mul(pipe(seg, "chan(1,0)"), pipe(_ra_source(rng), "softsign()")))
+    g = outs[0]
+    for o in outs[1:]:
+        g = add(g, o)
+    return pipe(g, f"mul({_c(rng, 0.2, 1)})")
+
+
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
+def test_random_spectral_graphs_on_the_frame_parallel_path(seed, monkeypatch):
+    """K5 against the time-vector kernel BIT FOR BIT and against the oracle within the float tolerance, across uneven calls;
+    every fifth seed also through K5s (the plan compiled into the kernels, ~2 s of NVRTC)"""
+    rng = np.random.default_rng(7000 + seed)
+    expr = spectral_graph(rng)
+    V, n = 3, int(rng.integers(300, 1500))
+    salts = np.arange(1, V + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15 + seed)
+    net = build(expr, Net)
+    assert (net.inputs(), net.outputs()) == (0, 1), expr
+    assert net.spectral_info() is not None, expr
+    ref = np.stack([build(expr, ONet).set_salt(int(s)).render(n).T for s in salts])
+    tv = Bank(net, V, salts=salts).set_path(qb.PATH_TV)
+    assert tv.kernel() == "k_interp_tv"
+    want = tv.render(n)
+    assert_parity(want, ref, "float", f"seed {seed} [time_vector] {expr}")
+    monkeypatch.setenv("QG_SPECTRAL_SPEC", "0")
+    k5 = Bank(net, V, salts=salts).set_path(qb.PATH_SPECTRAL)
+    cut = int(rng.integers(1, n - 1))
+    got = np.concatenate([k5.render(cut), k5.render(n - cut)], axis=2)
+    assert k5.kernel() == "k_spectral_frames"
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"seed {seed} K5 vs time-vector {expr}"
+    if seed % 5 == 0:
+        monkeypatch.setenv("QG_SPECTRAL_SPEC", "1")
+        k5s = Bank(net, V, salts=salts).set_path(qb.PATH_SPECTRAL)
+        try:
+            gs = np.concatenate([k5s.render(cut), k5s.render(n - cut)], axis=2)
+        except qb.QuartzGpuError as e:
+            if "NVRTC" in str(e):
+                pytest.skip("NVRTC not available on this box")
+            raise
+        assert k5s.kernel() == "k_sp_frames"
+        assert np.array_equal(gs.view(np.uint32), want.view(np.uint32)), f"seed {seed} K5s vs time-vector {expr}"
