@@ -439,10 +439,12 @@ def test_random_spectral_graphs_on_the_frame_parallel_path(seed, monkeypatch):
     assert (net.inputs(), net.outputs()) == (0, 1), expr
     assert net.spectral_info() is not None, expr
     ref = np.stack([build(expr, ONet).set_salt(int(s)).render(n).T for s in salts])
+    # the time-vector kernel when the tape is hop-alignable (start offsets with a common divisor >= 8), else a lane kernel
+    # with its per-lane transforms: the same butterfly network either way
     tv = Bank(net, V, salts=salts).set_path(qb.PATH_TV)
-    assert tv.kernel() == "k_interp_tv"
+    assert tv.kernel() in ("k_interp_tv", "k_interp_blk", "k_interp<uniform>")
     want = tv.render(n)
-    assert_parity(want, ref, "float", f"seed {seed} [time_vector] {expr}")
+    assert_parity(want, ref, "float", f"seed {seed} [{tv.kernel()}] {expr}")
     monkeypatch.setenv("QG_SPECTRAL_SPEC", "0")
     k5 = Bank(net, V, salts=salts).set_path(qb.PATH_SPECTRAL)
     cut = int(rng.integers(1, n - 1))
