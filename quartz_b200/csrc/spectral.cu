@@ -456,8 +456,9 @@ __global__ void __launch_bounds__(256, 3) k_spectral_frames(SpArgs a, long c0, i
   sp_stage(a, sm, v, tid, nth);
   float* ps = QG_SMEM_F + sm.ps_off;
   float* tmp = QG_SMEM_F + sm.tmp_off;
-  float2* f = reinterpret_cast<float2*>(QG_SMEM_F + sm.f_off);
-  float2* g = f + CPAD(N) + 1;
+  const int f_off = sm.f_off / 2, g_off = f_off + CPAD(N) + 1;     // float2 offsets into the CTA's shared memory
+  float2* f = QG_SMEM_C + f_off;
+  float2* g = QG_SMEM_C + g_off;
   __syncthreads();
   const float2* tw = reinterpret_cast<const float2*>(a.tables + sg.tw);
   const int sh = 32 - lg;
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(256, 3) k_spectral_frames(SpArgs a, long c0, i
     }
   }
   __syncthreads();
-  sp_fft(f, lg, tw, 1.0f, tid, nth);
+  sp_fft(f_off, lg, tw, 1.0f, tid, nth);
   // ---- the bin chain on the streamed bins (conjugate mirror above N/2, nodes.rs:637-642), into the inverse transform's
   // input; positions whose sample time was negative keep the buffer's initial zero.  A chain whose results have a known
   // behaviour under conjugation (plan: sym_re / sym_im) runs on bins 0 .. N/2 only.
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(256, 3) k_spectral_frames(SpArgs a, long c0, i
     }
   }
   __syncthreads();
-  sp_fft(g, lg, tw, -1.0f, tid, nth);
+  sp_fft(g_off, lg, tw, -1.0f, tid, nth);
   const float sc = 1.0f / (float)N;
   for (int i = i_lo + tid; i < i_hi; i += nth) {
     const float2 z = g[CPAD(i)];
@@ -553,6 +554,10 @@ size_t spectral_y_bytes(const SpPlan& p, long V, int* ring) {
   long mult = 2;
   while (mult < 64 && V * (long)p.items.size() * (mult - 1) < 2048 &&
          (size_t)p.n_streams * (size_t)V * (size_t)(2 * mult) * p.C * 4 <= ((size_t)256 << 20)) mult *= 2;
+  // full-size banks: four rounds of ring = three rounds per launch (measured on configs[3]: 103.8 -> 98.7 ms; the launch
+  // boundaries drain the machine), as long as the ring stays around the size of the L2
+  if (mult < 4 && (size_t)p.n_streams * (size_t)V * (size_t)4 * p.C * 4 <= ((size_t)160 << 20)) mult = 4;
+  if (const char* e = getenv("QG_SPECTRAL_RING_MULT")) { const long m = atol(e); if (m >= 2 && m <= 64 && (m & (m - 1)) == 0) mult = m; }
   if (ring) *ring = (int)(mult * p.C);
   return (size_t)p.n_streams * (size_t)V * (size_t)(mult * p.C) * sizeof(float);
 }
@@ -568,7 +573,7 @@ cudaError_t launch_spectral(const SpArgs& a, const SpPlan& p, cudaStream_t strea
   SpSmem sf, sp;
   sf.ps_off = sp.ps_off = a.n_code * (int)(sizeof(Instr) / 4);
   sf.tmp_off = sp.tmp_off = sf.ps_off + ((PS + 3) & ~3);
-  sf.f_off = (sf.tmp_off + std::max(2, p.n_slots_frame) * HBf + 3) & ~3;
+  sf.f_off = (sf.tmp_off + std::max(2, p.n_slots_frame) * HBf + 3) & ~3;   // even: the transform buffers are float2
   sp.f_off = 0;
   const size_t smem_f = (size_t)sf.f_off * 4 + 2 * (size_t)(CPAD(max_n) + 1) * 8, smem_p = (size_t)(sp.tmp_off + std::max(1, p.n_slots_post) * HBp) * 4;
   const bool spec = spec_frames && spec_post;                 // K5s: kernels compiled for this plan (spectral_kernel.cuh)
