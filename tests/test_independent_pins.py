@@ -186,3 +186,34 @@ def test_semitone_ratio_and_db_conversions_are_the_usual_definitions():
         assert np.isclose(y, 2.0 ** (float(x) / 12), rtol=1e-6)
         y = build(pipe(f"dc({float(x)!r})", "db_amp()"), ONet).render(1)[0, 0]
         assert np.isclose(y, 10.0 ** (float(x) / 20), rtol=1e-6)
+
+
+def _spectrum(op, n=48000):
+    x = build({"op": "sr()", "net": pipe(op), "n": SR}, ONet).render(n)[:, 0].astype(np.float64)
+    return x, np.abs(np.fft.rfft(x * np.hanning(n))) / (n / 4), np.fft.rfftfreq(n, 1 / SR)
+
+
+@pytest.mark.parametrize("op,law", [("saw", lambda k: 1.0 / k), ("square", lambda k: (k % 2) / k), ("triangle", lambda k: (k % 2) / k ** 2)])
+def test_wavetable_oscillators_have_the_fourier_series_of_their_waveform(op, law):
+    """band-limited saw / square / triangle: harmonic k of the ideal waveform has relative amplitude 1/k, 1/k (odd), 1/k^2
+    (odd); nothing between the harmonics (no aliasing), nothing above the table's band limit"""
+    f0 = 441.0
+    x, X, f = _spectrum(f"{op}({f0})")
+    h = np.array([X[int(round(k * f0))] for k in range(1, 21)])
+    want = np.array([law(k) for k in range(1, 21)], dtype=np.float64)
+    assert np.allclose(h / h[0], want, atol=0.01), (h / h[0], want)
+    between = np.array([X[int(round((k + 0.5) * f0))] for k in range(1, 40)])
+    assert between.max() < 1e-3 * h[0]                         # -60 dB: no aliased partials
+    assert 0.9 < np.abs(x).max() <= 1.0 + 1e-6                 # normalised to full scale
+
+
+@pytest.mark.parametrize("op,slope", [("pink()", -3.0), ("brown()", -6.0)])
+def test_coloured_noises_have_their_spectral_slope(op, slope):
+    """pink: -3 dB per octave, brown: -6 dB per octave (power, octave bands between 200 Hz and 12.8 kHz)"""
+    x, X, f = _spectrum(op, 1 << 17)
+    P = X ** 2
+    edges = [200, 400, 800, 1600, 3200, 6400, 12800]
+    db = np.array([10 * np.log10(P[(f >= a) & (f < b)].mean()) for a, b in zip(edges[:-1], edges[1:])])
+    fit = np.polyfit(np.arange(len(db)), db, 1)[0]
+    assert abs(fit - slope) < 0.6, (fit, db)
+    assert abs(x.mean()) < 0.05 and 0.05 < x.std() < 1.0
