@@ -298,6 +298,20 @@ class Runner:
 
         for _ in range(warmup):
             step()
+        # AUTO compiles a bank's tape / plan into its kernel once the bank's accumulated work pays for it (K1s, K5s): a small
+        # per-rank share (strong scaling at N = 8) reaches that point only after several renders.  Keep warming up until the
+        # kernel selection has been stable for one whole step, so that the timed region measures the steady state.
+        per_step = min(w.V * w.T for w in wls)
+        for _ in range(max(0, min(64, int(np.ceil(1.0e10 / per_step)) + 1 - warmup))):   # 1e10: the library's default K1s threshold
+            step()
+        names = [b.kernel() for b in banks]
+        for _ in range(8):
+            step()
+            now = [b.kernel() for b in banks]
+            stable = now == names
+            names = now
+            if stable:
+                break
         self.barrier()
         sampler = None
         if clocks:
