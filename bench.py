@@ -151,6 +151,9 @@ def _cpu_sample(wl, seconds_target, threads, build, ONet, render_bank):
 
 def make_workloads(name, rank, world=1, strong=False):
     from quartz_b200 import shard, workloads
+    fake = int(os.environ.get("QG_BENCH_FAKE_WORLD", "0"))    # experiment hook: rank 0's share of a `fake`-rank strong split, on one GPU
+    if fake > 1:
+        world, rank, strong = fake, 0, True
     w = shard.shard_workload(workloads.WORKLOADS[name], world, rank, strong=strong)
     return w if isinstance(w, list) else [w]
 
@@ -280,7 +283,9 @@ class Runner:
         # A sharded multi-bank workload (configs[4] over N ranks) leaves each bank too few voices to fill a GPU: V/N voices =
         # V/(32 N) warps of a latency-bound lane kernel.  The banks are independent, so each gets its own context = its own
         # stream and they render concurrently.  (At N = 1 every bank fills the machine: one stream, per-bank times add up.)
-        concurrent = len(wls) > 1 and world > 1
+        concurrent = len(wls) > 1 and (world > 1 or int(os.environ.get("QG_BENCH_FAKE_WORLD", "0")) > 1)
+        if os.environ.get("QG_BENCH_CONCURRENT") in ("0", "1"):
+            concurrent = len(wls) > 1 and os.environ["QG_BENCH_CONCURRENT"] == "1"
         if concurrent:
             streams = [torch.cuda.Stream() for _ in wls]
             ctxs = [qb.Context(self.local_rank, stream=st.cuda_stream) for st in streams]
