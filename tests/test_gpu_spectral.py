@@ -208,3 +208,19 @@ def test_specialised_spectral_kernels_on_other_bin_chains(chain, monkeypatch):
             pytest.skip("NVRTC not available on this box")
         raise
     assert b.kernel() == "k_sp_frames" and np.array_equal(got, tv)
+
+
+def test_single_graph_bulk_render_takes_the_frame_parallel_path_with_many_rounds_per_launch():
+    """the `render` op on ONE spectral graph (process.rs:1345-1351, up to 10^7 samples): a one-voice bank fills the machine by
+    taking up to 63 rounds per launch (Y ring of 64 rounds); same samples as the time-vector kernel"""
+    N, J, T = 256, 4, 300000
+    wl = _gate(N, J, 1, T)
+    net = build(wl.expr, Net)
+    b = Bank(net, 1, salts=wl.salts)
+    got = b.render(T)
+    assert b.kernel() in ("k_spectral_frames", "k_sp_frames")
+    want = Bank(net, 1, salts=wl.salts).set_path(qb.PATH_TV).render(T)
+    assert np.array_equal(got, want)
+    # and through the single-graph convenience call (qg_net_render)
+    one = build(wl.expr, Net)
+    assert np.array_equal(one.render(T)[:, 0], Bank(one, 1).set_path(qb.PATH_TV).render(T)[0, 0])
