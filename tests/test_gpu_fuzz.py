@@ -214,11 +214,11 @@ def _check(expr, tol, n, seed, n_out=1):
         seen.add(bank.kernel())
         # two calls of uneven length: state, rings and counters carry over
         got = np.concatenate([bank.render(n // 3 + 1), bank.render(n - n // 3 - 1)], axis=2)
-        assert_parity(got, ref, tol, f"seed {seed} [{pname}: {bank.kernel()}] {expr}")
+        assert_parity(got, ref, tol, f"seed {seed} [{pname}: {bank.kernel()}] {expr}", relative=True)
         if n_out > 1:   # the frame-major interleave of audio.rs:113-117
             bank.reset()
             fm = bank.render(n, layout=qb.LAYOUT_FRAME_MAJOR)                              # [n, V, outputs]
-            assert_parity(fm.transpose(1, 2, 0), ref, tol, f"seed {seed} frame-major [{pname}: {bank.kernel()}]")
+            assert_parity(fm.transpose(1, 2, 0), ref, tol, f"seed {seed} frame-major [{pname}: {bank.kernel()}]", relative=True)
 
 
 @pytest.mark.parametrize("seed", range(OFFSET, OFFSET + N_SEEDS))
@@ -312,10 +312,10 @@ def test_random_process_chains(seed):
         seen.add(bank.kernel())
         a = bank.process(x[:, :, :700], 700)[:, 0, :]
         b = bank.process(np.ascontiguousarray(x[:, :, 700:]), n - 700)[:, 0, :]
-        assert_parity(np.concatenate([a, b], axis=1), ref, tol, f"seed {seed} voice-major [{pname}: {bank.kernel()}] {g}")
+        assert_parity(np.concatenate([a, b], axis=1), ref, tol, f"seed {seed} voice-major [{pname}: {bank.kernel()}] {g}", relative=True)
         bank.reset()
         fm = bank.process(np.ascontiguousarray(x.transpose(2, 0, 1)), n, layout=qb.LAYOUT_FRAME_MAJOR)[:, :, 0].T
-        assert_parity(fm, ref, tol, f"seed {seed} frame-major [{pname}: {bank.kernel()}] {g}")
+        assert_parity(fm, ref, tol, f"seed {seed} frame-major [{pname}: {bank.kernel()}] {g}", relative=True)
 
 
 # ---------------------------------------------------------------- multi-output graphs (stereo patches end in out())
@@ -350,7 +350,7 @@ def test_random_graphs_in_ragged_banks(seed):
         for pname, path in (("lane_block", qb.PATH_INTERP), ("lane_sample", qb.PATH_INTERP_SAMPLE)):
             bank = Bank(net, V, salts=salts).set_path(path)
             got = np.concatenate([bank.render(401, group=G)[:, 0, :], bank.render(n - 401, group=G)[:, 0, :]], axis=1)
-            assert_parity(got, ref, "exact" if exact else "float", f"seed {seed} G={G} [{pname}: {bank.kernel()}] {g}")
+            assert_parity(got, ref, "exact" if exact else "float", f"seed {seed} G={G} [{pname}: {bank.kernel()}] {g}", relative=True)
 
 
 # ---------------------------------------------------------------- spectral family (the frame-parallel path, K5 / K5s)
@@ -444,7 +444,7 @@ def test_random_spectral_graphs_on_the_frame_parallel_path(seed, monkeypatch):
     tv = Bank(net, V, salts=salts).set_path(qb.PATH_TV)
     assert tv.kernel() in ("k_interp_tv", "k_interp_blk", "k_interp<uniform>")
     want = tv.render(n)
-    assert_parity(want, ref, "float", f"seed {seed} [{tv.kernel()}] {expr}")
+    assert_parity(want, ref, "float", f"seed {seed} [{tv.kernel()}] {expr}", relative=True)
     monkeypatch.setenv("QG_SPECTRAL_SPEC", "0")
     k5 = Bank(net, V, salts=salts).set_path(qb.PATH_SPECTRAL)
     cut = int(rng.integers(1, n - 1))

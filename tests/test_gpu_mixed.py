@@ -35,6 +35,19 @@ def test_structural_parameters_must_match_across_voices():
         Bank(build(wl.expr, Net), wl.V, raw=raw, salts=wl.salts)
 
 
+def test_structural_parameters_are_checked_for_tapes_without_device_parameters():
+    """`pass() >> delay(x)` lowers to a tape with a structural raw parameter but NO device parameters: per-voice delay times
+    that differ used to be accepted by qg_bank_create and every voice silently rendered with the template's length"""
+    from tests.graphs import pipe
+    net = build(pipe("white()", "delay(0.001)"), Net)
+    assert net.tape_info()["n_params"] == 0
+    raw = np.full((4, 1), np.float32(0.001))
+    Bank(net, 4, raw=raw)                              # equal everywhere: fine
+    raw[2, 0] = np.float32(0.002)
+    with pytest.raises(qb.QuartzGpuError, match="shapes the tape"):
+        Bank(net, 4, raw=raw)
+
+
 def test_single_process_sharded_render_matches_one_bank():
     """quartz is one process: render_sharded() drives one context + bank per device from host threads (no collective).
     With one GPU the device list repeats it — the sharding, row placement and thread safety are what is under test;

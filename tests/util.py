@@ -11,6 +11,11 @@ _LOG = os.environ.get("QG_PARITY_LOG")
 # That cannot hold for a signal far above full scale (one ulp of 1,500 is 1.2e-4), so the cases below — and only they — are
 # compared relative to the reference's peak.  The list is measured, not guessed: a full `-m gpu` run with QG_PARITY_LOG
 # (1,376 float comparisons, 676 of them on signals peaking above 1.0) found exactly one that needs it.
+# Random graphs (tests/test_gpu_fuzz.py) have unbounded gain — resonators, shelves, products and sums of sub-graphs — and no
+# names to list: they pass `relative=True`, i.e. a reference peaking above 1.0 is compared relative to its peak.  Measured: the
+# default 40 seeds per family all meet the ABSOLUTE bar; a 2,100-graph soak (QG_FUZZ_SEEDS=300 QG_FUZZ_OFFSET=1000) found one
+# graph that needs the rule (float seed 1272: square >> bell >> resonator + pink >> bell, peak 7.4, error 1.1e-4 = 1.5e-5 of
+# the peak, on the time-vector kernel's re-associated scans).
 RELATIVE_OK = {
     "lowpass(1.2)": "process case driven with inputs in [200, 2000]: output peak 1,494, error 2.4e-4 = 1.3 ulp of the signal",
 }
