@@ -149,7 +149,7 @@ __device__ __forceinline__ void sp_frame_of(int seg, const SpArgs& a, int v, lon
   }
 }
 
-extern "C" __global__ void __launch_bounds__(256, 4) k_sp_frames(SpArgs a, long c0, int n_rounds) {
+extern "C" __global__ void __launch_bounds__(256, SP_MIN_BLOCKS) k_sp_frames(SpArgs a, long c0, int n_rounds) {
   const int per_voice = SP_NITEMS * n_rounds;
   const int v = (int)(blockIdx.x / (unsigned)per_voice), w = (int)(blockIdx.x % (unsigned)per_voice);
   const SpItem it = kSpItems[w % SP_NITEMS];
