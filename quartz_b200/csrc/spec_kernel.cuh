@@ -110,13 +110,25 @@ __device__ __forceinline__ void spec_ring_writes(RegLane& L, DelayBlock& D, int 
 }
 
 struct SpecOut {
-  float* tiles;
-  int lane, warp, nwarps, warp_v0;
+  int tile0;        // float index (into the CTA's shared memory) of this lane's row in channel 0's tile: ((warp * 32) + lane) * 33
+  int chan_stride;  // floats between the tiles of consecutive output channels: nwarps * 32 * 33
+  int warp_tile0;   // float index of row 0 of this warp's tile for channel 0
+  int lane, warp_v0;
 };
 
-// one sample (index j of its block): inputs, the tape, outputs parked in the warp's 32 x 33 tile (or stored, frame-major)
+// one sample (index j of its block): inputs, the tape, outputs parked in the warp's 32 x 33 tile (or stored, frame-major).
+// `tt` (the sample's column in the tile) is a 32-bit value and the tile is addressed by index: the per-sample code of a
+// one-sample feedback voice is 16 instructions, and the loop around it used to cost twice that in 64-bit counters and
+// re-materialised shared-memory addresses (profiles/README.md, round 2).  The tape is instantiated ONCE per sample of a
+// block (NVRTC's compile time grows with every copy): the layout test and the tail test `j < n` stay run-time tests.
+// frame-major output [T][V][outputs] (the interleave of audio.rs:113-117; single graphs and small banks): out of line, the
+// voice-major loop pays one uniform test for it
+__device__ __noinline__ void spec_store_fm(const InterpArgs& a, const SpecOut& o, int v, long t, int tt) {
+  if (v >= a.V) return;
+  for (int c = 0; c < SPEC_NOUT; c++) a.out[((size_t)t * a.V + v) * SPEC_NOUT + c] = QG_SMEM_F[o.tile0 + c * o.chan_stride + tt];
+}
 template <int j>
-__device__ __forceinline__ void spec_sample(const InterpArgs& a, RegLane& L, DelayBlock& D, const SpecOut& o, long t) {
+__device__ __forceinline__ void spec_sample(const InterpArgs& a, RegLane& L, DelayBlock& D, const SpecOut& o, long t, int tt, bool FM) {
   const int v = L.v;
 #pragma unroll
   for (int c = 0; c < SPEC_NIN; c++) {
@@ -125,29 +137,21 @@ __device__ __forceinline__ void spec_sample(const InterpArgs& a, RegLane& L, Del
   }
   int pc = 0;
   spec_run_blk<0, j>(L, D, pc);
-  if (a.out_frame_major) {
-    if (v < a.V) {
+  // voice-major (the bulk layout): park the outputs in the tile; frame-major stores them from the same slots, out of line
 #pragma unroll
-      for (int c = 0; c < SPEC_NOUT; c++) a.out[((size_t)t * a.V + v) * SPEC_NOUT + c] = L.x[kOutX[c]];
-    }
-  } else {
-    const int tt = (int)(t & 31);
-#pragma unroll
-    for (int c = 0; c < SPEC_NOUT; c++) o.tiles[(((size_t)c * o.nwarps + o.warp) * 32 + o.lane) * 33 + tt] = L.x[kOutX[c]];
-  }
+  for (int c = 0; c < SPEC_NOUT; c++) QG_SMEM_F[o.tile0 + c * o.chan_stride + tt] = L.x[kOutX[c]];
+  if (FM) spec_store_fm(a, o, v, t, tt);
 }
-// voice-major outputs: the tile holds samples t - (t & 31) .. t; same staging and the same left-to-right group mix as k_interp
-__device__ __noinline__ void spec_flush(const InterpArgs& a, const SpecOut& o, long t) {
-  const int tt = (int)(t & 31);
+// voice-major outputs: the tile holds the `ncols` samples that start at t_base; same staging and the same left-to-right group
+// mix as k_interp
+__device__ __noinline__ void spec_flush(const InterpArgs& a, const SpecOut& o, long t_base, int ncols) {
   __syncwarp();
-  const long t_base = t - tt;
-  const int ncols = tt + 1;
   for (int c = 0; c < SPEC_NOUT; c++) {
-    const float* tile = o.tiles + ((size_t)c * o.nwarps + o.warp) * 32 * 33;
+    const int tile = o.warp_tile0 + c * o.chan_stride;
     if (a.group <= 1) {
       for (int r = 0; r < 32; r++) {
         int vv = o.warp_v0 + r;
-        if (vv < a.V && o.lane < ncols) a.out[((size_t)vv * SPEC_NOUT + c) * a.T + t_base + o.lane] = tile[r * 33 + o.lane];
+        if (vv < a.V && o.lane < ncols) a.out[((size_t)vv * SPEC_NOUT + c) * a.T + t_base + o.lane] = QG_SMEM_F[tile + r * 33 + o.lane];
       }
     } else {
       const int G = a.group;
@@ -155,8 +159,8 @@ __device__ __noinline__ void spec_flush(const InterpArgs& a, const SpecOut& o, l
       for (int g0 = 0; g0 < 32; g0 += G) {
         int gi = (o.warp_v0 + g0) / G;
         if (o.warp_v0 + g0 + G <= a.V && o.lane < ncols) {
-          float acc = tile[g0 * 33 + o.lane];
-          for (int r = 1; r < G; r++) acc += tile[(g0 + r) * 33 + o.lane];
+          float acc = QG_SMEM_F[tile + g0 * 33 + o.lane];
+          for (int r = 1; r < G; r++) acc += QG_SMEM_F[tile + (g0 + r) * 33 + o.lane];
           a.out[((size_t)gi * SPEC_NOUT + c) * a.T + t_base + o.lane] = acc * inv;
         }
       }
@@ -164,20 +168,43 @@ __device__ __noinline__ void spec_flush(const InterpArgs& a, const SpecOut& o, l
   }
   __syncwarp();
 }
+// a block of SPEC_BT samples whose first sample is t0 = tile column tt0
 template <int j>
-__device__ __forceinline__ void spec_block(const InterpArgs& a, RegLane& L, DelayBlock& D, const SpecOut& o, long t0, int n) {
+__device__ __forceinline__ void spec_block(const InterpArgs& a, RegLane& L, DelayBlock& D, const SpecOut& o, long t0, int tt0, int n, bool FM) {
   if constexpr (j < SPEC_BT) {
-    if (j < n) spec_sample<j>(a, L, D, o, t0 + j);
-    spec_block<j + 1>(a, L, D, o, t0, n);
+    if (SPEC_BT == 1 || j < n) spec_sample<j>(a, L, D, o, t0 + j, tt0 + j, FM);      // one-sample blocks are always full
+    spec_block<j + 1>(a, L, D, o, t0, tt0, n, FM);
   }
 }
 
-extern "C" __global__ void __launch_bounds__(128) k_spec(InterpArgs a) {
+__device__ __forceinline__ void spec_render(const InterpArgs& a, RegLane& L, const SpecOut& o) {
+  const bool FM = a.out_frame_major != 0;
+  DelayBlock D;
+  // tiles of 32 samples (one flush each); inside a tile, blocks of SPEC_BT samples (a divisor of 32) with 32-bit counters
+  for (long tb = 0; tb < a.T; tb += 32) {
+    const int nb = a.T - tb < 32 ? (int)(a.T - tb) : 32;
+    for (int j0 = 0; j0 < nb; j0 += SPEC_BT) {
+      const int n = nb - j0 < SPEC_BT ? nb - j0 : SPEC_BT;
+      spec_ring_reads<0>(L, D, n);
+      spec_block<0>(a, L, D, o, tb + j0, j0, n, FM);
+      spec_ring_writes<0>(L, D, n);
+    }
+    if (!FM) spec_flush(a, o, tb, nb);
+  }
+}
+
+#if !defined(QG_SPEC_MINB)
+#define QG_SPEC_MINB 8   // 64 registers: measured on configs[4] (a 192 -> 189, d 83 -> 67 ms; 10 blocks spill the delay kernel: 88 ms)
+#endif
+extern "C" __global__ void __launch_bounds__(128, QG_SPEC_MINB) k_spec(InterpArgs a) {
   const int nt = blockDim.x, tid = threadIdx.x;
   SpecOut o;
-  o.tiles = QG_SMEM_F;                                       // [n_out][nwarps][32][33]
-  o.lane = tid & 31; o.warp = tid >> 5; o.nwarps = nt >> 5;
-  o.warp_v0 = blockIdx.x * nt + o.warp * 32;
+  o.lane = tid & 31;
+  const int warp = tid >> 5, nwarps = nt >> 5;
+  o.chan_stride = nwarps * 32 * 33;                          // tiles: [n_out][nwarps][32][33]
+  o.warp_tile0 = warp * 32 * 33;
+  o.tile0 = o.warp_tile0 + o.lane * 33;
+  o.warp_v0 = blockIdx.x * nt + warp * 32;
   const int v = blockIdx.x * nt + tid;                       // padded voice index, always < Vp
   RegLane L;
   L.v = v; L.Vp = a.Vp; L.rings = a.rings; L.ring_tab = a.ring_tab; L.tables = a.tables;
@@ -187,15 +214,7 @@ extern "C" __global__ void __launch_bounds__(128) k_spec(InterpArgs a) {
   for (int s = 0; s < SPEC_NS; s++) L.x[SPEC_P + s] = a.state[(size_t)s * a.Vp + v];
 #pragma unroll
   for (int k = 0; k < SPEC_NT; k++) L.x[SPEC_P + SPEC_NS + k] = 0.0f;
-  DelayBlock D;
-  for (long t0 = 0; t0 < a.T; t0 += SPEC_BT) {
-    const int n = (a.T - t0) < SPEC_BT ? (int)(a.T - t0) : SPEC_BT;      // samples in this block
-    spec_ring_reads<0>(L, D, n);
-    spec_block<0>(a, L, D, o, t0, n);
-    spec_ring_writes<0>(L, D, n);
-    // blocks start on multiples of SPEC_BT (a divisor of 32): a tile fills exactly at a block's end
-    if (!a.out_frame_major && (((t0 + n) & 31) == 0 || t0 + n == a.T)) spec_flush(a, o, t0 + n - 1);
-  }
+  spec_render(a, L, o);
 #pragma unroll
   for (int s = 0; s < SPEC_NS; s++) a.state[(size_t)s * a.Vp + v] = L.x[SPEC_P + s];
 }
