@@ -379,7 +379,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
     } break;
     case OP_WAVE: QG_EACH {
       uint32_t i = XSU(I.s);
-      XO(0) = L.tables[I.aux + i];
+      XO(0) = __ldg(L.tables + I.aux + i);
       i += 1;
       if (i >= I.aux2) i = 0;
       SETSU(I.s, i);
@@ -545,7 +545,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
       float tb[8];
       const bool small = I.aux2 <= 8u;
 #pragma unroll
-      for (uint32_t k = 0; k < 8; k++) tb[k] = (small && k < I.aux2) ? L.tables[I.aux + k] : __int_as_float(0x7fc00000);
+      for (uint32_t k = 0; k < 8; k++) tb[k] = (small && k < I.aux2) ? __ldg(L.tables + I.aux + k) : __int_as_float(0x7fc00000);   // read-only for the kernel's lifetime: hoistable out of the sample loop
       QG_EACH {
         float n = XI(0), range = XS(I.p);
         float wrapped = n - range * floorf(n / range);
@@ -558,7 +558,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
           }
         } else {
           for (uint32_t k = 0; k < I.aux2; k++) {
-            float v = L.tables[I.aux + k];
+            float v = __ldg(L.tables + I.aux + k);
             float d = fabsf(wrapped - v);
             if (d < dist) { nearest = v; dist = d; }
           }
@@ -568,7 +568,7 @@ __device__ __forceinline__ void exec(const Instr& I, LaneT& L, int& pc) {
     } break;
     case OP_ARR_GET: QG_EACH {   // nodes.rs:143-149
       uint64_t k = d_as_usize(XI(0));
-      XO(0) = k < (uint64_t)I.aux2 ? L.tables[I.aux + (uint32_t)k] : 0.0f;
+      XO(0) = k < (uint64_t)I.aux2 ? __ldg(L.tables + I.aux + (uint32_t)k) : 0.0f;
     } break;
     // ---------------------------------------------------------------- control flow
     case OP_KR_BEGIN: {   // nodes.rs:272-275
