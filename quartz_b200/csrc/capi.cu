@@ -734,6 +734,65 @@ static void bank_auto_specialise(qg_bank* b, long T) {
 }
 
 static int ensure(float** p, size_t* have, size_t need, cudaStream_t s);
+
+// K5 / K5s: one render call on the frame-parallel spectral path.  *served = false (and QG_OK) when this call has to go to the
+// general kernels instead (ring or shared memory too large) — only possible while the bank has not started on K5.
+static int render_spectral(qg_bank* b, long T, int layout, float* d_out, bool* served) {
+  qg_ctx* c = b->ctx;
+  const Tape& t = b->tape;
+  const bool committed = b->sp_started || b->path == QG_PATH_SPECTRAL;
+  int ring = 0;
+  const size_t yb = spectral_y_bytes(b->sp, b->V, &ring);
+  if (yb > b->fused_scratch_bytes) {        // the ring of a very large bank (10^6 voices x 2048-point frames) may not fit
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && yb > free_b / 2) {
+      if (committed) return fail(QG_ERR_CUDA, "the frame-parallel spectral path needs " + std::to_string(yb >> 20) + " MiB for its ring");
+      return QG_OK;
+    }
+  }
+  int rc = ensure(&b->d_fused_scratch, &b->fused_scratch_bytes, yb, c->stream);
+  if (rc) return rc;
+  SpArgs sa;
+  memset(&sa, 0, sizeof sa);
+  sa.code = b->d_sp_code; sa.n_code = (int)b->sp.code.size(); sa.segs = b->d_sp_segs; sa.n_segs = (int)b->sp.segs.size();
+  sa.items = b->d_sp_items; sa.n_items = (int)b->sp.items.size(); sa.out_x = b->d_sp_out_x; sa.n_out = (int)t.h.n_outputs;
+  sa.params = b->d_params; sa.state_init = b->d_state_init; sa.tables = b->d_tables;
+  sa.P = (int)t.h.n_params; sa.NS = (int)t.h.n_state; sa.V = (int)b->V; sa.Vp = b->Vp;
+  sa.y = b->d_fused_scratch; sa.ring = ring; sa.n_streams = b->sp.n_streams; sa.out = d_out; sa.T = T; sa.t0 = b->sp_time;
+  sa.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
+  sa.C = b->sp.C; sa.post_lo = b->sp.post_lo; sa.post_hi = b->sp.post_hi;
+  sa.n_slots_frame = b->sp.n_slots_frame; sa.n_slots_post = b->sp.n_slots_post;
+  // K5s: compiling the plan into the kernels costs ~2 s of NVRTC once per plan and process (cached after that) and makes a
+  // render 2.2x faster: AUTO compiles once the bank has QG_SPECTRAL_MIN_WORK voice-samples (default 2e9) behind and ahead of
+  // it, or at once when the plan's kernels are already in the cache.  QG_SPECTRAL_SPEC=1 specialises every K5 bank, =0 none;
+  // a failed compile keeps the generic kernels.
+  if (!b->sp_spec.frames) {
+    const char* es = getenv("QG_SPECTRAL_SPEC");
+    const bool force = es && es[0] == '1', never = es && es[0] == '0';
+    if (!never && !b->sp_cache_checked) { b->sp_cache_checked = true; spectral_spec_cached(b->sp, t, &b->sp_spec); }
+    b->sp_work += (double)b->V * (double)T;
+    const char* ew = getenv("QG_SPECTRAL_MIN_WORK");
+    const double wv = ew ? atof(ew) : 0.0, min_work = wv > 0.0 ? wv : 2.0e9;
+    if (!never && !b->sp_spec.frames && !b->sp_spec_tried && (force || b->sp_work >= min_work)) {
+      b->sp_spec_tried = true;
+      std::string err;
+      try { spectral_spec_compile(b->sp, t, &b->sp_spec, &err); } catch (...) {}
+      if (!b->sp_spec.frames && force) return fail(QG_ERR_UNSUPPORTED, "QG_SPECTRAL_SPEC=1: " + err);
+    }
+  }
+  int l = 0;
+  cudaError_t se = launch_spectral(sa, b->sp, c->stream, &l, b->sp_spec.frames, b->sp_spec.post);
+  c->launches += l;
+  if (se == cudaErrorNotSupported) {
+    if (committed) return fail(QG_ERR_UNSUPPORTED, "the spectral path needs more shared memory than one SM offers");
+    return QG_OK;
+  }
+  CU(se);
+  b->sp_started = true; b->sp_time += T; b->last_k5 = true;
+  *served = true;
+  return QG_OK;
+}
+
 static int render_impl(qg_bank* b, long T, int layout, int group, const float* d_in, float* d_out) {
   qg_ctx* c = b->ctx;
   const Tape& t = b->tape;
@@ -742,47 +801,9 @@ static int render_impl(qg_bank* b, long T, int layout, int group, const float* d
   int rc = check_group(b, layout, group);
   if (rc) return rc;
   if (!d_in && group == 1 && bank_spectral(b, T)) {
-    SpArgs sa;
-    memset(&sa, 0, sizeof sa);
-    int ring = 0;
-    const size_t yb = spectral_y_bytes(b->sp, b->V, &ring);
-    rc = ensure(&b->d_fused_scratch, &b->fused_scratch_bytes, yb, b->ctx->stream);
-    if (rc) return rc;
-    sa.code = b->d_sp_code; sa.n_code = (int)b->sp.code.size(); sa.segs = b->d_sp_segs; sa.n_segs = (int)b->sp.segs.size();
-    sa.items = b->d_sp_items; sa.n_items = (int)b->sp.items.size(); sa.out_x = b->d_sp_out_x; sa.n_out = (int)t.h.n_outputs;
-    sa.params = b->d_params; sa.state_init = b->d_state_init; sa.tables = b->d_tables;
-    sa.P = (int)t.h.n_params; sa.NS = (int)t.h.n_state; sa.V = (int)b->V; sa.Vp = b->Vp;
-    sa.y = b->d_fused_scratch; sa.ring = ring; sa.n_streams = b->sp.n_streams; sa.out = d_out; sa.T = T; sa.t0 = b->sp_time;
-    sa.frame_major = layout == QG_LAYOUT_FRAME_MAJOR;
-    sa.C = b->sp.C; sa.post_lo = b->sp.post_lo; sa.post_hi = b->sp.post_hi;
-    sa.n_slots_frame = b->sp.n_slots_frame; sa.n_slots_post = b->sp.n_slots_post;
-    // K5s: compiling the plan into the kernels costs ~2 s of NVRTC once per plan and process (cached after that) and makes a
-    // render 2.2x faster: AUTO compiles once the bank has QG_SPECTRAL_MIN_WORK voice-samples (default 2e9) behind and ahead of
-    // it, or at once when the plan's kernels are already in the cache.  QG_SPECTRAL_SPEC=1 specialises every K5 bank, =0 none;
-    // a failed compile keeps the generic kernels.
-    if (!b->sp_spec.frames) {
-      const char* es = getenv("QG_SPECTRAL_SPEC");
-      const bool force = es && es[0] == '1', never = es && es[0] == '0';
-      if (!never && !b->sp_cache_checked) { b->sp_cache_checked = true; spectral_spec_cached(b->sp, t, &b->sp_spec); }
-      b->sp_work += (double)b->V * (double)T;
-      const char* ew = getenv("QG_SPECTRAL_MIN_WORK");
-      const double wv = ew ? atof(ew) : 0.0, min_work = wv > 0.0 ? wv : 2.0e9;
-      if (!never && !b->sp_spec.frames && !b->sp_spec_tried && (force || b->sp_work >= min_work)) {
-        b->sp_spec_tried = true;
-        std::string err;
-        try { spectral_spec_compile(b->sp, t, &b->sp_spec, &err); } catch (...) {}
-        if (!b->sp_spec.frames && force) return fail(QG_ERR_UNSUPPORTED, "QG_SPECTRAL_SPEC=1: " + err);
-      }
-    }
-    int l = 0;
-    cudaError_t se = launch_spectral(sa, b->sp, c->stream, &l, b->sp_spec.frames, b->sp_spec.post);
-    c->launches += l;
-    if (se != cudaErrorNotSupported) {
-      CU(se);
-      b->sp_started = true; b->sp_time += T; b->last_k5 = true;
-      return QG_OK;
-    }
-    if (b->sp_started || b->path == QG_PATH_SPECTRAL) return fail(QG_ERR_UNSUPPORTED, "the spectral path needs more shared memory than one SM offers");
+    bool served = false;
+    rc = render_spectral(b, T, layout, d_out, &served);
+    if (rc || served) return rc;
   }
   if (b->sp_started) return fail(QG_ERR_MISMATCH, "this bank is rendering on the frame-parallel spectral path (no group mix, no inputs): reset it first");
   if (b->path == QG_PATH_SPECTRAL) return fail(QG_ERR_ARG, "QG_PATH_SPECTRAL renders group-1 banks without inputs");
