@@ -66,3 +66,29 @@ def test_voice_range_partitions():
         assert spans[0][0] == 0 and spans[-1][1] == V
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert all((hi - lo) % G == 0 for lo, hi in spans)
+
+
+def test_bench_arms_share_config_keys_and_strong_shards_cover_the_bank():
+    """the reference arm and the B200 arm describe the workload with the same `config` object (the driver compares them), and
+    a strong split of configs[4] hands every voice to exactly one rank"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name in ("c1", "c2", "c3", "c4", "c5"):
+        wls = bench.make_workloads(name, 0)
+        cfg = bench.config_of(name, wls)
+        assert set(cfg) == {"workload", "voices", "samples", "sample_rate", "group", "layout", "note"}, name
+        assert cfg["voices"] == sum(w.V for w in wls) and cfg["sample_rate"] == 48000
+    assert bench.config_of("c3", bench.make_workloads("c3", 0))["workload"] == "c3_polysynth_65536"      # the north-star target
+    total = sum(w.V for w in bench.make_workloads("c5", 0))
+    for world in (2, 4, 8):
+        seen = 0
+        for rank in range(world):
+            share = bench.make_workloads("c5", rank, world, strong=True)
+            assert len(share) == 4 and all(w.V % w.group == 0 for w in share)
+            seen += sum(w.V for w in share)
+        assert seen == total == 1048576
+        weak = bench.make_workloads("c3", 1, world, strong=False)
+        assert weak[0].V == 65536                                   # weak scaling: a full-size bank per rank
