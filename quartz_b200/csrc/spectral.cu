@@ -66,7 +66,6 @@ struct Planner {
   std::vector<Instr> mt;
   int slots = 0;
   std::map<std::pair<int, long>, int> memo;   // (instruction, time offset) -> X index of its first output
-  std::map<std::pair<int, int>, int> memo_y;  // (ifft instruction, component) -> X index
   bool fail = false;
 
   Planner(const Tape& t_, SpPlan& p) : t(t_), pl(p), PS((int)(t_.h.n_params + t_.h.n_state)) {}
@@ -151,7 +150,7 @@ struct Planner {
       if (it != memo.end()) return it->second;
       const int base = new_slots(2);
       memo[{p, 0}] = base;
-      return base;           // the loads are added by finish_post(), for the components that are actually read
+      return base;           // the loads are added in build(), for the components that are actually read
     }
     auto it = memo.find({p, d});
     if (it != memo.end()) return it->second;
@@ -326,8 +325,8 @@ struct Planner {
     mt.insert(mt.begin(), loads.begin(), loads.end());
     std::vector<int*> live;
     for (int& o : ox) live.push_back(&o);
-    // STREAM_IN writes one slot although its ifft reserved two: compact() only looks at what instructions write
-    pl.n_slots_post = compact_post(mt, live);
+    // (a STREAM_IN writes one slot although its ifft reserved two: compact() only looks at what instructions write)
+    pl.n_slots_post = compact(mt, live, 0);
     pl.post_lo = (int)pl.code.size();
     pl.code.insert(pl.code.end(), mt.begin(), mt.end());
     pl.post_hi = (int)pl.code.size();
@@ -338,7 +337,6 @@ struct Planner {
     if (pl.n_slots_frame > 48 || pl.n_slots_post > 96 || pl.code.size() > 512) return false;
     return true;
   }
-  int compact_post(std::vector<Instr>& code, std::vector<int*> live) { return compact(code, live, 0); }
 };
 
 }  // namespace
