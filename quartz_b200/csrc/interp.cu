@@ -1014,58 +1014,6 @@ __device__ __noinline__ void exec_one_thread(const Instr& I, TvSample& L) {
   exec(I, L, dummy);
 }
 
-// Exact f32 phase accumulator with a CONSTANT increment (`sine(440)`, `dc(f) >> ramp()`: what quartz renders most), stepped a
-// BINADE at a time instead of a sample at a time.  The reference's recurrence `ph = fl(ph + inc)` cannot be re-associated —
-// its rounding drift is part of the signal — but inside one binade [2^e, 2^(e+1)) every ph is a multiple of ulp = 2^(e-23),
-// so fl(ph + inc) = ph + d with the SAME d = RN_ulp(inc) for every step that stays in the binade (no ties: checked), and
-// ph + m d is exact.  Lane 0 of a warp takes one real FADD step, reads d off it, counts the steps M that stay below the top of
-// the binade, and the warp's 32 lanes write those M phases (in f64: exact); the step that leaves the binade — or wraps — is
-// again a real FADD.  A 440 Hz phase at 48 kHz crosses ~8 binades per cycle of 109 samples.  WRAP_FLOOR: `ph -= floor(ph)`
-// (FunDSP sine), else `if (ph >= 1) ph -= 1` (nodes.rs:476-483 ramp).  Other increments (<= 0, >= 0.5) take one step at a time.
-template <bool WRAP_FLOOR>
-__device__ __forceinline__ float tv_phase_const(float* o, int n, float inc, float ph, int lane) {
-  const bool fast_ok = inc > 0.0f && inc < 0.5f;
-  for (int j = 0; j < n;) {
-    int cnt = 1;
-    float d = 0.0f, pn = 0.0f;
-    if (lane == 0) {
-      float p1 = ph + inc;
-      bool done = false;
-      const uint32_t eb = __float_as_uint(ph) & 0x7f800000u;
-      if (fast_ok && ph > 0.0f && p1 < 1.0f && eb >= (40u << 23) && (__float_as_uint(p1) & 0x7f800000u) == eb) {
-        const float ulp = __uint_as_float(eb - (23u << 23)), top = __uint_as_float(eb + (1u << 23));
-        const float dd = p1 - ph;                                        // exact: both are multiples of ulp
-        const float r = inc - floorf(inc / ulp) * ulp;                   // exact: inc modulo ulp
-        if (dd == 0.0f) { cnt = n - j; pn = ph; done = true; }           // the increment rounds away: the phase is stuck
-        else if (r != 0.5f * ulp) {                                      // (a tie would alternate between two steps)
-          const int M = (int)fmin(ceil(((double)top - (double)ph) / (double)dd), 1.0e9);   // ph + m dd < top for m < M
-          d = dd;
-          if (M <= n - j) {                                              // the segment ends inside this hop: leave the binade
-            cnt = M;
-            pn = (float)((double)ph + (double)(M - 1) * (double)dd) + inc;
-            if (WRAP_FLOOR) pn -= floorf(pn); else if (pn >= 1.0f) pn -= 1.0f;
-          } else {
-            cnt = n - j;
-            pn = (float)((double)ph + (double)cnt * (double)dd);
-          }
-          done = true;
-        }
-      }
-      if (!done) {
-        if (WRAP_FLOOR) p1 -= floorf(p1); else if (p1 >= 1.0f) p1 -= 1.0f;
-        pn = p1;
-      }
-    }
-    cnt = __shfl_sync(0xffffffffu, cnt, 0);
-    d = __shfl_sync(0xffffffffu, d, 0);
-    pn = __shfl_sync(0xffffffffu, pn, 0);
-    for (int m = lane; m < cnt; m += 32) o[j + m] = (float)((double)ph + (double)m * (double)d);
-    j += cnt;
-    ph = pn;
-  }
-  return ph;
-}
-
 constexpr int TV_SEGCAP = 72;   // lfo segments a 512-sample hop can cross when a segment is at least 8 samples long
 // (idx + j) mod len for idx < len: one conditional subtract in the common case (ring at least one hop long)
 __device__ __forceinline__ uint32_t tv_wrap(uint32_t p, uint32_t len) {
@@ -1291,14 +1239,11 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
               for (int j = tid; j < n; j += nth) TMP(Q.out)[j] = SRC(Q.in[0], j) * isr;
             }
             __syncthreads();
-            for (int q = pc + (tid >> 5); q < pe; q += nth >> 5) {   // one warp per oscillator
-              const Instr Q = code[q];
-              float* o = TMP(Q.out);
-              if ((int)Q.in[0] < PS) {                       // constant frequency: binade-at-a-time stepping by the whole warp
-                const float ph = tv_phase_const<true>(o, n, o[0], ps[Q.s], tid & 31);
-                if ((tid & 31) == 0) ps[Q.s] = ph;
-              } else if ((tid & 31) == 0) {                  // modulated frequency: the warp's leader steps sample by sample
+            if ((tid & 31) == 0) {
+              for (int q = pc + (tid >> 5); q < pe; q += nth >> 5) {
+                const Instr Q = code[q];
                 float ph = ps[Q.s];
+                float* o = TMP(Q.out);
                 for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = ph; ph += inc; ph -= floorf(ph); }
                 ps[Q.s] = ph;
               }
@@ -1316,16 +1261,11 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             __syncthreads();
             for (int j = tid; j < n; j += nth) TMP(I.out)[j] = SRC(I.in[0], j) / sr;
             __syncthreads();
-            if (tid < 32) {
+            if (tid == 0) {
+              float val = ps[I.s];
               float* o = TMP(I.out);
-              if ((int)I.in[0] < PS) {                       // constant frequency (`dc(f) >> ramp()`)
-                const float val = tv_phase_const<false>(o, n, o[0], ps[I.s], tid);
-                if (tid == 0) ps[I.s] = val;
-              } else if (tid == 0) {
-                float val = ps[I.s];
-                for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = val; val += inc; if (val >= 1.0f) val -= 1.0f; }
-                ps[I.s] = val;
-              }
+              for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = val; val += inc; if (val >= 1.0f) val -= 1.0f; }
+              ps[I.s] = val;
             }
             break;
           }
