@@ -48,12 +48,15 @@ __device__ __forceinline__ void lane_fft(const RegLane&, uint32_t, uint32_t, int
 // whole-block access): per block of 8 samples the kernel issues all ring reads of every such delay op up front (8
 // independent 128-byte lines per warp and op), runs the 8 samples out of registers, then stores the 8 writes.
 // Measured without it (round 1): one dependent load per sample made configs[4]'s delay archetype 6x SLOWER than K1b.
-__host__ __device__ constexpr bool spec_is_pref(int i) { return kTape[i].op == OP_DELAY && kRingLen[kTape[i].aux] >= 8u; }
+#if !defined(QG_SPEC_BT_DELAY)
+#define QG_SPEC_BT_DELAY 8   // samples per block when a delay line is prefetched (measured on configs[4] d: 4 / 8 / 16 in profiles/README.md)
+#endif
+__host__ __device__ constexpr bool spec_is_pref(int i) { return kTape[i].op == OP_DELAY && kRingLen[kTape[i].aux] >= (uint32_t)QG_SPEC_BT_DELAY; }
 __host__ __device__ constexpr int spec_pref_before(int upto) { int c = 0; for (int k = 0; k < upto; k++) c += spec_is_pref(k) ? 1 : 0; return c; }
 constexpr int SPEC_ND = spec_pref_before(SPEC_N);
 // samples per block: 8 when a delay line is prefetched, else 1 (the tape is instantiated once per sample of a block, and
 // NVRTC's compile time grows with it)
-constexpr int SPEC_BT = SPEC_ND > 0 ? 8 : 1;
+constexpr int SPEC_BT = SPEC_ND > 0 ? QG_SPEC_BT_DELAY : 1;
 
 struct DelayBlock {
   float rd[SPEC_ND > 0 ? SPEC_ND : 1][SPEC_BT];
