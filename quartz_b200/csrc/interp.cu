@@ -1244,7 +1244,16 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
                 const Instr Q = code[q];
                 float ph = ps[Q.s];
                 float* o = TMP(Q.out);
-                for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = ph; ph += inc; ph -= floorf(ph); }
+                const float inc0 = o[0];
+                if ((int)Q.in[0] < PS && inc0 >= 0.0f && inc0 < 1.0f && ph >= 0.0f && ph < 1.0f) {
+                  // constant frequency (`sine(440)`: what quartz renders most): the increment is not reloaded, and for a phase
+                  // in [0, 2) `ph -= floor(ph)` IS a conditional `- 1` (exact either way) — the dependent chain per sample is
+                  // FADD, FSETP, predicated FADD instead of LDS, FADD, FRND, FADD
+#pragma unroll 4
+                  for (int j = 0; j < n; j++) { o[j] = ph; ph += inc0; if (ph >= 1.0f) ph -= 1.0f; }
+                } else {
+                  for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = ph; ph += inc; ph -= floorf(ph); }
+                }
                 ps[Q.s] = ph;
               }
             }
@@ -1264,7 +1273,13 @@ __global__ void __launch_bounds__(256, 4) k_interp_tv(TvArgs a) {
             if (tid == 0) {
               float val = ps[I.s];
               float* o = TMP(I.out);
-              for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = val; val += inc; if (val >= 1.0f) val -= 1.0f; }
+              if ((int)I.in[0] < PS) {                      // constant frequency (`dc(f) >> ramp()`): the increment stays in a register
+                const float inc0 = o[0];
+#pragma unroll 4
+                for (int j = 0; j < n; j++) { o[j] = val; val += inc0; if (val >= 1.0f) val -= 1.0f; }
+              } else {
+                for (int j = 0; j < n; j++) { const float inc = o[j]; o[j] = val; val += inc; if (val >= 1.0f) val -= 1.0f; }
+              }
               ps[I.s] = val;
             }
             break;
